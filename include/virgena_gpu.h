@@ -1,0 +1,206 @@
+/*
+ * virgena_gpu.h — C ABI of libvirgena_gpu.so, the B200 (sm_100a) implementation
+ * of VirGenA's read-mapping hot path.
+ *
+ * The reference (gFedonin/VirGenA, pure Java) has no FFI/plugin interface; the
+ * seam this library replaces is the batch API used by RefBasedAssembler and
+ * MassRefBasedAssembler:
+ *
+ *   Mapper.mapReads(ArrayList<PairedRead>, Reference)          Mapper.java:420
+ *   Mapper.mapReads(MappedData, Reference)   (remap subset)    Mapper.java:477
+ *   MapperMSA.mapAllReads(ArrayList<PairedRead>, ReferenceAlignment)
+ *                                                              MapperMSA.java:274
+ *   ConsensusBuilderSimple.getConsensusSimple(boolean,int,byte[])
+ *                                                              ConsensusBuilderSimple.java:123
+ *
+ * Each entry point below names the reference code it stands in for. A JNI /
+ * Panama / ctypes stub binds exactly these symbols.
+ *
+ * Conventions
+ *   - plain C types only; all host buffers are owned by the caller and are not
+ *     retained past the call; device memory is owned by the context.
+ *   - every function returns VG_OK (0) or a negative vg_status; the message is
+ *     available from vg_last_error(ctx). There is NO CPU fallback: without a
+ *     CUDA device every compute entry point fails with VG_ERR_CUDA.
+ *   - calls on one context are serialised by the caller (one host thread per
+ *     context, like one `Mapper` instance per `mapReads` call).
+ *   - coordinates are 0-based offsets into the concatenated reference `seqB`
+ *     (Reference.java:207-256), exactly as in MappedRead / Alignment.
+ */
+#ifndef VIRGENA_GPU_H
+#define VIRGENA_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VG_ABI_VERSION 1
+
+typedef enum {
+  VG_OK = 0,
+  VG_ERR_INVALID = -1,     /* bad argument / unsupported parameter range        */
+  VG_ERR_CUDA = -2,        /* CUDA runtime failure, or no device                */
+  VG_ERR_STATE = -3,       /* call order (e.g. map before set_reference)        */
+  VG_ERR_CAPACITY = -4,    /* caller buffer too small; see vg_last_required()   */
+  VG_ERR_ALPHABET = -5,    /* a byte the Java reference would throw on          */
+  VG_ERR_INDEX = -6,       /* host-supplied k-mer index inconsistent with seqB  */
+  VG_ERR_OVERFLOW = -7     /* a device work buffer overflowed (see message)     */
+} vg_status;
+
+/* Pair classes = the six result lists of MappedData (MappedData.java:8-13);
+ * the two concordant sides are Mapper.java:226-263. */
+enum {
+  VG_CLS_CONCORDANT_FR = 0, /* side 0: forward mate1 x reverse mate2 */
+  VG_CLS_CONCORDANT_RF = 1, /* side 1: reverse mate1 x forward mate2 */
+  VG_CLS_DISCORDANT = 2,
+  VG_CLS_LEFT = 3,          /* leftMateMapped  */
+  VG_CLS_RIGHT = 4,         /* rightMateMapped */
+  VG_CLS_UNMAPPED = 5
+};
+
+/* Parameters read by the reference from config.xml at construction
+ * (Mapper.java:27-37, KMerCounter.java:14-33, SmithWatermanGotoh.java:7-14).
+ * low_coef/high_coef are passed verbatim (Q3: the single-reference Mapper runs
+ * with lowCoef == 0.0f). cutoffs[len] is KMerCounterBase.cutoffs (an input:
+ * the reference derives it from an unseeded RNG, Q10). */
+typedef struct {
+  int32_t K;
+  float low_coef;
+  float high_coef;
+  const int32_t* cutoffs; /* n_cutoffs = maxReadLen + 1 entries */
+  int32_t n_cutoffs;
+  int32_t insert_len;     /* Data/InsertionLength */
+  int32_t match, mismatch, gop, gep;
+} vg_params;
+
+/* One mapped mate = MappedRead (MappedRead.java:4-16) + its Alignment
+ * (Alignment.java:4-35). `present == 0` means the Java field (r1/r2) is null.
+ * seq1_offset/length address Alignment.sequence1 inside the caller's pool. */
+typedef struct {
+  int32_t present;
+  int32_t start, end, count;   /* MappedRead.start/end/count (candidate window) */
+  int32_t reverse;             /* MappedRead.reverse */
+  int32_t fragment_id;         /* MappedRead.fragmentID */
+  int32_t score, start1, end1, start2, end2, identity, length; /* Alignment.* */
+  int32_t pad_;
+  int64_t seq1_offset;         /* -1 when there is no alignment (MSA mode)      */
+} vg_mate;
+
+typedef struct {
+  int32_t cls;                 /* VG_CLS_* */
+  int32_t pad_;
+  vg_mate m[2];                /* r1, r2 */
+} vg_pair_result;
+
+/* Mapping stats 1)-7) logged by Mapper.java:462-473 (a parity checksum). */
+typedef struct {
+  int64_t total_pairs, both_exist, reads_total, total_mapped;
+  int64_t mapped_forward, mapped_reverse, both_mapped, total_score, total_concordant;
+} vg_map_stats;
+
+typedef struct vg_ctx vg_ctx;
+
+/* Library / device probes (no context needed). */
+int vg_abi_version(void);
+int vg_device_count(void);           /* 0 when no CUDA device is usable */
+
+/* new Mapper(document) [Mapper.java:27] + KMerCounter + SmithWatermanGotoh
+ * parameters, bound to one CUDA device. */
+int vg_ctx_create(const vg_params* params, int device, vg_ctx** out);
+void vg_ctx_destroy(vg_ctx* ctx);
+const char* vg_last_error(const vg_ctx* ctx);
+int64_t vg_last_required(const vg_ctx* ctx);
+
+/* new Reference(...) [Reference.java:98-205]: the concatenated sequence, contig
+ * and fragment ends, and the k-mer index of StringIndexer.buildIndexPara
+ * [StringIndexer.java:47-83]. Either pass the host-built index as CSR
+ * (n_keys K-byte keys, offsets[n_keys+1], positions) or pass keys == NULL and
+ * the thread count the Java would have used (index_thread_num; it determines
+ * the duplicated boundary positions, Q1) and the library rebuilds it. */
+int vg_set_reference(vg_ctx* ctx, const uint8_t* seq, int32_t G, const int32_t* contig_ends, int32_t n_contigs,
+                     const int32_t* fragment_ends, int32_t n_fragments, int32_t is_fragmented,
+                     const uint8_t* keys, const int64_t* offsets, const int32_t* positions, int32_t n_keys,
+                     int32_t index_thread_num);
+
+/* ReferenceAlignment.refAlnIndex [ReferenceAlignment.java:138-209] + the
+ * KMerCounterMSA parameters [KMerCounterMSA.java:14-47]: k-mer -> sorted
+ * distinct alignment columns, as CSR. */
+int vg_set_msa_index(vg_ctx* ctx, int32_t K, float low_coef, float high_coef, const int32_t* cutoffs,
+                     int32_t n_cutoffs, const uint8_t* keys, const int64_t* offsets, const int32_t* columns,
+                     int32_t n_keys, int32_t msa_length);
+
+/* DataReader.pairedReads made resident on the device: `bases` is one byte
+ * pool; mate k of pair i is bases[off_k[i] .. off_k[i]+len_k[i]). An absent
+ * mate is the single byte '*' (Constants.NULL_SEQ). Reads stay resident across
+ * mapping passes (iterations 1..3 of ConsensusBuilderWithReassembling). */
+int vg_upload_reads(vg_ctx* ctx, const uint8_t* bases, int64_t n_bases, const int64_t* off1, const int32_t* len1,
+                    const int64_t* off2, const int32_t* len2, int64_t n_pairs);
+
+/* Mapper.mapReads(reads, genome) [Mapper.java:420] when pair_idx == NULL
+ * (all resident pairs, in order), or Mapper.mapReads(mappedData, genome)
+ * [Mapper.java:477] over the subset pair_idx[0..n_idx) (needToRemap).
+ * Results stay on the device; fetch them with vg_get_results. */
+int vg_map_pairs(vg_ctx* ctx, const int64_t* pair_idx, int64_t n_idx, vg_map_stats* stats);
+
+/* MapperMSA.mapAllReads [MapperMSA.java:274]: same pairing logic in MSA column
+ * coordinates, no alignment; score = k-mer count. */
+int vg_map_pairs_msa(vg_ctx* ctx, vg_map_stats* stats);
+
+/* Number of results of the last map call and the bytes of all sequence1. */
+int vg_result_sizes(vg_ctx* ctx, int64_t* n_results, int64_t* seq1_bytes);
+
+/* Copies the per-pair results (input order) and the sequence1 byte pool of the
+ * last map call to the host. seq1_offset values index `seq1_pool`. */
+int vg_get_results(vg_ctx* ctx, vg_pair_result* out, int64_t n_out, uint8_t* seq1_pool, int64_t pool_cap);
+
+/* ConsensusBuilderSimple.ReadCounting [ConsensusBuilderSimple.java:56-75] +
+ * the partial-matrix sum [:138-145] over the mapped reads of the last
+ * vg_map_pairs call (accumulate != 0 adds to the counts of earlier calls, the
+ * way remapped reads join mappedData.mappedReads). Counts are int32[G][5]
+ * (A,T,G,C,gap). The device buffer is exposed so that the host plumbing can
+ * all-reduce it across GPUs (the multi-GPU replacement of the serial sum). */
+int vg_pileup(vg_ctx* ctx, int32_t accumulate);
+int vg_pileup_counts_device(vg_ctx* ctx, void** dev_ptr, int64_t* n_int32);
+int vg_pileup_counts_host(vg_ctx* ctx, int32_t* out, int64_t n_int32);
+
+/* ConsensusBuildingSimple [ConsensusBuilderSimple.java:98-120] on the current
+ * (possibly all-reduced) counts. */
+int vg_consensus(vg_ctx* ctx, int32_t save_uncovered, int32_t coverage_threshold, const uint8_t* genome, int32_t G,
+                 uint8_t* out);
+
+/* Aligner.align [Aligner.java:14, SmithWatermanGotoh.java:51] over a batch of
+ * independent (s1, s2) pairs given as byte pools + offsets (n+1 entries each).
+ * rec[i] = {score,start1,end1,start2,end2,identity,length}; sequence1 of task
+ * i is written at seq1_pool + seq1_off[i] (caller provides len1+len2 bytes per
+ * task). Used by tests and by the "next" callers. */
+int vg_sw_align_batch(vg_ctx* ctx, const uint8_t* s1_pool, const int64_t* s1_off, const uint8_t* s2_pool,
+                      const int64_t* s2_off, int64_t n, int32_t* rec, uint8_t* seq1_pool, const int64_t* seq1_off);
+
+/* Aligner.findMaxScore [Aligner.java:16, SmithWatermanGotoh.java:240]. */
+int vg_sw_max_score_batch(vg_ctx* ctx, const uint8_t* s1_pool, const int64_t* s1_off, const uint8_t* s2_pool,
+                          const int64_t* s2_off, int64_t n, int32_t* score);
+
+/* KMerCounter.getNBestRegions [KMerCounter.java:223] /
+ * KMerCounterMSA.getNBestRegions [KMerCounterMSA.java:71] for a batch of
+ * single reads (no pairing): windows[i] = up to max_windows (start,end,count)
+ * triples, n_windows[i] their number. */
+int vg_seed_batch(vg_ctx* ctx, int32_t msa, const uint8_t* pool, const int64_t* off, int64_t n, int32_t max_windows,
+                  int32_t* windows, int32_t* n_windows);
+
+/* Timing of the device stages of the last map / pileup call, in milliseconds
+ * (CUDA events on the context's stream): [0]=seeding+pair select, [1]=SW fill,
+ * [2]=traceback, [3]=pileup, [4]=total, [5]=SW cells (as a double count). */
+int vg_last_timings(vg_ctx* ctx, double* out6);
+
+/* Measurement helpers (bench.py): a DPX issue-rate microbenchmark that defines
+ * the denominator of the SW roofline (packed s16x2 ops/s), and counters of the
+ * kernels launched by this context. */
+int vg_dpx_peak(vg_ctx* ctx, double* ops_per_s);
+int64_t vg_kernel_launches(const vg_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIRGENA_GPU_H */

@@ -1,0 +1,128 @@
+// Host-side context of libvirgena_gpu.so.
+#pragma once
+#include <stdarg.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+// A growable device buffer owned by the context.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return (T*)p;
+  }
+};
+
+struct SeedConfig {  // one k-mer counter (KMerCounter or KMerCounterMSA)
+  int K = 0;
+  float lowCoef = 0.f, highCoef = 0.f;
+  std::vector<int32_t> cutoffs;
+  DevBuf d_cutoffs;
+};
+
+struct vg_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  int smCount = 148;
+  char err[1024] = {0};
+  int64_t required = 0;
+  int64_t launches = 0;
+
+  // parameters
+  SeedConfig seed;      // single-reference KMerCounter
+  SeedConfig seedMsa;   // KMerCounterMSA
+  int insertLen = 1000;
+  SwParams sw{2, -3, 5, 2};
+
+  // reference (Reference.java fields)
+  int G = 0;
+  bool haveRef = false;
+  std::vector<uint8_t> h_ref;
+  std::vector<int32_t> contigEnds, fragmentEnds;
+  bool isFragmented = false;
+  DevBuf d_ref, d_contigEnds, d_fragmentEnds;
+  // single-reference seeding tables (see seed.cuh)
+  DevBuf d_poscode;   // u32 per reference position: k-mer id | dup flag
+  DevBuf d_exoKeys;   // sorted 64-bit packed exotic k-mers (contain a non-ACGT byte)
+  int nExo = 0;
+  // MSA index
+  bool haveMsa = false;
+  int msaLength = 0;
+  DevBuf d_msaOff, d_msaCols, d_msaExoKeys;  // CSR: 4^K + nExo keys
+  int nMsaExo = 0;
+
+  // resident reads
+  bool haveReads = false;
+  int64_t nPairs = 0, nBases = 0;
+  int maxReadLen = 0;
+  DevBuf d_bases, d_off1, d_off2, d_len1, d_len2;
+  std::vector<uint8_t> h_exist;  // per pair: bit0 mate1 exists, bit1 mate2 exists
+
+  // results of the last map call
+  int64_t nResults = 0, seq1Bytes = 0;
+  bool resultsMsa = false;
+  DevBuf d_results, d_seq1pool, d_pairIdx;
+  // scratch
+  DevBuf d_tasks, d_fill, d_alns, d_rev, d_rowck, d_colck, d_counter, d_scratch, d_seqOff, d_cand, d_ncand, d_misc;
+  DevBuf d_s1pool, d_s2pool, d_s1off, d_s2off;
+  // pileup
+  DevBuf d_counts;
+  bool haveCounts = false;
+  double timings[6] = {0, 0, 0, 0, 0, 0};
+};
+
+static inline int vg_fail(vg_ctx* c, int code, const char* fmt, ...) {
+  if (c) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c->err, sizeof c->err, fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define VG_CUDA(c, call)                                                                                   \
+  do {                                                                                                     \
+    cudaError_t e__ = (call);                                                                              \
+    if (e__ != cudaSuccess)                                                                                \
+      return vg_fail((c), VG_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,                \
+                     cudaGetErrorString(e__));                                                             \
+  } while (0)
+
+#define VG_TRY(expr)              \
+  do {                            \
+    int rc__ = (expr);            \
+    if (rc__ != VG_OK) return rc__; \
+  } while (0)
+
+#define VG_LAUNCH_CHECK(c)                                                                              \
+  do {                                                                                                  \
+    (c)->launches++;                                                                                    \
+    cudaError_t e__ = cudaGetLastError();                                                               \
+    if (e__ != cudaSuccess)                                                                             \
+      return vg_fail((c), VG_ERR_CUDA, "kernel launch failed at %s:%d: %s", __FILE__, __LINE__,         \
+                     cudaGetErrorString(e__));                                                          \
+  } while (0)

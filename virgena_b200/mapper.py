@@ -1,0 +1,394 @@
+"""Host-side mirror of the reference's batch API for the read-mapping hot path.
+
+The reference is Java and no JVM exists in this environment, so the host layer above the C ABI is
+written in Python with the same names, argument meaning and error behaviour as the Java classes:
+
+    Mapper.mapReads(reads, genome)                  Mapper.java:420
+    Mapper.mapReads(mappedData, genome)             Mapper.java:477   (remap of needToRemap)
+    MapperMSA.mapAllReads(reads, refAlignment)      MapperMSA.java:274
+    ConsensusBuilderSimple.getConsensusSimple(...)  ConsensusBuilderSimple.java:123
+
+Everything here is plumbing (ctypes + numpy); all computation happens in libvirgena_gpu.so.
+The Java shim a maintainer would add instead is in virgena_b200/java/ and INTEGRATION.md.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import PAIR_DTYPE, VgError, VgMapStats, VgParams, ptr
+
+NULL_SEQ = b"*"  # Constants.NULL_SEQ (Constants.java:8)
+
+
+def _u8(x):
+    if isinstance(x, (bytes, bytearray)):
+        return np.frombuffer(bytes(x), dtype=np.uint8)
+    if isinstance(x, str):
+        return np.frombuffer(x.encode("latin1"), dtype=np.uint8)
+    return np.ascontiguousarray(x, dtype=np.uint8)
+
+
+class Reference:
+    """Reference (Reference.java): concatenated sequence, contig/fragment ends and the thread count that
+    StringIndexer.buildIndexPara would use (it determines the duplicated boundary positions, Q1)."""
+
+    def __init__(self, seq, K=5, contig_ends=None, fragment_ends=None, is_fragmented=False, thread_num=1,
+                 index_csr=None):
+        self.seqB = _u8(seq)
+        self.length = len(self.seqB)
+        self.K = K
+        self.contigEnds = np.ascontiguousarray(contig_ends if contig_ends is not None else [self.length], np.int32)
+        self.fragmentEnds = np.ascontiguousarray(fragment_ends if fragment_ends is not None else self.contigEnds,
+                                                 np.int32)
+        self.isFragmented = bool(is_fragmented)
+        self.threadNum = int(thread_num)
+        self.index_csr = index_csr  # optional (keys[nk,K] u8, offsets[nk+1] i64, positions i32) built by the host
+
+    def derive(self, seq):
+        """new Reference(byte[] g, K, genome, threadNum) (Reference.java:185-205): same layout, new bases."""
+        return Reference(seq, self.K, self.contigEnds, self.fragmentEnds, self.isFragmented, self.threadNum)
+
+
+class ReferenceAlignment:
+    """ReferenceAlignment (ReferenceAlignment.java): gapped rows of equal length and the index
+    k-mer -> sorted distinct alignment columns (buildAlnIndex :138-209), built on the host."""
+
+    def __init__(self, rows, K=7):
+        rows = np.ascontiguousarray(rows, np.uint8)
+        self.rows = rows
+        self.length = rows.shape[1]
+        self.refNum = rows.shape[0]
+        self.K = K
+        table = {}
+        for r in range(rows.shape[0]):
+            cols = np.nonzero(rows[r] != ord("-"))[0]
+            seq = rows[r][cols].tobytes()
+            for i in range(len(seq) - K + 1):
+                table.setdefault(seq[i:i + K], set()).add(int(cols[i]))
+        keys = sorted(table)
+        self.keys = np.frombuffer(b"".join(keys), np.uint8).reshape(len(keys), K).copy() if keys else np.zeros((0, K), np.uint8)
+        self.offsets = np.zeros(len(keys) + 1, np.int64)
+        cols_all = []
+        for i, k in enumerate(keys):
+            c = sorted(table[k])
+            cols_all.extend(c)
+            self.offsets[i + 1] = self.offsets[i] + len(c)
+        self.columns = np.array(cols_all, np.int32)
+
+
+class PairedReads:
+    """DataReader.pairedReads in the layout of vg_upload_reads: one byte pool + per-mate offsets/lengths."""
+
+    def __init__(self, bases, off1, len1, off2, len2):
+        self.bases = _u8(bases)
+        self.off1 = np.ascontiguousarray(off1, np.int64)
+        self.len1 = np.ascontiguousarray(len1, np.int32)
+        self.off2 = np.ascontiguousarray(off2, np.int64)
+        self.len2 = np.ascontiguousarray(len2, np.int32)
+
+    def __len__(self):
+        return len(self.off1)
+
+    def seq1(self, i):
+        return self.bases[self.off1[i]:self.off1[i] + self.len1[i]].tobytes()
+
+    def seq2(self, i):
+        return self.bases[self.off2[i]:self.off2[i] + self.len2[i]].tobytes()
+
+
+class MappedData:
+    """MappedData (MappedData.java): per-pair records in input order + the sequence1 byte pool.
+    The six Java lists are views by class (task order == input order, Mapper.java:446-461)."""
+
+    def __init__(self, pair_index, records, pool, stats, msa=False):
+        self.pair_index = pair_index      # index of each record's pair in the resident read set
+        self.records = records            # PAIR_DTYPE
+        self.seq1_pool = pool
+        self.stats = stats
+        self.msa = msa
+        self.needToRemap = np.zeros(0, np.int64)
+
+    def _cls(self, *classes):
+        return np.nonzero(np.isin(self.records["cls"], classes))[0]
+
+    @property
+    def concordant(self):
+        return self._cls(_lib.CLS_CONCORDANT_FR, _lib.CLS_CONCORDANT_RF)
+
+    @property
+    def discordant(self):
+        return self._cls(_lib.CLS_DISCORDANT)
+
+    @property
+    def leftMateMapped(self):
+        return self._cls(_lib.CLS_LEFT)
+
+    @property
+    def rightMateMapped(self):
+        return self._cls(_lib.CLS_RIGHT)
+
+    @property
+    def unmapped(self):
+        return self._cls(_lib.CLS_UNMAPPED)
+
+    @property
+    def mappedReads(self):
+        """(record, mate) pairs in the order of MappedData.mappedReads (r1 then r2 of each pair)."""
+        pres = self.records["m"]["present"]
+        rec, mate = np.nonzero(pres)
+        return rec, mate
+
+    def sequence1(self, rec, mate):
+        m = self.records["m"][rec, mate]
+        return self.seq1_pool[m["seq1_offset"]:m["seq1_offset"] + m["length"]].tobytes()
+
+
+class Context:
+    """One vg_ctx: Mapper + KMerCounter + SmithWatermanGotoh parameters bound to a CUDA device."""
+
+    def __init__(self, K=5, low_coef=0.0, high_coef=1.25, cutoffs=None, insert_len=1000, match=2, mismatch=-3,
+                 gop=5, gep=2, device=0):
+        self.L = _lib.lib()
+        self.cutoffs = np.ascontiguousarray(cutoffs if cutoffs is not None else np.zeros(1024, np.int32), np.int32)
+        self.K = K
+        p = VgParams(K, low_coef, high_coef, self.cutoffs.ctypes.data, len(self.cutoffs), insert_len, match, mismatch,
+                     gop, gep)
+        h = C.c_void_p()
+        rc = self.L.vg_ctx_create(C.byref(p), device, C.byref(h))
+        self.h = h
+        if rc != 0:
+            msg = self.L.vg_last_error(h).decode() if h else "context allocation failed"
+            if h:
+                self.L.vg_ctx_destroy(h)
+                self.h = None
+            raise VgError(rc, msg)
+        self.n_pairs = 0
+        self.G = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vg_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise VgError(rc, self.L.vg_last_error(self.h).decode())
+
+    # --- reference / index -------------------------------------------------------------------
+    def set_reference(self, ref: Reference):
+        keys = offs = pos = None
+        nk = 0
+        if ref.index_csr is not None:
+            keys, offs, pos = ref.index_csr
+            keys = np.ascontiguousarray(keys, np.uint8)
+            offs = np.ascontiguousarray(offs, np.int64)
+            pos = np.ascontiguousarray(pos, np.int32)
+            nk = len(offs) - 1
+        self._chk(self.L.vg_set_reference(self.h, ptr(ref.seqB), ref.length, ptr(ref.contigEnds), len(ref.contigEnds),
+                                          ptr(ref.fragmentEnds), len(ref.fragmentEnds), int(ref.isFragmented),
+                                          ptr(keys), ptr(offs), ptr(pos), nk, ref.threadNum))
+        self.G = ref.length
+
+    def set_msa(self, aln: ReferenceAlignment, low_coef, high_coef, cutoffs):
+        cut = np.ascontiguousarray(cutoffs, np.int32)
+        self._chk(self.L.vg_set_msa_index(self.h, aln.K, low_coef, high_coef, ptr(cut), len(cut), ptr(aln.keys),
+                                          ptr(aln.offsets), ptr(aln.columns), len(aln.offsets) - 1, aln.length))
+
+    # --- reads -------------------------------------------------------------------------------
+    def upload_reads(self, reads: PairedReads):
+        self._chk(self.L.vg_upload_reads(self.h, ptr(reads.bases), len(reads.bases), ptr(reads.off1), ptr(reads.len1),
+                                         ptr(reads.off2), ptr(reads.len2), len(reads)))
+        self.n_pairs = len(reads)
+
+    # --- mapping -----------------------------------------------------------------------------
+    def map_pairs(self, pair_idx=None, fetch=True):
+        st = VgMapStats()
+        if pair_idx is None:
+            self._chk(self.L.vg_map_pairs(self.h, None, 0, C.byref(st)))
+            idx = np.arange(self.n_pairs, dtype=np.int64)
+        else:
+            idx = np.ascontiguousarray(pair_idx, np.int64)
+            self._chk(self.L.vg_map_pairs(self.h, ptr(idx), len(idx), C.byref(st)))
+        if not fetch:
+            return st.as_array()
+        rec, pool = self.get_results()
+        return MappedData(idx, rec, pool, st.as_array())
+
+    def map_pairs_msa(self, fetch=True):
+        st = VgMapStats()
+        self._chk(self.L.vg_map_pairs_msa(self.h, C.byref(st)))
+        if not fetch:
+            return st.as_array()
+        rec, pool = self.get_results()
+        return MappedData(np.arange(self.n_pairs, dtype=np.int64), rec, pool, st.as_array(), msa=True)
+
+    def get_results(self):
+        n = C.c_int64()
+        nb = C.c_int64()
+        self._chk(self.L.vg_result_sizes(self.h, C.byref(n), C.byref(nb)))
+        rec = np.zeros(n.value, PAIR_DTYPE)
+        pool = np.zeros(max(nb.value, 1), np.uint8)
+        self._chk(self.L.vg_get_results(self.h, ptr(rec), n.value, ptr(pool), len(pool)))
+        return rec, pool[:nb.value]
+
+    # --- pileup / consensus ------------------------------------------------------------------
+    def pileup(self, accumulate=False):
+        self._chk(self.L.vg_pileup(self.h, int(accumulate)))
+
+    def counts_device(self):
+        p = C.c_void_p()
+        n = C.c_int64()
+        self._chk(self.L.vg_pileup_counts_device(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def counts(self):
+        out = np.zeros((self.G, 5), np.int32)
+        self._chk(self.L.vg_pileup_counts_host(self.h, ptr(out), out.size))
+        return out
+
+    def consensus(self, genome, save_uncovered=False, coverage_threshold=0):
+        genome = _u8(genome)
+        out = np.zeros(len(genome), np.uint8)
+        self._chk(self.L.vg_consensus(self.h, int(save_uncovered), coverage_threshold, ptr(genome), len(genome),
+                                      ptr(out)))
+        return out
+
+    # --- batch kernels exposed for the "next" callers and the tests ---------------------------
+    def sw_align_batch(self, s1_pool, s1_off, s2_pool, s2_off):
+        s1_pool, s2_pool = _u8(s1_pool), _u8(s2_pool)
+        s1_off = np.ascontiguousarray(s1_off, np.int64)
+        s2_off = np.ascontiguousarray(s2_off, np.int64)
+        n = len(s1_off) - 1
+        rec = np.zeros((n, 7), np.int32)
+        cap = np.diff(s1_off) + np.diff(s2_off)
+        soff = np.zeros(n + 1, np.int64)
+        np.cumsum(cap, out=soff[1:])
+        pool = np.zeros(int(soff[-1]) + 1, np.uint8)
+        self._chk(self.L.vg_sw_align_batch(self.h, ptr(s1_pool), ptr(s1_off), ptr(s2_pool), ptr(s2_off), n, ptr(rec),
+                                           ptr(pool), ptr(soff)))
+        return rec, pool, soff
+
+    def sw_max_score_batch(self, s1_pool, s1_off, s2_pool, s2_off):
+        s1_pool, s2_pool = _u8(s1_pool), _u8(s2_pool)
+        s1_off = np.ascontiguousarray(s1_off, np.int64)
+        s2_off = np.ascontiguousarray(s2_off, np.int64)
+        n = len(s1_off) - 1
+        out = np.zeros(n, np.int32)
+        self._chk(self.L.vg_sw_max_score_batch(self.h, ptr(s1_pool), ptr(s1_off), ptr(s2_pool), ptr(s2_off), n, ptr(out)))
+        return out
+
+    def seed_batch(self, pool, off, msa=False, max_windows=64):
+        pool = _u8(pool)
+        off = np.ascontiguousarray(off, np.int64)
+        n = len(off) - 1
+        win = np.zeros((n, max_windows, 3), np.int32)
+        nwin = np.zeros(n, np.int32)
+        self._chk(self.L.vg_seed_batch(self.h, int(msa), ptr(pool), ptr(off), n, max_windows, ptr(win), ptr(nwin)))
+        return win, nwin
+
+    def timings(self):
+        t = np.zeros(6, np.float64)
+        self._chk(self.L.vg_last_timings(self.h, ptr(t)))
+        return dict(seed_ms=t[0], sw_fill_ms=t[1], traceback_ms=t[2], pileup_ms=t[3], total_ms=t[4], sw_cells=t[5])
+
+    def dpx_peak(self):
+        v = C.c_double()
+        self._chk(self.L.vg_dpx_peak(self.h, C.byref(v)))
+        return v.value
+
+    def kernel_launches(self):
+        return int(self.L.vg_kernel_launches(self.h))
+
+
+class Mapper:
+    """Mapper (Mapper.java). `counter` carries K / cutoffs / coefficients like KMerCounter; the aligner
+    parameters are those of SmithWatermanGotoh. One Mapper owns one device context; reads are uploaded once
+    and stay resident across mapping passes (iterations of ConsensusBuilderWithReassembling)."""
+
+    def __init__(self, K=5, pValue=0.01, indel_tolerance=1.25, low_coef=0.0, cutoffs=None, insert_len=1000,
+                 match=2, mismatch=-3, gop=5, gep=2, device=0):
+        self.ctx = Context(K, low_coef, indel_tolerance, cutoffs, insert_len, match, mismatch, gop, gep, device)
+        self._reads = None
+        self._genome = None
+
+    def _bind(self, reads, genome):
+        if reads is not None and reads is not self._reads:
+            self.ctx.upload_reads(reads)
+            self._reads = reads
+        if genome is not self._genome:
+            self.ctx.set_reference(genome)
+            self._genome = genome
+
+    def mapReads(self, reads_or_mapped, genome):
+        """mapReads(ArrayList<PairedRead>, Reference) -> MappedData, or
+        mapReads(MappedData, Reference): remaps mappedData.needToRemap in place (Mapper.java:477-536)."""
+        if isinstance(reads_or_mapped, MappedData):
+            md = reads_or_mapped
+            if genome.length == 0:
+                return None
+            self._bind(None, genome)
+            idx = md.pair_index[md.needToRemap] if len(md.needToRemap) else np.zeros(0, np.int64)
+            sub = self.ctx.map_pairs(idx)
+            md.remapped = sub
+            md.needToRemap = np.zeros(0, np.int64)
+            return None
+        reads = reads_or_mapped
+        if genome.length == 0:
+            # Mapper.java:422-426: empty reference -> every pair unmapped
+            rec = np.zeros(len(reads), PAIR_DTYPE)
+            rec["cls"] = _lib.CLS_UNMAPPED
+            rec["m"]["seq1_offset"] = -1
+            return MappedData(np.arange(len(reads), dtype=np.int64), rec, np.zeros(0, np.uint8), np.zeros(9, np.int64))
+        self._bind(reads, genome)
+        return self.ctx.map_pairs()
+
+
+class MapperMSA:
+    """MapperMSA (MapperMSA.java): seeding + pairing against the reference MSA index, no alignment."""
+
+    def __init__(self, K=7, indel_tolerance=1.5, cutoffs=None, insert_len=1000, device=0, ctx=None):
+        self.ctx = ctx or Context(K, 1.0 / indel_tolerance, indel_tolerance, cutoffs, insert_len, device=device)
+        self.K = K
+        self.low = np.float32(1.0) / np.float32(indel_tolerance)  # KMerCounterMSA.java:22-23
+        self.high = np.float32(indel_tolerance)
+        self.cutoffs = np.ascontiguousarray(cutoffs if cutoffs is not None else np.zeros(1024, np.int32), np.int32)
+        self._reads = None
+        self._aln = None
+
+    def mapAllReads(self, reads, refAlignment):
+        if reads is not self._reads:
+            self.ctx.upload_reads(reads)
+            self._reads = reads
+        if refAlignment is not self._aln:
+            self.ctx.set_msa(refAlignment, float(self.low), float(self.high), self.cutoffs)
+            self._aln = refAlignment
+        return self.ctx.map_pairs_msa()
+
+
+class ConsensusBuilderSimple:
+    """ConsensusBuilderSimple (ConsensusBuilderSimple.java): pileup of the last mapping + per-position argmax."""
+
+    def __init__(self, mapper: Mapper, coverage_threshold=0, allreduce=None):
+        self.mapper = mapper
+        self.coverageThreshold = coverage_threshold
+        self.mappedData = None
+        self._allreduce = allreduce  # callable(dev_ptr, n_int32) summing the counts over ranks (multi-GPU)
+
+    def buildConsensus(self, genome, reads):
+        self.mappedData = self.mapper.mapReads(reads, genome)
+        return self.getConsensusSimple(False, self.coverageThreshold, genome.seqB)
+
+    def getConsensusSimple(self, saveUncovered, coverageThreshold, genome):
+        ctx = self.mapper.ctx
+        ctx.pileup(False)
+        if self._allreduce is not None:
+            p, n = ctx.counts_device()
+            self._allreduce(p, n)
+        return ctx.consensus(genome, saveUncovered, coverageThreshold)
