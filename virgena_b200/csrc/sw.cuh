@@ -36,18 +36,22 @@ __device__ __forceinline__ uint8_t sw_s1_byte(const uint8_t* s1, int m, int rc, 
   return rc ? vg_complement(s1[m - 1 - idx]) : s1[idx];
 }
 
+// Checkpoint layout (written by the fill kernel, read by the traceback kernel), per *pair* p of tasks
+// (2p, 2p+1) whose values sit in the lo / hi s16 lanes:
+//   rowck[p][t][lane]  = uint2{V, Es} of lane's bottom row at wavefront step t (column j = t - lane)
+//   colck[p][tb][row]  = uint2{V, Fs} of row (0-based) at step t = 32*tb           (column j = 32*tb - row/R)
+// Indexing by the wavefront step makes every store warp-uniform and fully coalesced.
 template <int R, bool STORE>
 __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__ tasks, int ntasks,
                                                       const uint8_t* __restrict__ s1pool,
                                                       const uint8_t* __restrict__ s2pool, SwParams prm,
-                                                      uint32_t* __restrict__ rowck, uint32_t* __restrict__ colck,
-                                                      int nW, int ncb, SwFillOut* __restrict__ out,
+                                                      uint2* __restrict__ rowck, uint2* __restrict__ colck,
+                                                      int nT, int nTb, SwFillOut* __restrict__ out,
                                                       int* __restrict__ counter, int smemWordsPerWarp) {
   extern __shared__ uint32_t sw_smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   uint32_t* wsym = sw_smem + (size_t)warp * smemWordsPerWarp;
-  const int mW = 32 * R + 1;
   const uint32_t NEGp = vg_pk2(SW_NEG);
   const uint32_t NGEPp = vg_pk2(-prm.gep);
   const uint32_t NGOPp = vg_pk2(-prm.gop);
@@ -101,11 +105,9 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
     bool tieA = false, tieB = false;
     // lanes whose strip starts beyond both reads never influence a result
     const int lastLane = min(31, (mmax - 1) / R);
-    const int64_t rowBaseA = ((int64_t)ia * 32 + lane) * nW;
-    const int64_t rowBaseB = ((int64_t)ib * 32 + lane) * nW;
-    const bool rowStoreA = STORE && ((lane + 1) * R < ta.m);
-    const bool rowStoreB = STORE && ((lane + 1) * R < tb.m);
     const int tEnd = nmax + lastLane;
+    uint2* rowp = rowck + ((int64_t)pi * nT) * 32 + lane;
+    uint2* colp = colck + ((int64_t)pi * nTb) * (32 * R) + lane * R;
 
     for (int t = 1; t <= tEnd; t++) {
       uint32_t vin = __shfl_up_sync(VG_FULL, vbot, 1);
@@ -115,7 +117,8 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
         ein = NEGp;
       }
       const int j = t - lane;
-      if (j >= 1 && j <= nmax && lane <= lastLane) {
+      const bool active = (j >= 1 && j <= nmax && lane <= lastLane);
+      if (active) {
         const uint32_t b = wsym[j];
         uint32_t vd = vup_prev, vu = vin, e = ein, cm = 0;
 #pragma unroll
@@ -148,24 +151,13 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
           colB = ph ? colB : j;
           lanemax = nm;
         }
-        if (STORE) {
-          if (rowStoreA && j <= ta.n) rowck[rowBaseA + j] = __byte_perm(vbot, ebot, 0x5410);
-          if (rowStoreB && j <= tb.n) rowck[rowBaseB + j] = __byte_perm(vbot, ebot, 0x7632);
-          if ((j & (SW_TC - 1)) == 0) {
-            const int c = j / SW_TC - 1;
-            if (j < ta.n) {
-              uint32_t* dst = colck + ((int64_t)ia * ncb + c) * mW + lane * R + 1;
+        if (STORE) rowp[(int64_t)t * 32] = make_uint2(vbot, ebot);
+      }
+      if (STORE && (t & (SW_TC - 1)) == 0) {  // warp-uniform: every lane checkpoints its rows at this step
+        if (active) {
+          uint2* dst = colp + (int64_t)(t / SW_TC) * (32 * R);
 #pragma unroll
-              for (int r = 0; r < R; r++)
-                if (lane * R + r < ta.m) dst[r] = __byte_perm(V[r], F[r], 0x5410);
-            }
-            if (j < tb.n) {
-              uint32_t* dst = colck + ((int64_t)ib * ncb + c) * mW + lane * R + 1;
-#pragma unroll
-              for (int r = 0; r < R; r++)
-                if (lane * R + r < tb.m) dst[r] = __byte_perm(V[r], F[r], 0x7632);
-            }
-          }
+          for (int r = 0; r < R; r++) dst[r] = make_uint2(V[r], F[r]);
         }
       }
     }
@@ -190,178 +182,212 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// Traceback: recompute one R x SW_TC tile from the checkpoints. Cell flags (4 bits):
+// Traceback. One thread = one alignment. A "tile" is the strip k (rows k*R+1 .. k*R+R) between two
+// column checkpoints of that strip: columns cl+1 .. cl+32 where cl = 32*tb - k (or 0). The tile is
+// recomputed column by column from its top boundary (rowck of strip k-1) and left boundary (colck),
+// producing for every cell the 4 flag bits
 //   bits 0-1 pointer (STOP=0, LEFT=1, DIAGONAL=2, UP=3 — SmithWatermanGotoh.Directions :31-48),
 //   bit 2 vertical-gap extended here (sizesOfVerticalGaps[l] = [l-n] + 1, :117),
-//   bit 3 horizontal-gap extended here (:126).
-// Optionally probes for cells equal to S (end-cell search, row-major minimum).
+//   bit 3 horizontal-gap extended here (:126),
+// one 32-bit word per column (R <= 8) or two (R <= 16), kept in shared memory.
+// All lanes of a warp recompute together (one tile per outer iteration), then walk inside their tile.
 // ---------------------------------------------------------------------------------------------
 template <int R>
-struct SwTile {
-  int k, c;  // strip / column block held in flags
+struct SwTb {
+  static constexpr int WPC = (R + 7) / 8;  // flag words per column
 };
 
 template <int R>
 __device__ __forceinline__ void sw_tile_recompute(const SwTask& tk, const uint8_t* __restrict__ s1,
                                                   const uint8_t* __restrict__ s2, const SwParams& prm,
-                                                  const uint32_t* __restrict__ rowckT,  // [32][nW] of this task
-                                                  const uint32_t* __restrict__ colckT,  // [ncb][mW] of this task
-                                                  int nW, int k, int c, uint32_t* __restrict__ flags, int fstride,
-                                                  int probeS, int probeCol, int& bestI, int& bestJ) {
-  const int mW = 32 * R + 1;
-  const int r0 = k * R, c0 = c * SW_TC;
-  int v[SW_TC + 1], g[SW_TC + 1];
-  uint8_t bsym[SW_TC + 1];
+                                                  const uint2* __restrict__ rowckP, const uint2* __restrict__ colckP,
+                                                  int hi, int k, int cl, int jmax, uint32_t* __restrict__ flags,
+                                                  int fstride, int probeS, int probeCol, int& bestI, int& bestJ) {
+  constexpr int WPC = SwTb<R>::WPC;
+  const int r0 = k * R;
+  int v[R], hs[R];
+  uint8_t asym[R];
+  // left boundary: column cl
+  const int tb = (cl + k) / SW_TC;
 #pragma unroll
-  for (int jj = 0; jj <= SW_TC; jj++) {
-    int col = c0 + jj;
-    int vv = 0, ee = SW_NEG;
-    if (k > 0 && col >= 1 && col <= tk.n) {
-      uint32_t w = rowckT[(int64_t)(k - 1) * nW + col];
-      vv = vg_lo(w);
-      ee = vg_hi(w);
+  for (int r = 0; r < R; r++) {
+    const int i = r0 + r + 1;
+    v[r] = 0;
+    hs[r] = SW_NEG;
+    asym[r] = 0;
+    if (i <= tk.m) {
+      asym[r] = sw_s1_byte(s1, tk.m, tk.rc, i - 1);
+      if (cl > 0) {
+        uint2 w = colckP[(int64_t)tb * (32 * R) + (i - 1)];
+        v[r] = hi ? vg_hi(w.x) : vg_lo(w.x);
+        hs[r] = hi ? vg_hi(w.y) : vg_lo(w.y);
+      }
     }
-    if (k > 0 && col == 0) vv = 0;
-    v[jj] = vv;
-    g[jj] = ee;
-    bsym[jj] = (col >= 1 && col <= tk.n) ? s2[col - 1] : 0;
   }
-  int vdiagRow = v[0];  // V(r0 + rr, c0) of the previous row
-  for (int rr = 0; rr < R; rr++) {
-    const int i = r0 + rr + 1;
-    if (i > tk.m) break;
-    int vleft = 0, hs = SW_NEG;
-    if (c > 0) {
-      uint32_t w = colckT[(int64_t)(c - 1) * mW + i];
-      vleft = vg_lo(w);
-      hs = vg_hi(w);
+  // V(r0, cl): corner for the first diagonal
+  int vtopPrev = 0;
+  if (k > 0 && cl > 0) {
+    uint2 w = rowckP[(int64_t)(cl + k - 1) * 32 + (k - 1)];
+    vtopPrev = hi ? vg_hi(w.x) : vg_lo(w.x);
+  }
+  for (int j = cl + 1; j <= jmax; j++) {
+    int vtop = 0, es = SW_NEG;
+    if (k > 0) {
+      uint2 w = rowckP[(int64_t)(j + k - 1) * 32 + (k - 1)];
+      vtop = hi ? vg_hi(w.x) : vg_lo(w.x);
+      es = hi ? vg_hi(w.y) : vg_lo(w.y);
     }
-    const uint8_t asym = sw_s1_byte(s1, tk.m, tk.rc, i - 1);
-    int vd = vdiagRow;
-    vdiagRow = vleft;
-    uint32_t words[SW_TC / 8];
+    const uint8_t bsym = s2[j - 1];
+    int vd = vtopPrev, vu = vtop;
+    vtopPrev = vtop;
+    uint32_t word[WPC];
 #pragma unroll
-    for (int w = 0; w < SW_TC / 8; w++) words[w] = 0;
+    for (int w = 0; w < WPC; w++) word[w] = 0;
 #pragma unroll
-    for (int jj = 1; jj <= SW_TC; jj++) {
-      const int j = c0 + jj;
-      if (j <= tk.n) {
-        int sim = (asym == bsym[jj]) ? prm.match : prm.mismatch;
-        int f = vd + sim;
-        int g1 = g[jj] - prm.gep, g2 = v[jj];
-        bool vext = g1 > g2;
-        int es = vext ? g1 : g2;
-        int h1 = hs - prm.gep, h2 = vleft;
-        bool hext = h1 > h2;
-        hs = hext ? h1 : h2;
-        vd = v[jj];
-        int E = es - prm.gop, Fv = hs - prm.gop;
-        int V = max(max(f, E), max(Fv, 0));
-        uint32_t dir = (V == 0) ? 0u : (V == f) ? 2u : (V == E) ? 3u : 1u;
-        uint32_t nib = dir | (vext ? 4u : 0u) | (hext ? 8u : 0u);
-        words[(jj - 1) >> 3] |= nib << (((jj - 1) & 7) * 4);
-        g[jj] = es;
-        v[jj] = V;
-        vleft = V;
-        if (V == probeS && (probeCol < 0 || probeCol == j)) {
-          if (i < bestI || (i == bestI && j < bestJ)) {
-            bestI = i;
-            bestJ = j;
-          }
+    for (int r = 0; r < R; r++) {
+      const int i = r0 + r + 1;
+      int sim = (asym[r] == bsym) ? prm.match : prm.mismatch;
+      int f = vd + sim;
+      int g1 = es - prm.gep;
+      bool vext = g1 > vu;
+      es = vext ? g1 : vu;
+      int h1 = hs[r] - prm.gep;
+      bool hext = h1 > v[r];
+      hs[r] = hext ? h1 : v[r];
+      vd = v[r];
+      int E = es - prm.gop, Fv = hs[r] - prm.gop;
+      int V = max(max(f, E), max(Fv, 0));
+      uint32_t dir = (V == 0) ? 0u : (V == f) ? 2u : (V == E) ? 3u : 1u;
+      uint32_t nib = dir | (vext ? 4u : 0u) | (hext ? 8u : 0u);
+      word[r >> 3] |= nib << ((r & 7) * 4);
+      v[r] = V;
+      vu = V;
+      if (V == probeS && i <= tk.m && (probeCol < 0 || probeCol == j)) {
+        if (i < bestI || (i == bestI && j < bestJ)) {
+          bestI = i;
+          bestJ = j;
         }
       }
     }
 #pragma unroll
-    for (int w = 0; w < SW_TC / 8; w++) flags[(rr * (SW_TC / 8) + w) * fstride] = words[w];
+    for (int w = 0; w < WPC; w++) flags[((j - cl - 1) * WPC + w) * fstride] = word[w];
   }
+}
+
+// left checkpoint column of the tile of strip k that contains column j (0 = the matrix edge)
+__device__ __forceinline__ int sw_tile_left(int k, int j) {
+  int tb = (j - 1 + k) / SW_TC;
+  int cl = SW_TC * tb - k;
+  return cl < 1 ? 0 : cl;
 }
 
 template <int R>
 __global__ void __launch_bounds__(128) sw_traceback_kernel(const SwTask* __restrict__ tasks, int ntasks,
                                                            const uint8_t* __restrict__ s1pool,
                                                            const uint8_t* __restrict__ s2pool, SwParams prm,
-                                                           const uint32_t* __restrict__ rowck,
-                                                           const uint32_t* __restrict__ colck, int nW, int ncb,
+                                                           const uint2* __restrict__ rowck,
+                                                           const uint2* __restrict__ colck, int nT, int nTb,
                                                            const SwFillOut* __restrict__ fill,
                                                            SwAln* __restrict__ alns, uint8_t* __restrict__ rev,
                                                            int64_t revStride) {
-  __shared__ uint32_t flagS[R * (SW_TC / 8) * 128];
+  constexpr int WPC = SwTb<R>::WPC;
+  __shared__ uint32_t flagS[SW_TC * WPC * 128];
   const int tid = threadIdx.x;
   const int ti = blockIdx.x * blockDim.x + tid;
-  if (ti >= ntasks) return;
-  const SwTask tk = tasks[ti];
+  const bool valid = ti < ntasks;
+  SwTask tk;
+  tk.m = tk.n = 0;
+  tk.s1_off = tk.s2_off = 0;
+  tk.rc = 0;
+  tk.out = 0;
+  SwFillOut fo;
+  fo.score = 0, fo.strip = 0, fo.col = 0, fo.tie = 0;
+  if (valid) {
+    tk = tasks[ti];
+    fo = fill[ti];
+  }
   const uint8_t* s1 = s1pool + tk.s1_off;
   const uint8_t* s2 = s2pool + tk.s2_off;
-  const int mW = 32 * R + 1;
-  const uint32_t* rowckT = rowck + (int64_t)ti * 32 * nW;
-  const uint32_t* colckT = colck + (int64_t)ti * ncb * mW;
+  const int hi = ti & 1;
+  const uint2* rowckP = rowck + ((int64_t)(ti >> 1) * nT) * 32;
+  const uint2* colckP = colck + ((int64_t)(ti >> 1) * nTb) * (32 * R);
   uint32_t* flags = flagS + tid;
-  const SwFillOut fo = fill[ti];
-  SwAln al;
-  al.score = fo.score;
   uint8_t* out = rev + (int64_t)tk.out * revStride;
-  if (fo.score <= 0) {  // Q8: no cell > 0 -> empty alignment at (0,0)
-    al.score = 0, al.start1 = al.end1 = al.start2 = al.end2 = al.identity = al.length = 0;
-    alns[tk.out] = al;
-    return;
-  }
   int no1 = 1 << 30, no2 = 1 << 30;
-  int bi = 1 << 30, bj = 1 << 30;
-  int curK = -1, curC = -1;
-  if (!fo.tie) {
-    curK = fo.strip, curC = (fo.col - 1) / SW_TC;
-    sw_tile_recompute<R>(tk, s1, s2, prm, rowckT, colckT, nW, curK, curC, flags, 128, fo.score, fo.col, bi, bj);
-  } else {
-    const int nc = (tk.n + SW_TC - 1) / SW_TC;
-    for (int c = 0; c < nc; c++)
-      sw_tile_recompute<R>(tk, s1, s2, prm, rowckT, colckT, nW, fo.strip, c, flags, 128, fo.score, -1, bi, bj);
-    curK = -1;
+  int i = 0, j = 0, len = 0, identity = 0, end1 = 0, end2 = 0;
+  bool done = !valid || fo.score <= 0;  // Q8: no cell > 0 -> empty alignment at (0,0)
+
+  // ---- locate the end cell: smallest (row, column) with V == S ------------------------------------------
+  int haveK = -1, haveCl = -1;  // tile whose flags are in shared memory
+  if (!done) {
+    int bi = 1 << 30, bj = 1 << 30;
+    if (!fo.tie) {
+      int cl = sw_tile_left(fo.strip, fo.col);
+      sw_tile_recompute<R>(tk, s1, s2, prm, rowckP, colckP, hi, fo.strip, cl, fo.col, flags, 128, fo.score, fo.col, bi, bj);
+      haveK = fo.strip, haveCl = cl;
+    } else {
+      for (int jj = tk.n; jj >= 1;) {  // rare: the strip reached S at several columns
+        int cl = sw_tile_left(fo.strip, jj);
+        sw_tile_recompute<R>(tk, s1, s2, prm, rowckP, colckP, hi, fo.strip, cl, jj, flags, 128, fo.score, -1, bi, bj);
+        jj = cl;
+      }
+    }
+    i = bi, j = bj;
+    end1 = i, end2 = j;
   }
-  int i = bi, j = bj;
-  al.end1 = i;
-  al.end2 = j;
-  int len = 0, identity = 0;
+  // ---- walk: one tile recompute per outer iteration, all lanes of the warp together ---------------------
   int mode = 0;  // 0 normal, 1 inside a vertical gap run, 2 inside a horizontal gap run
-  for (;;) {
-    uint32_t nib = 0;
-    if (i >= 1 && j >= 1) {
-      int k = (i - 1) / R, c = (j - 1) / SW_TC;
-      if (k != curK || c != curC) {
-        curK = k, curC = c;
-        sw_tile_recompute<R>(tk, s1, s2, prm, rowckT, colckT, nW, k, c, flags, 128, -1, -1, no1, no2);
-      }
-      int rr = (i - 1) - k * R, jj = (j - 1) - c * SW_TC;
-      nib = (flags[(rr * (SW_TC / 8) + (jj >> 3)) * 128] >> ((jj & 7) * 4)) & 15u;
+  while (__any_sync(VG_FULL, !done)) {
+    int k = 0, cl = 0;
+    if (!done) {
+      k = (i - 1) / R;
+      cl = sw_tile_left(k, j);
+      if (k != haveK || cl != haveCl)
+        sw_tile_recompute<R>(tk, s1, s2, prm, rowckP, colckP, hi, k, cl, j, flags, 128, -1, -1, no1, no2);
+      haveK = -1;
     }
-    if (mode == 0) {
-      uint32_t dir = nib & 3u;
-      if (dir == 0u) break;  // STOP (also the row-0 / column-0 boundary)
-      if (dir == 2u) {       // DIAGONAL
-        uint8_t c1 = sw_s1_byte(s1, tk.m, tk.rc, i - 1), c2 = s2[j - 1];
-        out[len++] = c1;
-        if (c1 == c2) identity++;
-        i--, j--;
-        continue;
+    while (!done) {
+      if (i < 1 || j < 1) {  // row 0 / column 0 pointers are STOP (:58-64)
+        done = true;
+        break;
       }
-      mode = (dir == 3u) ? 1 : 2;
-    }
-    if (mode == 1) {  // UP: sizesOfVerticalGaps[k+j] lower-case read bases
-      out[len++] = vg_lower(sw_s1_byte(s1, tk.m, tk.rc, i - 1));
-      bool ext = (nib & 4u) != 0;
-      i--;
-      if (!ext) mode = 0;
-    } else {  // LEFT: sizesOfHorizontalGaps[k+j] gap characters
-      out[len++] = '-';
-      bool ext = (nib & 8u) != 0;
-      j--;
-      if (!ext) mode = 0;
+      if ((i - 1) / R != k || j <= cl) break;  // left the tile
+      const int rr = (i - 1) - k * R;
+      const uint32_t nib = (flags[((j - cl - 1) * WPC + (rr >> 3)) * 128] >> ((rr & 7) * 4)) & 15u;
+      if (mode == 0) {
+        const uint32_t dir = nib & 3u;
+        if (dir == 0u) {
+          done = true;
+          break;
+        }
+        if (dir == 2u) {  // DIAGONAL
+          uint8_t c1 = sw_s1_byte(s1, tk.m, tk.rc, i - 1), c2 = s2[j - 1];
+          out[len++] = c1;
+          if (c1 == c2) identity++;
+          i--, j--;
+          continue;
+        }
+        mode = (dir == 3u) ? 1 : 2;
+      }
+      if (mode == 1) {  // UP: sizesOfVerticalGaps[k+j] lower-case read bases
+        out[len++] = vg_lower(sw_s1_byte(s1, tk.m, tk.rc, i - 1));
+        const bool ext = (nib & 4u) != 0;
+        i--;
+        if (!ext) mode = 0;
+      } else {  // LEFT: sizesOfHorizontalGaps[k+j] gap characters
+        out[len++] = '-';
+        const bool ext = (nib & 8u) != 0;
+        j--;
+        if (!ext) mode = 0;
+      }
     }
   }
-  al.start1 = i;
-  al.start2 = j;
-  al.identity = identity;
-  al.length = len;
-  alns[tk.out] = al;
+  if (valid) {
+    SwAln al;
+    al.score = fo.score > 0 ? fo.score : 0;
+    al.start1 = i, al.end1 = end1, al.start2 = j, al.end2 = end2, al.identity = identity, al.length = len;
+    alns[tk.out] = al;
+  }
 }
 
 // sequence1 = reverse(reversed1) into the caller's pool (SmithWatermanGotoh.reverse :309-315)

@@ -30,9 +30,10 @@ static int sw_launch_R(vg_ctx* c, const SwTask* d_tasks, int ntasks, const uint8
                        int nmax, bool traceback, SwFillOut* d_fill, SwAln* d_alns, uint8_t* d_rev, int64_t revStride,
                        double* msFill, double* msTb) {
   const int nW = nmax + 1;
-  const int ncb = std::max(1, (nmax - 1) / SW_TC);
-  const int mW = 32 * R + 1;
-  const size_t perTask = ((size_t)32 * nW + (size_t)ncb * mW) * sizeof(uint32_t);
+  const int nT = nmax + 32;           // wavefront steps 1 .. nmax + 31
+  const int nTb = nT / SW_TC + 1;     // column checkpoints at t = 32, 64, ...
+  const size_t perPair = ((size_t)nT * 32 + (size_t)nTb * 32 * R) * sizeof(uint2);
+  const size_t perTask = perPair / 2;
   size_t budget = (size_t)24 << 30;
   if (const char* e = getenv("VG_CKPT_BYTES")) budget = (size_t)atoll(e);
   int64_t chunk = ntasks;
@@ -40,8 +41,8 @@ static int sw_launch_R(vg_ctx* c, const SwTask* d_tasks, int ntasks, const uint8
     chunk = std::min<int64_t>(ntasks, std::max<int64_t>(2, (int64_t)(budget / perTask)));
     chunk &= ~(int64_t)1;
     if (chunk < 2) chunk = 2;
-    VG_CUDA(c, c->d_rowck.reserve((size_t)chunk * 32 * nW * 4));
-    VG_CUDA(c, c->d_colck.reserve((size_t)chunk * ncb * mW * 4));
+    VG_CUDA(c, c->d_rowck.reserve((size_t)(chunk / 2) * nT * 32 * sizeof(uint2)));
+    VG_CUDA(c, c->d_colck.reserve((size_t)(chunk / 2) * nTb * 32 * R * sizeof(uint2)));
   }
   VG_CUDA(c, c->d_counter.reserve(sizeof(int)));
   const int threads = 256, warps = threads / 32;
@@ -64,17 +65,17 @@ static int sw_launch_R(vg_ctx* c, const SwTask* d_tasks, int ntasks, const uint8
     VG_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
     if (traceback)
       sw_fill_kernel<R, true><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw,
-                                                                    c->d_rowck.as<uint32_t>(), c->d_colck.as<uint32_t>(),
-                                                                    nW, ncb, d_fill + s, c->d_counter.as<int>(), nW);
+                                                                    c->d_rowck.as<uint2>(), c->d_colck.as<uint2>(),
+                                                                    nT, nTb, d_fill + s, c->d_counter.as<int>(), nW);
     else
       sw_fill_kernel<R, false><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw, nullptr, nullptr,
-                                                                     nW, ncb, d_fill + s, c->d_counter.as<int>(), nW);
+                                                                     nT, nTb, d_fill + s, c->d_counter.as<int>(), nW);
     VG_LAUNCH_CHECK(c);
     VG_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
     if (traceback) {
       sw_traceback_kernel<R><<<(nt + 127) / 128, 128, 0, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw,
-                                                                      c->d_rowck.as<uint32_t>(), c->d_colck.as<uint32_t>(),
-                                                                      nW, ncb, d_fill + s, d_alns, d_rev, revStride);
+                                                                      c->d_rowck.as<uint2>(), c->d_colck.as<uint2>(),
+                                                                      nT, nTb, d_fill + s, d_alns, d_rev, revStride);
       VG_LAUNCH_CHECK(c);
     }
     VG_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
