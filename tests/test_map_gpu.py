@@ -1,0 +1,255 @@
+"""GPU parity: seeding, pair selection, full Mapper.mapReads / MapperMSA.mapAllReads, pileup and
+consensus vs the oracle, through the C ABI. Everything is bit-exact (integer / byte / index work)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ["present", "start", "end", "count", "reverse", "fragment_id", "score", "start1", "end1", "start2", "end2",
+          "identity", "length"]
+
+
+def _offs(seqs):
+    return np.concatenate([[0], np.cumsum([len(x) for x in seqs])]).astype(np.int64)
+
+
+def _compare(md, orec, opool, ostats):
+    rec = md.records
+    assert len(rec) == len(orec)
+    bad = np.nonzero(rec["cls"] != orec["cls"])[0]
+    assert len(bad) == 0, ("class mismatch", bad[:10], rec["cls"][bad[:10]], orec["cls"][bad[:10]])
+    for f in FIELDS:
+        b = np.nonzero(rec["m"][f] != orec["m"][f])
+        assert len(b[0]) == 0, (f, b[0][:5], b[1][:5], rec["m"][f][b][:5], orec["m"][f][b][:5])
+    # sequence1 bytes (offsets are deterministic: prefix sums in (pair, mate) order)
+    pres = rec["m"]["present"] == 1
+    assert (rec["m"]["seq1_offset"][pres] == orec["m"]["seq1_offset"][pres]).all()
+    assert md.seq1_pool.tobytes() == opool.tobytes()
+    assert (md.stats == ostats).all(), (md.stats, ostats)
+
+
+@pytest.fixture(scope="module")
+def hiv(built):
+    import oracle
+    from virgena_b200 import synth
+    ref, ends = synth.config_reference(1)
+    cut = oracle.cutoffs(ref, K=5, coef=1.25, read_num=1500, min_len=250, max_len=250, step=10, seed=7,
+                         index_thread_num=8)
+    return ref, cut
+
+
+def test_seed_hits_and_windows(hiv):
+    import oracle
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    ref, cut = hiv
+    for threads in (1, 8):
+        o = oracle.Oracle(K=5, cutoffs=cut)
+        o.set_reference(ref, index_thread_num=threads)
+        ctx = vg.Context(K=5, cutoffs=cut)
+        ctx.set_reference(vg.Reference(ref, K=5, thread_num=threads))
+        m1, m2 = synth.config_pairs(1, 60)
+        reads = [m1[i].tobytes() for i in range(60)] + [synth.revcomp(m2[i]).tobytes() for i in range(60)]
+        reads += [b"ACGTACGTAC", b"ACG", b"N" * 50, b"A" * 250, (b"ACGTN" * 50)]
+        for r in reads[:12]:
+            h = ctx.debug_seed_hits(r)
+            oh = o.get_hits(r)
+            assert h.shape == oh.shape and (h == oh).all(), (threads, r[:20], h[:5], oh[:5])
+        win, nwin = ctx.seed_batch(b"".join(reads), _offs(reads), max_windows=64)
+        for i, r in enumerate(reads):
+            ow = o.seed(r)
+            assert nwin[i] == len(ow), (threads, i, nwin[i], len(ow))
+            assert (win[i, :nwin[i]] == ow).all(), (threads, i)
+        ctx.close()
+
+
+def test_seed_host_csr_index(hiv):
+    """The host-built CSR index (with its duplicated boundary positions, Q1) gives the same result as
+    letting the library rebuild it from the thread count."""
+    import oracle
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    ref, cut = hiv
+    o = oracle.Oracle(K=5, cutoffs=cut)
+    o.set_reference(ref, index_thread_num=6)
+    keys, offs, pos = o.index_csr()
+    ctx = vg.Context(K=5, cutoffs=cut)
+    ctx.set_reference(vg.Reference(ref, K=5, thread_num=1, index_csr=(keys, offs, pos)))
+    m1, _ = synth.config_pairs(1, 40)
+    reads = [m1[i].tobytes() for i in range(40)]
+    win, nwin = ctx.seed_batch(b"".join(reads), _offs(reads))
+    for i, r in enumerate(reads):
+        ow = o.seed(r)
+        assert nwin[i] == len(ow) and (win[i, :nwin[i]] == ow).all()
+    # an index that does not match the reference is refused
+    bad = pos.copy()
+    bad[0] += 1
+    with pytest.raises(vg.VgError) as e:
+        ctx.set_reference(vg.Reference(ref, K=5, index_csr=(keys, offs, bad)))
+    assert e.value.code == -6
+
+
+@pytest.mark.parametrize("cfg,n,threads", [(1, 1500, 8), (3, 1500, 8), (1, 300, 1)])
+def test_map_reads_single_reference(hiv, cfg, n, threads):
+    import oracle
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    ref, cut = hiv
+    m1, m2 = synth.config_pairs(cfg, n)
+    bases, off1, len1, off2, len2 = synth.pack_pairs(m1, m2)
+    o = oracle.Oracle(K=5, cutoffs=cut)
+    o.set_reference(ref, index_thread_num=threads)
+    orec, opool, ostats = o.map_pairs(bases, off1, len1, off2, len2, n_threads=8)
+    mapper = vg.Mapper(K=5, cutoffs=cut)
+    reads = vg.PairedReads(bases, off1, len1, off2, len2)
+    genome = vg.Reference(ref, K=5, thread_num=threads)
+    md = mapper.mapReads(reads, genome)
+    _compare(md, orec, opool, ostats)
+    # pileup + consensus (both flavours of saveUncovered)
+    cb = vg.ConsensusBuilderSimple(mapper)
+    cons = cb.getConsensusSimple(True, 0, genome.seqB)
+    ocounts = oracle.pileup(orec, opool, len(ref))
+    assert (mapper.ctx.counts() == ocounts).all()
+    assert cons.tobytes() == oracle.consensus(ocounts, ref, True, 0).tobytes()
+    cons2 = mapper.ctx.consensus(genome.seqB, False, 3)
+    assert cons2.tobytes() == oracle.consensus(ocounts, ref, False, 3).tobytes()
+    # iteration 2 of ConsensusBuilderWithReassembling: re-index on the consensus, reads stay resident
+    genome2 = genome.derive(cons)
+    o.set_reference(cons, index_thread_num=threads)
+    orec2, opool2, ostats2 = o.map_pairs(bases, off1, len1, off2, len2, n_threads=8)
+    md2 = mapper.mapReads(reads, genome2)
+    _compare(md2, orec2, opool2, ostats2)
+    # Mapper.mapReads(MappedData, genome): remap a subset
+    sub = np.arange(0, n, 7, dtype=np.int64)
+    md2.needToRemap = sub
+    mapper.mapReads(md2, genome2)
+    osub = orec2[sub]
+    for f in FIELDS:
+        assert (md2.remapped.records["m"][f] == osub["m"][f]).all(), f
+    assert (md2.remapped.records["cls"] == osub["cls"]).all()
+
+
+def test_map_reads_fragmented_reference(built):
+    import oracle
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    ref, ends = synth.config_reference(4)
+    cut = oracle.cutoffs(ref, K=5, coef=1.25, read_num=1000, min_len=150, max_len=150, step=10, seed=9,
+                         contig_ends=ends, is_fragmented=True, index_thread_num=8)
+    m1, m2 = synth.config_pairs(4, 1200)
+    # some pairs whose mates come from different segments (discordant across fragments)
+    m2[:60] = m2[600:660]
+    bases, off1, len1, off2, len2 = synth.pack_pairs(m1, m2)
+    o = oracle.Oracle(K=5, cutoffs=cut)
+    o.set_reference(ref, contig_ends=ends, fragment_ends=ends, is_fragmented=True, index_thread_num=8)
+    orec, opool, ostats = o.map_pairs(bases, off1, len1, off2, len2, n_threads=8)
+    mapper = vg.Mapper(K=5, cutoffs=cut)
+    genome = vg.Reference(ref, K=5, contig_ends=ends, fragment_ends=ends, is_fragmented=True, thread_num=8)
+    md = mapper.mapReads(vg.PairedReads(bases, off1, len1, off2, len2), genome)
+    _compare(md, orec, opool, ostats)
+    assert len(md.concordant) > 1000 and len(md.concordant) < 1200  # the cross-segment pairs are not concordant
+    mapper.ctx.pileup()
+    assert (mapper.ctx.counts() == oracle.pileup(orec, opool, len(ref))).all()
+
+
+def test_map_reads_ragged_and_edge_cases(hiv):
+    import oracle
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    ref, cut = hiv
+    cut = np.concatenate([cut, np.full(300, cut[-1], np.int32)])
+    m1, m2 = synth.config_pairs(1, 200)
+    rng = np.random.default_rng(3)
+    r1, r2 = [], []
+    for i in range(200):
+        a, b = m1[i].tobytes(), m2[i].tobytes()
+        a = a[:int(rng.integers(30, 251))]
+        b = b[:int(rng.integers(30, 251))]
+        if i % 17 == 0:
+            a = b"*"                       # absent mate (Constants.NULL_SEQ)
+        if i % 19 == 0:
+            b = b"*"
+        if i % 23 == 0:
+            a = a[:60] + b"NNNRYK" + a[66:]  # N and IUPAC bytes
+        if i % 29 == 0:
+            b = bytes(rng.integers(65, 85, 120).astype(np.uint8))  # junk read
+        if i % 31 == 0:
+            a = b"ACG"                     # shorter than K
+        r1.append(a)
+        r2.append(b)
+    r1 += [b"*", b"A" * 100, ref[100:350].tobytes()]
+    r2 += [b"*", b"T" * 100, synth.revcomp(ref[500:750]).tobytes()]
+    bases, off1, len1, off2, len2 = synth.pack_ragged(r1, r2)
+    o = oracle.Oracle(K=5, cutoffs=cut)
+    o.set_reference(ref, index_thread_num=8)
+    orec, opool, ostats = o.map_pairs(bases, off1, len1, off2, len2, n_threads=8)
+    mapper = vg.Mapper(K=5, cutoffs=cut)
+    md = mapper.mapReads(vg.PairedReads(bases, off1, len1, off2, len2), vg.Reference(ref, K=5, thread_num=8))
+    _compare(md, orec, opool, ostats)
+    mapper.ctx.pileup()
+    assert (mapper.ctx.counts() == oracle.pileup(orec, opool, len(ref))).all()
+
+
+def test_reference_with_gaps_and_n(hiv):
+    """Iteration-2 references contain '-' (uncovered) and may contain N: k-mers with such bytes are
+    indexed and matched like any other byte string."""
+    import oracle
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    ref, cut = hiv
+    ref2 = ref.copy()
+    ref2[1000:1040] = ord("-")
+    ref2[3000:3003] = ord("N")
+    ref2[5000] = ord("N")
+    m1, m2 = synth.config_pairs(1, 400)
+    m1[:50, 100:103] = ord("N")
+    bases, off1, len1, off2, len2 = synth.pack_pairs(m1, m2)
+    o = oracle.Oracle(K=5, cutoffs=cut)
+    o.set_reference(ref2, index_thread_num=8)
+    orec, opool, ostats = o.map_pairs(bases, off1, len1, off2, len2, n_threads=8)
+    mapper = vg.Mapper(K=5, cutoffs=cut)
+    md = mapper.mapReads(vg.PairedReads(bases, off1, len1, off2, len2), vg.Reference(ref2, K=5, thread_num=8))
+    _compare(md, orec, opool, ostats)
+
+
+def test_map_all_reads_msa(built):
+    import oracle
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    rows = synth.config_msa(n_refs=12)
+    ref, _ = synth.config_reference(1)
+    cut = oracle.cutoffs(ref, K=7, coef=1.5, read_num=800, min_len=250, max_len=250, step=10, seed=5, msa_rows=rows)
+    m1, m2 = synth.config_pairs(2, 800)
+    bases, off1, len1, off2, len2 = synth.pack_pairs(m1, m2)
+    o = oracle.Oracle(K=5)
+    o.set_msa(rows, K=7, low_coef=float(np.float32(1) / np.float32(1.5)), high_coef=1.5, cutoffs=cut)
+    orec, opool, ostats = o.map_pairs(bases, off1, len1, off2, len2, msa=True, n_threads=8)
+    aln = vg.ReferenceAlignment(rows, K=7)
+    # the host-built MSA index equals the oracle's restatement of buildAlnIndex
+    okeys, ooffs, ocols = o.index_csr(msa=True)
+    assert (aln.keys == okeys).all() and (aln.offsets == ooffs).all() and (aln.columns == ocols).all()
+    mapper = vg.MapperMSA(K=7, indel_tolerance=1.5, cutoffs=cut)
+    md = mapper.mapAllReads(vg.PairedReads(bases, off1, len1, off2, len2), aln)
+    rec = md.records
+    assert (rec["cls"] == orec["cls"]).all()
+    for f in ["present", "start", "end", "count", "reverse"]:
+        assert (rec["m"][f] == orec["m"][f]).all(), f
+    assert (md.stats == ostats).all(), (md.stats, ostats)
+    assert ostats[3] > 800  # most reads map
+
+
+def test_errors(hiv):
+    import virgena_b200 as vg
+    ref, cut = hiv
+    ctx = vg.Context(K=5, cutoffs=cut)
+    with pytest.raises(vg.VgError) as e:
+        ctx.map_pairs()
+    assert e.value.code == -3  # VG_ERR_STATE: nothing uploaded
+    bad = np.frombuffer(b"ACGT" * 10 + b"\xff" + b"ACGT" * 10, np.uint8)
+    with pytest.raises(vg.VgError) as e:
+        ctx.upload_reads(vg.PairedReads(bad, [0], [41], [41], [40]))
+    assert e.value.code == -5  # VG_ERR_ALPHABET
+    with pytest.raises(vg.VgError):
+        vg.Context(K=5, cutoffs=cut, match=2, mismatch=3)  # created fine ...
+        c2 = vg.Context(K=5, cutoffs=cut, mismatch=3)
+        c2.sw_align_batch(b"ACGT", [0, 4], b"ACGT", [0, 4])  # ... but the aligner refuses mismatch >= 0

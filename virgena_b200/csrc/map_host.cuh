@@ -1,17 +1,595 @@
+// Host orchestration of the mapping pipeline: reference/reads upload, Mapper.mapReads,
+// MapperMSA.mapAllReads, result retrieval, pileup and consensus.
 #pragma once
 #include "ctx.cuh"
-// temporary stubs
-extern "C" {
-int vg_set_reference(vg_ctx* c, const uint8_t*, int32_t, const int32_t*, int32_t, const int32_t*, int32_t, int32_t, const uint8_t*, const int64_t*, const int32_t*, int32_t, int32_t) { return vg_fail(c, VG_ERR_STATE, "not implemented"); }
-int vg_set_msa_index(vg_ctx* c, int32_t, float, float, const int32_t*, int32_t, const uint8_t*, const int64_t*, const int32_t*, int32_t, int32_t) { return vg_fail(c, VG_ERR_STATE, "not implemented"); }
-int vg_upload_reads(vg_ctx* c, const uint8_t*, int64_t, const int64_t*, const int32_t*, const int64_t*, const int32_t*, int64_t) { return vg_fail(c, VG_ERR_STATE, "not implemented"); }
-int vg_map_pairs(vg_ctx* c, const int64_t*, int64_t, vg_map_stats*) { return vg_fail(c, VG_ERR_STATE, "not implemented"); }
-int vg_map_pairs_msa(vg_ctx* c, vg_map_stats*) { return vg_fail(c, VG_ERR_STATE, "not implemented"); }
-int vg_result_sizes(vg_ctx* c, int64_t*, int64_t*) { return vg_fail(c, VG_ERR_STATE, "not implemented"); }
-int vg_get_results(vg_ctx* c, vg_pair_result*, int64_t, uint8_t*, int64_t) { return vg_fail(c, VG_ERR_STATE, "not implemented"); }
-int vg_pileup(vg_ctx* c, int32_t) { return vg_fail(c, VG_ERR_STATE, "not implemented"); }
-int vg_pileup_counts_device(vg_ctx* c, void**, int64_t*) { return vg_fail(c, VG_ERR_STATE, "not implemented"); }
-int vg_pileup_counts_host(vg_ctx* c, int32_t*, int64_t) { return vg_fail(c, VG_ERR_STATE, "not implemented"); }
-int vg_consensus(vg_ctx* c, int32_t, int32_t, const uint8_t*, int32_t, uint8_t*) { return vg_fail(c, VG_ERR_STATE, "not implemented"); }
-int vg_seed_batch(vg_ctx* c, int32_t, const uint8_t*, const int64_t*, int64_t, int32_t, int32_t*, int32_t*) { return vg_fail(c, VG_ERR_STATE, "not implemented"); }
+#include "pileup.cuh"
+#include "seed_host.cuh"
+#include "sw_host.cuh"
+
+// ---- small utility kernels ------------------------------------------------------------------------
+__global__ void mh_iota_kernel(int64_t* a, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = i;
 }
+
+// Bytes the Java reference would throw on: >= 127 (Constants.complement has 127 entries, bytes are
+// signed) and ('T','a') exclusive (Constants.nToI has 'T'+1 entries; such a byte aligned on the diagonal
+// makes the pileup throw).
+__global__ void mh_validate_kernel(const uint8_t* __restrict__ b, int64_t n, int* __restrict__ flag) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int bad = 0;
+  for (; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint8_t c = b[i];
+    bad |= (c >= 127) || (c > 'T' && c < 'a');
+  }
+  if (__any_sync(VG_FULL, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+// exclusive scan int32 -> int64, three kernels
+__global__ void mh_scan1_kernel(const int32_t* __restrict__ in, int64_t* __restrict__ out, int64_t* __restrict__ blockSums, int64_t n) {
+  __shared__ int64_t wsum[32];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int64_t v = (i < n) ? in[i] : 0, x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int64_t y = __shfl_up_sync(VG_FULL, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) wsum[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    int64_t s = wsum[lane], t = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int64_t y = __shfl_up_sync(VG_FULL, t, d);
+      if (lane >= d) t += y;
+    }
+    wsum[lane] = t - s;
+    if (lane == 31) blockSums[blockIdx.x] = t;
+  }
+  __syncthreads();
+  if (i < n) out[i] = wsum[w] + x - v;
+}
+__global__ void mh_scan2_kernel(int64_t* blockSums, int64_t nb, int64_t* total) {
+  // single thread block of 1 warp: sequential over chunks of 32 with carry (nb is small)
+  const int lane = threadIdx.x;
+  int64_t carry = 0;
+  for (int64_t b0 = 0; b0 < nb; b0 += 32) {
+    int64_t v = (b0 + lane < nb) ? blockSums[b0 + lane] : 0, x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int64_t y = __shfl_up_sync(VG_FULL, x, d);
+      if (lane >= d) x += y;
+    }
+    if (b0 + lane < nb) blockSums[b0 + lane] = carry + x - v;
+    carry += __shfl_sync(VG_FULL, x, 31);
+  }
+  if (lane == 0) *total = carry;
+}
+__global__ void mh_scan3_kernel(int64_t* __restrict__ out, const int64_t* __restrict__ blockSums, const int32_t* __restrict__ in,
+                                int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] > 0 ? out[i] + blockSums[blockIdx.x] : -1;  // -1: nothing to emit
+}
+
+__global__ void mh_lengths_kernel(const vg_pair_result* __restrict__ res, const SwAln* __restrict__ alns, int64_t n2,
+                                  int32_t* __restrict__ lens) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n2) return;
+  const vg_mate& m = res[q >> 1].m[q & 1];
+  lens[q] = m.present ? alns[q].length : 0;
+}
+
+__global__ void mh_finalize_kernel(vg_pair_result* __restrict__ res, const SwAln* __restrict__ alns,
+                                   const int64_t* __restrict__ seqOff, int64_t n2) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n2) return;
+  vg_mate& m = res[q >> 1].m[q & 1];
+  if (!m.present) return;
+  const SwAln a = alns[q];
+  m.score = a.score, m.start1 = a.start1, m.end1 = a.end1, m.start2 = a.start2, m.end2 = a.end2;
+  m.identity = a.identity, m.length = a.length;
+  // an empty alignment still has a (zero-length) sequence1; give it a valid offset
+  m.seq1_offset = seqOff[q] >= 0 ? seqOff[q] : 0;
+}
+
+// Mapping stats 1)-7) (Mapper.java:446-473 / MapperMSA.java:335-357)
+__global__ void mh_stats_kernel(const vg_pair_result* __restrict__ res, int64_t n, const int64_t* __restrict__ pairIdx,
+                                const uint8_t* __restrict__ bases, const int64_t* __restrict__ off1,
+                                const int32_t* __restrict__ len1, const int64_t* __restrict__ off2,
+                                const int32_t* __restrict__ len2, int msa, unsigned long long* __restrict__ st) {
+  __shared__ unsigned long long acc[9];
+  if (threadIdx.x < 9) acc[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t pi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pi < n) {
+    const int64_t p = pairIdx[pi];
+    const vg_pair_result& r = res[pi];
+    const bool e1 = !(len1[p] == 1 && bases[off1[p]] == '*'), e2 = !(len2[p] == 1 && bases[off2[p]] == '*');
+    unsigned long long v[9] = {1, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (e1 && e2) v[1] = 1, v[2] = 2;
+    else if (e1 || e2) v[2] = 1;
+    long long score = 0;
+    for (int k = 0; k < 2; k++)
+      if (r.m[k].present) {
+        v[3]++;
+        score += msa ? r.m[k].count : r.m[k].score;
+      }
+    const bool conc = r.cls == VG_CLS_CONCORDANT_FR || r.cls == VG_CLS_CONCORDANT_RF;
+    if (conc) {
+      v[4] = 1, v[5] = 1, v[8] = 1;
+    } else {
+      for (int k = 0; k < 2; k++)
+        if (r.m[k].present) (r.m[k].reverse ? v[5] : v[4])++;
+    }
+    if (conc || r.cls == VG_CLS_DISCORDANT) v[6] = 1;
+    v[7] = (unsigned long long)score;
+    for (int k = 0; k < 9; k++)
+      if (v[k]) atomicAdd(&acc[k], v[k]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 9 && acc[threadIdx.x]) atomicAdd(&st[threadIdx.x], acc[threadIdx.x]);
+}
+
+static int mh_exclusive_scan(vg_ctx* c, const int32_t* d_in, int64_t* d_out, int64_t n, int64_t* totalOut) {
+  const int threads = 1024;
+  const int64_t nb = (n + threads - 1) / threads;
+  VG_CUDA(c, c->d_misc.reserve((size_t)(nb + 2) * 8 + 64));
+  int64_t* bs = c->d_misc.as<int64_t>() + 1;
+  int64_t* tot = c->d_misc.as<int64_t>();
+  mh_scan1_kernel<<<(unsigned)nb, threads, 0, c->stream>>>(d_in, d_out, bs, n);
+  VG_LAUNCH_CHECK(c);
+  mh_scan2_kernel<<<1, 32, 0, c->stream>>>(bs, nb, tot);
+  VG_LAUNCH_CHECK(c);
+  mh_scan3_kernel<<<(unsigned)nb, threads, 0, c->stream>>>(d_out, bs, d_in, n);
+  VG_LAUNCH_CHECK(c);
+  VG_CUDA(c, cudaMemcpyAsync(totalOut, tot, 8, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VG_OK;
+}
+
+static int mh_map(vg_ctx* c, bool msa, const int64_t* pair_idx, int64_t n_idx, vg_map_stats* stats) {
+  if (!c) return VG_ERR_INVALID;
+  VG_CUDA(c, cudaSetDevice(c->device));
+  if (!c->haveReads) return vg_fail(c, VG_ERR_STATE, "vg_upload_reads has not been called");
+  if (msa ? !c->haveMsa : !c->haveRef) return vg_fail(c, VG_ERR_STATE, msa ? "vg_set_msa_index has not been called" : "vg_set_reference has not been called");
+  const int64_t n = pair_idx ? n_idx : c->nPairs;
+  if (n < 0) return vg_fail(c, VG_ERR_INVALID, "negative pair count");
+  c->nResults = n;
+  c->seq1Bytes = 0;
+  c->resultsMsa = msa;
+  for (double& t : c->timings) t = 0;
+  if (stats) memset(stats, 0, sizeof *stats);
+  VG_CUDA(c, c->d_pairIdx.reserve((size_t)std::max<int64_t>(n, 1) * 8));
+  if (pair_idx) {
+    for (int64_t i = 0; i < n; i++)
+      if (pair_idx[i] < 0 || pair_idx[i] >= c->nPairs) return vg_fail(c, VG_ERR_INVALID, "pair index %lld out of range", (long long)pair_idx[i]);
+    VG_CUDA(c, cudaMemcpyAsync(c->d_pairIdx.p, pair_idx, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  } else if (n > 0) {
+    mh_iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_pairIdx.as<int64_t>(), n);
+    VG_LAUNCH_CHECK(c);
+  }
+  VG_CUDA(c, c->d_results.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(vg_pair_result)));
+  if (n == 0) return VG_OK;
+  const bool emptyRef = !msa && c->G == 0;  // Mapper.java:422-426: everything unmapped
+  VG_CUDA(c, c->d_tasks.reserve((size_t)n * 2 * sizeof(SwTask)));
+  VG_CUDA(c, c->d_ncand.reserve(64));
+  // task counter + max window length live in d_fill's head (two ints), zeroed here
+  VG_CUDA(c, c->d_alns.reserve((size_t)n * 2 * sizeof(SwAln) + 64));
+  int* d_nTasks = nullptr;
+  {
+    VG_CUDA(c, c->d_s1off.reserve(64));
+    d_nTasks = c->d_s1off.as<int>();
+    VG_CUDA(c, cudaMemsetAsync(d_nTasks, 0, 16, c->stream));
+  }
+  const SeedConfig& sc = msa ? c->seedMsa : c->seed;
+  const int range = msa ? c->msaLength : c->G;
+  VG_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+  // ---- seeding + pair selection, in chunks of pairs -------------------------------------------------
+  int maxWin = 64;
+  if (c->maxReadLen > 0) maxWin = std::max(8, std::min(256, range / std::max(1, c->maxReadLen / 2) + (int)c->contigEnds.size() + 4));
+  const int64_t chunkPairs = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)((size_t)(3ull << 30) / ((size_t)maxWin * 48 + 64))));
+  const int nf = (int)c->fragmentEnds.size();
+  if (emptyRef) {
+    VG_CUDA(c, cudaMemsetAsync(c->d_results.p, 0, (size_t)n * sizeof(vg_pair_result), c->stream));
+  }
+  for (int64_t s = 0; s < n && !emptyRef; s += chunkPairs) {
+    const int64_t np = std::min(chunkPairs, n - s);
+    VG_TRY(seed_launch(c, msa, c->d_bases.as<uint8_t>(), c->d_off1.as<int64_t>(), c->d_len1.as<int32_t>(),
+                       c->d_off2.as<int64_t>(), c->d_len2.as<int32_t>(), c->d_pairIdx.as<int64_t>() + s, np * 4, false,
+                       c->maxReadLen, maxWin, nullptr, nullptr));
+    PairArgs P;
+    memset(&P, 0, sizeof P);
+    P.windows = c->d_cand.as<int32_t>();
+    P.nWindows = c->d_ncand.as<int32_t>();
+    P.maxWin = maxWin;
+    P.nPairs = np;
+    P.pairIdx = c->d_pairIdx.as<int64_t>() + s;
+    P.off1 = c->d_off1.as<int64_t>(), P.len1 = c->d_len1.as<int32_t>();
+    P.off2 = c->d_off2.as<int64_t>(), P.len2 = c->d_len2.as<int32_t>();
+    P.fragmentEnds = c->d_fragmentEnds.as<int32_t>();
+    P.nFragments = nf;
+    P.isFragmented = (c->isFragmented && !msa) ? 1 : 0;
+    P.insertLen = c->insertLen;
+    P.msa = msa ? 1 : 0;
+    P.results = c->d_results.as<vg_pair_result>() + s;
+    P.tasks = c->d_tasks.as<SwTask>();
+    P.nTasks = d_nTasks;
+    P.outBase = s * 2;
+    if (P.isFragmented) {
+      VG_CUDA(c, c->d_s2off.reserve((size_t)np * 6 * nf * 4));
+      P.fragScratch = c->d_s2off.as<int32_t>();
+    }
+    pair_select_kernel<<<(unsigned)((np + 127) / 128), 128, 0, c->stream>>>(P);
+    VG_LAUNCH_CHECK(c);
+  }
+  VG_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  struct { int nTasks, maxN; unsigned long long cells; } hostCnt = {0, 0, 0};
+  VG_CUDA(c, cudaMemcpyAsync(&hostCnt, d_nTasks, 16, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int64_t nTasks = hostCnt.nTasks;
+  const int nmaxWinLen = hostCnt.maxN;
+  c->timings[5] = (double)hostCnt.cells;
+  (void)sc;
+  // ---- alignment ------------------------------------------------------------------------------------
+  if (!msa && !emptyRef) {
+    const int mmax = c->maxReadLen;
+    const int64_t revStride = mmax + nmaxWinLen + 1;
+    VG_CUDA(c, cudaMemsetAsync(c->d_alns.p, 0, (size_t)n * 2 * sizeof(SwAln), c->stream));
+    VG_CUDA(c, c->d_rev.reserve((size_t)n * 2 * revStride + 64));
+    VG_CUDA(c, c->d_fill.reserve((size_t)std::max<int64_t>(nTasks, 1) * sizeof(SwFillOut)));
+    VG_TRY(sw_run(c, c->d_tasks.as<SwTask>(), nTasks, c->d_bases.as<uint8_t>(), c->d_ref.as<uint8_t>(), mmax, nmaxWinLen,
+                  true, c->d_fill.as<SwFillOut>(), c->d_alns.as<SwAln>(), c->d_rev.as<uint8_t>(), revStride,
+                  &c->timings[1], &c->timings[2]));
+    // sequence1 pool offsets = exclusive prefix sum of the alignment lengths in (pair, mate) order
+    VG_CUDA(c, c->d_s2off.reserve((size_t)n * 2 * 4 + 64));
+    int32_t* d_lens = c->d_s2off.as<int32_t>();
+    VG_CUDA(c, c->d_seqOff.reserve((size_t)n * 2 * 8 + 64));
+    mh_lengths_kernel<<<(unsigned)((n * 2 + 255) / 256), 256, 0, c->stream>>>(c->d_results.as<vg_pair_result>(),
+                                                                              c->d_alns.as<SwAln>(), n * 2, d_lens);
+    VG_LAUNCH_CHECK(c);
+    int64_t total = 0;
+    VG_TRY(mh_exclusive_scan(c, d_lens, c->d_seqOff.as<int64_t>(), n * 2, &total));
+    c->seq1Bytes = total;
+    VG_CUDA(c, c->d_seq1pool.reserve((size_t)total + 64));
+    VG_CUDA(c, c->d_rowpool.reserve((size_t)total + 64));
+    VG_CUDA(c, c->d_rowLen.reserve((size_t)n * 2 * 4 + 64));
+    pu_emit_kernel<<<(unsigned)((n * 2 * 32 + 255) / 256), 256, 0, c->stream>>>(
+        c->d_alns.as<SwAln>(), n * 2, c->d_rev.as<uint8_t>(), revStride, c->d_seqOff.as<int64_t>(),
+        c->d_seq1pool.as<uint8_t>(), c->d_rowpool.as<uint8_t>(), c->d_rowLen.as<int32_t>());
+    VG_LAUNCH_CHECK(c);
+    mh_finalize_kernel<<<(unsigned)((n * 2 + 255) / 256), 256, 0, c->stream>>>(c->d_results.as<vg_pair_result>(),
+                                                                               c->d_alns.as<SwAln>(), c->d_seqOff.as<int64_t>(),
+                                                                               n * 2);
+    VG_LAUNCH_CHECK(c);
+  }
+  VG_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  // ---- stats ----------------------------------------------------------------------------------------
+  VG_CUDA(c, c->d_ncand.reserve(9 * 8 + 64));
+  unsigned long long* d_st = c->d_ncand.as<unsigned long long>();
+  VG_CUDA(c, cudaMemsetAsync(d_st, 0, 9 * 8, c->stream));
+  mh_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+      c->d_results.as<vg_pair_result>(), n, c->d_pairIdx.as<int64_t>(), c->d_bases.as<uint8_t>(), c->d_off1.as<int64_t>(),
+      c->d_len1.as<int32_t>(), c->d_off2.as<int64_t>(), c->d_len2.as<int32_t>(), msa ? 1 : 0, d_st);
+  VG_LAUNCH_CHECK(c);
+  unsigned long long st[9];
+  VG_CUDA(c, cudaMemcpyAsync(st, d_st, sizeof st, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (stats) {
+    stats->total_pairs = (int64_t)st[0], stats->both_exist = (int64_t)st[1], stats->reads_total = (int64_t)st[2];
+    stats->total_mapped = (int64_t)st[3], stats->mapped_forward = (int64_t)st[4], stats->mapped_reverse = (int64_t)st[5];
+    stats->both_mapped = (int64_t)st[6], stats->total_score = (int64_t)st[7], stats->total_concordant = (int64_t)st[8];
+  }
+  float a = 0, b = 0;
+  cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
+  cudaEventElapsedTime(&b, c->ev[0], c->ev[3]);
+  c->timings[0] = a;
+  c->timings[4] = b;
+  c->lastTasks = nTasks;
+  return VG_OK;
+}
+
+extern "C" {
+
+int vg_set_reference(vg_ctx* c, const uint8_t* seq, int32_t G, const int32_t* contig_ends, int32_t n_contigs,
+                     const int32_t* fragment_ends, int32_t n_fragments, int32_t is_fragmented, const uint8_t* keys,
+                     const int64_t* offsets, const int32_t* positions, int32_t n_keys, int32_t index_thread_num) {
+  if (!c) return VG_ERR_INVALID;
+  VG_CUDA(c, cudaSetDevice(c->device));
+  if (G < 0 || (G > 0 && !seq)) return vg_fail(c, VG_ERR_INVALID, "bad reference");
+  if (n_contigs < 1 || !contig_ends || contig_ends[n_contigs - 1] != G)
+    return vg_fail(c, VG_ERR_INVALID, "contig_ends must be ascending and end at the reference length");
+  for (int i = 0; i < n_contigs; i++)
+    if (contig_ends[i] < 0 || (i && contig_ends[i] < contig_ends[i - 1])) return vg_fail(c, VG_ERR_INVALID, "contig_ends not ascending");
+  if (n_fragments < 1 || !fragment_ends) return vg_fail(c, VG_ERR_INVALID, "fragment_ends missing");
+  if (keys && (!offsets || !positions || n_keys < 0)) return vg_fail(c, VG_ERR_INVALID, "incomplete CSR index");
+  for (int i = 0; i < G; i++)
+    if (seq[i] >= 128) return vg_fail(c, VG_ERR_ALPHABET, "reference byte %d at %d is not ASCII", (int)seq[i], i);
+  c->haveRef = false;
+  c->haveCounts = false;
+  c->G = G;
+  c->h_ref.assign(seq, seq + G);
+  c->contigEnds.assign(contig_ends, contig_ends + n_contigs);
+  c->fragmentEnds.assign(fragment_ends, fragment_ends + n_fragments);
+  c->isFragmented = is_fragmented != 0;
+  VG_CUDA(c, c->d_ref.reserve((size_t)G + 64));
+  if (G) VG_CUDA(c, cudaMemcpy(c->d_ref.p, seq, G, cudaMemcpyHostToDevice));
+  VG_CUDA(c, c->d_contigEnds.reserve((size_t)n_contigs * 4));
+  VG_CUDA(c, cudaMemcpy(c->d_contigEnds.p, contig_ends, (size_t)n_contigs * 4, cudaMemcpyHostToDevice));
+  VG_CUDA(c, c->d_fragmentEnds.reserve((size_t)n_fragments * 4));
+  VG_CUDA(c, cudaMemcpy(c->d_fragmentEnds.p, fragment_ends, (size_t)n_fragments * 4, cudaMemcpyHostToDevice));
+  if (G >= c->seed.K) VG_TRY(seed_build_reference(c, keys, offsets, positions, n_keys, index_thread_num));
+  else if (G > 0) {
+    // no k-mer fits: nothing is ever seeded; keep an all-absent table
+    VG_TRY(seed_build_reference(c, nullptr, nullptr, nullptr, 0, 1));
+  }
+  c->haveRef = true;
+  return VG_OK;
+}
+
+int vg_set_msa_index(vg_ctx* c, int32_t K, float low_coef, float high_coef, const int32_t* cutoffs, int32_t n_cutoffs,
+                     const uint8_t* keys, const int64_t* offsets, const int32_t* columns, int32_t n_keys,
+                     int32_t msa_length) {
+  if (!c) return VG_ERR_INVALID;
+  VG_CUDA(c, cudaSetDevice(c->device));
+  if (n_keys < 0 || (n_keys > 0 && (!keys || !offsets || !columns)) || msa_length < 0)
+    return vg_fail(c, VG_ERR_INVALID, "bad MSA index");
+  c->haveMsa = false;
+  if (K < 1 || K > 7) return vg_fail(c, VG_ERR_INVALID, "K=%d outside the supported range 1..7", K);
+  if (!cutoffs || n_cutoffs < 1) return vg_fail(c, VG_ERR_INVALID, "cutoffs missing");
+  c->seedMsa.K = K;
+  c->seedMsa.lowCoef = low_coef;
+  c->seedMsa.highCoef = high_coef;
+  c->seedMsa.cutoffs.assign(cutoffs, cutoffs + n_cutoffs);
+  VG_CUDA(c, c->seedMsa.d_cutoffs.reserve((size_t)n_cutoffs * 4));
+  VG_CUDA(c, cudaMemcpy(c->seedMsa.d_cutoffs.p, cutoffs, (size_t)n_cutoffs * 4, cudaMemcpyHostToDevice));
+  c->msaLength = msa_length;
+  static const int64_t zero = 0;
+  VG_TRY(seed_build_msa(c, keys, n_keys ? offsets : &zero, columns, n_keys));
+  c->haveMsa = true;
+  return VG_OK;
+}
+
+int vg_upload_reads(vg_ctx* c, const uint8_t* bases, int64_t n_bases, const int64_t* off1, const int32_t* len1,
+                    const int64_t* off2, const int32_t* len2, int64_t n_pairs) {
+  if (!c) return VG_ERR_INVALID;
+  VG_CUDA(c, cudaSetDevice(c->device));
+  if (n_pairs < 0 || n_bases < 0 || (n_pairs > 0 && (!bases || !off1 || !len1 || !off2 || !len2)))
+    return vg_fail(c, VG_ERR_INVALID, "bad read arrays");
+  c->haveReads = false;
+  int maxLen = 0;
+  for (int64_t i = 0; i < n_pairs; i++) {
+    if (len1[i] < 0 || len2[i] < 0 || off1[i] < 0 || off2[i] < 0 || off1[i] + len1[i] > n_bases || off2[i] + len2[i] > n_bases)
+      return vg_fail(c, VG_ERR_INVALID, "read %lld lies outside the byte pool", (long long)i);
+    maxLen = std::max(maxLen, std::max(len1[i], len2[i]));
+  }
+  VG_CUDA(c, c->d_bases.reserve((size_t)n_bases + 64));
+  VG_CUDA(c, c->d_off1.reserve((size_t)n_pairs * 8 + 8));
+  VG_CUDA(c, c->d_off2.reserve((size_t)n_pairs * 8 + 8));
+  VG_CUDA(c, c->d_len1.reserve((size_t)n_pairs * 4 + 8));
+  VG_CUDA(c, c->d_len2.reserve((size_t)n_pairs * 4 + 8));
+  if (n_pairs > 0) {
+    VG_CUDA(c, cudaMemcpyAsync(c->d_bases.p, bases, (size_t)n_bases, cudaMemcpyHostToDevice, c->stream));
+    VG_CUDA(c, cudaMemcpyAsync(c->d_off1.p, off1, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, c->stream));
+    VG_CUDA(c, cudaMemcpyAsync(c->d_off2.p, off2, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, c->stream));
+    VG_CUDA(c, cudaMemcpyAsync(c->d_len1.p, len1, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+    VG_CUDA(c, cudaMemcpyAsync(c->d_len2.p, len2, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+    VG_CUDA(c, c->d_counter.reserve(16));
+    VG_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, 16, c->stream));
+    if (n_bases > 0) {
+      mh_validate_kernel<<<c->smCount * 8, 256, 0, c->stream>>>(c->d_bases.as<uint8_t>(), n_bases, c->d_counter.as<int>());
+      VG_LAUNCH_CHECK(c);
+    }
+    int flag = 0;
+    VG_CUDA(c, cudaMemcpyAsync(&flag, c->d_counter.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    VG_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (flag)
+      return vg_fail(c, VG_ERR_ALPHABET, "a read contains a byte >= 127 or in ('T','a'): the Java reference throws on it");
+  }
+  c->nPairs = n_pairs;
+  c->nBases = n_bases;
+  c->maxReadLen = maxLen;
+  c->haveReads = true;
+  return VG_OK;
+}
+
+int vg_map_pairs(vg_ctx* c, const int64_t* pair_idx, int64_t n_idx, vg_map_stats* stats) {
+  return mh_map(c, false, pair_idx, n_idx, stats);
+}
+
+int vg_map_pairs_msa(vg_ctx* c, vg_map_stats* stats) { return mh_map(c, true, nullptr, 0, stats); }
+
+int vg_result_sizes(vg_ctx* c, int64_t* n_results, int64_t* seq1_bytes) {
+  if (!c) return VG_ERR_INVALID;
+  if (n_results) *n_results = c->nResults;
+  if (seq1_bytes) *seq1_bytes = c->seq1Bytes;
+  return VG_OK;
+}
+
+int vg_get_results(vg_ctx* c, vg_pair_result* out, int64_t n_out, uint8_t* seq1_pool, int64_t pool_cap) {
+  if (!c) return VG_ERR_INVALID;
+  VG_CUDA(c, cudaSetDevice(c->device));
+  if (n_out < c->nResults || pool_cap < c->seq1Bytes) {
+    c->required = n_out < c->nResults ? c->nResults : c->seq1Bytes;
+    return vg_fail(c, VG_ERR_CAPACITY, "output buffers too small (%lld results, %lld sequence1 bytes)",
+                   (long long)c->nResults, (long long)c->seq1Bytes);
+  }
+  if (c->nResults > 0) {
+    if (!out) return vg_fail(c, VG_ERR_INVALID, "null output");
+    VG_CUDA(c, cudaMemcpyAsync(out, c->d_results.p, (size_t)c->nResults * sizeof(vg_pair_result), cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (c->seq1Bytes > 0) {
+    if (!seq1_pool) return vg_fail(c, VG_ERR_INVALID, "null sequence1 pool");
+    VG_CUDA(c, cudaMemcpyAsync(seq1_pool, c->d_seq1pool.p, (size_t)c->seq1Bytes, cudaMemcpyDeviceToHost, c->stream));
+  }
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VG_OK;
+}
+
+int vg_pileup(vg_ctx* c, int32_t accumulate) {
+  if (!c) return VG_ERR_INVALID;
+  VG_CUDA(c, cudaSetDevice(c->device));
+  if (!c->haveRef) return vg_fail(c, VG_ERR_STATE, "vg_set_reference has not been called");
+  if (c->resultsMsa) return vg_fail(c, VG_ERR_STATE, "the last mapping was MSA mode (no alignments to pile up)");
+  const int G = c->G;
+  const int64_t n = c->nResults;
+  VG_CUDA(c, c->d_counts.reserve((size_t)std::max(G, 1) * 5 * 4));
+  if (!accumulate || !c->haveCounts) {
+    VG_CUDA(c, cudaMemsetAsync(c->d_counts.p, 0, (size_t)std::max(G, 1) * 5 * 4, c->stream));
+    accumulate = c->haveCounts ? accumulate : 0;
+  }
+  c->haveCounts = true;
+  if (G == 0 || n == 0) {
+    VG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VG_OK;
+  }
+  VG_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+  const int nTiles = (G + PU_TILE - 1) / PU_TILE;
+  const int64_t n2 = n * 2;
+  VG_CUDA(c, c->d_tasks.reserve((size_t)n2 * sizeof(PuRead) * 2 + 64));  // unsorted + sorted lists
+  PuRead* d_reads = c->d_tasks.as<PuRead>();
+  PuRead* d_sorted = d_reads + n2;
+  VG_CUDA(c, c->d_fill.reserve((size_t)n2 * 4 + 64));
+  int32_t* d_tileOf = c->d_fill.as<int32_t>();
+  const size_t cntBytes = ((size_t)(nTiles + 2) * 4 + 15) & ~(size_t)15;
+  VG_CUDA(c, c->d_misc.reserve(cntBytes + (size_t)(nTiles + 2) * 16 + 64));
+  int32_t* d_tileCount = c->d_misc.as<int32_t>();
+  int64_t* d_tileStart = (int64_t*)(c->d_misc.as<uint8_t>() + cntBytes);
+  int64_t* d_cursor = d_tileStart + nTiles + 2;
+  VG_CUDA(c, cudaMemsetAsync(d_tileCount, 0, (size_t)(nTiles + 2) * 4, c->stream));
+  VG_CUDA(c, c->d_counter.reserve(16));
+  VG_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, 16, c->stream));
+  pu_list_kernel<<<(unsigned)((n2 + 255) / 256), 256, nTiles * 4, c->stream>>>(
+      c->d_results.as<vg_pair_result>(), n, c->d_rowLen.as<int32_t>(), G, nTiles, d_reads, d_tileOf, d_tileCount,
+      c->d_counter.as<int>());
+  VG_LAUNCH_CHECK(c);
+  pu_scan_kernel<<<1, 32, 0, c->stream>>>(d_tileCount, nTiles, d_tileStart, d_cursor);
+  VG_LAUNCH_CHECK(c);
+  pu_scatter_kernel<<<(unsigned)((n2 + 255) / 256), 256, (size_t)(2 * nTiles + 2) * 4 + (size_t)nTiles * 8, c->stream>>>(
+      d_reads, d_tileOf, n2, nTiles, (unsigned long long*)d_cursor, d_sorted);
+  VG_LAUNCH_CHECK(c);
+  const int maxRow = c->maxReadLen * 3 + 16;  // rows are at most |read| + |window| long
+  const int backTiles = maxRow / PU_TILE + 1;
+  const int nSlices = std::max(1, std::min(64, (c->smCount * 4) / nTiles));
+  VG_CUDA(c, c->d_scratch.reserve((size_t)nSlices * G * 5 * 4 + 64));
+  dim3 grid(nTiles, nSlices);
+  pu_count_kernel<<<grid, PU_TILE, 0, c->stream>>>(d_sorted, d_tileStart, nTiles, backTiles, c->d_rowpool.as<uint8_t>(), G,
+                                                   nSlices, c->d_scratch.as<int32_t>());
+  VG_LAUNCH_CHECK(c);
+  pu_reduce_kernel<<<(unsigned)(((int64_t)G * 5 + 255) / 256), 256, 0, c->stream>>>(c->d_scratch.as<int32_t>(), G, nSlices,
+                                                                                    accumulate ? 1 : 0, c->d_counts.as<int32_t>());
+  VG_LAUNCH_CHECK(c);
+  VG_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  int flag = 0;
+  VG_CUDA(c, cudaMemcpyAsync(&flag, c->d_counter.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+  c->timings[3] = ms;
+  if (flag) return vg_fail(c, VG_ERR_ALPHABET, "an aligned read runs past the end of the reference (the Java pileup would throw)");
+  return VG_OK;
+}
+
+int vg_pileup_counts_device(vg_ctx* c, void** dev_ptr, int64_t* n_int32) {
+  if (!c || !dev_ptr) return VG_ERR_INVALID;
+  if (!c->haveCounts) return vg_fail(c, VG_ERR_STATE, "vg_pileup has not been called");
+  *dev_ptr = c->d_counts.p;
+  if (n_int32) *n_int32 = (int64_t)c->G * 5;
+  return VG_OK;
+}
+
+int vg_pileup_counts_host(vg_ctx* c, int32_t* out, int64_t n_int32) {
+  if (!c || !out) return VG_ERR_INVALID;
+  VG_CUDA(c, cudaSetDevice(c->device));
+  if (!c->haveCounts) return vg_fail(c, VG_ERR_STATE, "vg_pileup has not been called");
+  if (n_int32 < (int64_t)c->G * 5) {
+    c->required = (int64_t)c->G * 5;
+    return vg_fail(c, VG_ERR_CAPACITY, "counts buffer too small");
+  }
+  VG_CUDA(c, cudaMemcpyAsync(out, c->d_counts.p, (size_t)c->G * 5 * 4, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VG_OK;
+}
+
+int vg_consensus(vg_ctx* c, int32_t save_uncovered, int32_t coverage_threshold, const uint8_t* genome, int32_t G,
+                 uint8_t* out) {
+  if (!c || !out) return VG_ERR_INVALID;
+  VG_CUDA(c, cudaSetDevice(c->device));
+  if (!c->haveCounts) return vg_fail(c, VG_ERR_STATE, "vg_pileup has not been called");
+  if (G != c->G) return vg_fail(c, VG_ERR_INVALID, "genome length %d differs from the reference length %d", G, c->G);
+  if (G == 0) return VG_OK;
+  if (save_uncovered && !genome) return vg_fail(c, VG_ERR_INVALID, "genome missing");
+  VG_CUDA(c, c->d_s1pool.reserve((size_t)G * 2 + 64));
+  uint8_t* d_gen = c->d_s1pool.as<uint8_t>();
+  uint8_t* d_out = d_gen + G;
+  if (genome) VG_CUDA(c, cudaMemcpyAsync(d_gen, genome, G, cudaMemcpyHostToDevice, c->stream));
+  pu_consensus_kernel<<<(G + 255) / 256, 256, 0, c->stream>>>(c->d_counts.as<int32_t>(), G, save_uncovered, coverage_threshold,
+                                                             d_gen, d_out);
+  VG_LAUNCH_CHECK(c);
+  VG_CUDA(c, cudaMemcpyAsync(out, d_out, G, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VG_OK;
+}
+
+static int mh_seed_batch(vg_ctx* c, int32_t msa, const uint8_t* pool, const int64_t* off, int64_t n, int32_t max_windows,
+                         int32_t* windows, int32_t* n_windows, int32_t* dbgHits, int32_t dbgCap, int32_t* dbgN) {
+  if (!c) return VG_ERR_INVALID;
+  VG_CUDA(c, cudaSetDevice(c->device));
+  if (msa ? !c->haveMsa : !c->haveRef) return vg_fail(c, VG_ERR_STATE, "reference / MSA index not set");
+  if (n < 0 || max_windows < 1 || (n > 0 && (!pool || !off))) return vg_fail(c, VG_ERR_INVALID, "bad arguments");
+  if (n == 0) return VG_OK;
+  std::vector<int32_t> len(n);
+  int maxLen = 0;
+  for (int64_t i = 0; i < n; i++) {
+    int64_t l = off[i + 1] - off[i];
+    if (l < 0 || l > (1 << 20)) return vg_fail(c, VG_ERR_INVALID, "bad offsets");
+    len[i] = (int32_t)l;
+    maxLen = std::max(maxLen, len[i]);
+  }
+  for (int64_t i = 0; i < off[n]; i++)
+    if (pool[i] >= 127) return vg_fail(c, VG_ERR_ALPHABET, "read byte >= 127");
+  VG_CUDA(c, c->d_s1pool.reserve((size_t)off[n] + 64));
+  VG_CUDA(c, c->d_s1off.reserve((size_t)(n + 1) * 8));
+  VG_CUDA(c, c->d_s2off.reserve((size_t)n * 4 + 64));
+  VG_CUDA(c, cudaMemcpyAsync(c->d_s1pool.p, pool, (size_t)off[n], cudaMemcpyHostToDevice, c->stream));
+  VG_CUDA(c, cudaMemcpyAsync(c->d_s1off.p, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  VG_CUDA(c, cudaMemcpyAsync(c->d_s2off.p, len.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  int32_t* d_dbg = nullptr;
+  int32_t* d_dbgN = nullptr;
+  if (dbgHits) {
+    VG_CUDA(c, c->d_rev.reserve((size_t)4096 * 3 * 4 + 64));
+    d_dbgN = c->d_rev.as<int32_t>();
+    d_dbg = d_dbgN + 4;
+    VG_CUDA(c, cudaMemsetAsync(d_dbgN, 0, 16, c->stream));
+  }
+  VG_TRY(seed_launch(c, msa != 0, c->d_s1pool.as<uint8_t>(), c->d_s1off.as<int64_t>(), c->d_s2off.as<int32_t>(), nullptr,
+                     nullptr, nullptr, n, true, maxLen, max_windows, d_dbg, d_dbgN));
+  VG_CUDA(c, cudaMemcpyAsync(windows, c->d_cand.p, (size_t)n * max_windows * 3 * 4, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaMemcpyAsync(n_windows, c->d_ncand.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (dbgHits) {
+    int nh = 0;
+    VG_CUDA(c, cudaMemcpyAsync(&nh, d_dbgN, 4, cudaMemcpyDeviceToHost, c->stream));
+    VG_CUDA(c, cudaStreamSynchronize(c->stream));
+    *dbgN = nh;
+    VG_CUDA(c, cudaMemcpyAsync(dbgHits, d_dbg, (size_t)std::min(nh, dbgCap) * 3 * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VG_OK;
+}
+
+int vg_seed_batch(vg_ctx* c, int32_t msa, const uint8_t* pool, const int64_t* off, int64_t n, int32_t max_windows,
+                  int32_t* windows, int32_t* n_windows) {
+  return mh_seed_batch(c, msa, pool, off, n, max_windows, windows, n_windows, nullptr, 0, nullptr);
+}
+
+// Test hook (not part of the reference-facing ABI): LongHits of one read after mergeHits + splitLongHits.
+int vg_debug_seed_hits(vg_ctx* c, int32_t msa, const uint8_t* read, int32_t L, int32_t* hits, int32_t cap, int32_t* n_hits) {
+  int64_t off[2] = {0, L};
+  std::vector<int32_t> win(64 * 3);
+  int32_t nw = 0;
+  return mh_seed_batch(c, msa, read, off, 1, 64, win.data(), &nw, hits, cap, n_hits);
+}
+
+}  // extern "C"

@@ -1,2 +1,264 @@
+// Host side of seeding: index tables (vg_set_reference / vg_set_msa_index) and kernel launches.
 #pragma once
+#include <stdlib.h>
+
 #include "ctx.cuh"
+#include "seed.cuh"
+
+struct SeedHostState {  // lives in vg_ctx via the DevBufs; plain helpers here
+};
+
+static inline int sdh_code2(uint8_t b) { return b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : b == 'T' ? 3 : -1; }
+
+// k-mer of K bytes -> (pure, code, packed key)
+static inline bool sdh_pack(const uint8_t* p, int K, uint32_t* code, uint64_t* key) {
+  bool pure = true;
+  uint32_t c = 0;
+  uint64_t k = 0;
+  for (int t = 0; t < K; t++) {
+    int v = sdh_code2(p[t]);
+    pure &= v >= 0;
+    c = (c << 2) | (uint32_t)(v & 3);
+    k = (k << 8) | p[t];
+  }
+  *code = c;
+  *key = k;
+  return pure;
+}
+
+// StringIndexer.buildIndexPara position multiplicities (Q1): thread i indexes [i*size, (i+1)*size]
+// inclusive (clipped to G-K), the last thread [(T-1)*size, G-K].
+static void sdh_multiplicity_from_threads(int G, int K, int threadNum, std::vector<uint8_t>& mult) {
+  mult.assign(std::max(G, 1), 0);
+  if (threadNum < 1) threadNum = 1;
+  const int size = G / threadNum;
+  const int last = G - K;
+  for (int i = 0; i < threadNum; i++) {
+    int from = i * size;
+    int to = (i == threadNum - 1) ? last : std::min((i + 1) * size, last);
+    for (int p = from; p <= to; p++)
+      if (mult[p] < 255) mult[p]++;
+  }
+}
+
+static int seed_build_reference(vg_ctx* c, const uint8_t* keys, const int64_t* offsets, const int32_t* positions,
+                                int n_keys, int index_thread_num) {
+  const int G = c->G, K = c->seed.K;
+  const uint8_t* ref = c->h_ref.data();
+  std::vector<uint8_t> mult;
+  const int nPos = G - K + 1;  // indexed positions 0..G-K (may be <= 0)
+  if (keys) {
+    mult.assign(std::max(G, 1), 0);
+    for (int k = 0; k < n_keys; k++) {
+      for (int64_t q = offsets[k]; q < offsets[k + 1]; q++) {
+        const int p = positions[q];
+        if (p < 0 || p > G - K || memcmp(ref + p, keys + (size_t)k * K, K) != 0)
+          return vg_fail(c, VG_ERR_INDEX, "index entry (key %d, position %d) does not match the reference", k, p);
+        if (q > offsets[k] && positions[q - 1] > p)
+          return vg_fail(c, VG_ERR_INDEX, "index list of key %d is not ascending", k);
+        if (mult[p] < 255) mult[p]++;
+      }
+    }
+  } else {
+    sdh_multiplicity_from_threads(G, K, index_thread_num, mult);
+  }
+  for (int p = 0; p < nPos; p++) {
+    if (mult[p] == 0) return vg_fail(c, VG_ERR_INDEX, "reference position %d is missing from the k-mer index", p);
+    if (mult[p] > 2)
+      return vg_fail(c, VG_ERR_INDEX, "reference position %d is indexed %d times (supported: <= 2; the reference is "
+                                      "shorter than the indexing thread count?)", p, (int)mult[p]);
+    if (mult[p] == 2 && p + 1 < nPos && mult[p + 1] == 2)
+      return vg_fail(c, VG_ERR_INDEX, "adjacent duplicated index positions %d,%d are not supported", p, p + 1);
+  }
+  // exotic k-mers (containing a byte outside ACGT): sorted distinct packed keys
+  std::vector<uint64_t> exo;
+  for (int p = 0; p < nPos; p++) {
+    uint32_t code;
+    uint64_t key;
+    if (!sdh_pack(ref + p, K, &code, &key)) exo.push_back(key);
+  }
+  std::sort(exo.begin(), exo.end());
+  exo.erase(std::unique(exo.begin(), exo.end()), exo.end());
+  if ((1u << (2 * K)) + exo.size() >= SD_NONE16)
+    return vg_fail(c, VG_ERR_INVALID, "too many distinct k-mers for the 15-bit id table (K=%d, %zu exotic)", K, exo.size());
+  // blob = [ref padded to 16][poscode u16 padded to 16]
+  const int refPad = (G + 15) & ~15;
+  const int codePad = (G * 2 + 15) & ~15;
+  std::vector<uint8_t> blob((size_t)refPad + codePad + 16, 0);
+  memcpy(blob.data(), ref, G);
+  uint16_t* pc = (uint16_t*)(blob.data() + refPad);
+  for (int p = 0; p < G; p++) {
+    uint16_t v = SD_NONE16;
+    if (p < nPos) {
+      uint32_t code;
+      uint64_t key;
+      if (sdh_pack(ref + p, K, &code, &key))
+        v = (uint16_t)code;
+      else
+        v = (uint16_t)((1u << (2 * K)) + (std::lower_bound(exo.begin(), exo.end(), key) - exo.begin()));
+      if (mult[p] == 2) v |= 0x8000u;
+    }
+    pc[p] = v;
+  }
+  VG_CUDA(c, c->d_poscode.reserve(blob.size()));
+  VG_CUDA(c, cudaMemcpy(c->d_poscode.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  VG_CUDA(c, c->d_exoKeys.reserve(exo.size() * 8 + 8));
+  if (!exo.empty()) VG_CUDA(c, cudaMemcpy(c->d_exoKeys.p, exo.data(), exo.size() * 8, cudaMemcpyHostToDevice));
+  c->nExo = (int)exo.size();
+  return VG_OK;
+}
+
+static int seed_build_msa(vg_ctx* c, const uint8_t* keys, const int64_t* offsets, const int32_t* columns, int n_keys) {
+  const int K = c->seedMsa.K;
+  std::vector<std::pair<uint64_t, int>> exo;  // packed key -> key index
+  const uint32_t nPure = 1u << (2 * K);
+  for (int k = 0; k < n_keys; k++) {
+    uint32_t code;
+    uint64_t key;
+    if (!sdh_pack(keys + (size_t)k * K, K, &code, &key)) exo.push_back({key, k});
+  }
+  std::sort(exo.begin(), exo.end());
+  if (nPure + exo.size() >= SD_NONE16)
+    return vg_fail(c, VG_ERR_INVALID, "too many distinct k-mers for the 15-bit id table (K=%d)", K);
+  const size_t nIds = nPure + exo.size();
+  std::vector<int32_t> off(nIds + 1, 0);
+  std::vector<int> keyOfId(nIds, -1);
+  for (int k = 0; k < n_keys; k++) {
+    uint32_t code;
+    uint64_t key;
+    if (sdh_pack(keys + (size_t)k * K, K, &code, &key)) keyOfId[code] = k;
+  }
+  for (size_t e = 0; e < exo.size(); e++) keyOfId[nPure + e] = exo[e].second;
+  std::vector<int32_t> cols;
+  cols.reserve((size_t)offsets[n_keys]);
+  for (size_t id = 0; id < nIds; id++) {
+    off[id] = (int32_t)cols.size();
+    const int k = keyOfId[id];
+    if (k >= 0)
+      for (int64_t q = offsets[k]; q < offsets[k + 1]; q++) {
+        if (columns[q] < 0 || columns[q] >= c->msaLength || (q > offsets[k] && columns[q - 1] >= columns[q]))
+          return vg_fail(c, VG_ERR_INDEX, "MSA index list of key %d is not strictly ascending within [0, length)", k);
+        cols.push_back(columns[q]);
+      }
+  }
+  off[nIds] = (int32_t)cols.size();
+  std::vector<uint64_t> exoKeys(exo.size());
+  for (size_t e = 0; e < exo.size(); e++) exoKeys[e] = exo[e].first;
+  VG_CUDA(c, c->d_msaOff.reserve(off.size() * 4));
+  VG_CUDA(c, cudaMemcpy(c->d_msaOff.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+  VG_CUDA(c, c->d_msaCols.reserve(cols.size() * 4 + 4));
+  if (!cols.empty()) VG_CUDA(c, cudaMemcpy(c->d_msaCols.p, cols.data(), cols.size() * 4, cudaMemcpyHostToDevice));
+  VG_CUDA(c, c->d_msaExoKeys.reserve(exoKeys.size() * 8 + 8));
+  if (!exoKeys.empty()) VG_CUDA(c, cudaMemcpy(c->d_msaExoKeys.p, exoKeys.data(), exoKeys.size() * 8, cudaMemcpyHostToDevice));
+  c->nMsaExo = (int)exoKeys.size();
+  return VG_OK;
+}
+
+// Launches seed_kernel over nItems work items. Windows land in c->d_cand ([nItems][maxWin][3]) and
+// c->d_ncand ([nItems]).
+static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_t* d_off1, const int32_t* d_len1,
+                       const int64_t* d_off2, const int32_t* d_len2, const int64_t* d_pairIdx, int64_t nItems,
+                       bool singleReads, int maxReadLen, int maxWin, int32_t* dbgHits, int32_t* dbgNHits) {
+  const SeedConfig& sc = msa ? c->seedMsa : c->seed;
+  const int K = sc.K;
+  const int range = msa ? c->msaLength : c->G;
+  if (K < 1 || K > 7) return vg_fail(c, VG_ERR_INVALID, "K=%d outside the supported range 1..7", K);
+  if (range >= 65535) return vg_fail(c, VG_ERR_INVALID, "reference longer than 65534 is not supported by the 16-bit seeding tables");
+  if (maxReadLen > SD_MAXL) return vg_fail(c, VG_ERR_INVALID, "read length %d exceeds the supported %d", maxReadLen, SD_MAXL);
+  if (maxReadLen >= K && maxReadLen >= (int)sc.cutoffs.size())
+    return vg_fail(c, VG_ERR_INVALID, "cutoffs has %zu entries but a read has length %d (the Java would throw)",
+                   sc.cutoffs.size(), maxReadLen);
+  if (nItems > 0x7fffffff) return vg_fail(c, VG_ERR_INVALID, "too many reads in one call");
+  SeedArgs A;
+  memset(&A, 0, sizeof A);
+  A.G = range;
+  A.K = K;
+  A.lowCoef = sc.lowCoef;
+  A.highCoef = sc.highCoef;
+  A.cutoffs = sc.d_cutoffs.as<int32_t>();
+  A.nCutoffs = (int)sc.cutoffs.size();
+  A.msa = msa ? 1 : 0;
+  SeedGeom g;
+  const int nContigs = msa ? 1 : (int)c->contigEnds.size();
+  g.capR = std::max(1152, std::min(4096, range / K + nContigs + 16));
+  g.nBuckets = (range >> 5) + 2;
+  const int auxBytes = SD_PENDING * 8 + 1024 + ((g.nBuckets * 2 + 15) & ~15) + (SD_MAXL + 16) + SD_MAXL * 2;
+  g.warpBytes = (g.capR * 8 + auxBytes + 15) & ~15;
+  g.refBytes = 0;
+  if (!msa) {
+    const int refPad = (c->G + 15) & ~15, codePad = (c->G * 2 + 15) & ~15;
+    A.blob = c->d_poscode.as<uint8_t>();
+    A.blobRefBytes = refPad;
+    A.blobBytes = refPad + codePad;
+    A.ref = A.blob;
+    A.poscode = (const uint16_t*)(A.blob + refPad);
+    A.exoKeys = c->d_exoKeys.as<uint64_t>();
+    A.nExo = c->nExo;
+    A.contigEnds = c->d_contigEnds.as<int32_t>();
+    A.nContigs = nContigs;
+    if (A.blobBytes + 4 * g.warpBytes <= 200 * 1024) g.refBytes = A.blobBytes;  // stage in shared memory via TMA
+  } else {
+    A.exoKeys = c->d_msaExoKeys.as<uint64_t>();
+    A.nExo = c->nMsaExo;
+    A.msaOff = c->d_msaOff.as<int32_t>();
+    A.msaCols = c->d_msaCols.as<int32_t>();
+    // single "contig" = the whole alignment: kept in d_misc[0]
+    VG_CUDA(c, c->d_misc.reserve(64));
+    int32_t len = c->msaLength;
+    VG_CUDA(c, cudaMemcpyAsync(c->d_misc.p, &len, 4, cudaMemcpyHostToDevice, c->stream));
+    A.contigEnds = c->d_misc.as<int32_t>();
+    A.nContigs = 1;
+  }
+  const int smemMax = 220 * 1024;
+  int warps = std::min(8, (smemMax - g.refBytes) / g.warpBytes);
+  if (warps < 1) return vg_fail(c, VG_ERR_INVALID, "reference too large for the seeding kernel's shared memory");
+  const size_t smem = (size_t)g.refBytes + (size_t)warps * g.warpBytes;
+  VG_CUDA(c, cudaFuncSetAttribute(seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int perSm = 1;
+  VG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, seed_kernel, warps * 32, smem));
+  if (perSm < 1) return vg_fail(c, VG_ERR_INVALID, "seeding kernel does not fit on the device");
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((nItems + warps - 1) / warps, (int64_t)c->smCount * perSm));
+  const int warpSlots = blocks * warps;
+  A.capS = 1 << 16;
+  if (const char* e = getenv("VG_SEED_CAPS")) A.capS = atoi(e);
+  VG_CUDA(c, c->d_scratch.reserve((size_t)warpSlots * A.capS * 8));
+  VG_CUDA(c, c->d_seqOff.reserve((size_t)warpSlots * 2 * g.capR * 4 * 2));
+  A.scratchS = c->d_scratch.as<uint64_t>();
+  A.candKey = c->d_seqOff.as<uint32_t>();
+  A.candVal = A.candKey + (size_t)warpSlots * 2 * g.capR;
+  VG_CUDA(c, c->d_cand.reserve((size_t)std::max<int64_t>(nItems, 1) * maxWin * 3 * 4));
+  VG_CUDA(c, c->d_ncand.reserve((size_t)std::max<int64_t>(nItems, 1) * 4));
+  VG_CUDA(c, c->d_counter.reserve(16));
+  VG_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, 16, c->stream));
+  A.windows = c->d_cand.as<int32_t>();
+  A.nWindows = c->d_ncand.as<int32_t>();
+  A.maxWin = maxWin;
+  A.counter = c->d_counter.as<int>();
+  A.errFlag = c->d_counter.as<int>() + 1;
+  A.bases = d_bases;
+  A.off1 = d_off1;
+  A.len1 = d_len1;
+  A.off2 = d_off2;
+  A.len2 = d_len2;
+  A.pairIdx = d_pairIdx;
+  A.nItems = nItems;
+  A.singleReads = singleReads ? 1 : 0;
+  A.dbgHits = dbgHits;
+  A.dbgNHits = dbgNHits;
+  A.geom = g;
+  if (nItems > 0) {
+    seed_kernel<<<blocks, warps * 32, smem, c->stream>>>(A);
+    VG_LAUNCH_CHECK(c);
+  }
+  int flags[2] = {0, 0};
+  VG_CUDA(c, cudaMemcpyAsync(flags, c->d_counter.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (flags[1]) {
+    const int f = flags[1];
+    return vg_fail(c, VG_ERR_OVERFLOW,
+                   "seeding work buffer overflow (flags 0x%x:%s%s%s%s%s); raise VG_SEED_CAPS or shorten reads", f,
+                   (f & 1) ? " raw-hit buffer" : "", (f & 2) ? " LongHit buffer" : "", (f & 4) ? " re-insertion queue" : "",
+                   (f & 8) ? " window list" : "", (f & 16) ? " read too long" : "");
+  }
+  return VG_OK;
+}

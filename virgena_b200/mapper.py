@@ -293,6 +293,17 @@ class Context:
         self._chk(self.L.vg_seed_batch(self.h, int(msa), ptr(pool), ptr(off), n, max_windows, ptr(win), ptr(nwin)))
         return win, nwin
 
+    def debug_seed_hits(self, read, msa=False):
+        """Test hook: LongHits (genomePos, readPos, len) of one read after mergeHits + splitLongHits."""
+        read = _u8(read)
+        fn = self.L.vg_debug_seed_hits
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        out = np.zeros((4096, 3), np.int32)
+        n = C.c_int32()
+        self._chk(fn(self.h, int(msa), ptr(read), len(read), ptr(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
     def timings(self):
         t = np.zeros(6, np.float64)
         self._chk(self.L.vg_last_timings(self.h, ptr(t)))
