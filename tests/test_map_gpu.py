@@ -129,16 +129,25 @@ def test_map_reads_single_reference(hiv, cfg, n, threads):
     assert (md2.remapped.records["cls"] == osub["cls"]).all()
 
 
-def test_map_reads_fragmented_reference(built):
+@pytest.mark.parametrize("cutv", [None, 30, 60])
+def test_map_reads_fragmented_reference(built, cutv):
+    """Multi-fragment reference (config 4): chooseFragment, per-fragment bests, the fragment-aware
+    discordant rule (Mapper.java:309-353) and splitLongHits at segment boundaries."""
     import oracle
     import virgena_b200 as vg
     from virgena_b200 import synth
     ref, ends = synth.config_reference(4)
-    cut = oracle.cutoffs(ref, K=5, coef=1.25, read_num=1000, min_len=150, max_len=150, step=10, seed=9,
-                         contig_ends=ends, is_fragmented=True, index_thread_num=8)
-    m1, m2 = synth.config_pairs(4, 1200)
-    # some pairs whose mates come from different segments (discordant across fragments)
-    m2[:60] = m2[600:660]
+    if cutv is None:
+        cut = oracle.cutoffs(ref, K=5, coef=1.25, read_num=1000, min_len=150, max_len=150, step=10, seed=9,
+                             contig_ends=ends, is_fragmented=True, index_thread_num=8)
+    else:
+        cut = np.full(400, cutv, np.int32)
+    m1, m2 = synth.config_pairs(4, 800)
+    m2[:60] = m2[400:460]  # mates from different segments
+    m1[60:80] = np.frombuffer(b"ACGT", np.uint8)[np.random.default_rng(1).integers(0, 4, (20, 150))]  # junk mates
+    # reads straddling a segment boundary (LongHits must be split there)
+    for t, e in enumerate(ends[:-1]):
+        m1[100 + t] = ref[e - 75:e + 75]
     bases, off1, len1, off2, len2 = synth.pack_pairs(m1, m2)
     o = oracle.Oracle(K=5, cutoffs=cut)
     o.set_reference(ref, contig_ends=ends, fragment_ends=ends, is_fragmented=True, index_thread_num=8)
@@ -147,7 +156,8 @@ def test_map_reads_fragmented_reference(built):
     genome = vg.Reference(ref, K=5, contig_ends=ends, fragment_ends=ends, is_fragmented=True, thread_num=8)
     md = mapper.mapReads(vg.PairedReads(bases, off1, len1, off2, len2), genome)
     _compare(md, orec, opool, ostats)
-    assert len(md.concordant) > 1000 and len(md.concordant) < 1200  # the cross-segment pairs are not concordant
+    if cutv is not None:
+        assert len(md.discordant) > 0 and len(md.unmapped) > 0 and len(md.rightMateMapped) > 0
     mapper.ctx.pileup()
     assert (mapper.ctx.counts() == oracle.pileup(orec, opool, len(ref))).all()
 
@@ -170,7 +180,7 @@ def test_map_reads_ragged_and_edge_cases(hiv):
         if i % 19 == 0:
             b = b"*"
         if i % 23 == 0:
-            a = a[:60] + b"NNNRYK" + a[66:]  # N and IUPAC bytes
+            a = a[:60] + b"NNNRKM" + a[66:]  # N and IUPAC bytes (<= T: the Java pileup maps them to A, Q11)
         if i % 29 == 0:
             b = bytes(rng.integers(65, 85, 120).astype(np.uint8))  # junk read
         if i % 31 == 0:

@@ -77,8 +77,9 @@ struct SeedArgs {
   // scratch + outputs
   uint64_t* scratchS;          // [warpSlots][capS]
   int capS;
-  uint32_t* candKey;           // [warpSlots][2][capR]
-  uint32_t* candVal;           // [warpSlots][2][capR]
+  uint32_t* candKey;           // [warpSlots][2][capC]
+  uint32_t* candVal;           // [warpSlots][2][capC]
+  int capC;                    // >= capR; larger in MSA mode (holds the unsorted raw LongHits)
   int32_t* windows;            // [nItems][maxWin][3]
   int32_t* nWindows;           // [nItems]
   int maxWin;
@@ -256,8 +257,9 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
   uint16_t* ids = (uint16_t*)(rd + SD_MAXL + 16);
 
   uint64_t* S = A.scratchS + (size_t)warpSlot * A.capS;
-  uint32_t* ckey = A.candKey + (size_t)warpSlot * 2 * capR;
-  uint32_t* cval = A.candVal + (size_t)warpSlot * 2 * capR;
+  const int capC = A.capC;
+  uint32_t* ckey = A.candKey + (size_t)warpSlot * 2 * capC;
+  uint32_t* cval = A.candVal + (size_t)warpSlot * 2 * capC;
 
   for (;;) {
     int wi = 0;
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
           }
           const int incl = sd_warp_incl_scan(cnt, lane);
           const int total = __shfl_sync(VG_FULL, incl, 31);
-          if (nS + total > A.capS || nS + total > capR) {
+          if (nS + total > A.capS || nS + total > capC) {
             overflow = true;
             break;
           }
@@ -416,9 +418,9 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
         }
         __syncwarp();
         if (!overflow && nS > 0) {
-          const int srcb = sd_radix_sort(ckey, cval, capR, nS, bins, lane, 32);
-          const uint32_t* ks = ckey + (size_t)srcb * capR;
-          const uint32_t* vs = cval + (size_t)srcb * capR;
+          const int srcb = sd_radix_sort(ckey, cval, capC, nS, bins, lane, 32);
+          const uint32_t* ks = ckey + (size_t)srcb * capC;
+          const uint32_t* vs = cval + (size_t)srcb * capC;
           for (int e = lane; e < nS; e += 32)
             S[e] = ((uint64_t)(ks[e] >> 16) << 32) | ((uint64_t)(ks[e] & 0xFFFFu) << 16) | (uint64_t)vs[e];
         }
@@ -624,11 +626,11 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
         __syncwarp();
         // ---- G: stable sort by (start asc, end desc) + pruneWindows (serial, lane 0) ----------------
         if (nC > 0) {
-          const int srcb = sd_radix_sort(ckey, cval, capR, nC, bins, lane, 32);
+          const int srcb = sd_radix_sort(ckey, cval, capC, nC, bins, lane, 32);
           __threadfence_block();
           if (lane == 0) {
-            const uint32_t* ks = ckey + (size_t)srcb * capR;
-            const uint32_t* vs = cval + (size_t)srcb * capR;
+            const uint32_t* ks = ckey + (size_t)srcb * capC;
+            const uint32_t* vs = cval + (size_t)srcb * capC;
             int32_t* W = A.windows + (size_t)wi * A.maxWin * 3;
             int ps = ks[0] >> 16, pe = 0xFFFF - (ks[0] & 0xFFFF), pc = vs[0];
             auto put = [&](int s, int e, int c) {

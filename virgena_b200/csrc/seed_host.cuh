@@ -222,10 +222,11 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   A.capS = 1 << 16;
   if (const char* e = getenv("VG_SEED_CAPS")) A.capS = atoi(e);
   VG_CUDA(c, c->d_scratch.reserve((size_t)warpSlots * A.capS * 8));
-  VG_CUDA(c, c->d_seqOff.reserve((size_t)warpSlots * 2 * g.capR * 4 * 2));
+  A.capC = msa ? std::max(g.capR, 16384) : g.capR;
+  VG_CUDA(c, c->d_seqOff.reserve((size_t)warpSlots * 2 * A.capC * 4 * 2));
   A.scratchS = c->d_scratch.as<uint64_t>();
   A.candKey = c->d_seqOff.as<uint32_t>();
-  A.candVal = A.candKey + (size_t)warpSlots * 2 * g.capR;
+  A.candVal = A.candKey + (size_t)warpSlots * 2 * A.capC;
   VG_CUDA(c, c->d_cand.reserve((size_t)std::max<int64_t>(nItems, 1) * maxWin * 3 * 4));
   VG_CUDA(c, c->d_ncand.reserve((size_t)std::max<int64_t>(nItems, 1) * 4));
   VG_CUDA(c, c->d_counter.reserve(16));
