@@ -199,6 +199,9 @@ int vg_last_timings(vg_ctx* ctx, double* out6);
  * kernels launched by this context. */
 int vg_dpx_peak(vg_ctx* ctx, double* ops_per_s);
 int64_t vg_kernel_launches(const vg_ctx* ctx);
+/* The CUDA stream (cudaStream_t) all of this context's kernels and copies are issued on, so that a
+ * caller can bracket calls with its own CUDA events. */
+int vg_ctx_stream(vg_ctx* ctx, void** stream);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,7 @@ _SIGS = {
     "vg_last_timings": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vg_dpx_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "vg_kernel_launches": (C.c_int64, [C.c_void_p]),
+    "vg_ctx_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

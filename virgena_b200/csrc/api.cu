@@ -76,6 +76,12 @@ const char* vg_last_error(const vg_ctx* c) { return c ? c->err : "null context";
 int64_t vg_last_required(const vg_ctx* c) { return c ? c->required : 0; }
 int64_t vg_kernel_launches(const vg_ctx* c) { return c ? c->launches : 0; }
 
+int vg_ctx_stream(vg_ctx* c, void** stream) {
+  if (!c || !stream) return VG_ERR_INVALID;
+  *stream = (void*)c->stream;
+  return VG_OK;
+}
+
 int vg_last_timings(vg_ctx* c, double* out6) {
   if (!c || !out6) return VG_ERR_INVALID;
   for (int i = 0; i < 6; i++) out6[i] = c->timings[i];

@@ -38,6 +38,7 @@
 #define SD_HS 1024              // hash slots (>= 2 x k-mers of a 512-base read)
 #define SD_MAXL 512             // longest supported read
 #define SD_PENDING 32           // capacity of the re-insertion queue of phase C
+#define SD_WIN 512              // entries of the shared-memory window over the sorted LongHit stream
 
 struct SeedGeom {       // sizes of the per-warp shared-memory regions (bytes), computed on the host
   int capR;             // max LongHits after phase C (per orientation)
@@ -221,7 +222,7 @@ __device__ __forceinline__ void sd_tma_stage(uint8_t* smemDst, const uint8_t* gs
 // Per-warp region (geom.warpBytes):
 //   R-region   : hitG u16[capR], hitR u16[capR], hitL u16[capR], P u16[capR]
 //                (during phases A/B it is aliased by hkey u32[SD_HS], hval u32[SD_HS], nxt u16[SD_MAXL])
-//   aux        : bucket u16[nBuckets] | bins int[256] | pending u64[SD_PENDING]
+//   aux        : pending u64[SD_PENDING] | bins int[256] | bucket u16[nBuckets] | win u64[SD_WIN]
 //   rd         : u8[SD_MAXL + 16], ids u16[SD_MAXL] (MSA)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
@@ -253,7 +254,8 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
   uint64_t* pending = (uint64_t*)aux;                                  // SD_PENDING x 8
   int* bins = (int*)(aux + SD_PENDING * 8);                            // 256 x 4
   uint16_t* bucket = (uint16_t*)(aux + SD_PENDING * 8 + 1024);         // nBuckets x 2
-  uint8_t* rd = aux + SD_PENDING * 8 + 1024 + ((A.geom.nBuckets * 2 + 15) & ~15);
+  uint64_t* win = (uint64_t*)(aux + SD_PENDING * 8 + 1024 + ((A.geom.nBuckets * 2 + 15) & ~15));  // SD_WIN x 8
+  uint8_t* rd = (uint8_t*)(win + SD_WIN);
   uint16_t* ids = (uint16_t*)(rd + SD_MAXL + 16);
 
   uint64_t* S = A.scratchS + (size_t)warpSlot * A.capS;
@@ -432,97 +434,135 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
         nS = 0;
       }
       // ---- C: mergeHits phase 2 (serial, lane 0) + splitLongHits on emit ---------------------------
+      // The sorted stream S is consumed through a sliding shared-memory window (2 x SD_WIN/2 entries,
+      // refilled by the whole warp) so that the serial lane never waits on global memory.
       int nR = 0;
       if (nS > 0) {
         int err = 0;
-        if (lane == 0) {
-          int si = 0, np = 0;
-          int ci = 0, contigEnd = A.contigEnds[0];
-          auto emit = [&](int g, int r, int len) {
-            for (;;) {  // KMerCounter.splitLongHits (the MSA path has a single "contig")
-              while (g >= contigEnd) contigEnd = A.contigEnds[++ci];
-              if (g + K + len > contigEnd) {
-                if (contigEnd - g >= K) {
-                  if (nR < capR) hitG[nR] = (uint16_t)g, hitR[nR] = (uint16_t)r, hitL[nR] = (uint16_t)(contigEnd - g - K);
-                  nR++;
+        int wbase = 0;
+        for (int e = lane; e < SD_WIN && e < nS; e += 32) win[e] = S[e];
+        __syncwarp();
+        // lane-0 state of the sweep
+        int si = 0, np = 0, ci = 0, contigEnd = A.contigEnds[0];
+        int pg = 0, pr = 0, pl = 0;
+        bool started = false, done = false;
+        for (;;) {
+          if (lane == 0) {
+            auto emit = [&](int g, int r, int len) {
+              for (;;) {  // KMerCounter.splitLongHits (the MSA path has a single "contig")
+                while (g >= contigEnd) contigEnd = A.contigEnds[++ci];
+                if (g + K + len > contigEnd) {
+                  if (contigEnd - g >= K) {
+                    if (nR < capR) hitG[nR] = (uint16_t)g, hitR[nR] = (uint16_t)r, hitL[nR] = (uint16_t)(contigEnd - g - K);
+                    nR++;
+                  }
+                  if (g + K + len - contigEnd >= K) {
+                    r += contigEnd - g;
+                    len -= contigEnd - g;
+                    g = contigEnd;
+                    continue;
+                  }
+                  break;
                 }
-                if (g + K + len - contigEnd >= K) {
-                  r += contigEnd - g;
-                  len -= contigEnd - g;
-                  g = contigEnd;
-                  continue;
-                }
+                if (nR < capR) hitG[nR] = (uint16_t)g, hitR[nR] = (uint16_t)r, hitL[nR] = (uint16_t)len;
+                nR++;
                 break;
               }
-              if (nR < capR) hitG[nR] = (uint16_t)g, hitR[nR] = (uint16_t)r, hitL[nR] = (uint16_t)len;
-              nR++;
-              break;
-            }
-          };
-          auto pop = [&](int& g, int& r, int& len) {
-            uint64_t v;
-            if (np > 0 && (si >= nS || (pending[0] >> 16) < (S[si] >> 16))) {
-              v = pending[0];
-              for (int t = 1; t < np; t++) pending[t - 1] = pending[t];
-              np--;
-            } else {
-              v = S[si++];
-            }
-            g = (int)(v >> 32);
-            r = (int)((v >> 16) & 0xFFFFu);
-            len = (int)(v & 0xFFFFu);
-          };
-          int pg, pr, pl;
-          pop(pg, pr, pl);
-          while (si < nS || np > 0) {
-            int cg, cr, cl;
-            pop(cg, cr, cl);
-            if (pg + pl + K - 1 >= cg) {
-              if (pl < cl) {
-                pl = cg - pg - K;
-                if (pl >= 0) emit(pg, pr, pl);
-                pg = cg, pr = cr, pl = cl;
+            };
+            while (!done) {
+              if (si >= wbase + SD_WIN / 2 && wbase + SD_WIN < nS) break;  // slide the window first
+              if (si >= nS && np == 0) {
+                if (started) emit(pg, pr, pl);
+                done = true;
+                break;
+              }
+              // TreeSet.pollFirst: the smaller of the stream head and the re-insertion queue head
+              uint64_t v;
+              if (np > 0 && (si >= nS || (pending[0] >> 16) < (win[si - wbase] >> 16))) {
+                v = pending[0];
+                for (int t = 1; t < np; t++) pending[t - 1] = pending[t];
+                np--;
               } else {
-                const int lenDiff = pg + pl + K - cg;
-                cl -= lenDiff;
-                if (cl >= 0) {
-                  cg += lenDiff;
-                  cr += lenDiff;
-                  // TreeSet.add: dropped when an element with the same (genomePos, readPos) is present
-                  const uint64_t key = ((uint64_t)cg << 16) | (uint64_t)cr;
-                  bool present = false;
-                  int ins = np;
-                  for (int t = 0; t < np; t++) {
-                    const uint64_t pk = pending[t] >> 16;
-                    if (pk == key) present = true;
-                    if (pk > key && ins == np) ins = t;
-                  }
-                  if (!present) {
-                    int lo = si, hi = nS;
-                    while (lo < hi) {
-                      int mid = (lo + hi) >> 1;
-                      if ((S[mid] >> 16) < key) lo = mid + 1;
-                      else hi = mid;
+                v = win[si - wbase];
+                si++;
+              }
+              int cg = (int)(v >> 32), cr = (int)((v >> 16) & 0xFFFFu), cl = (int)(v & 0xFFFFu);
+              if (!started) {
+                pg = cg, pr = cr, pl = cl;
+                started = true;
+                continue;
+              }
+              if (pg + pl + K - 1 >= cg) {
+                if (pl < cl) {
+                  pl = cg - pg - K;
+                  if (pl >= 0) emit(pg, pr, pl);
+                  pg = cg, pr = cr, pl = cl;
+                } else {
+                  const int lenDiff = pg + pl + K - cg;
+                  cl -= lenDiff;
+                  if (cl >= 0) {
+                    cg += lenDiff;
+                    cr += lenDiff;
+                    // TreeSet.add: dropped when an element with the same (genomePos, readPos) is present
+                    const uint64_t key = ((uint64_t)cg << 16) | (uint64_t)cr;
+                    bool present = false;
+                    int ins = np;
+                    for (int t = 0; t < np; t++) {
+                      const uint64_t pk = pending[t] >> 16;
+                      if (pk == key) present = true;
+                      if (pk > key && ins == np) ins = t;
                     }
-                    if (lo < nS && (S[lo] >> 16) == key) present = true;
-                  }
-                  if (!present) {
-                    if (np >= SD_PENDING) {
-                      err |= 4;
-                    } else {
-                      for (int t = np; t > ins; t--) pending[t] = pending[t - 1];
-                      pending[ins] = (key << 16) | (uint64_t)cl;
-                      np++;
+                    if (!present) {
+                      bool resolved = false;
+                      const int wend = min(nS, wbase + SD_WIN);
+                      for (int j = si; j < wend; j++) {
+                        const uint64_t k = win[j - wbase] >> 16;
+                        if (k >= key) {
+                          present = (k == key);
+                          resolved = true;
+                          break;
+                        }
+                      }
+                      if (!resolved && wend < nS) {  // beyond the window (dense repeats): search the global stream
+                        int lo = wend, hi = nS;
+                        while (lo < hi) {
+                          int mid = (lo + hi) >> 1;
+                          if ((S[mid] >> 16) < key) lo = mid + 1;
+                          else hi = mid;
+                        }
+                        if (lo < nS && (S[lo] >> 16) == key) present = true;
+                      }
+                    }
+                    if (!present) {
+                      if (np >= SD_PENDING) {
+                        err |= 4;
+                      } else {
+                        for (int t = np; t > ins; t--) pending[t] = pending[t - 1];
+                        pending[ins] = (key << 16) | (uint64_t)cl;
+                        np++;
+                      }
                     }
                   }
                 }
+              } else {
+                emit(pg, pr, pl);
+                pg = cg, pr = cr, pl = cl;
               }
-            } else {
-              emit(pg, pr, pl);
-              pg = cg, pr = cr, pl = cl;
             }
           }
-          emit(pg, pr, pl);
+          done = __shfl_sync(VG_FULL, (int)done, 0) != 0;
+          if (done) break;
+          // slide by half a window
+          for (int e = lane; e < SD_WIN / 2; e += 32) win[e] = win[e + SD_WIN / 2];
+          __syncwarp();
+          wbase += SD_WIN / 2;
+          for (int e = lane; e < SD_WIN / 2; e += 32) {
+            const int idx = wbase + SD_WIN / 2 + e;
+            if (idx < nS) win[SD_WIN / 2 + e] = S[idx];
+          }
+          __syncwarp();
+        }
+        if (lane == 0) {
           if (nR > capR) err |= 2;
           if (err) atomicOr(A.errFlag, err);
         }

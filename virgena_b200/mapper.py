@@ -314,6 +314,25 @@ class Context:
         self._chk(self.L.vg_dpx_peak(self.h, C.byref(v)))
         return v.value
 
+    def stream(self):
+        p = C.c_void_p()
+        self._chk(self.L.vg_ctx_stream(self.h, C.byref(p)))
+        return p.value or 0
+
+    def upload_reads_raw(self, bases_ptr, n_bases, off1, len1, off2, len2):
+        """vg_upload_reads from a caller-owned (e.g. pinned) host byte pool given as a raw address."""
+        self._chk(self.L.vg_upload_reads(self.h, C.c_void_p(bases_ptr), n_bases, ptr(off1), ptr(len1), ptr(off2),
+                                         ptr(len2), len(off1)))
+        self.n_pairs = len(off1)
+
+    def get_results_into(self, rec, pool):
+        """vg_get_results into caller-owned (e.g. pinned) arrays; returns (n_results, seq1_bytes)."""
+        n = C.c_int64()
+        nb = C.c_int64()
+        self._chk(self.L.vg_result_sizes(self.h, C.byref(n), C.byref(nb)))
+        self._chk(self.L.vg_get_results(self.h, ptr(rec), len(rec), ptr(pool), len(pool)))
+        return n.value, nb.value
+
     def kernel_launches(self):
         return int(self.L.vg_kernel_launches(self.h))
 
