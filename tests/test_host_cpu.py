@@ -1,0 +1,136 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every declared symbol, fails loudly without a
+device (no CPU fallback), host-side index construction, golden fixtures, and the 2-rank (gloo) sharding +
+all-reduce logic."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    import ctypes
+    from virgena_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "virgena_gpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(vg_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert set(_lib.EXPORTED_SYMBOLS) == declared
+    assert L.vg_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_a_device(built):
+    import torch
+    import virgena_b200 as vg
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert vg._lib.lib().vg_device_count() == 0
+    with pytest.raises(vg.VgError) as e:
+        vg.Context()
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "virgena_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".java")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                # mentions in prose are fine; imports, loads and links are not
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), f
+                assert "liboracle" not in txt and "oracle.cpp" not in txt, f
+
+
+def test_reference_alignment_index_matches_oracle(built):
+    import oracle
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    rows = synth.config_msa(n_refs=6)
+    aln = vg.ReferenceAlignment(rows, K=7)
+    o = oracle.Oracle()
+    o.set_msa(rows, K=7)
+    k, off, cols = o.index_csr(msa=True)
+    assert (aln.keys == k).all() and (aln.offsets == off).all() and (aln.columns == cols).all()
+    assert aln.length == rows.shape[1]
+
+
+def test_shard_ranges_cover_everything():
+    from virgena_b200.dist import shard_range
+    for n in (0, 1, 7, 100, 12500001):
+        for w in (1, 2, 3, 8):
+            r = [shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+def test_golden_fixture_is_reproduced_by_the_oracle(built):
+    """tests/golden/small_case.npz (made by tests/golden/make_golden.py) freezes the oracle's outputs for a small
+    seeded case; it is also what the GPU parity tests are checked against, and guards the oracle itself."""
+    import oracle
+    g = np.load(os.path.join(ROOT, "tests", "golden", "small_case.npz"))
+    o = oracle.Oracle(K=5, cutoffs=g["cutoffs"])
+    o.set_reference(g["ref"], index_thread_num=int(g["index_thread_num"]))
+    rec, pool, st = o.map_pairs(g["bases"], g["off1"], g["len1"], g["off2"], g["len2"])
+    assert rec.tobytes() == g["records"].tobytes()
+    assert pool.tobytes() == g["seq1_pool"].tobytes()
+    assert (st == g["stats"]).all()
+    counts = oracle.pileup(rec, pool, len(g["ref"]))
+    assert (counts == g["counts"]).all()
+    assert oracle.consensus(counts, g["ref"], True, 0).tobytes() == g["consensus"].tobytes()
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np
+import torch.distributed as dist
+import oracle
+from virgena_b200 import synth
+from virgena_b200.dist import shard_range, allreduce_counts_host, gather_records
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+g = np.load(os.path.join(%(root)r, "tests", "golden", "small_case.npz"))
+o = oracle.Oracle(K=5, cutoffs=g["cutoffs"])
+o.set_reference(g["ref"], index_thread_num=int(g["index_thread_num"]))
+n = len(g["off1"])
+lo, hi = shard_range(n, rank, world)
+rec, pool, st = o.map_pairs(g["bases"], g["off1"][lo:hi], g["len1"][lo:hi], g["off2"][lo:hi], g["len2"][lo:hi])
+counts = allreduce_counts_host(oracle.pileup(rec, pool, len(g["ref"])))
+cons = oracle.consensus(counts, g["ref"], True, 0)
+allrec = gather_records(rec, world)
+ok = (counts == g["counts"]).all() and cons.tobytes() == g["consensus"].tobytes()
+for f in ("start", "end", "count", "score", "start2", "end2", "identity", "length"):
+    ok = ok and (allrec["m"][f] == g["records"]["m"][f]).all()
+ok = ok and (allrec["cls"] == g["records"]["cls"]).all()
+print("RANK", rank, "OK" if ok else "MISMATCH")
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+'''
+
+
+def test_two_rank_sharding_and_allreduce_gloo(built, tmp_path):
+    """N>1 host logic on CPU: contiguous shards + integer all-reduce of the counts give exactly the single-rank
+    counts and consensus; gathering the per-pair records in rank order restores the input order."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29511", str(script)],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("OK") == 2
+
+
+def test_cutoffs_fixture_has_all_configs():
+    d = json.load(open(os.path.join(ROOT, "tests", "golden", "cutoffs.json")))
+    for k in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5"):
+        assert len(d[k]["cutoffs"]) == d[k]["L"] + 1

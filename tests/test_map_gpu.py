@@ -263,3 +263,59 @@ def test_errors(hiv):
         vg.Context(K=5, cutoffs=cut, match=2, mismatch=3)  # created fine ...
         c2 = vg.Context(K=5, cutoffs=cut, mismatch=3)
         c2.sw_align_batch(b"ACGT", [0, 4], b"ACGT", [0, 4])  # ... but the aligner refuses mismatch >= 0
+
+
+def test_golden_fixture_through_c_abi(built):
+    """The committed golden case (tests/golden/small_case.npz): ragged, absent and N-containing reads."""
+    import os
+    import virgena_b200 as vg
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "small_case.npz"))
+    mapper = vg.Mapper(K=5, cutoffs=g["cutoffs"])
+    genome = vg.Reference(g["ref"], K=5, thread_num=int(g["index_thread_num"]))
+    md = mapper.mapReads(vg.PairedReads(g["bases"], g["off1"], g["len1"], g["off2"], g["len2"]), genome)
+    _compare(md, g["records"], g["seq1_pool"], g["stats"])
+    cons = vg.ConsensusBuilderSimple(mapper).getConsensusSimple(True, 0, genome.seqB)
+    assert (mapper.ctx.counts() == g["counts"]).all()
+    assert cons.tobytes() == g["consensus"].tobytes()
+
+
+def test_full_size_properties(hiv):
+    """At a larger size (100k pairs) the oracle is too slow; check size-independent properties instead:
+    idempotence (same call twice), sharding invariance (two halves == whole, counts add up), and the
+    stats checksum vs the per-pair records."""
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    ref, cut = hiv
+    m1, m2 = synth.config_pairs(3, 20000)
+    m1, m2 = np.tile(m1, (5, 1)), np.tile(m2, (5, 1))
+    n = len(m1)
+    ctx = vg.Context(K=5, cutoffs=cut)
+    ctx.set_reference(vg.Reference(ref, K=5, thread_num=8))
+    ctx.upload_reads(vg.PairedReads(*synth.pack_pairs(m1, m2)))
+    a = ctx.map_pairs()
+    ctx.pileup()
+    ca = ctx.counts()
+    b = ctx.map_pairs()
+    assert a.records.tobytes() == b.records.tobytes() and a.seq1_pool.tobytes() == b.seq1_pool.tobytes()
+    # the 5 tiled copies give identical per-pair answers
+    r0 = a.records[:20000]
+    for k in range(1, 5):
+        rk = a.records[20000 * k:20000 * (k + 1)]
+        for f in FIELDS:
+            assert (rk["m"][f] == r0["m"][f]).all()
+    # shards: first half + second half
+    h1 = ctx.map_pairs(np.arange(0, n // 2, dtype=np.int64))
+    ctx.pileup(False)
+    c1 = ctx.counts()
+    h2 = ctx.map_pairs(np.arange(n // 2, n, dtype=np.int64))
+    ctx.pileup(True)  # accumulate
+    assert (ctx.counts() == ca).all() and (c1 <= ca).all()
+    assert (np.concatenate([h1.records["cls"], h2.records["cls"]]) == a.records["cls"]).all()
+    assert (h1.stats + h2.stats == a.stats).all()
+    # checksum: stats vs records
+    pres = a.records["m"]["present"] == 1
+    assert a.stats[3] == pres.sum() and a.stats[7] == a.records["m"]["score"][pres].sum()
+    # every alignment lies inside its window and the pileup total equals the aligned reference columns
+    m = a.records["m"][pres]
+    assert (m["start"] + m["end2"] <= m["end"]).all() and (m["start2"] >= 0).all()
+    assert ca.sum() == (m["end2"] - m["start2"]).sum()

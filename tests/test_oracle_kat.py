@@ -1,0 +1,329 @@
+"""Known-answer tests that pin the oracle (oracle/oracle.cpp).
+
+The reference ships no tests, fixtures or golden vectors and cannot run here, so each case
+below was worked out BY HAND from the Java source (file:line cited) — one per quirk of SURVEY.md §8a.
+They run on the CPU (no GPU needed)."""
+import numpy as np
+import pytest
+
+import oracle
+
+
+def _o(**kw):
+    return oracle.Oracle(**kw)
+
+
+# --------------------------------------------------------------------------------------------------
+# Constants.java
+# --------------------------------------------------------------------------------------------------
+def test_complement_table():
+    # Constants.java:11-20,42-49: A<->T, G<->C, '-'->'-', N->N, any other byte < 127 -> 0; reversed
+    assert oracle.revcomp(b"AACGTN-").tobytes() == b"-NACGTT"
+    assert oracle.revcomp(b"AR*a").tobytes() == b"\x00\x00\x00T"
+
+
+# --------------------------------------------------------------------------------------------------
+# StringIndexer.buildIndexPara — Q1
+# --------------------------------------------------------------------------------------------------
+def test_index_single_thread():
+    o = _o(K=3)
+    o.set_reference(b"ACGACGT", index_thread_num=1)
+    keys, offs, pos = o.index_csr()
+    got = {keys[i].tobytes(): pos[offs[i]:offs[i + 1]].tolist() for i in range(len(keys))}
+    assert got == {b"ACG": [0, 3], b"CGA": [1], b"GAC": [2], b"CGT": [4]}
+
+
+def test_index_q1_duplicate_boundary_position():
+    # StringIndexer.java:35,50-58: with 2 threads and |s| = 8, size = 4: task 0 indexes [0,4] INCLUSIVE and
+    # task 1 starts at 4, so position 4 is listed twice for its k-mer; lists are concatenated in task order.
+    o = _o(K=3)
+    o.set_reference(b"ACGTACGT", index_thread_num=2)
+    keys, offs, pos = o.index_csr()
+    got = {keys[i].tobytes(): pos[offs[i]:offs[i + 1]].tolist() for i in range(len(keys))}
+    assert got == {b"ACG": [0, 4, 4], b"CGT": [1, 5], b"GTA": [2], b"TAC": [3]}
+
+
+# --------------------------------------------------------------------------------------------------
+# mergeHits (KMerCounterBase.java:337-450)
+# --------------------------------------------------------------------------------------------------
+def test_merge_hits_diagonal_chain():
+    # read = ref[2:10]: all 6 k-mers (K=3) chain on one diagonal: LongHit(g=2, r=0, len=5); no other 3-mer of
+    # the read occurs elsewhere in this reference.
+    ref = b"TTACGATCGGAA"
+    o = _o(K=3)
+    o.set_reference(ref, index_thread_num=1)
+    assert o.get_hits(ref[2:10]).tolist() == [[2, 0, 5]]
+
+
+def test_merge_hits_overlap_truncation_and_drop():
+    # ref = ACGTTACGA, read = ACGA (K=3). Raw hits: i=0 "ACG" -> [0,5]; i=1 "CGA" -> [6].
+    # Phase 1: LongHit A(0,0,len0), B(5,0) extended by the hit (1,6) to len1. TreeSet order: A, B.
+    # Phase 2 (:425-447): A.end = 0+0+3-1 = 2 < 5 -> A emitted whole; B last. => [[0,0,0],[5,0,1]]
+    o = _o(K=3)
+    o.set_reference(b"ACGTTACGA", index_thread_num=1)
+    assert o.get_hits(b"ACGA").tolist() == [[0, 0, 0], [5, 0, 1]]
+
+
+def test_merge_hits_shorter_overlapping_hit_is_trimmed_away():
+    # ref = AAAAAA (K=3), read = AAAA: read k-mers at i=0,1 are both AAA -> positions [0,1,2,3].
+    # Phase 1: i=0 creates (0,0),(1,0),(2,0),(3,0); i=1: rHit 0: lHit(0) end+1=1 > 0 -> new (0,1); rHit 1 ==
+    # lHit(0).end+1 -> (0,0).len=1; rHit 2 extends (1,0); rHit 3 extends (2,0); (3,0) stays len 0.
+    # TreeSet order: (0,0,1) (0,1,0) (1,0,1) (2,0,1) (3,0,0).
+    # Phase 2: prev=(0,0,1) end incl = 0+1+3-1 = 3. (0,1,0): overlap, prev.len(1) !< 0 -> lenDiff = 4-0 = 4,
+    # curr.len = -4 -> dropped. (1,0,1): not longer -> lenDiff = 3, len = -2 dropped. (2,0,1): lenDiff 2, len -1
+    # dropped. (3,0,0): lenDiff 1, len -1 dropped. => [[0,0,1]]
+    o = _o(K=3)
+    o.set_reference(b"AAAAAA", index_thread_num=1)
+    assert o.get_hits(b"AAAA").tolist() == [[0, 0, 1]]
+
+
+def test_merge_hits_longer_later_hit_truncates_prev():
+    # ref = ACGTACGTTT (K=3), read = CGTACGTT.
+    # read k-mers: 0 CGT [1,5]; 1 GTA [2]; 2 TAC [3]; 3 ACG [0,4]; 4 CGT [1,5]; 5 GTT [6].
+    # chains: (1,0) extended by (1,2),(2,3),(3,4),(4,5),(5,6) -> (1,0,len5); (5,0,len0); (0,3) -> extended by
+    # (4,1)? lHit(0,3).end+1 = 1 == 1 -> yes len1, and 5: (5,6)? (0,3,1).end+1=2 != 6 -> stops: (0,3,1).
+    # TreeSet: (0,3,1) (1,0,5) (5,0,0).
+    # Phase 2: prev=(0,3,1): end incl 0+1+3-1 = 3 >= 1 and prev.len 1 < 5 -> prev.len = 1-0-3 = -2 -> not emitted;
+    # prev=(1,0,5): end incl 8 >= 5: (5,0,0) not longer: lenDiff = 9-5 = 4, len -4 dropped. => [[1,0,5]]
+    o = _o(K=3)
+    o.set_reference(b"ACGTACGTTT", index_thread_num=1)
+    assert o.get_hits(b"CGTACGTT").tolist() == [[1, 0, 5]]
+
+
+def test_merge_hits_q1_duplicate_adds_zero_length_hit():
+    # ref ACGTACGT with 2 index threads: "ACG" -> [0,4,4] (see above). read = TACGT (K=3):
+    # i=0 TAC [3]; i=1 ACG [0,4,4]; i=2 CGT [1,5].
+    # Phase 1: X=(3,0). i=1: rHit 0: X.end+1 = 4 > 0 -> new (0,1); rHit 4 == 4 -> X.len=1, iterator exhausted ->
+    # break; the remainder loop adds the second copy as new Z=(4,1). i=2: currSet [(0,1), X(end 4), Z(end 4)]:
+    # rHit 1 extends (0,1) -> len1; rHit 5: X.end+1 = 5 -> X.len=2; iterator -> Z; j exhausted -> break.
+    # TreeSet: (0,1,1) (3,0,2) (4,1,0). Phase 2: prev (0,1,1) end incl 3 >= 3, prev.len 1 < 2 -> prev.len = 3-0-3 = 0
+    # -> emitted (0,1,0); prev = X(3,0,2) end incl 7 >= 4: Z not longer: lenDiff 4, len -4 dropped. => [[0,1,0],[3,0,2]]
+    o = _o(K=3)
+    o.set_reference(b"ACGTACGT", index_thread_num=2)
+    assert o.get_hits(b"TACGT").tolist() == [[0, 1, 0], [3, 0, 2]]
+    # with one thread the same read gives the same list here (the extra hit was dropped by the sweep)
+    o1 = _o(K=3)
+    o1.set_reference(b"ACGTACGT", index_thread_num=1)
+    assert o1.get_hits(b"TACGT").tolist() == [[0, 1, 0], [3, 0, 2]]
+
+
+def test_read_shorter_than_k_and_null_seq():
+    o = _o(K=5)
+    o.set_reference(b"ACGTACGTACGT", index_thread_num=1)
+    assert len(o.get_hits(b"ACG")) == 0 and len(o.seed(b"*")) == 0
+
+
+# --------------------------------------------------------------------------------------------------
+# splitLongHits (KMerCounter.java:142-185)
+# --------------------------------------------------------------------------------------------------
+def test_split_long_hits_at_contig_boundary():
+    # two contigs of 8: ref = ACGTTGCA|GGATCCAT ; the read spans the boundary: read = ref[3:13] (len 10), K=3.
+    # One diagonal chain (3,0,len7) spanning 3..12. contigEnd = 8: crosses; first part: 8-3 = 5 >= 3 -> (3,0,len 2);
+    # second part: 3+3+7-8 = 5 >= 3 -> readPos += 5, len -= 5, g = 8 -> (8,5,2).
+    ref = b"ACGTTGCAGGATCCAT"
+    o = _o(K=3)
+    o.set_reference(ref, contig_ends=[8, 16], index_thread_num=1)
+    h = o.get_hits(ref[3:13]).tolist()
+    assert [3, 0, 2] in h and [8, 5, 2] in h
+    assert all(not (g < 8 < g + 3 + ln) for g, r, ln in h)  # nothing straddles the boundary any more
+
+
+# --------------------------------------------------------------------------------------------------
+# concordanceArray — Q3, window walk — Q4/Q5, pruneWindows
+# --------------------------------------------------------------------------------------------------
+def test_window_count_and_prune_by_hand():
+    # ref: two copies of the 12-mer W = ACGGTCATTGCA separated by a spacer; read = W; K=4, cutoff 0.
+    # Each copy gives one chain (g, 0, len 8). Window of hit i (KMerCounter.java:72-116, 169-191):
+    #   start = max(0, g - 0*3/2) = g ; end = min(g + 8 + 4 + (12-0-8-4)*3/2, G) = g + 12 ; count = len = 8.
+    # Both exceed the cutoff; they do not overlap -> pruneWindows keeps both.
+    W = b"ACGGTCATTGCA"
+    ref = W + b"TTTTTTTTTTTTTTTTTTTT" + W
+    cut = np.zeros(64, np.int32)
+    o = _o(K=4, cutoffs=cut)
+    o.set_reference(ref, index_thread_num=1)
+    assert o.get_hits(W).tolist() == [[0, 0, 8], [32, 0, 8]]
+    assert o.seed(W).tolist() == [[0, 12, 8], [32, 44, 8]]
+    # cutoff is strict: count > cutoffs[L]
+    cut[12] = 8
+    o2 = _o(K=4, cutoffs=cut)
+    o2.set_reference(ref, index_thread_num=1)
+    assert len(o2.seed(W)) == 0
+
+
+def test_concordance_bonus_q3_low_coef_zero_vs_msa():
+    # read = P + x + Q against ref = P + Q' ... two chains on nearby diagonals. K=4.
+    # ref  = ACGGTCAT  TGCAAGCT            (16)
+    # read = ACGGTCAT G TGCAAGCT           (17: one inserted base)
+    # chains: (0,0,len4) and (8,9,len4). rate = (8-0)/(9-0) = 0.888..: with lowCoef=0 (single-reference Mapper, Q3)
+    # 0 <= 0.888 <= 1.25 -> adjacent -> bonus +1; with lowCoef = 1/1.05, highCoef = 1.05 it is NOT adjacent.
+    ref = b"ACGGTCATTGCAAGCT"
+    read = b"ACGGTCATGTGCAAGCT"
+    cut = np.zeros(64, np.int32)
+    o = _o(K=4, cutoffs=cut, low_coef=0.0, high_coef=1.25)
+    o.set_reference(ref, index_thread_num=1)
+    assert o.get_hits(read).tolist() == [[0, 0, 4], [8, 9, 4]]
+    # window of hit 0: start 0, end = min(0+4+4+(17-0-4-4)*3/2, 16) = min(21,16) = 16: both hits inside: 4+4+1 = 9
+    w = o.window_walk(read)
+    assert w[0].tolist() == [0, 16, 9, 9]
+    o2 = _o(K=4, cutoffs=cut, low_coef=1 / 1.05, high_coef=1.05)
+    o2.set_reference(ref, index_thread_num=1)
+    assert o2.window_walk(read)[0].tolist() == [0, 16, 8, 8]
+
+
+def test_incremental_window_count_equals_direct_recount():
+    """The GPU path evaluates every window independently; this is exact because after mergeHits the LongHits
+    are sorted and non-overlapping, for which updateCount (KMerCounterBase.java:38-158) equals a recount."""
+    from virgena_b200 import synth
+    ref, _ = synth.config_reference(1)
+    o = _o(K=5, cutoffs=np.zeros(512, np.int32))
+    o.set_reference(ref, index_thread_num=8)
+    m1, m2 = synth.config_pairs(3, 40)
+    n = 0
+    for r in list(m1) + [synth.revcomp(x) for x in m2]:
+        w = o.window_walk(r)
+        assert (w[:, 2] == w[:, 3]).all()
+        h = o.get_hits(r)
+        assert (np.diff(h[:, 0]) > 0).all() and (h[:-1, 0] + 5 + h[:-1, 2] <= h[1:, 0]).all()
+        n += len(w)
+    assert n > 10000
+
+
+def test_prune_windows_ties_first_wins():
+    # pruneWindows (KMerCounterBase.java:317-335): among overlapping windows the larger count wins, ties keep the
+    # first in (start asc, end desc) order. Crafted through equal k-mer content at two overlapping loci is hard to
+    # do by hand; this is covered by the seeded parity tests. Here: a single window survives a self-overlap.
+    W = b"ACGGTCATTGCA"
+    o = _o(K=4, cutoffs=np.zeros(64, np.int32))
+    o.set_reference(W + W, index_thread_num=1)
+    # hits: (0,0,8) and (12,0,8); windows [0,12) and [12,24): touching (end == start) is NOT an overlap (>)
+    assert o.seed(W).tolist() == [[0, 12, 8], [12, 24, 8]]
+
+
+# --------------------------------------------------------------------------------------------------
+# SmithWatermanGotoh (SmithWatermanGotoh.java:51-222)
+# --------------------------------------------------------------------------------------------------
+def test_sw_identical():
+    rec, seq = _o().sw_align(b"ACGTACGT", b"ACGTACGT")
+    assert rec.tolist() == [16, 0, 8, 0, 8, 8, 8] and seq == b"ACGTACGT"
+
+
+def test_sw_q8_no_positive_cell():
+    # no cell > 0: Cell stays (0,0), score 0, empty alignment (:146-150, :178-221)
+    rec, seq = _o().sw_align(b"AAAA", b"CCCC")
+    assert rec.tolist() == [0, 0, 0, 0, 0, 0, 0] and seq == b""
+
+
+def test_sw_mismatch_inside():
+    # ACGTTACGT vs ACGTAACGT with 2/-3/5/2: through the mismatch 4*2 - 3 + 4*2 = 13 > 8 (either flank alone);
+    # a gap would cost 5. identity = 8, sequence1 carries the read base at the mismatch.
+    rec, seq = _o().sw_align(b"ACGTTACGT", b"ACGTAACGT")
+    assert rec.tolist() == [13, 0, 9, 0, 9, 8, 9] and seq == b"ACGTTACGT"
+
+
+def test_sw_deletion_in_read_is_gap_run_with_affine_cost():
+    # read lacks 2 bases of the window: 10 matches on each side: 20*2 - (5 + 2) = 33; '-' x 2 in sequence1.
+    a, b = b"ACGGTCATTG", b"CAAGCTGGAT"
+    rec, seq = _o().sw_align(a + b, a + b"TT" + b)
+    assert rec[0] == 33 and seq == a + b"--" + b
+    assert rec.tolist() == [33, 0, 20, 0, 22, 20, 22]
+
+
+def test_sw_insertion_in_read_is_lower_case():
+    a, b = b"ACGGTCATTG", b"CAAGCTGGAT"
+    rec, seq = _o().sw_align(a + b"TTT" + b, a + b)
+    # 20 matches - (5 + 2*2) = 31; inserted read bases are lower-cased (Constants.lower, :191)
+    assert rec.tolist() == [31, 0, 23, 0, 20, 20, 23] and seq == a + b"ttt" + b
+
+
+def test_sw_first_maximum_in_row_major_order():
+    # two equally good local alignments: the first strictly-greater cell in row-major order wins (:146-150).
+    # s1 = ACGT, s2 = ACGTNNACGT: row 4 reaches 8 first at column 4 -> end2 = 4.
+    rec, seq = _o().sw_align(b"ACGT", b"ACGTNNACGT")
+    assert rec.tolist() == [8, 0, 4, 0, 4, 4, 4]
+    # s1 = ACGTNNACGT, s2 = ACGT: 8 is reached in row 4 (col 4) before row 10
+    rec, seq = _o().sw_align(b"ACGTTTACGT", b"ACGT")
+    assert rec.tolist() == [8, 0, 4, 0, 4, 4, 4]
+
+
+def test_sw_q9_unknown_base_in_insertion_becomes_zero_byte():
+    a, b = b"ACGGTCATTG", b"CAAGCTGGAT"
+    rec, seq = _o().sw_align(a + b"R" + b, a + b)
+    assert seq == a + b"\x00" + b  # Constants.lower has no entry for 'R' (:22-30)
+
+
+def test_sw_n_matches_n():
+    rec, seq = _o().sw_align(b"ACNGT", b"ACNGT")
+    assert rec[0] == 10 and rec[5] == 5  # byte equality: N == N scores as a match (:108)
+
+
+def test_find_max_score_equals_align_score():
+    o = _o()
+    for a, b in ((b"ACGTTACGT", b"ACGTAACGT"), (b"AAAA", b"CCCC"), (b"GATTACA", b"GCATGCT")):
+        assert o.sw_max_score(a, b) == o.sw_align(a, b)[0][0]
+
+
+# --------------------------------------------------------------------------------------------------
+# pileup / consensus / CIGAR
+# --------------------------------------------------------------------------------------------------
+def _rec(start, start2, seq1):
+    r = np.zeros(1, oracle.PAIR_DTYPE)
+    r["m"]["seq1_offset"] = -1
+    m = r["m"][0, 0]
+    m["present"], m["start"], m["start2"], m["length"], m["seq1_offset"] = 1, start, start2, len(seq1), 0
+    r["m"][0, 0] = m
+    return r
+
+
+def test_pileup_q11_and_insertions():
+    # ConsensusBuilderSimple.java:56-75: lower case skipped, '-' -> column 4, N (and any unlisted byte) -> A.
+    counts = oracle.pileup(_rec(2, 1, b"ANt-G"), np.frombuffer(b"ANt-G", np.uint8), 10)
+    exp = np.zeros((10, 5), np.int32)
+    exp[3, 0] = 1   # A at 2+1
+    exp[4, 0] = 1   # N -> A (Q11)
+    exp[5, 4] = 1   # '-' ; the insertion 't' does not advance
+    exp[6, 2] = 1   # G
+    assert (counts == exp).all()
+
+
+def test_consensus_argmax_first_max_wins_and_threshold():
+    counts = np.zeros((4, 5), np.int32)
+    counts[0] = [2, 2, 0, 0, 9]   # tie A/T -> A (strict >); the gap column is ignored
+    counts[1] = [0, 1, 3, 3, 0]   # tie G/C -> G
+    counts[2] = [0, 0, 0, 1, 0]   # 1 <= threshold 1 -> uncovered
+    counts[3] = [0, 0, 0, 5, 0]
+    assert oracle.consensus(counts, b"TTTT", False, 1).tobytes() == b"AG-C"
+    assert oracle.consensus(counts, b"TTTT", True, 1).tobytes() == b"AGTC"
+
+
+def test_cigar_and_xn():
+    # BamPrinter.setCigar (BamPrinter.java:121-171)
+    assert oracle.cigar(b"ACGT--ACgtAC", 2, 10, 12, 7) == ("2S4M2D2M2I2M2S", 1)
+    # an alignment cannot start with an insertion or deletion in practice; a leading I would emit "0M" first
+    assert oracle.cigar(b"aCG", 0, 3, 3, 2)[0] == "0M1I2M"
+
+
+# --------------------------------------------------------------------------------------------------
+# Mapper.mapRead pairing (Mapper.java:92-390)
+# --------------------------------------------------------------------------------------------------
+def test_map_read_classes():
+    from virgena_b200 import synth
+    ref, _ = synth.config_reference(1)
+    cut = np.full(400, 100, np.int32)  # above any random window (~70), below a true one (~240)
+    o = _o(K=5, cutoffs=cut)
+    o.set_reference(ref, index_thread_num=1)
+    f = ref[1000:1250].tobytes()
+    r = synth.revcomp(ref[1300:1550]).tobytes()
+    junk = bytes(np.random.default_rng(0).integers(65, 70, 250).astype(np.uint8))
+    far = synth.revcomp(ref[6000:6250]).tobytes()
+    r1 = [f, r, f, junk, junk, f, b"*"]
+    r2 = [r, f, junk, r, junk, far, r]
+    b = synth.pack_ragged(r1, r2)
+    rec, pool, st = o.map_pairs(*b)
+    # FR concordant, RF concordant, left only, right only, unmapped, discordant (insert > 1000), right only
+    assert rec["cls"].tolist() == [0, 1, 3, 4, 5, 2, 4]
+    assert rec["m"]["reverse"][0].tolist() == [0, 1] and rec["m"]["reverse"][1].tolist() == [1, 0]
+    # perfect 250-mers: score 500, identity 250, full-length alignment inside the candidate window
+    m = rec["m"][0, 0]
+    assert m["score"] == 500 and m["identity"] == 250 and m["start"] + m["start2"] == 1000
+    # stats 1)-7): pairs, bothExist, readsTotal, totalMapped, fwd, rev, bothMapped, totalScore, concordant
+    assert st[0] == 7 and st[1] == 6 and st[2] == 13 and st[3] == 9 and st[6] == 3 and st[8] == 2
