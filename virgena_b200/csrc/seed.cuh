@@ -39,6 +39,7 @@
 #define SD_MAXL 512             // longest supported read
 #define SD_PENDING 32           // capacity of the re-insertion queue of phase C
 #define SD_WIN 512              // entries of the shared-memory window over the sorted LongHit stream
+#define SD_LPEND 6              // per-lane re-insertion queue of the segment-parallel sweep
 
 struct SeedGeom {       // sizes of the per-warp shared-memory regions (bytes), computed on the host
   int capR;             // max LongHits after phase C (per orientation)
@@ -255,7 +256,9 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
   int* bins = (int*)(aux + SD_PENDING * 8);                            // 256 x 4
   uint16_t* bucket = (uint16_t*)(aux + SD_PENDING * 8 + 1024);         // nBuckets x 2
   uint64_t* win = (uint64_t*)(aux + SD_PENDING * 8 + 1024 + ((A.geom.nBuckets * 2 + 15) & ~15));  // SD_WIN x 8
-  uint8_t* rd = (uint8_t*)(win + SD_WIN);
+  uint64_t* pendL = win + SD_WIN;                       // 32 x SD_LPEND x 8
+  uint16_t* segBuf = (uint16_t*)(pendL + 32 * SD_LPEND); // 2 x (SD_WIN + 2) x 2
+  uint8_t* rd = (uint8_t*)(segBuf + 2 * (SD_WIN + 2) + 4);
   uint16_t* ids = (uint16_t*)(rd + SD_MAXL + 16);
 
   uint64_t* S = A.scratchS + (size_t)warpSlot * A.capS;
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
           const bool valid = id != SD_NONE16;
           const unsigned grp = __match_any_sync(VG_FULL, valid ? id : (0x80000000u | lane));
           const int leader = __ffs(grp) - 1;
-          uint32_t slot = 0, old = SD_NOPOS;
+          uint32_t slot = 0, old = SD_NOPOS;  // old = head | count << 16
           if (valid && lane == leader) {
             slot = sd_hash(id);
             for (;;) {
@@ -321,53 +324,75 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
           if (valid) {
             const unsigned higher = grp & ~((2u << lane) - 1u);
             nxt[i] = higher ? (uint16_t)(base + __ffs(higher) - 1) : (uint16_t)(old & 0xFFFFu);
-            if (lane == leader) hval[slot] = (uint32_t)i;
+            if (lane == leader) hval[slot] = (uint32_t)i | ((((old >> 16) + (uint32_t)__popc(grp)) & 0xFFFFu) << 16);
           }
           __syncwarp();
         }
         // ---- B: scan the reference in genome order -> LongHits sorted by (g, i) ------------------
-        for (int g0 = 0; g0 <= G - K && !overflow; g0 += 32) {
-          const int g = g0 + lane;
-          uint32_t code = (g <= G - K) ? poscode[g] : SD_NONE16;
-          const uint32_t id = code & 0x7FFFu;
-          const bool dup = (code & 0x8000u) != 0;
-          uint32_t head = SD_NOPOS;
-          if (id != SD_NONE16) {
-            uint32_t slot = sd_hash(id);
-            for (;;) {
-              uint32_t k = hkey[slot];
-              if (k == SD_EMPTY) break;
-              if (k == id) {
-                head = hval[slot] & 0xFFFFu;
-                break;
+        // B1: genome positions whose k-mer occurs in the read are queued (ballot compaction, genome order);
+        // B2: one lane per queued position walks its chain of read positions: count the LongHit starts,
+        //     exclusive scan, ordered writes (two passes over a chain of ~1.3 entries).
+        uint32_t* queue = (uint32_t*)win;                 // g << 16 | chain head ; SD_WIN * 2 entries
+        const int QCAP = SD_WIN * 2;
+        for (int gb = 0; gb <= G - K && !overflow;) {
+          int nq = 0;
+          for (; gb <= G - K && nq + 32 <= QCAP; gb += 32) {
+            const int g = gb + lane;
+            const uint32_t code = (g <= G - K) ? poscode[g] : SD_NONE16;
+            const uint32_t id = code & 0x7FFFu;
+            uint32_t head = SD_NOPOS;
+            if (id != SD_NONE16) {
+              uint32_t slot = sd_hash(id);
+              for (;;) {
+                const uint32_t k = hkey[slot];
+                if (k == SD_EMPTY) break;
+                if (k == id) {
+                  head = hval[slot] & 0xFFFFu;
+                  break;
+                }
+                slot = (slot + 1) & (SD_HS - 1);
               }
-              slot = (slot + 1) & (SD_HS - 1);
             }
+            const unsigned m = __ballot_sync(VG_FULL, head != SD_NOPOS);
+            if (head != SD_NOPOS) queue[nq + __popc(m & ((1u << lane) - 1))] = ((uint32_t)g << 16) | head;
+            nq += __popc(m);
           }
-          if (!__any_sync(VG_FULL, head != SD_NOPOS)) continue;
-          int cnt = 0;
-          for (uint32_t i = head; i != SD_NOPOS; i = nxt[i]) {
-            const bool start = (i == 0) || (g == 0) || (rd[i - 1] != ref[g - 1]);
-            cnt += (start || dup) ? 1 : 0;
-          }
-          const int incl = sd_warp_incl_scan(cnt, lane);
-          const int total = __shfl_sync(VG_FULL, incl, 31);
-          if (nS + total > A.capS) {
-            overflow = true;
-            break;
-          }
-          int o = nS + incl - cnt;
-          for (uint32_t i = head; i != SD_NOPOS; i = nxt[i]) {
-            const bool start = (i == 0) || (g == 0) || (rd[i - 1] != ref[g - 1]);
-            if (start) {
-              int len = 0;
-              while ((int)i + K + len < L && g + K + len < G && rd[i + K + len] == ref[g + K + len]) len++;
-              S[o++] = ((uint64_t)g << 32) | ((uint64_t)i << 16) | (uint64_t)len;
-            } else if (dup) {
-              S[o++] = ((uint64_t)g << 32) | ((uint64_t)i << 16);
+          __syncwarp();
+          for (int q0 = 0; q0 < nq; q0 += 32) {
+            const int q = q0 + lane;
+            int g = 0;
+            uint32_t head = SD_NOPOS;
+            bool dup = false;
+            if (q < nq) {
+              g = (int)(queue[q] >> 16);
+              head = queue[q] & 0xFFFFu;
+              dup = (poscode[g] & 0x8000u) != 0;
             }
+            int cnt = 0;
+            for (uint32_t i = head; i != SD_NOPOS; i = nxt[i]) {
+              const bool start = (i == 0) || (g == 0) || (rd[i - 1] != ref[g - 1]);
+              cnt += (start || dup) ? 1 : 0;
+            }
+            const int incl = sd_warp_incl_scan(cnt, lane);
+            const int total = __shfl_sync(VG_FULL, incl, 31);
+            if (nS + total > A.capS) {
+              overflow = true;
+              break;
+            }
+            int o = nS + incl - cnt;
+            for (uint32_t i = head; i != SD_NOPOS; i = nxt[i]) {
+              const bool start = (i == 0) || (g == 0) || (rd[i - 1] != ref[g - 1]);
+              if (start) {
+                int len = 0;
+                while ((int)i + K + len < L && g + K + len < G && rd[i + K + len] == ref[g + K + len]) len++;
+                S[o++] = ((uint64_t)g << 32) | ((uint64_t)i << 16) | (uint64_t)len;
+              } else if (dup) {
+                S[o++] = ((uint64_t)g << 32) | ((uint64_t)i << 16);
+              }
+            }
+            nS += total;
           }
-          nS += total;
+          __syncwarp();
         }
       } else {
         // ---- MSA: raw hits from the CSR index; chain starts by membership in the neighbour list --
@@ -433,37 +458,181 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
         if (lane == 0) atomicOr(A.errFlag, 1);
         nS = 0;
       }
-      // ---- C: mergeHits phase 2 (serial, lane 0) + splitLongHits on emit ---------------------------
-      // The sorted stream S is consumed through a sliding shared-memory window (2 x SD_WIN/2 entries,
-      // refilled by the whole warp) so that the serial lane never waits on global memory.
+      // ---- C: mergeHits phase 2 (KMerCounterBase.java:422-449) ------------------------------------
+      // The sweep keeps one `prev` and re-inserts clipped hits into the TreeSet. An element x whose
+      // genomePos exceeds the maximum end (g + len + K) of ALL earlier elements is a synchronisation
+      // point: when it is polled nothing earlier is left in the set (re-inserted keys are ends of earlier
+      // elements, hence < g_x) and prev cannot overlap it, so the state becomes (prev = x) whatever the
+      // history was. The stream therefore splits into independent segments; each lane sweeps whole
+      // segments verbatim (in place in the shared-memory window), results are compacted in order.
       int nR = 0;
+      const uint64_t* Sall = S;
+      const int nSall = nS;
+      int serialFrom = -1;
+      int err = 0;
       if (nS > 0) {
-        int err = 0;
+        constexpr int CH = SD_WIN / 32;  // entries per lane when flagging
+        uint16_t* segStart = (uint16_t*)bucket;          // nBuckets >= SD_WIN/2 + 2 is not guaranteed -> own region
+        segStart = segBuf;
+        uint16_t* segCnt = segBuf + SD_WIN + 2;
+        uint64_t* pend = pendL + lane * SD_LPEND;
+        int tbase = 0, runMaxE = -1;
+        while (tbase < nS) {
+          const int cnt = min(SD_WIN, nS - tbase);
+          for (int e = lane; e < cnt; e += 32) win[e] = S[tbase + e];
+          __syncwarp();
+          const int lo = lane * CH, hi = min(lo + CH, cnt);
+          int locMax = -1;
+          for (int j = lo; j < hi; j++) {
+            const uint64_t v = win[j];
+            locMax = max(locMax, (int)(v >> 32) + (int)(v & 0xFFFFu) + K);
+          }
+          int incl = locMax;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(VG_FULL, incl, d);
+            if (lane >= d) incl = max(incl, t);
+          }
+          int excl = __shfl_up_sync(VG_FULL, incl, 1);
+          excl = (lane == 0) ? runMaxE : max(excl, runMaxE);
+          uint32_t fmask = 0;
+          {
+            int m = excl;
+            for (int j = lo; j < hi; j++) {
+              const uint64_t v = win[j];
+              const int g = (int)(v >> 32);
+              if (g > m) fmask |= 1u << (j - lo);
+              m = max(m, g + (int)(v & 0xFFFFu) + K);
+            }
+          }
+          const int nflag = __popc(fmask);
+          const int inclF = sd_warp_incl_scan(nflag, lane);
+          const int nSeg = __shfl_sync(VG_FULL, inclF, 31);
+          {
+            int o = inclF - nflag;
+            for (uint32_t fm = fmask; fm; fm &= fm - 1) segStart[o++] = (uint16_t)(lo + __ffs(fm) - 1);
+          }
+          if (lane == 0) segStart[nSeg] = (uint16_t)cnt;
+          __syncwarp();
+          const bool more = tbase + cnt < nS;
+          const int nDo = more ? nSeg - 1 : nSeg;
+          if (nDo <= 0) {  // a single segment longer than the window
+            serialFrom = tbase;
+            break;
+          }
+          const int tailStart = more ? (int)segStart[nSeg - 1] : cnt;
+          {  // running maximum end over the entries that are consumed now (original ends)
+            int m2 = -1;
+            for (int j = lo; j < hi && j < tailStart; j++) {
+              const uint64_t v = win[j];
+              m2 = max(m2, (int)(v >> 32) + (int)(v & 0xFFFFu) + K);
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) m2 = max(m2, __shfl_xor_sync(VG_FULL, m2, d));
+            runMaxE = max(runMaxE, m2);
+          }
+          bool ovf = false;
+          for (int sg = lane; sg < nDo; sg += 32) {
+            const int s0 = segStart[sg], s1 = segStart[sg + 1];
+            int si = s0, w = s0, np = 0;
+            uint64_t v = win[si++];
+            int pg = (int)(v >> 32), pr = (int)((v >> 16) & 0xFFFFu), pl = (int)(v & 0xFFFFu);
+            while (si < s1 || np > 0) {
+              if (np > 0 && (si >= s1 || (pend[0] >> 16) < (win[si] >> 16))) {  // TreeSet.pollFirst
+                v = pend[0];
+                for (int t = 1; t < np; t++) pend[t - 1] = pend[t];
+                np--;
+              } else {
+                v = win[si++];
+              }
+              int cg = (int)(v >> 32), cr = (int)((v >> 16) & 0xFFFFu), cl = (int)(v & 0xFFFFu);
+              if (pg + pl + K - 1 >= cg) {
+                if (pl < cl) {
+                  pl = cg - pg - K;
+                  if (pl >= 0) win[w++] = ((uint64_t)pg << 32) | ((uint64_t)pr << 16) | (uint64_t)pl;
+                  pg = cg, pr = cr, pl = cl;
+                } else {
+                  const int lenDiff = pg + pl + K - cg;
+                  cl -= lenDiff;
+                  if (cl >= 0) {
+                    cg += lenDiff;
+                    cr += lenDiff;
+                    const uint64_t key = ((uint64_t)cg << 16) | (uint64_t)cr;
+                    bool present = false;
+                    int ins = np;
+                    for (int t = 0; t < np; t++) {
+                      const uint64_t pk = pend[t] >> 16;
+                      if (pk == key) present = true;
+                      if (pk > key && ins == np) ins = t;
+                    }
+                    if (!present)
+                      for (int j = si; j < s1; j++) {  // the key lies before the next synchronisation point
+                        const uint64_t k = win[j] >> 16;
+                        if (k >= key) {
+                          present = (k == key);
+                          break;
+                        }
+                      }
+                    if (!present) {
+                      if (np >= SD_LPEND) {
+                        ovf = true;
+                        np = 0;
+                        si = s1;
+                      } else {
+                        for (int t = np; t > ins; t--) pend[t] = pend[t - 1];
+                        pend[ins] = (key << 16) | (uint64_t)cl;
+                        np++;
+                      }
+                    }
+                  }
+                }
+              } else {
+                win[w++] = ((uint64_t)pg << 32) | ((uint64_t)pr << 16) | (uint64_t)pl;
+                pg = cg, pr = cr, pl = cl;
+              }
+            }
+            win[w++] = ((uint64_t)pg << 32) | ((uint64_t)pr << 16) | (uint64_t)pl;
+            segCnt[sg] = (uint16_t)(w - s0);
+          }
+          __syncwarp();
+          if (__any_sync(VG_FULL, ovf)) {
+            serialFrom = tbase;
+            break;
+          }
+          for (int sg0 = 0; sg0 < nDo; sg0 += 32) {  // ordered compaction into the LongHit arrays
+            const int sg = sg0 + lane;
+            const int c = (sg < nDo) ? (int)segCnt[sg] : 0;
+            const int ic = sd_warp_incl_scan(c, lane);
+            int o = nR + ic - c;
+            if (sg < nDo) {
+              const int s0 = segStart[sg];
+              for (int t = 0; t < c; t++, o++) {
+                const uint64_t v = win[s0 + t];
+                if (o < capR) hitG[o] = (uint16_t)(v >> 32), hitR[o] = (uint16_t)((v >> 16) & 0xFFFFu), hitL[o] = (uint16_t)(v & 0xFFFFu);
+              }
+            }
+            nR += __shfl_sync(VG_FULL, ic, 31);
+          }
+          __syncwarp();
+          tbase += tailStart;
+        }
+      }
+      if (serialFrom >= 0) {
+        // Fallback (a segment longer than the window, or a full re-insertion queue): the verbatim serial
+        // sweep by lane 0 from the synchronisation point `serialFrom`, through a sliding window.
+        const uint64_t* S = Sall + serialFrom;
+        const int nS = nSall - serialFrom;
         int wbase = 0;
         for (int e = lane; e < SD_WIN && e < nS; e += 32) win[e] = S[e];
         __syncwarp();
         // lane-0 state of the sweep
-        int si = 0, np = 0, ci = 0, contigEnd = A.contigEnds[0];
+        int si = 0, np = 0;
         int pg = 0, pr = 0, pl = 0;
         bool started = false, done = false;
         for (;;) {
           if (lane == 0) {
             auto emit = [&](int g, int r, int len) {
-              for (;;) {  // KMerCounter.splitLongHits (the MSA path has a single "contig")
-                while (g >= contigEnd) contigEnd = A.contigEnds[++ci];
-                if (g + K + len > contigEnd) {
-                  if (contigEnd - g >= K) {
-                    if (nR < capR) hitG[nR] = (uint16_t)g, hitR[nR] = (uint16_t)r, hitL[nR] = (uint16_t)(contigEnd - g - K);
-                    nR++;
-                  }
-                  if (g + K + len - contigEnd >= K) {
-                    r += contigEnd - g;
-                    len -= contigEnd - g;
-                    g = contigEnd;
-                    continue;
-                  }
-                  break;
-                }
+              for (;;) {
                 if (nR < capR) hitG[nR] = (uint16_t)g, hitR[nR] = (uint16_t)r, hitL[nR] = (uint16_t)len;
                 nR++;
                 break;
@@ -562,13 +731,69 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
           }
           __syncwarp();
         }
-        if (lane == 0) {
-          if (nR > capR) err |= 2;
-          if (err) atomicOr(A.errFlag, err);
-        }
         nR = __shfl_sync(VG_FULL, nR, 0);
         err = __shfl_sync(VG_FULL, err, 0);
-        if (err || nR > capR) nR = 0;
+      }
+      if (nS > 0) {
+        __syncwarp();
+        // ---- D: KMerCounter.splitLongHits (KMerCounter.java:142-185); hits are independent given their contig
+        if (!err && nR <= capR && A.nContigs > 1 && nR > 0) {
+          uint32_t* tg = ckey;   // pieces: g | (r << 16) in ckey, len in cval
+          uint32_t* tl = cval;
+          int nOut = 0;
+          bool bad = false;
+          for (int j0 = 0; j0 < nR; j0 += 32) {
+            const int j = j0 + lane;
+            int pg[3], pr[3], pl[3], np2 = 0;
+            if (j < nR) {
+              int g = hitG[j], r = hitR[j], len = hitL[j];
+              for (;;) {
+                int lo2 = 0, hi2 = A.nContigs - 1;
+                while (lo2 < hi2) {
+                  const int mid = (lo2 + hi2) >> 1;
+                  if (A.contigEnds[mid] > g) hi2 = mid;
+                  else lo2 = mid + 1;
+                }
+                const int contigEnd = A.contigEnds[lo2];
+                if (g + K + len > contigEnd) {
+                  if (contigEnd - g >= K) {
+                    if (np2 < 3) pg[np2] = g, pr[np2] = r, pl[np2] = contigEnd - g - K;
+                    np2++;
+                  }
+                  if (g + K + len - contigEnd >= K) {
+                    r += contigEnd - g;
+                    len -= contigEnd - g;
+                    g = contigEnd;
+                    continue;
+                  }
+                  break;
+                }
+                if (np2 < 3) pg[np2] = g, pr[np2] = r, pl[np2] = len;
+                np2++;
+                break;
+              }
+              if (np2 > 3) bad = true, np2 = 3;  // a hit across > 2 contig boundaries (contigs shorter than K + 1)
+            }
+            const int ic = sd_warp_incl_scan(np2, lane);
+            int o = nOut + ic - np2;
+            for (int t = 0; t < np2; t++, o++)
+              if (o < capC) tg[o] = (uint32_t)pg[t] | ((uint32_t)pr[t] << 16), tl[o] = (uint32_t)pl[t];
+            nOut += __shfl_sync(VG_FULL, ic, 31);
+          }
+          __syncwarp();
+          if (__any_sync(VG_FULL, bad) || nOut > capR) {
+            err |= 2;
+          } else {
+            for (int j = lane; j < nOut; j += 32) hitG[j] = (uint16_t)(tg[j] & 0xFFFFu), hitR[j] = (uint16_t)(tg[j] >> 16), hitL[j] = (uint16_t)tl[j];
+            nR = nOut;
+          }
+          __syncwarp();
+        }
+        if (nR > capR) err |= 2;
+        if (err) {
+          if (lane == 0) atomicOr(A.errFlag, err);
+          nR = 0;
+        }
       }
       __syncwarp();
       if (A.dbgHits && wi == 0) {

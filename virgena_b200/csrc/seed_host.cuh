@@ -182,7 +182,7 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   const int nContigs = msa ? 1 : (int)c->contigEnds.size();
   g.capR = std::max(1152, std::min(4096, range / K + nContigs + 16));
   g.nBuckets = (range >> 5) + 2;
-  const int auxBytes = SD_PENDING * 8 + 1024 + ((g.nBuckets * 2 + 15) & ~15) + SD_WIN * 8 + (SD_MAXL + 16) + SD_MAXL * 2;
+  const int auxBytes = SD_PENDING * 8 + 1024 + ((g.nBuckets * 2 + 15) & ~15) + SD_WIN * 8 + 32 * SD_LPEND * 8 + (2 * (SD_WIN + 2) + 4) * 2 + (SD_MAXL + 16) + SD_MAXL * 2 + 16;
   g.warpBytes = (g.capR * 8 + auxBytes + 15) & ~15;
   g.refBytes = 0;
   if (!msa) {
