@@ -89,6 +89,7 @@ struct SeedArgs {
   int* errFlag;                // 1: capS overflow, 2: capR overflow, 4: pending overflow, 8: window overflow
   int32_t* dbgHits;            // optional: [capR*3] LongHits of item 0 after phase C (tests)
   int32_t* dbgNHits;
+  unsigned long long* prof;    // optional: cycles per phase [A,B,C,D,E,F,G,total] (VG_SEED_PROF=1)
   SeedGeom geom;
 };
 
@@ -288,6 +289,7 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
     }
     int nWin = 0;
     const int nk = L - K + 1;
+    const long long tph0 = A.prof ? clock64() : 0;
     // MapperMSA.mapReadFast short-circuits NULL_SEQ (Q6); the single-reference path relies on L < K.
     if (nk >= 1 && L <= SD_MAXL) {
       const uint8_t* src = A.bases + off;
@@ -297,6 +299,14 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
       __syncwarp();
       int nS = 0;
       bool overflow = false;
+      long long tph = A.prof ? clock64() : 0;
+#define SD_PH(k)                                                        \
+  if (A.prof) {                                                         \
+    __syncwarp();                                                       \
+    long long t2 = clock64();                                           \
+    if (lane == 0) atomicAdd(A.prof + (k), (unsigned long long)(t2 - tph)); \
+    tph = t2;                                                           \
+  }
       if (!A.msa) {
         // ---- A: read k-mer table (id -> ascending chain of read positions) ----------------------
         for (int base = ((nk - 1) >> 5) << 5; base >= 0; base -= 32) {
@@ -328,6 +338,7 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
           }
           __syncwarp();
         }
+        SD_PH(0)
         // ---- B: scan the reference in genome order -> LongHits sorted by (g, i) ------------------
         // B1: genome positions whose k-mer occurs in the read are queued (ballot compaction, genome order);
         // B2: one lane per queued position walks its chain of read positions: count the LongHit starts,
@@ -458,6 +469,7 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
         if (lane == 0) atomicOr(A.errFlag, 1);
         nS = 0;
       }
+      SD_PH(1)
       // ---- C: mergeHits phase 2 (KMerCounterBase.java:422-449) ------------------------------------
       // The sweep keeps one `prev` and re-inserts clipped hits into the TreeSet. An element x whose
       // genomePos exceeds the maximum end (g + len + K) of ALL earlier elements is a synchronisation
@@ -734,6 +746,7 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
         nR = __shfl_sync(VG_FULL, nR, 0);
         err = __shfl_sync(VG_FULL, err, 0);
       }
+      SD_PH(2)
       if (nS > 0) {
         __syncwarp();
         // ---- D: KMerCounter.splitLongHits (KMerCounter.java:142-185); hits are independent given their contig
@@ -804,6 +817,7 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
         }
         if (lane == 0) *A.dbgNHits = nR;
       }
+      SD_PH(3)
       if (nR > 0) {
         // ---- E: isAdjacent + prefix sums P[j] = sum_{t<=j}(len_t + isAdjacent[t-1]) (mod 2^16) ------
         int carry = 0;
@@ -848,6 +862,7 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
           }
         }
         __syncwarp();
+        SD_PH(4)
         // ---- F: every window independently; candidates (count > cutoff) compacted in hit order ------
         const int cutoff = (L < A.nCutoffs) ? A.cutoffs[L] : 0x7fffffff;
         int nC = 0;
@@ -889,9 +904,11 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
           nC += __popc(m);
         }
         __syncwarp();
+        SD_PH(5)
         // ---- G: stable sort by (start asc, end desc) + pruneWindows (serial, lane 0) ----------------
         if (nC > 0) {
           const int srcb = sd_radix_sort(ckey, cval, capC, nC, bins, lane, 32);
+          SD_PH(6)
           __threadfence_block();
           if (lane == 0) {
             const uint32_t* ks = ckey + (size_t)srcb * capC;
@@ -924,6 +941,10 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
     }
     if (lane == 0) A.nWindows[wi] = nWin;
     __syncwarp();
+    if (A.prof && nk >= 1 && L <= SD_MAXL) {
+      long long t2 = clock64();
+      if (lane == 0) atomicAdd(A.prof + 7, (unsigned long long)(t2 - tph0));
+    }
   }
 }
 

@@ -247,6 +247,12 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   A.dbgHits = dbgHits;
   A.dbgNHits = dbgNHits;
   A.geom = g;
+  const bool prof = getenv("VG_SEED_PROF") != nullptr;
+  if (prof) {
+    VG_CUDA(c, c->d_rev.reserve(4096 * 3 * 4 + 256));
+    A.prof = (unsigned long long*)(c->d_rev.as<uint8_t>() + 4096 * 3 * 4 + 64);
+    VG_CUDA(c, cudaMemsetAsync(A.prof, 0, 64, c->stream));
+  }
   if (nItems > 0) {
     seed_kernel<<<blocks, warps * 32, smem, c->stream>>>(A);
     VG_LAUNCH_CHECK(c);
@@ -254,6 +260,13 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   int flags[2] = {0, 0};
   VG_CUDA(c, cudaMemcpyAsync(flags, c->d_counter.p, 8, cudaMemcpyDeviceToHost, c->stream));
   VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (prof) {
+    unsigned long long ph[8];
+    cudaMemcpy(ph, A.prof, 64, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[seed prof] items=%lld cycles/item: A=%.0f B=%.0f C=%.0f D=%.0f E=%.0f F=%.0f Gsort=%.0f (prune+rest in total) total=%.0f\n", (long long)nItems,
+            ph[0] / (double)nItems, ph[1] / (double)nItems, ph[2] / (double)nItems, ph[3] / (double)nItems, ph[4] / (double)nItems,
+            ph[5] / (double)nItems, ph[6] / (double)nItems, ph[7] / (double)nItems);
+  }
   if (flags[1]) {
     const int f = flags[1];
     return vg_fail(c, VG_ERR_OVERFLOW,
