@@ -147,7 +147,7 @@ def run_reference(args):
     cut, meta = load_cutoffs(3)
     ref, ends = synth.config_reference(3)
     threads = os.cpu_count() or 1
-    n_sample = args.ref_pairs
+    n_sample = args.ref_pairs or 1000 * threads  # BatchSize=1000 pairs per task: one task per thread
     m1, m2 = synth.config_pairs(3, n_sample)
     for _ in range(args.warmup):
         cpu_baseline(ref, cut, m1, m2, min(n_sample, 200), threads, meta["index_thread_num"])
@@ -175,8 +175,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--pairs", type=int, default=1000000, help="read pairs per step per GPU")
-    ap.add_argument("--ref-pairs", type=int, default=3000, help="pairs per step of the CPU reference arm")
-    ap.add_argument("--cpu-pairs", type=int, default=4000, help="pairs of the cpu_baseline sample")
+    ap.add_argument("--ref-pairs", type=int, default=0, help="pairs per step of the CPU reference arm (0: 1000 x host threads)")
+    ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs of the cpu_baseline sample (0: 3000 x host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -359,12 +359,13 @@ def main():
             "mapping_stats": [int(x) for x in stats],
         }
         if not args.no_cpu_baseline:
-            m1 = host_batches[0][0][:args.cpu_pairs].numpy()
-            m2 = host_batches[0][1][:args.cpu_pairs].numpy()
             threads = os.cpu_count() or 1
-            v, dt = cpu_baseline(ref, cut, m1, m2, args.cpu_pairs, threads, meta["index_thread_num"])
+            ncpu = min(n, args.cpu_pairs or 3000 * threads)
+            m1 = host_batches[0][0][:ncpu].numpy()
+            m2 = host_batches[0][1][:ncpu].numpy()
+            v, dt = cpu_baseline(ref, cut, m1, m2, ncpu, threads, meta["index_thread_num"])
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                   "sample": "first %d pairs of batch 0 (%.1f s of CPU work on %d threads)" % (args.cpu_pairs, dt, threads),
+                                   "sample": "first %d pairs of batch 0 (%.1f s wall on %d threads, BatchSize=1000 tasks)" % (ncpu, dt, threads),
                                    "note": "C++ restatement of the reference (oracle/), not the JVM"}
         print(json.dumps(out))
     if world > 1:
