@@ -87,7 +87,7 @@ struct vg_ctx {
   DevBuf d_results, d_seq1pool, d_pairIdx;
   // scratch
   DevBuf d_tasks, d_fill, d_alns, d_rev, d_rowck, d_colck, d_counter, d_scratch, d_seqOff, d_cand, d_ncand, d_misc;
-  DevBuf d_s1pool, d_s2pool, d_s1off, d_s2off, d_rowpool, d_rowLen;
+  DevBuf d_s1pool, d_s2pool, d_s1off, d_s2off, d_rowpool, d_rowLen, d_scratchR;
   int64_t lastTasks = 0;
   // pileup
   DevBuf d_counts;

@@ -42,6 +42,7 @@
 #define SD_LPEND 6              // per-lane re-insertion queue of the segment-parallel sweep
 
 struct SeedGeom {       // sizes of the per-warp shared-memory regions (bytes), computed on the host
+  int regA;             // bytes of the phase-aliased region
   int capR;             // max LongHits after phase C (per orientation)
   int nBuckets;         // (coordinate range >> 5) + 2
   int warpBytes;        // total per warp
@@ -64,6 +65,8 @@ struct SeedArgs {
   const int32_t* cutoffs;
   int nCutoffs;
   // MSA index (CSR over ids)
+  int lockstep;                // 1: static work assignment with a CTA barrier per item
+  int direct;                  // 1: ids < 2048 -> direct-addressed read table instead of the hash
   int msa;
   const int32_t* msaOff;
   const int32_t* msaCols;
@@ -78,6 +81,7 @@ struct SeedArgs {
   int singleReads;             // 1: items are single forward reads (vg_seed_batch)
   // scratch + outputs
   uint64_t* scratchS;          // [warpSlots][capS]
+  uint16_t* scratchR;          // [warpSlots][4][capR]: hitG, hitR, hitL, P
   int capS;
   uint32_t* candKey;           // [warpSlots][2][capC]
   uint32_t* candVal;           // [warpSlots][2][capC]
@@ -227,7 +231,7 @@ __device__ __forceinline__ void sd_tma_stage(uint8_t* smemDst, const uint8_t* gs
 //   aux        : pending u64[SD_PENDING] | bins int[256] | bucket u16[nBuckets] | win u64[SD_WIN]
 //   rd         : u8[SD_MAXL + 16], ids u16[SD_MAXL] (MSA)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
+__global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
   extern __shared__ __align__(16) uint8_t sd_smem[];
   __shared__ uint64_t sd_mbar;
   const int lane = threadIdx.x & 31;
@@ -243,35 +247,52 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
     ref = sd_smem;
     poscode = (const uint16_t*)(sd_smem + A.blobRefBytes);
   }
+  // Per-warp shared memory (geom.warpBytes):
+  //   regA  (SD_REGA bytes): phases A/B: tab u32[2048] (or hash hkey/hval u32[1024] each) + nxt u16[SD_MAXL];
+  //                          phases C..G (aliased): pending | bins | bucket | pendL | segBuf
+  //   win   (SD_WIN x 8)   : B: raw-hit queue; C: window over the sorted stream; MSA B': ids
+  //   rd    (SD_MAXL + 16) : the read in its orientation
+  // The LongHit arrays (hitG/hitR/hitL/P, capR each) live in an L2-resident per-warp global scratch.
   uint8_t* wbase = sd_smem + A.geom.refBytes + (size_t)warp * A.geom.warpBytes;
   const int capR = A.geom.capR;
-  uint16_t* hitG = (uint16_t*)wbase;
+  uint16_t* hitG = A.scratchR + (size_t)warpSlot * 4 * capR;
   uint16_t* hitR = hitG + capR;
   uint16_t* hitL = hitR + capR;
   uint16_t* Pp = hitL + capR;
-  uint32_t* hkey = (uint32_t*)wbase;  // aliases the R-region during A/B
+  uint32_t* hkey = (uint32_t*)wbase;
   uint32_t* hval = hkey + SD_HS;
   uint16_t* nxt = (uint16_t*)(hval + SD_HS);
-  uint8_t* aux = wbase + (size_t)capR * 8;
+  uint8_t* aux = wbase;  // aliases regA after phase B
   uint64_t* pending = (uint64_t*)aux;                                  // SD_PENDING x 8
   int* bins = (int*)(aux + SD_PENDING * 8);                            // 256 x 4
   uint16_t* bucket = (uint16_t*)(aux + SD_PENDING * 8 + 1024);         // nBuckets x 2
-  uint64_t* win = (uint64_t*)(aux + SD_PENDING * 8 + 1024 + ((A.geom.nBuckets * 2 + 15) & ~15));  // SD_WIN x 8
-  uint64_t* pendL = win + SD_WIN;                       // 32 x SD_LPEND x 8
-  uint16_t* segBuf = (uint16_t*)(pendL + 32 * SD_LPEND); // 2 x (SD_WIN + 2) x 2
-  uint8_t* rd = (uint8_t*)(segBuf + 2 * (SD_WIN + 2) + 4);
-  uint16_t* ids = (uint16_t*)(rd + SD_MAXL + 16);
+  uint64_t* pendL = (uint64_t*)(aux + SD_PENDING * 8 + 1024 + ((A.geom.nBuckets * 2 + 15) & ~15));  // 32 x SD_LPEND x 8
+  uint16_t* segBuf = (uint16_t*)(pendL + 32 * SD_LPEND);               // 2 x (SD_WIN + 2) x 2
+  uint64_t* win = (uint64_t*)(wbase + A.geom.regA);                    // SD_WIN x 8
+  uint8_t* rd = (uint8_t*)(win + SD_WIN);
+  uint16_t* ids = (uint16_t*)win;                                      // MSA only (win is unused until phase C)
 
   uint64_t* S = A.scratchS + (size_t)warpSlot * A.capS;
   const int capC = A.capC;
   uint32_t* ckey = A.candKey + (size_t)warpSlot * 2 * capC;
   uint32_t* cval = A.candVal + (size_t)warpSlot * 2 * capC;
 
-  for (;;) {
+  // Work distribution. lockstep: static round-robin with a CTA barrier per item, so that all warps of the
+  // SM run the same phase at the same time (the kernel is instruction-cache bound otherwise); else a
+  // global atomic work counter.
+  const int totalWarps = gridDim.x * warpsPerBlock;
+  for (int64_t itBase = 0;; itBase += totalWarps) {
     int wi = 0;
-    if (lane == 0) wi = atomicAdd(A.counter, 1);
-    wi = __shfl_sync(VG_FULL, wi, 0);
-    if (wi >= A.nItems) break;
+    if (A.lockstep) {
+      __syncthreads();
+      if (itBase >= A.nItems) break;
+      if (itBase + warpSlot >= A.nItems) continue;
+      wi = (int)(itBase + warpSlot);
+    } else {
+      if (lane == 0) wi = atomicAdd(A.counter, 1);
+      wi = __shfl_sync(VG_FULL, wi, 0);
+      if (wi >= A.nItems) break;
+    }
     // ---- which read, which orientation ---------------------------------------------------------
     int64_t off;
     int L, rev;
@@ -309,6 +330,32 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
   }
       if (!A.msa) {
         // ---- A: read k-mer table (id -> ascending chain of read positions) ----------------------
+        // direct mode: tab[id] = head | count << 16 (ids < 2048, i.e. K <= 5); else an open-addressing hash.
+        uint32_t* tab = hkey;  // 2048 x u32 (aliases hkey + hval)
+        bool direct = A.direct != 0;
+      retry_hash:
+        if (direct) {
+          for (int t = lane; t < 2 * SD_HS; t += 32) tab[t] = SD_NOPOS;
+          __syncwarp();
+          for (int base = ((nk - 1) >> 5) << 5; base >= 0; base -= 32) {
+            const int i = base + lane;
+            uint32_t id = SD_NONE16;
+            if (i < nk) id = sd_kmer_id(rd + i, K, A.exoKeys, A.nExo);
+            const bool valid = id != SD_NONE16;
+            const unsigned grp = __match_any_sync(VG_FULL, valid ? id : (0x80000000u | lane));
+            if (valid) {
+              const int leader = __ffs(grp) - 1;
+              const uint32_t old = tab[id];  // read by the whole group before the leader overwrites it
+              const unsigned higher = grp & ~((2u << lane) - 1u);
+              nxt[i] = higher ? (uint16_t)(base + __ffs(higher) - 1) : (uint16_t)(old & 0xFFFFu);
+              __syncwarp(grp);
+              if (lane == leader) tab[id] = (uint32_t)i | ((((old >> 16) + (uint32_t)__popc(grp)) & 0xFFFFu) << 16);
+            }
+            __syncwarp();
+          }
+        } else {
+        for (int s2 = lane; s2 < SD_HS; s2 += 32) hkey[s2] = SD_EMPTY;
+        __syncwarp();
         for (int base = ((nk - 1) >> 5) << 5; base >= 0; base -= 32) {
           const int i = base + lane;
           uint32_t id = SD_NONE16;
@@ -338,11 +385,112 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
           }
           __syncwarp();
         }
+        }
         SD_PH(0)
         // ---- B: scan the reference in genome order -> LongHits sorted by (g, i) ------------------
         // B1: genome positions whose k-mer occurs in the read are queued (ballot compaction, genome order);
         // B2: one lane per queued position walks its chain of read positions: count the LongHit starts,
         //     exclusive scan, ordered writes (two passes over a chain of ~1.3 entries).
+        if (direct) {
+          // B1 (direct): every raw hit (g, i) is queued, flattened, in (g, i) order: lanes look their id up
+          //     in the table (head, count), offsets come from three ballots (chains longer than 3 take a scan);
+          // B2: one lane per raw hit: chain-start test, extension, ballot-compacted ordered writes. One pass.
+          uint32_t* queue = (uint32_t*)win;  // g << 16 | i ; SD_WIN * 2 entries
+          const int QCAP = SD_WIN * 2;
+          for (int gb = 0; gb <= G - K && !overflow;) {
+            int nq = 0;
+            bool qfull = false;
+            long long tb1 = A.prof ? clock64() : 0;
+            // B1: 128 genome positions per iteration, 4 consecutive positions per lane (4 independent lookups)
+            for (; gb <= G - K && !qfull; gb += 128) {
+              const int g0 = gb + 4 * lane;
+              uint32_t hv[4];
+              int cnt[4], tot = 0;
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                const int g = g0 + u;
+                const uint32_t code = (g <= G - K) ? poscode[g] : SD_NONE16;
+                const uint32_t id = code & 0x7FFFu;
+                hv[u] = (id != SD_NONE16) ? tab[id] : SD_NOPOS;
+              }
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                cnt[u] = (hv[u] == SD_NOPOS) ? 0 : (int)(hv[u] >> 16);
+                tot += cnt[u];
+              }
+              if (!__any_sync(VG_FULL, tot > 0)) continue;
+              const int incl = sd_warp_incl_scan(tot, lane);
+              const int total = __shfl_sync(VG_FULL, incl, 31);
+              if (total > QCAP) {  // > QCAP raw hits in 128 positions (low-complexity read): hash path
+                direct = false;
+                nS = 0;
+                goto retry_hash;
+              }
+              if (nq + total > QCAP) {  // does not fit any more: flush first, then redo this block
+                qfull = true;
+                gb -= 128;
+                continue;
+              }
+              int o = nq + incl - tot;
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                uint32_t i = hv[u] & 0xFFFFu;
+                for (int t = 0; t < cnt[u]; t++, i = nxt[i]) queue[o++] = ((uint32_t)(g0 + u) << 16) | i;
+              }
+              nq += total;
+            }
+            __syncwarp();
+            long long tb2 = A.prof ? clock64() : 0;
+            if (A.prof && lane == 0) atomicAdd(A.prof + 8, (unsigned long long)(tb2 - tb1));
+            // B2: two raw hits per lane per iteration (independent loads in flight)
+            for (int q0 = 0; q0 < nq; q0 += 64) {
+              bool em[2] = {false, false};
+              int gg[2] = {0, 0}, ii[2] = {0, 0}, ll[2] = {0, 0};
+              uint32_t e[2];
+              uint8_t ca[2], cb[2];
+#pragma unroll
+              for (int u = 0; u < 2; u++) {
+                const int q = q0 + 32 * u + lane;
+                e[u] = (q < nq) ? queue[q] : 0xFFFFFFFFu;
+              }
+#pragma unroll
+              for (int u = 0; u < 2; u++) {
+                gg[u] = (int)(e[u] >> 16);
+                ii[u] = (int)(e[u] & 0xFFFFu);
+                const bool ok = e[u] != 0xFFFFFFFFu;
+                ca[u] = (ok && ii[u] > 0) ? rd[ii[u] - 1] : 0;
+                cb[u] = (ok && gg[u] > 0) ? ref[gg[u] - 1] : 1;
+              }
+#pragma unroll
+              for (int u = 0; u < 2; u++) {
+                if (e[u] == 0xFFFFFFFFu) continue;
+                const int g = gg[u], i = ii[u];
+                const bool start = (i == 0) || (g == 0) || (ca[u] != cb[u]);
+                if (start) {
+                  em[u] = true;
+                  int len = 0;
+                  while (i + K + len < L && g + K + len < G && rd[i + K + len] == ref[g + K + len]) len++;
+                  ll[u] = len;
+                } else if (poscode[g] & 0x8000u) {
+                  em[u] = true;  // Q1: a chain passing through a twice-indexed position adds a zero-length hit
+                }
+              }
+              const unsigned m0 = __ballot_sync(VG_FULL, em[0]);
+              const unsigned m1 = __ballot_sync(VG_FULL, em[1]);
+              const int t0 = __popc(m0), total = t0 + __popc(m1);
+              if (nS + total > A.capS) {
+                overflow = true;
+                break;
+              }
+              const unsigned lt = (1u << lane) - 1u;
+              if (em[0]) S[nS + __popc(m0 & lt)] = ((uint64_t)gg[0] << 32) | ((uint64_t)ii[0] << 16) | (uint64_t)ll[0];
+              if (em[1]) S[nS + t0 + __popc(m1 & lt)] = ((uint64_t)gg[1] << 32) | ((uint64_t)ii[1] << 16) | (uint64_t)ll[1];
+              nS += total;
+            }
+            __syncwarp();
+            if (A.prof && lane == 0) atomicAdd(A.prof + 9, (unsigned long long)(clock64() - tb2));
+          }
+        } else {
         uint32_t* queue = (uint32_t*)win;                 // g << 16 | chain head ; SD_WIN * 2 entries
         const int QCAP = SD_WIN * 2;
         for (int gb = 0; gb <= G - K && !overflow;) {
@@ -404,6 +552,7 @@ __global__ void __launch_bounds__(256) seed_kernel(SeedArgs A) {
             nS += total;
           }
           __syncwarp();
+        }
         }
       } else {
         // ---- MSA: raw hits from the CSR index; chain starts by membership in the neighbour list --

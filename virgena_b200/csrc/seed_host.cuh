@@ -180,10 +180,12 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   A.msa = msa ? 1 : 0;
   SeedGeom g;
   const int nContigs = msa ? 1 : (int)c->contigEnds.size();
-  g.capR = std::max(1152, std::min(4096, range / K + nContigs + 16));
+  g.capR = std::max(256, std::min(16384, range / K + nContigs + 16));
   g.nBuckets = (range >> 5) + 2;
-  const int auxBytes = SD_PENDING * 8 + 1024 + ((g.nBuckets * 2 + 15) & ~15) + SD_WIN * 8 + 32 * SD_LPEND * 8 + (2 * (SD_WIN + 2) + 4) * 2 + (SD_MAXL + 16) + SD_MAXL * 2 + 16;
-  g.warpBytes = (g.capR * 8 + auxBytes + 15) & ~15;
+  const int regAB = 2 * SD_HS * 4 + SD_MAXL * 2;  // table/hash + nxt
+  const int regCG = SD_PENDING * 8 + 1024 + ((g.nBuckets * 2 + 15) & ~15) + 32 * SD_LPEND * 8 + (2 * (SD_WIN + 2) + 4) * 2;
+  g.regA = (std::max(regAB, regCG) + 15) & ~15;
+  g.warpBytes = (g.regA + SD_WIN * 8 + SD_MAXL + 16 + 15) & ~15;
   g.refBytes = 0;
   if (!msa) {
     const int refPad = (c->G + 15) & ~15, codePad = (c->G * 2 + 15) & ~15;
@@ -196,6 +198,7 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     A.nExo = c->nExo;
     A.contigEnds = c->d_contigEnds.as<int32_t>();
     A.nContigs = nContigs;
+    A.direct = ((1 << (2 * K)) + c->nExo <= 2 * SD_HS && !getenv("VG_SEED_HASH")) ? 1 : 0;
     if (A.blobBytes + 4 * g.warpBytes <= 200 * 1024) g.refBytes = A.blobBytes;  // stage in shared memory via TMA
   } else {
     A.exoKeys = c->d_msaExoKeys.as<uint64_t>();
@@ -210,7 +213,10 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     A.nContigs = 1;
   }
   const int smemMax = 220 * 1024;
+  // 8 warps/SM measured best: the kernel is front-end (instruction fetch / branch) bound, more warps only
+  // add instruction-cache pressure (profiles/seed_r1.md)
   int warps = std::min(8, (smemMax - g.refBytes) / g.warpBytes);
+  if (const char* e = getenv("VG_SEED_WARPS")) warps = std::max(1, std::min(warps, atoi(e)));
   if (warps < 1) return vg_fail(c, VG_ERR_INVALID, "reference too large for the seeding kernel's shared memory");
   const size_t smem = (size_t)g.refBytes + (size_t)warps * g.warpBytes;
   VG_CUDA(c, cudaFuncSetAttribute(seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -224,6 +230,8 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   VG_CUDA(c, c->d_scratch.reserve((size_t)warpSlots * A.capS * 8));
   A.capC = msa ? std::max(g.capR, 16384) : g.capR;
   VG_CUDA(c, c->d_seqOff.reserve((size_t)warpSlots * 2 * A.capC * 4 * 2));
+  VG_CUDA(c, c->d_scratchR.reserve((size_t)warpSlots * 4 * g.capR * 2 + 64));
+  A.scratchR = c->d_scratchR.as<uint16_t>();
   A.scratchS = c->d_scratch.as<uint64_t>();
   A.candKey = c->d_seqOff.as<uint32_t>();
   A.candVal = A.candKey + (size_t)warpSlots * 2 * A.capC;
@@ -247,11 +255,12 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   A.dbgHits = dbgHits;
   A.dbgNHits = dbgNHits;
   A.geom = g;
+  A.lockstep = getenv("VG_SEED_LOCKSTEP") ? 1 : 0;  // measured: no gain over the atomic work counter
   const bool prof = getenv("VG_SEED_PROF") != nullptr;
   if (prof) {
-    VG_CUDA(c, c->d_rev.reserve(4096 * 3 * 4 + 256));
+    VG_CUDA(c, c->d_rev.reserve(4096 * 3 * 4 + 512));
     A.prof = (unsigned long long*)(c->d_rev.as<uint8_t>() + 4096 * 3 * 4 + 64);
-    VG_CUDA(c, cudaMemsetAsync(A.prof, 0, 64, c->stream));
+    VG_CUDA(c, cudaMemsetAsync(A.prof, 0, 128, c->stream));
   }
   if (nItems > 0) {
     seed_kernel<<<blocks, warps * 32, smem, c->stream>>>(A);
@@ -261,8 +270,9 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   VG_CUDA(c, cudaMemcpyAsync(flags, c->d_counter.p, 8, cudaMemcpyDeviceToHost, c->stream));
   VG_CUDA(c, cudaStreamSynchronize(c->stream));
   if (prof) {
-    unsigned long long ph[8];
-    cudaMemcpy(ph, A.prof, 64, cudaMemcpyDeviceToHost);
+    unsigned long long ph[16];
+    cudaMemcpy(ph, A.prof, 128, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[seed prof] B1=%.0f B2=%.0f\n", ph[8] / (double)nItems, ph[9] / (double)nItems);
     fprintf(stderr, "[seed prof] items=%lld cycles/item: A=%.0f B=%.0f C=%.0f D=%.0f E=%.0f F=%.0f Gsort=%.0f (prune+rest in total) total=%.0f\n", (long long)nItems,
             ph[0] / (double)nItems, ph[1] / (double)nItems, ph[2] / (double)nItems, ph[3] / (double)nItems, ph[4] / (double)nItems,
             ph[5] / (double)nItems, ph[6] / (double)nItems, ph[7] / (double)nItems);
