@@ -105,7 +105,7 @@ __device__ __forceinline__ int sd_code2(uint8_t b) {  // A,C,G,T -> 0..3, else -
 
 // id of the K-mer at p: 2-bit code when purely ACGT, else 4^K + rank among the reference's exotic
 // k-mers, or SD_NONE16 when the reference has no such k-mer.
-__device__ __forceinline__ uint32_t sd_kmer_id(const uint8_t* p, int K, const uint64_t* exoKeys, int nExo) {
+__device__ __noinline__ uint32_t sd_kmer_id(const uint8_t* p, int K, const uint64_t* exoKeys, int nExo) {
   uint32_t code = 0;
   uint64_t key = 0;
   bool pure = true;
@@ -138,7 +138,7 @@ __device__ __forceinline__ int sd_warp_incl_scan(int v, int lane) {
 
 // Stable LSD radix sort of n (key,val) pairs by 32-bit key, 8 bits per pass; buffers k[2][cap], v[2][cap].
 // Returns the index (0/1) of the buffer holding the result. `bins` = 256 ints of shared memory.
-__device__ int sd_radix_sort(uint32_t* kbuf, uint32_t* vbuf, int cap, int n, int* bins, int lane, uint32_t keyBits) {
+__device__ __noinline__ int sd_radix_sort(uint32_t* kbuf, uint32_t* vbuf, int cap, int n, int* bins, int lane, uint32_t keyBits) {
   int src = 0;
   for (int shift = 0; shift < (int)keyBits; shift += 8) {
     uint32_t* ks = kbuf + (size_t)src * cap;
@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
   // SM run the same phase at the same time (the kernel is instruction-cache bound otherwise); else a
   // global atomic work counter.
   const int totalWarps = gridDim.x * warpsPerBlock;
+#pragma unroll 1
   for (int64_t itBase = 0;; itBase += totalWarps) {
     int wi = 0;
     if (A.lockstep) {
@@ -315,7 +316,9 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
     if (nk >= 1 && L <= SD_MAXL) {
       const uint8_t* src = A.bases + off;
       __syncwarp();
+#pragma unroll 1
       for (int i = lane; i < L; i += 32) rd[i] = rev ? vg_complement(src[L - 1 - i]) : src[i];
+#pragma unroll 1
       for (int s = lane; s < SD_HS; s += 32) hkey[s] = SD_EMPTY;
       __syncwarp();
       int nS = 0;
@@ -335,8 +338,10 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
         bool direct = A.direct != 0;
       retry_hash:
         if (direct) {
+#pragma unroll 1
           for (int t = lane; t < 2 * SD_HS; t += 32) tab[t] = SD_NOPOS;
           __syncwarp();
+#pragma unroll 1
           for (int base = ((nk - 1) >> 5) << 5; base >= 0; base -= 32) {
             const int i = base + lane;
             uint32_t id = SD_NONE16;
@@ -354,8 +359,10 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
             __syncwarp();
           }
         } else {
+#pragma unroll 1
         for (int s2 = lane; s2 < SD_HS; s2 += 32) hkey[s2] = SD_EMPTY;
         __syncwarp();
+#pragma unroll 1
         for (int base = ((nk - 1) >> 5) << 5; base >= 0; base -= 32) {
           const int i = base + lane;
           uint32_t id = SD_NONE16;
@@ -397,11 +404,13 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
           // B2: one lane per raw hit: chain-start test, extension, ballot-compacted ordered writes. One pass.
           uint32_t* queue = (uint32_t*)win;  // g << 16 | i ; SD_WIN * 2 entries
           const int QCAP = SD_WIN * 2;
+#pragma unroll 1
           for (int gb = 0; gb <= G - K && !overflow;) {
             int nq = 0;
             bool qfull = false;
             long long tb1 = A.prof ? clock64() : 0;
             // B1: 128 genome positions per iteration, 4 consecutive positions per lane (4 independent lookups)
+#pragma unroll 1
             for (; gb <= G - K && !qfull; gb += 128) {
               const int g0 = gb + 4 * lane;
               uint32_t hv[4];
@@ -435,6 +444,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
 #pragma unroll
               for (int u = 0; u < 4; u++) {
                 uint32_t i = hv[u] & 0xFFFFu;
+#pragma unroll 1
                 for (int t = 0; t < cnt[u]; t++, i = nxt[i]) queue[o++] = ((uint32_t)(g0 + u) << 16) | i;
               }
               nq += total;
@@ -443,6 +453,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
             long long tb2 = A.prof ? clock64() : 0;
             if (A.prof && lane == 0) atomicAdd(A.prof + 8, (unsigned long long)(tb2 - tb1));
             // B2: two raw hits per lane per iteration (independent loads in flight)
+#pragma unroll 1
             for (int q0 = 0; q0 < nq; q0 += 64) {
               bool em[2] = {false, false};
               int gg[2] = {0, 0}, ii[2] = {0, 0}, ll[2] = {0, 0};
@@ -469,6 +480,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
                 if (start) {
                   em[u] = true;
                   int len = 0;
+#pragma unroll 1
                   while (i + K + len < L && g + K + len < G && rd[i + K + len] == ref[g + K + len]) len++;
                   ll[u] = len;
                 } else if (poscode[g] & 0x8000u) {
@@ -493,8 +505,10 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
         } else {
         uint32_t* queue = (uint32_t*)win;                 // g << 16 | chain head ; SD_WIN * 2 entries
         const int QCAP = SD_WIN * 2;
+#pragma unroll 1
         for (int gb = 0; gb <= G - K && !overflow;) {
           int nq = 0;
+#pragma unroll 1
           for (; gb <= G - K && nq + 32 <= QCAP; gb += 32) {
             const int g = gb + lane;
             const uint32_t code = (g <= G - K) ? poscode[g] : SD_NONE16;
@@ -517,6 +531,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
             nq += __popc(m);
           }
           __syncwarp();
+#pragma unroll 1
           for (int q0 = 0; q0 < nq; q0 += 32) {
             const int q = q0 + lane;
             int g = 0;
@@ -528,6 +543,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
               dup = (poscode[g] & 0x8000u) != 0;
             }
             int cnt = 0;
+#pragma unroll 1
             for (uint32_t i = head; i != SD_NOPOS; i = nxt[i]) {
               const bool start = (i == 0) || (g == 0) || (rd[i - 1] != ref[g - 1]);
               cnt += (start || dup) ? 1 : 0;
@@ -539,10 +555,12 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
               break;
             }
             int o = nS + incl - cnt;
+#pragma unroll 1
             for (uint32_t i = head; i != SD_NOPOS; i = nxt[i]) {
               const bool start = (i == 0) || (g == 0) || (rd[i - 1] != ref[g - 1]);
               if (start) {
                 int len = 0;
+#pragma unroll 1
                 while ((int)i + K + len < L && g + K + len < G && rd[i + K + len] == ref[g + K + len]) len++;
                 S[o++] = ((uint64_t)g << 32) | ((uint64_t)i << 16) | (uint64_t)len;
               } else if (dup) {
@@ -556,8 +574,10 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
         }
       } else {
         // ---- MSA: raw hits from the CSR index; chain starts by membership in the neighbour list --
+#pragma unroll 1
         for (int i = lane; i < nk; i += 32) ids[i] = (uint16_t)sd_kmer_id(rd + i, K, A.exoKeys, A.nExo);
         __syncwarp();
+#pragma unroll 1
         for (int base = 0; base < nk && !overflow; base += 32) {
           const int i = base + lane;
           int lo = 0, hi = 0, plo = 0, phi = 0;
@@ -570,9 +590,11 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
             }
           }
           int cnt = 0;
+#pragma unroll 1
           for (int q = lo; q < hi; q++) {
             const int c = A.msaCols[q];
             bool cont = false;  // does hit (i-1, c-1) exist?
+#pragma unroll 1
             for (int z = plo; z < phi; z++) cont |= (A.msaCols[z] == c - 1);
             cnt += cont ? 0 : 1;
           }
@@ -583,9 +605,11 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
             break;
           }
           int o = nS + incl - cnt;
+#pragma unroll 1
           for (int q = lo; q < hi; q++) {
             const int c = A.msaCols[q];
             bool cont = false;
+#pragma unroll 1
             for (int z = plo; z < phi; z++) cont |= (A.msaCols[z] == c - 1);
             if (cont) continue;
             int len = 0;
@@ -593,6 +617,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
               const int ii = i + len + 1;
               if (ii >= nk || ids[ii] == SD_NONE16) break;
               bool found = false;
+#pragma unroll 1
               for (int z = A.msaOff[ids[ii]], ze = A.msaOff[ids[ii] + 1]; z < ze; z++) found |= (A.msaCols[z] == c + len + 1);
               if (!found) break;
               len++;
@@ -608,6 +633,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
           const int srcb = sd_radix_sort(ckey, cval, capC, nS, bins, lane, 32);
           const uint32_t* ks = ckey + (size_t)srcb * capC;
           const uint32_t* vs = cval + (size_t)srcb * capC;
+#pragma unroll 1
           for (int e = lane; e < nS; e += 32)
             S[e] = ((uint64_t)(ks[e] >> 16) << 32) | ((uint64_t)(ks[e] & 0xFFFFu) << 16) | (uint64_t)vs[e];
         }
@@ -638,12 +664,15 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
         uint16_t* segCnt = segBuf + SD_WIN + 2;
         uint64_t* pend = pendL + lane * SD_LPEND;
         int tbase = 0, runMaxE = -1;
+#pragma unroll 1
         while (tbase < nS) {
           const int cnt = min(SD_WIN, nS - tbase);
+#pragma unroll 1
           for (int e = lane; e < cnt; e += 32) win[e] = S[tbase + e];
           __syncwarp();
           const int lo = lane * CH, hi = min(lo + CH, cnt);
           int locMax = -1;
+#pragma unroll 1
           for (int j = lo; j < hi; j++) {
             const uint64_t v = win[j];
             locMax = max(locMax, (int)(v >> 32) + (int)(v & 0xFFFFu) + K);
@@ -659,6 +688,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
           uint32_t fmask = 0;
           {
             int m = excl;
+#pragma unroll 1
             for (int j = lo; j < hi; j++) {
               const uint64_t v = win[j];
               const int g = (int)(v >> 32);
@@ -671,6 +701,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
           const int nSeg = __shfl_sync(VG_FULL, inclF, 31);
           {
             int o = inclF - nflag;
+#pragma unroll 1
             for (uint32_t fm = fmask; fm; fm &= fm - 1) segStart[o++] = (uint16_t)(lo + __ffs(fm) - 1);
           }
           if (lane == 0) segStart[nSeg] = (uint16_t)cnt;
@@ -684,6 +715,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
           const int tailStart = more ? (int)segStart[nSeg - 1] : cnt;
           {  // running maximum end over the entries that are consumed now (original ends)
             int m2 = -1;
+#pragma unroll 1
             for (int j = lo; j < hi && j < tailStart; j++) {
               const uint64_t v = win[j];
               m2 = max(m2, (int)(v >> 32) + (int)(v & 0xFFFFu) + K);
@@ -693,14 +725,17 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
             runMaxE = max(runMaxE, m2);
           }
           bool ovf = false;
+#pragma unroll 1
           for (int sg = lane; sg < nDo; sg += 32) {
             const int s0 = segStart[sg], s1 = segStart[sg + 1];
             int si = s0, w = s0, np = 0;
             uint64_t v = win[si++];
             int pg = (int)(v >> 32), pr = (int)((v >> 16) & 0xFFFFu), pl = (int)(v & 0xFFFFu);
+#pragma unroll 1
             while (si < s1 || np > 0) {
               if (np > 0 && (si >= s1 || (pend[0] >> 16) < (win[si] >> 16))) {  // TreeSet.pollFirst
                 v = pend[0];
+#pragma unroll 1
                 for (int t = 1; t < np; t++) pend[t - 1] = pend[t];
                 np--;
               } else {
@@ -721,12 +756,14 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
                     const uint64_t key = ((uint64_t)cg << 16) | (uint64_t)cr;
                     bool present = false;
                     int ins = np;
+#pragma unroll 1
                     for (int t = 0; t < np; t++) {
                       const uint64_t pk = pend[t] >> 16;
                       if (pk == key) present = true;
                       if (pk > key && ins == np) ins = t;
                     }
                     if (!present)
+#pragma unroll 1
                       for (int j = si; j < s1; j++) {  // the key lies before the next synchronisation point
                         const uint64_t k = win[j] >> 16;
                         if (k >= key) {
@@ -740,6 +777,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
                         np = 0;
                         si = s1;
                       } else {
+#pragma unroll 1
                         for (int t = np; t > ins; t--) pend[t] = pend[t - 1];
                         pend[ins] = (key << 16) | (uint64_t)cl;
                         np++;
@@ -760,6 +798,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
             serialFrom = tbase;
             break;
           }
+#pragma unroll 1
           for (int sg0 = 0; sg0 < nDo; sg0 += 32) {  // ordered compaction into the LongHit arrays
             const int sg = sg0 + lane;
             const int c = (sg < nDo) ? (int)segCnt[sg] : 0;
@@ -767,6 +806,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
             int o = nR + ic - c;
             if (sg < nDo) {
               const int s0 = segStart[sg];
+#pragma unroll 1
               for (int t = 0; t < c; t++, o++) {
                 const uint64_t v = win[s0 + t];
                 if (o < capR) hitG[o] = (uint16_t)(v >> 32), hitR[o] = (uint16_t)((v >> 16) & 0xFFFFu), hitL[o] = (uint16_t)(v & 0xFFFFu);
@@ -784,6 +824,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
         const uint64_t* S = Sall + serialFrom;
         const int nS = nSall - serialFrom;
         int wbase = 0;
+#pragma unroll 1
         for (int e = lane; e < SD_WIN && e < nS; e += 32) win[e] = S[e];
         __syncwarp();
         // lane-0 state of the sweep
@@ -799,6 +840,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
                 break;
               }
             };
+#pragma unroll 1
             while (!done) {
               if (si >= wbase + SD_WIN / 2 && wbase + SD_WIN < nS) break;  // slide the window first
               if (si >= nS && np == 0) {
@@ -810,6 +852,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
               uint64_t v;
               if (np > 0 && (si >= nS || (pending[0] >> 16) < (win[si - wbase] >> 16))) {
                 v = pending[0];
+#pragma unroll 1
                 for (int t = 1; t < np; t++) pending[t - 1] = pending[t];
                 np--;
               } else {
@@ -837,6 +880,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
                     const uint64_t key = ((uint64_t)cg << 16) | (uint64_t)cr;
                     bool present = false;
                     int ins = np;
+#pragma unroll 1
                     for (int t = 0; t < np; t++) {
                       const uint64_t pk = pending[t] >> 16;
                       if (pk == key) present = true;
@@ -845,6 +889,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
                     if (!present) {
                       bool resolved = false;
                       const int wend = min(nS, wbase + SD_WIN);
+#pragma unroll 1
                       for (int j = si; j < wend; j++) {
                         const uint64_t k = win[j - wbase] >> 16;
                         if (k >= key) {
@@ -855,6 +900,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
                       }
                       if (!resolved && wend < nS) {  // beyond the window (dense repeats): search the global stream
                         int lo = wend, hi = nS;
+#pragma unroll 1
                         while (lo < hi) {
                           int mid = (lo + hi) >> 1;
                           if ((S[mid] >> 16) < key) lo = mid + 1;
@@ -867,6 +913,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
                       if (np >= SD_PENDING) {
                         err |= 4;
                       } else {
+#pragma unroll 1
                         for (int t = np; t > ins; t--) pending[t] = pending[t - 1];
                         pending[ins] = (key << 16) | (uint64_t)cl;
                         np++;
@@ -883,9 +930,11 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
           done = __shfl_sync(VG_FULL, (int)done, 0) != 0;
           if (done) break;
           // slide by half a window
+#pragma unroll 1
           for (int e = lane; e < SD_WIN / 2; e += 32) win[e] = win[e + SD_WIN / 2];
           __syncwarp();
           wbase += SD_WIN / 2;
+#pragma unroll 1
           for (int e = lane; e < SD_WIN / 2; e += 32) {
             const int idx = wbase + SD_WIN / 2 + e;
             if (idx < nS) win[SD_WIN / 2 + e] = S[idx];
@@ -904,6 +953,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
           uint32_t* tl = cval;
           int nOut = 0;
           bool bad = false;
+#pragma unroll 1
           for (int j0 = 0; j0 < nR; j0 += 32) {
             const int j = j0 + lane;
             int pg[3], pr[3], pl[3], np2 = 0;
@@ -911,6 +961,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
               int g = hitG[j], r = hitR[j], len = hitL[j];
               for (;;) {
                 int lo2 = 0, hi2 = A.nContigs - 1;
+#pragma unroll 1
                 while (lo2 < hi2) {
                   const int mid = (lo2 + hi2) >> 1;
                   if (A.contigEnds[mid] > g) hi2 = mid;
@@ -938,6 +989,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
             }
             const int ic = sd_warp_incl_scan(np2, lane);
             int o = nOut + ic - np2;
+#pragma unroll 1
             for (int t = 0; t < np2; t++, o++)
               if (o < capC) tg[o] = (uint32_t)pg[t] | ((uint32_t)pr[t] << 16), tl[o] = (uint32_t)pl[t];
             nOut += __shfl_sync(VG_FULL, ic, 31);
@@ -946,6 +998,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
           if (__any_sync(VG_FULL, bad) || nOut > capR) {
             err |= 2;
           } else {
+#pragma unroll 1
             for (int j = lane; j < nOut; j += 32) hitG[j] = (uint16_t)(tg[j] & 0xFFFFu), hitR[j] = (uint16_t)(tg[j] >> 16), hitL[j] = (uint16_t)tl[j];
             nR = nOut;
           }
@@ -959,6 +1012,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
       }
       __syncwarp();
       if (A.dbgHits && wi == 0) {
+#pragma unroll 1
         for (int j = lane; j < nR; j += 32) {
           A.dbgHits[3 * j] = hitG[j];
           A.dbgHits[3 * j + 1] = hitR[j];
@@ -970,6 +1024,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
       if (nR > 0) {
         // ---- E: isAdjacent + prefix sums P[j] = sum_{t<=j}(len_t + isAdjacent[t-1]) (mod 2^16) ------
         int carry = 0;
+#pragma unroll 1
         for (int j0 = 0; j0 < nR; j0 += 32) {
           const int j = j0 + lane;
           int val = 0;
@@ -986,8 +1041,10 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
         }
         // bucket[b] = first hit index with g >= 32 b
         const int nb = A.geom.nBuckets;
+#pragma unroll 1
         for (int b = lane; b < nb; b += 32) bucket[b] = (uint16_t)nR;
         __syncwarp();
+#pragma unroll 1
         for (int j = lane; j < nR; j += 32) {
           const int b = hitG[j] >> 5;
           if (j == 0 || (hitG[j - 1] >> 5) != b) bucket[b] = (uint16_t)j;
@@ -995,6 +1052,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
         __syncwarp();
         {  // suffix fill of empty buckets (serial over chunks from the top, parallel inside a chunk)
           int nextv = nR;
+#pragma unroll 1
           for (int b0 = ((nb - 1) >> 5) << 5; b0 >= 0; b0 -= 32) {
             const int b = b0 + lane;
             int v = (b < nb) ? bucket[b] : nR;
@@ -1015,6 +1073,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
         // ---- F: every window independently; candidates (count > cutoff) compacted in hit order ------
         const int cutoff = (L < A.nCutoffs) ? A.cutoffs[L] : 0x7fffffff;
         int nC = 0;
+#pragma unroll 1
         for (int j0 = 0; j0 < nR; j0 += 32) {
           const int j = j0 + lane;
           bool isCand = false;
@@ -1024,6 +1083,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
             int cs = 0, ce = G;
             if (A.nContigs > 1) {
               int lo = 0, hi = A.nContigs - 1;
+#pragma unroll 1
               while (lo < hi) {
                 int mid = (lo + hi) >> 1;
                 if (A.contigEnds[mid] > g) hi = mid;
@@ -1035,8 +1095,10 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
             const int start = max(cs, g - r * 3 / 2);
             const int end = min(g + len + K + (L - r - len - K) * 3 / 2, ce);
             int a = bucket[start >> 5];
+#pragma unroll 1
             while (hitG[a] < start) a++;
             int u = bucket[min(end, G) >> 5];
+#pragma unroll 1
             while (u < nR && hitG[u] < end) u++;
             int b = u - 1;
             if ((int)hitG[b] + K + (int)hitL[b] > end) b--;
@@ -1068,6 +1130,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
               if (nWin < A.maxWin) W[3 * nWin] = s, W[3 * nWin + 1] = e, W[3 * nWin + 2] = c;
               nWin++;
             };
+#pragma unroll 1
             for (int t = 1; t < nC; t++) {
               const int cs_ = ks[t] >> 16, ce_ = 0xFFFF - (ks[t] & 0xFFFF), cc = vs[t];
               if (pe > cs_) {

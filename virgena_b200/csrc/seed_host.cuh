@@ -215,7 +215,7 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   const int smemMax = 220 * 1024;
   // 8 warps/SM measured best: the kernel is front-end (instruction fetch / branch) bound, more warps only
   // add instruction-cache pressure (profiles/seed_r1.md)
-  int warps = std::min(8, (smemMax - g.refBytes) / g.warpBytes);
+  int warps = std::min(16, (smemMax - g.refBytes) / g.warpBytes);
   if (const char* e = getenv("VG_SEED_WARPS")) warps = std::max(1, std::min(warps, atoi(e)));
   if (warps < 1) return vg_fail(c, VG_ERR_INVALID, "reference too large for the seeding kernel's shared memory");
   const size_t smem = (size_t)g.refBytes + (size_t)warps * g.warpBytes;
