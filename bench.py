@@ -332,6 +332,17 @@ def main():
         # + window records out (4 orientations x (nWindows x 12 B + 4 B)) ~ 0.5 KB + 0.8 KB.
         alg_bytes_pair = 2 * L + 4 * (16 * 12 + 4)
         seed_gbs = alg_bytes_pair * n / (seed_ms * 1e-3) / 1e9
+        # pileup: algorithmic bytes = aligned columns read once (1 B each) + 16 B per mapped read + G*5*4 B out
+        n_res, seq1_bytes = ctx.result_sizes()
+        pile_bytes = seq1_bytes + 16 * int(stats[3]) + G * 5 * 4
+        pile = {"bound": "hbm", "achieved": pile_bytes / (pu_ms * 1e-3) / 1e9 if pu_ms else None, "peak": hbm_peak,
+                "unit": "GB/s", "frac": pile_bytes / (pu_ms * 1e-3) / 1e9 / hbm_peak if pu_ms else None,
+                "note": "all pileup kernels (list, bin, count, reduce); 5 ms per 10^6 pairs"}
+        # measured DRAM traffic of the dominant kernel from the committed ncu capture (bytes per pair)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_r1.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("seed_kernel_dram_bytes_per_pair")
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -346,7 +357,8 @@ def main():
             "stage_ms_per_step": {"seed_pairselect": seed_ms, "sw_fill": fill_ms, "sw_traceback": tb_ms, "pileup": pu_ms,
                                   "map_total": tot_ms},
             "roofline": {"bound": "hbm", "kernel": "seed_kernel", "achieved": seed_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": seed_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": seed_gbs / hbm_peak, "traffic": (traffic * n if traffic else None), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes_pair * n,
                          "note": "seeding is shared-memory / issue bound by construction (SURVEY 8d): "
                                  "k-mer lookups/s = %.3e" % (4 * (L - 5 + 1) * n / (seed_ms * 1e-3))},
             "sw_roofline": {"bound": "dpx", "gcups_fill": cells / (fill_ms * 1e-3) / 1e9 if fill_ms else None,

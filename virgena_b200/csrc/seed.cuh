@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
   uint16_t* bucket = (uint16_t*)(aux + SD_PENDING * 8 + 1024);         // nBuckets x 2
   uint64_t* pendL = (uint64_t*)(aux + SD_PENDING * 8 + 1024 + ((A.geom.nBuckets * 2 + 15) & ~15));  // 32 x SD_LPEND x 8
   uint16_t* segBuf = (uint16_t*)(pendL + 32 * SD_LPEND);               // 2 x (SD_WIN + 2) x 2
+  int* segNext = (int*)(segBuf + 2 * (SD_WIN + 2) + 2);                // work counter of the segment sweep
   uint64_t* win = (uint64_t*)(wbase + A.geom.regA);                    // SD_WIN x 8
   uint8_t* rd = (uint8_t*)(win + SD_WIN);
   uint16_t* ids = (uint16_t*)win;                                      // MSA only (win is unused until phase C)
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
       wi = __shfl_sync(VG_FULL, wi, 0);
       if (wi >= A.nItems) break;
     }
+    hitG = A.scratchR + (size_t)warpSlot * 4 * capR;  // (phase E may have redirected it to shared memory)
     // ---- which read, which orientation ---------------------------------------------------------
     int64_t off;
     int L, rev;
@@ -667,7 +669,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
 #pragma unroll 1
         while (tbase < nS) {
           const int cnt = min(SD_WIN, nS - tbase);
-#pragma unroll 1
+#pragma unroll 8
           for (int e = lane; e < cnt; e += 32) win[e] = S[tbase + e];
           __syncwarp();
           const int lo = lane * CH, hi = min(lo + CH, cnt);
@@ -725,14 +727,29 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
             runMaxE = max(runMaxE, m2);
           }
           bool ovf = false;
+          if (lane == 0) *segNext = 32;
+          __syncwarp();
 #pragma unroll 1
-          for (int sg = lane; sg < nDo; sg += 32) {
+          for (int sg = lane; sg < nDo; sg = atomicAdd(segNext, 1)) {  // lanes grab segments as they finish
             const int s0 = segStart[sg], s1 = segStart[sg + 1];
             int si = s0, w = s0, np = 0;
             uint64_t v = win[si++];
             int pg = (int)(v >> 32), pr = (int)((v >> 16) & 0xFFFFu), pl = (int)(v & 0xFFFFu);
 #pragma unroll 1
             while (si < s1 || np > 0) {
+              if (np == 0) {
+                // fast path: stream elements that overlap prev, are not longer, and whose clipped remainder is
+                // shorter than K are dropped without any other effect (the common case)
+                const int ePrev = pg + pl + K;
+#pragma unroll 1
+                while (si < s1) {
+                  const uint64_t t = win[si];
+                  const int tg = (int)(t >> 32), tl = (int)(t & 0xFFFFu);
+                  if (tg < ePrev && tl <= pl && tg + tl < ePrev) si++;
+                  else break;
+                }
+                if (si >= s1) break;
+              }
               if (np > 0 && (si >= s1 || (pend[0] >> 16) < (win[si] >> 16))) {  // TreeSet.pollFirst
                 v = pend[0];
 #pragma unroll 1
@@ -1023,8 +1040,21 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
       SD_PH(3)
       if (nR > 0) {
         // ---- E: isAdjacent + prefix sums P[j] = sum_{t<=j}(len_t + isAdjacent[t-1]) (mod 2^16) ------
+        // genomePos of the LongHits is searched at random by E/F: keep a shared-memory copy when it fits
+        // (it overlays the phase-C buffers pendL/segBuf, which are dead now)
+        const uint16_t* hitGg = hitG;
+        {
+          uint16_t* cp = (uint16_t*)pendL;
+          const int room = (int)((wbase + A.geom.regA - (uint8_t*)cp) / 2);
+          if (nR <= room) {
+#pragma unroll 4
+            for (int j = lane; j < nR; j += 32) cp[j] = hitGg[j];
+            __syncwarp();
+            hitG = cp;
+          }
+        }
         int carry = 0;
-#pragma unroll 1
+#pragma unroll 2
         for (int j0 = 0; j0 < nR; j0 += 32) {
           const int j = j0 + lane;
           int val = 0;
@@ -1073,7 +1103,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
         // ---- F: every window independently; candidates (count > cutoff) compacted in hit order ------
         const int cutoff = (L < A.nCutoffs) ? A.cutoffs[L] : 0x7fffffff;
         int nC = 0;
-#pragma unroll 1
+#pragma unroll 2
         for (int j0 = 0; j0 < nR; j0 += 32) {
           const int j = j0 + lane;
           bool isCand = false;

@@ -183,7 +183,7 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   g.capR = std::max(256, std::min(16384, range / K + nContigs + 16));
   g.nBuckets = (range >> 5) + 2;
   const int regAB = 2 * SD_HS * 4 + SD_MAXL * 2;  // table/hash + nxt
-  const int regCG = SD_PENDING * 8 + 1024 + ((g.nBuckets * 2 + 15) & ~15) + 32 * SD_LPEND * 8 + (2 * (SD_WIN + 2) + 4) * 2;
+  const int regCG = SD_PENDING * 8 + 1024 + ((g.nBuckets * 2 + 15) & ~15) + 32 * SD_LPEND * 8 + (2 * (SD_WIN + 2) + 4) * 2 + 16;
   g.regA = (std::max(regAB, regCG) + 15) & ~15;
   g.warpBytes = (g.regA + SD_WIN * 8 + SD_MAXL + 16 + 15) & ~15;
   g.refBytes = 0;

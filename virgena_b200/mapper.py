@@ -229,6 +229,12 @@ class Context:
         rec, pool = self.get_results()
         return MappedData(np.arange(self.n_pairs, dtype=np.int64), rec, pool, st.as_array(), msa=True)
 
+    def result_sizes(self):
+        n = C.c_int64()
+        nb = C.c_int64()
+        self._chk(self.L.vg_result_sizes(self.h, C.byref(n), C.byref(nb)))
+        return n.value, nb.value
+
     def get_results(self):
         n = C.c_int64()
         nb = C.c_int64()
