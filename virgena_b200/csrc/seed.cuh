@@ -40,6 +40,8 @@
 #define SD_PENDING 32           // capacity of the re-insertion queue of phase C
 #define SD_WIN 512              // entries of the shared-memory window over the sorted LongHit stream
 #define SD_LPEND 6              // per-lane re-insertion queue of the segment-parallel sweep
+// padded window index (one spare slot per 16 entries: no bank conflicts when every lane walks its own 16-entry chunk)
+__device__ __forceinline__ int SD_WI(int e) { return e + (e >> 4); }
 
 struct SeedGeom {       // sizes of the per-warp shared-memory regions (bytes), computed on the host
   int regA;             // bytes of the phase-aliased region
@@ -78,6 +80,7 @@ struct SeedArgs {
   const int32_t* len2;
   const int64_t* pairIdx;      // optional indirection (remap subset)
   int64_t nItems;              // 4 x pairs (pair mode) or number of single reads
+  const int32_t* itemList;     // optional: nItems indices of the items to do (fallback of the fast path)
   int singleReads;             // 1: items are single forward reads (vg_seed_batch)
   // scratch + outputs
   uint64_t* scratchS;          // [warpSlots][capS]
@@ -125,6 +128,27 @@ __device__ __noinline__ uint32_t sd_kmer_id(const uint8_t* p, int K, const uint6
   }
   if (lo < nExo && exoKeys[lo] == key) return (1u << (2 * K)) + (uint32_t)lo;
   return SD_NONE16;
+}
+
+// 4 bytes starting at base + pos (base 4-byte aligned; may read up to 7 bytes past pos)
+__device__ __forceinline__ uint32_t sd_load4(const uint8_t* base, int pos) {
+  const uint32_t* p = (const uint32_t*)(base + (pos & ~3));
+  return __funnelshift_r(p[0], p[1], (pos & 3) * 8);
+}
+// number of further matching bases of the chain that starts with the K-mer hit (i, g): 4 bytes per trip
+__device__ __forceinline__ int sd_extend(const uint8_t* rd, const uint8_t* ref, int i, int g, int K, int L, int G) {
+  const int maxLen = min(L - i - K, G - g - K);
+  int len = 0;
+#pragma unroll 1
+  while (len < maxLen) {
+    const uint32_t x = sd_load4(rd, i + K + len) ^ sd_load4(ref, g + K + len);
+    if (x) {
+      len += (__ffs(x) - 1) >> 3;
+      break;
+    }
+    len += 4;
+  }
+  return min(len, maxLen);
 }
 
 __device__ __forceinline__ int sd_warp_incl_scan(int v, int lane) {
@@ -267,10 +291,8 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
   int* bins = (int*)(aux + SD_PENDING * 8);                            // 256 x 4
   uint16_t* bucket = (uint16_t*)(aux + SD_PENDING * 8 + 1024);         // nBuckets x 2
   uint64_t* pendL = (uint64_t*)(aux + SD_PENDING * 8 + 1024 + ((A.geom.nBuckets * 2 + 15) & ~15));  // 32 x SD_LPEND x 8
-  uint16_t* segBuf = (uint16_t*)(pendL + 32 * SD_LPEND);               // 2 x (SD_WIN + 2) x 2
-  int* segNext = (int*)(segBuf + 2 * (SD_WIN + 2) + 2);                // work counter of the segment sweep
-  uint64_t* win = (uint64_t*)(wbase + A.geom.regA);                    // SD_WIN x 8
-  uint8_t* rd = (uint8_t*)(win + SD_WIN);
+  uint64_t* win = (uint64_t*)(wbase + A.geom.regA);                    // (SD_WIN + 32) x 8 (padded, SD_WI)
+  uint8_t* rd = (uint8_t*)(win + SD_WIN + 32);
   uint16_t* ids = (uint16_t*)win;                                      // MSA only (win is unused until phase C)
 
   uint64_t* S = A.scratchS + (size_t)warpSlot * A.capS;
@@ -295,6 +317,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
       wi = __shfl_sync(VG_FULL, wi, 0);
       if (wi >= A.nItems) break;
     }
+    if (A.itemList) wi = A.itemList[wi];
     hitG = A.scratchR + (size_t)warpSlot * 4 * capR;  // (phase E may have redirected it to shared memory)
     // ---- which read, which orientation ---------------------------------------------------------
     int64_t off;
@@ -426,7 +449,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
               }
 #pragma unroll
               for (int u = 0; u < 4; u++) {
-                cnt[u] = (hv[u] == SD_NOPOS) ? 0 : (int)(hv[u] >> 16);
+                cnt[u] = (int)(hv[u] >> 16);  // SD_NOPOS carries count 0
                 tot += cnt[u];
               }
               if (!__any_sync(VG_FULL, tot > 0)) continue;
@@ -444,10 +467,22 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
               }
               int o = nq + incl - tot;
 #pragma unroll
-              for (int u = 0; u < 4; u++) {
-                uint32_t i = hv[u] & 0xFFFFu;
+              for (int u = 0; u < 4; u++) {  // chains of 1 or 2 read positions are the rule: straight-line code
+                if (cnt[u]) {
+                  uint32_t i = hv[u] & 0xFFFFu;
+                  const uint32_t gk = (uint32_t)(g0 + u) << 16;
+                  queue[o] = gk | i;
+                  if (cnt[u] > 1) {
+                    i = nxt[i];
+                    queue[o + 1] = gk | i;
 #pragma unroll 1
-                for (int t = 0; t < cnt[u]; t++, i = nxt[i]) queue[o++] = ((uint32_t)(g0 + u) << 16) | i;
+                    for (int t = 2; t < cnt[u]; t++) {
+                      i = nxt[i];
+                      queue[o + t] = gk | i;
+                    }
+                  }
+                  o += cnt[u];
+                }
               }
               nq += total;
             }
@@ -481,10 +516,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
                 const bool start = (i == 0) || (g == 0) || (ca[u] != cb[u]);
                 if (start) {
                   em[u] = true;
-                  int len = 0;
-#pragma unroll 1
-                  while (i + K + len < L && g + K + len < G && rd[i + K + len] == ref[g + K + len]) len++;
-                  ll[u] = len;
+                  ll[u] = sd_extend(rd, ref, i, g, K, L, G);
                 } else if (poscode[g] & 0x8000u) {
                   em[u] = true;  // Q1: a chain passing through a twice-indexed position adds a zero-length hit
                 }
@@ -561,9 +593,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
             for (uint32_t i = head; i != SD_NOPOS; i = nxt[i]) {
               const bool start = (i == 0) || (g == 0) || (rd[i - 1] != ref[g - 1]);
               if (start) {
-                int len = 0;
-#pragma unroll 1
-                while ((int)i + K + len < L && g + K + len < G && rd[i + K + len] == ref[g + K + len]) len++;
+                const int len = sd_extend(rd, ref, (int)i, g, K, L, G);
                 S[o++] = ((uint64_t)g << 32) | ((uint64_t)i << 16) | (uint64_t)len;
               } else if (dup) {
                 S[o++] = ((uint64_t)g << 32) | ((uint64_t)i << 16);
@@ -661,22 +691,19 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
       int err = 0;
       if (nS > 0) {
         constexpr int CH = SD_WIN / 32;  // entries per lane when flagging
-        uint16_t* segStart = (uint16_t*)bucket;          // nBuckets >= SD_WIN/2 + 2 is not guaranteed -> own region
-        segStart = segBuf;
-        uint16_t* segCnt = segBuf + SD_WIN + 2;
         uint64_t* pend = pendL + lane * SD_LPEND;
         int tbase = 0, runMaxE = -1;
 #pragma unroll 1
         while (tbase < nS) {
           const int cnt = min(SD_WIN, nS - tbase);
 #pragma unroll 8
-          for (int e = lane; e < cnt; e += 32) win[e] = S[tbase + e];
+          for (int e = lane; e < cnt; e += 32) win[SD_WI(e)] = S[tbase + e];
           __syncwarp();
           const int lo = lane * CH, hi = min(lo + CH, cnt);
           int locMax = -1;
 #pragma unroll 1
           for (int j = lo; j < hi; j++) {
-            const uint64_t v = win[j];
+            const uint64_t v = win[SD_WI(j)];
             locMax = max(locMax, (int)(v >> 32) + (int)(v & 0xFFFFu) + K);
           }
           int incl = locMax;
@@ -692,77 +719,76 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
             int m = excl;
 #pragma unroll 1
             for (int j = lo; j < hi; j++) {
-              const uint64_t v = win[j];
+              const uint64_t v = win[SD_WI(j)];
               const int g = (int)(v >> 32);
               if (g > m) fmask |= 1u << (j - lo);
               m = max(m, g + (int)(v & 0xFFFFu) + K);
             }
           }
-          const int nflag = __popc(fmask);
-          const int inclF = sd_warp_incl_scan(nflag, lane);
-          const int nSeg = __shfl_sync(VG_FULL, inclF, 31);
-          {
-            int o = inclF - nflag;
-#pragma unroll 1
-            for (uint32_t fm = fmask; fm; fm &= fm - 1) segStart[o++] = (uint16_t)(lo + __ffs(fm) - 1);
-          }
-          if (lane == 0) segStart[nSeg] = (uint16_t)cnt;
-          __syncwarp();
+          // Lane ranges: lane l sweeps all segments that START in its chunk, i.e. the entries from its first
+          // flag up to the first flag of the next flagged lane. The last segment of a window that is not the
+          // last one may continue in the next window and is carried over (tailStart).
+          const int nSeg = __reduce_add_sync(VG_FULL, __popc(fmask));
+          const int firstFlag = fmask ? lo + __ffs(fmask) - 1 : 0x7fff;
+          const int lastFlag = fmask ? lo + 31 - __clz(fmask) : -1;
           const bool more = tbase + cnt < nS;
           const int nDo = more ? nSeg - 1 : nSeg;
           if (nDo <= 0) {  // a single segment longer than the window
             serialFrom = tbase;
             break;
           }
-          const int tailStart = more ? (int)segStart[nSeg - 1] : cnt;
+          const int tailStart = more ? __reduce_max_sync(VG_FULL, lastFlag) : cnt;
+          int nextFirst = 0x7fff;  // first flag of the lanes above
+          {
+            int v = firstFlag;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const int o = __shfl_down_sync(VG_FULL, v, d);
+              if (lane + d < 32) v = min(v, o);
+            }
+            nextFirst = __shfl_down_sync(VG_FULL, v, 1);
+            if (lane == 31) nextFirst = 0x7fff;
+          }
           {  // running maximum end over the entries that are consumed now (original ends)
             int m2 = -1;
 #pragma unroll 1
             for (int j = lo; j < hi && j < tailStart; j++) {
-              const uint64_t v = win[j];
+              const uint64_t v = win[SD_WI(j)];
               m2 = max(m2, (int)(v >> 32) + (int)(v & 0xFFFFu) + K);
             }
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) m2 = max(m2, __shfl_xor_sync(VG_FULL, m2, d));
-            runMaxE = max(runMaxE, m2);
+            runMaxE = max(runMaxE, __reduce_max_sync(VG_FULL, m2));
           }
-          bool ovf = false;
-          if (lane == 0) *segNext = 32;
+          const int s0 = min(firstFlag, tailStart), s1 = min(nextFirst, tailStart);  // s0 == s1: nothing to do
           __syncwarp();
+          // All lanes step through their ranges in lock-step (one polled element per trip), so the warp stays
+          // converged: the sweep of KMerCounterBase.java:422-449 verbatim, started afresh at a synchronisation
+          // point. Results are written in place (w never overtakes si).
+          bool ovf = false;
+          int si = s0, w = s0, np = 0;
+          bool have = false;
+          int pg = 0, pr = 0, pl = 0;
 #pragma unroll 1
-          for (int sg = lane; sg < nDo; sg = atomicAdd(segNext, 1)) {  // lanes grab segments as they finish
-            const int s0 = segStart[sg], s1 = segStart[sg + 1];
-            int si = s0, w = s0, np = 0;
-            uint64_t v = win[si++];
-            int pg = (int)(v >> 32), pr = (int)((v >> 16) & 0xFFFFu), pl = (int)(v & 0xFFFFu);
-#pragma unroll 1
-            while (si < s1 || np > 0) {
-              if (np == 0) {
-                // fast path: stream elements that overlap prev, are not longer, and whose clipped remainder is
-                // shorter than K are dropped without any other effect (the common case)
-                const int ePrev = pg + pl + K;
-#pragma unroll 1
-                while (si < s1) {
-                  const uint64_t t = win[si];
-                  const int tg = (int)(t >> 32), tl = (int)(t & 0xFFFFu);
-                  if (tg < ePrev && tl <= pl && tg + tl < ePrev) si++;
-                  else break;
-                }
-                if (si >= s1) break;
-              }
-              if (np > 0 && (si >= s1 || (pend[0] >> 16) < (win[si] >> 16))) {  // TreeSet.pollFirst
+          for (;;) {
+            const bool act = si < s1 || np > 0;
+            if (!__any_sync(VG_FULL, act)) break;
+            if (act) {
+              uint64_t v;
+              if (np > 0 && (si >= s1 || (pend[0] >> 16) < (win[SD_WI(si)] >> 16))) {  // TreeSet.pollFirst
                 v = pend[0];
 #pragma unroll 1
                 for (int t = 1; t < np; t++) pend[t - 1] = pend[t];
                 np--;
               } else {
-                v = win[si++];
+                v = win[SD_WI(si++)];
               }
               int cg = (int)(v >> 32), cr = (int)((v >> 16) & 0xFFFFu), cl = (int)(v & 0xFFFFu);
-              if (pg + pl + K - 1 >= cg) {
+              if (!have) {
+                have = true;
+                pg = cg, pr = cr, pl = cl;
+              } else if (pg + pl + K - 1 >= cg) {
                 if (pl < cl) {
                   pl = cg - pg - K;
-                  if (pl >= 0) win[w++] = ((uint64_t)pg << 32) | ((uint64_t)pr << 16) | (uint64_t)pl;
+                  if (pl >= 0) win[SD_WI(w++)] = ((uint64_t)pg << 32) | ((uint64_t)pr << 16) | (uint64_t)pl;
                   pg = cg, pr = cr, pl = cl;
                 } else {
                   const int lenDiff = pg + pl + K - cg;
@@ -782,7 +808,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
                     if (!present)
 #pragma unroll 1
                       for (int j = si; j < s1; j++) {  // the key lies before the next synchronisation point
-                        const uint64_t k = win[j] >> 16;
+                        const uint64_t k = win[SD_WI(j)] >> 16;
                         if (k >= key) {
                           present = (k == key);
                           break;
@@ -803,33 +829,29 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
                   }
                 }
               } else {
-                win[w++] = ((uint64_t)pg << 32) | ((uint64_t)pr << 16) | (uint64_t)pl;
+                win[SD_WI(w++)] = ((uint64_t)pg << 32) | ((uint64_t)pr << 16) | (uint64_t)pl;
                 pg = cg, pr = cr, pl = cl;
               }
             }
-            win[w++] = ((uint64_t)pg << 32) | ((uint64_t)pr << 16) | (uint64_t)pl;
-            segCnt[sg] = (uint16_t)(w - s0);
+            __syncwarp();
           }
+          if (have) win[SD_WI(w++)] = ((uint64_t)pg << 32) | ((uint64_t)pr << 16) | (uint64_t)pl;
+#pragma unroll 1
+          for (int t = w; t < s1; t++) win[SD_WI(t)] = ~0ull;  // consumed, not emitted
           __syncwarp();
           if (__any_sync(VG_FULL, ovf)) {
             serialFrom = tbase;
             break;
           }
 #pragma unroll 1
-          for (int sg0 = 0; sg0 < nDo; sg0 += 32) {  // ordered compaction into the LongHit arrays
-            const int sg = sg0 + lane;
-            const int c = (sg < nDo) ? (int)segCnt[sg] : 0;
-            const int ic = sd_warp_incl_scan(c, lane);
-            int o = nR + ic - c;
-            if (sg < nDo) {
-              const int s0 = segStart[sg];
-#pragma unroll 1
-              for (int t = 0; t < c; t++, o++) {
-                const uint64_t v = win[s0 + t];
-                if (o < capR) hitG[o] = (uint16_t)(v >> 32), hitR[o] = (uint16_t)((v >> 16) & 0xFFFFu), hitL[o] = (uint16_t)(v & 0xFFFFu);
-              }
-            }
-            nR += __shfl_sync(VG_FULL, ic, 31);
+          for (int e0 = 0; e0 < tailStart; e0 += 32) {  // ordered compaction into the LongHit arrays
+            const int e = e0 + lane;
+            const uint64_t v = (e < tailStart) ? win[SD_WI(e)] : ~0ull;
+            const bool ok = v != ~0ull;
+            const unsigned m = __ballot_sync(VG_FULL, ok);
+            const int o = nR + __popc(m & ((1u << lane) - 1u));
+            if (ok && o < capR) hitG[o] = (uint16_t)(v >> 32), hitR[o] = (uint16_t)((v >> 16) & 0xFFFFu), hitL[o] = (uint16_t)(v & 0xFFFFu);
+            nR += __popc(m);
           }
           __syncwarp();
           tbase += tailStart;
@@ -1151,28 +1173,39 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
           const int srcb = sd_radix_sort(ckey, cval, capC, nC, bins, lane, 32);
           SD_PH(6)
           __threadfence_block();
-          if (lane == 0) {
+          {
+            // pruneWindows (KMerCounterBase.java:317-335). The pivot only changes at the first later candidate
+            // that either does not overlap it (emit, new pivot) or overlaps with a larger count (new pivot);
+            // everything in between is dropped. The warp looks at 32 candidates at a time.
             const uint32_t* ks = ckey + (size_t)srcb * capC;
             const uint32_t* vs = cval + (size_t)srcb * capC;
             int32_t* W = A.windows + (size_t)wi * A.maxWin * 3;
             int ps = ks[0] >> 16, pe = 0xFFFF - (ks[0] & 0xFFFF), pc = vs[0];
-            auto put = [&](int s, int e, int c) {
-              if (nWin < A.maxWin) W[3 * nWin] = s, W[3 * nWin + 1] = e, W[3 * nWin + 2] = c;
-              nWin++;
-            };
 #pragma unroll 1
-            for (int t = 1; t < nC; t++) {
-              const int cs_ = ks[t] >> 16, ce_ = 0xFFFF - (ks[t] & 0xFFFF), cc = vs[t];
-              if (pe > cs_) {
-                if (pc < cc) ps = cs_, pe = ce_, pc = cc;
-              } else {
-                put(ps, pe, pc);
-                ps = cs_, pe = ce_, pc = cc;
+            for (int t0 = 1; t0 < nC; t0 += 32) {
+              const int idx = t0 + lane;
+              const bool valid = idx < nC;
+              const uint32_t k = valid ? ks[idx] : 0u;
+              const int cs_ = k >> 16, ce_ = 0xFFFF - (k & 0xFFFF), cc = valid ? (int)vs[idx] : 0;
+              int from = 0;  // lanes below `from` are already behind the pivot
+#pragma unroll 1
+              for (;;) {
+                const unsigned m = __ballot_sync(VG_FULL, valid && lane >= from && (pe <= cs_ || pc < cc));
+                if (!m) break;
+                const int f = __ffs(m) - 1;
+                const int ns = __shfl_sync(VG_FULL, cs_, f), ne = __shfl_sync(VG_FULL, ce_, f), nc = __shfl_sync(VG_FULL, cc, f);
+                if (pe <= ns) {
+                  if (lane == 0 && nWin < A.maxWin) W[3 * nWin] = ps, W[3 * nWin + 1] = pe, W[3 * nWin + 2] = pc;
+                  nWin++;
+                }
+                ps = ns, pe = ne, pc = nc;
+                from = f + 1;
               }
             }
-            put(ps, pe, pc);
+            if (lane == 0 && nWin < A.maxWin) W[3 * nWin] = ps, W[3 * nWin + 1] = pe, W[3 * nWin + 2] = pc;
+            nWin++;
             if (nWin > A.maxWin) {
-              atomicOr(A.errFlag, 8);
+              if (lane == 0) atomicOr(A.errFlag, 8);
               nWin = 0;
             }
           }

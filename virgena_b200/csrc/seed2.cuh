@@ -1,0 +1,713 @@
+// Seeding fast path for sm_100a: the single-reference KMerCounter chain split into two kernels so that each
+// runs at 32 warps per SM (the monolithic seed_kernel of seed.cuh is limited to 14 by its per-warp shared
+// memory and is latency bound there). Same restatement of the Java as seed.cuh (see its header for the
+// file:line map); the phases are unchanged, only where the data lives between them:
+//
+//   seed_gen_kernel   A (read k-mer table) + B (genome-ordered raw hits -> LongHit stream)
+//                     KMerCounterBase.getHits + mergeHits phase 1 (KMerCounterBase.java:337-421,452-466)
+//                     -> per item: S[item][0..nS) = LongHits sorted by (genomePos, readPos), in HBM
+//   seed_win_kernel   C (mergeHits phase 2, :422-449) + D (splitLongHits, KMerCounter.java:142-185)
+//                     + E (concordanceArray, :266-279) + F (window counts, KMerCounter.java:72-221)
+//                     + G (pruneWindows, KMerCounterBase.java:317-335) -> windows
+//
+// Anything the fast path cannot hold (a k-mer occurring > 127 times in a read, more LongHits than the per-item
+// slot, a sweep segment longer than the shared-memory window, a full re-insertion queue) is not an error: the
+// item is appended to a fallback list and redone by seed_kernel, which has the general (hash / serial) paths.
+#pragma once
+#include "seed.cuh"
+
+struct Seed2Args {
+  // reference
+  const uint8_t* blob;         // [ref padded to 16][poscode u16 padded to a multiple of 128 entries]
+  int blobRefBytes, blobBytes;
+  const uint64_t* exoKeys;
+  int nExo;
+  const int32_t* contigEnds;
+  int nContigs;
+  int G, K;
+  float lowCoef, highCoef;
+  const int32_t* cutoffs;
+  int nCutoffs;
+  // reads: global work item gi = itemBase + local item
+  const uint8_t* bases;
+  const int64_t* off1;
+  const int32_t* len1;
+  const int64_t* off2;
+  const int32_t* len2;
+  const int64_t* pairIdx;
+  int64_t itemBase;
+  int nItems;                  // items of this launch
+  int singleReads;
+  // per-item scratch
+  uint64_t* S;                 // [nItems][capS]  g << 32 | r << 16 | len
+  int capS;
+  int32_t* nS;                 // [nItems]; -1 = handed to the fallback
+  // per-warp-slot scratch of the window kernel
+  uint32_t* candKey;           // [warpSlots][2][capC]
+  uint32_t* candVal;
+  int capC;
+  uint16_t* scratchR;          // [warpSlots][2][capR]: hitG, P when they do not fit in shared memory
+  int capR;
+  // outputs
+  int32_t* windows;            // [all items][maxWin][3]
+  int32_t* nWindows;
+  int maxWin;
+  int* counters;               // [0] gen work counter, [1] window work counter, [2] error flags, [3] fallback count
+  int32_t* fallback;           // global item indices to redo with seed_kernel
+  int32_t* dbgHits;
+  int32_t* dbgNHits;
+  // geometry (host computed)
+  int emptyId;                 // 4^K + nExo: a table slot that is never filled
+  int tabBytes, nxtBytes, qcap, rdBytes, genWarpBytes;
+  int capRs, nBuckets, winWarpBytes;
+};
+
+__device__ __forceinline__ void sd2_item(const Seed2Args& A, int local, int64_t& off, int& L, int& rev) {
+  const int64_t gi = A.itemBase + local;
+  if (A.singleReads) {
+    off = A.off1[gi];
+    L = A.len1[gi];
+    rev = 0;
+  } else {
+    int64_t p = gi >> 2;
+    if (A.pairIdx) p = A.pairIdx[p];
+    const int o = (int)(gi & 3);  // 0 fwd1, 1 rev1, 2 fwd2, 3 rev2
+    off = (o < 2) ? A.off1[p] : A.off2[p];
+    L = (o < 2) ? A.len1[p] : A.len2[p];
+    rev = o & 1;
+  }
+}
+
+__device__ __forceinline__ void sd2_fallback(const Seed2Args& A, int local) {
+  const int slot = atomicAdd(A.counters + 3, 1);
+  A.fallback[slot] = (int32_t)(A.itemBase + local);
+  A.nS[local] = -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 1: LongHit stream. One warp per read orientation; blockDim = 32 * warps.
+// Dynamic shared memory: [staged blob][per warp: tab u16 | nxt u16 | queue u32[qcap] | rd]
+//   tab[id] = head | count << 9 (count 0 = the k-mer does not occur in the read), nxt = chain of ascending
+//   read positions, queue = flattened raw hits (g << 16 | i) of the current batch of genome positions.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
+  extern __shared__ __align__(16) uint8_t sd_smem[];
+  __shared__ uint64_t sd_mbar;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int K = A.K, G = A.G;
+  sd_tma_stage(sd_smem, A.blob, A.blobBytes, &sd_mbar);
+  const uint8_t* ref = sd_smem;
+  const uint16_t* poscode = (const uint16_t*)(sd_smem + A.blobRefBytes);
+  uint8_t* wbase = sd_smem + A.blobBytes + (size_t)warp * A.genWarpBytes;
+  uint16_t* tab = (uint16_t*)wbase;
+  uint16_t* nxt = (uint16_t*)(wbase + A.tabBytes);
+  uint32_t* queue = (uint32_t*)(wbase + A.tabBytes + A.nxtBytes);
+  uint8_t* rd = (uint8_t*)(queue + A.qcap);
+  const int QCAP = A.qcap;
+  const int emptyId = A.emptyId;
+  const unsigned lt = (1u << lane) - 1u;
+
+#pragma unroll 1
+  for (;;) {
+    int it = 0;
+    if (lane == 0) it = atomicAdd(A.counters, 1);
+    it = __shfl_sync(VG_FULL, it, 0);
+    if (it >= A.nItems) break;
+    int64_t off;
+    int L, rev;
+    sd2_item(A, it, off, L, rev);
+    const int nk = L - K + 1;
+    if (nk < 1 || L > SD_MAXL) {  // L < K: no k-mer (Q6); too long: reported by the window kernel
+      if (lane == 0) A.nS[it] = 0;
+      continue;
+    }
+    const uint8_t* src = A.bases + off;
+    __syncwarp();
+#pragma unroll 1
+    for (int i = lane; i < L; i += 32) rd[i] = rev ? vg_complement(src[L - 1 - i]) : src[i];
+#pragma unroll 1
+    for (int t = lane; t < (A.tabBytes >> 2); t += 32) ((uint32_t*)tab)[t] = 0;
+    __syncwarp();
+    // ---- A: read k-mer table, chains built from the last chunk down so that they ascend ------------
+    bool bad = false;
+#pragma unroll 1
+    for (int base = ((nk - 1) >> 5) << 5; base >= 0; base -= 32) {
+      const int i = base + lane;
+      uint32_t id = SD_NONE16;
+      if (i < nk) id = sd_kmer_id(rd + i, K, A.exoKeys, A.nExo);
+      const bool valid = id != SD_NONE16;
+      const unsigned grp = __match_any_sync(VG_FULL, valid ? id : (0x80000000u | lane));
+      if (valid) {
+        const int leader = __ffs(grp) - 1;
+        const uint32_t old = tab[id];  // read by the whole group before the leader overwrites it
+        const unsigned higher = grp & ~((2u << lane) - 1u);
+        nxt[i] = higher ? (uint16_t)(base + __ffs(higher) - 1) : (uint16_t)(old & 511u);
+        __syncwarp(grp);
+        if (lane == leader) {
+          const uint32_t cnt = (old >> 9) + (uint32_t)__popc(grp);
+          if (cnt > 127u) bad = true;
+          tab[id] = (uint16_t)((uint32_t)i | (cnt << 9));
+        }
+      }
+      __syncwarp();
+    }
+    bad = __any_sync(VG_FULL, bad);
+    // ---- B: scan the reference in genome order -> LongHits sorted by (g, i) -------------------------
+    uint64_t* S = A.S + (size_t)it * A.capS;
+    int nS = 0;
+#pragma unroll 1
+    for (int gb = 0; gb <= G - K && !bad;) {
+      int nq = 0;
+      bool qfull = false;
+      // B1: 128 genome positions per trip, 4 consecutive positions per lane; every raw hit (g, i) is queued in
+      // (g, i) order. Offsets come from ballots over the bits of the per-lane hit count.
+#pragma unroll 1
+      for (; gb <= G - K && !qfull; gb += 128) {
+        const int g0 = gb + 4 * lane;
+        const uint2 pc = *(const uint2*)(poscode + g0);  // beyond G-K the table holds SD_NONE16
+        uint32_t hv[4];
+        hv[0] = tab[min((int)(pc.x & 0x7FFFu), emptyId)];
+        hv[1] = tab[min((int)((pc.x >> 16) & 0x7FFFu), emptyId)];
+        hv[2] = tab[min((int)(pc.y & 0x7FFFu), emptyId)];
+        hv[3] = tab[min((int)((pc.y >> 16) & 0x7FFFu), emptyId)];
+        const int c0 = hv[0] >> 9, c1 = hv[1] >> 9, c2 = hv[2] >> 9, c3 = hv[3] >> 9;
+        const int tot = c0 + c1 + c2 + c3;
+        const unsigned b0 = __ballot_sync(VG_FULL, tot & 1), b1 = __ballot_sync(VG_FULL, tot & 2),
+                       b2 = __ballot_sync(VG_FULL, tot & 4), bh = __ballot_sync(VG_FULL, tot >> 3);
+        int excl, total;
+        if (bh == 0) {
+          total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+          if (total == 0) continue;
+          excl = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+        } else {
+          const int incl = sd_warp_incl_scan(tot, lane);
+          total = __shfl_sync(VG_FULL, incl, 31);
+          excl = incl - tot;
+        }
+        if (total > QCAP) {  // low-complexity read: the general kernel has a path for it
+          bad = true;
+          break;
+        }
+        if (nq + total > QCAP) {  // does not fit any more: flush first, then redo this block
+          qfull = true;
+          gb -= 128;
+          continue;
+        }
+        int o = nq + excl;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {  // chains of 1 or 2 read positions are the rule: straight-line code
+          const int cu = hv[u] >> 9;
+          if (cu) {
+            uint32_t i = hv[u] & 511u;
+            const uint32_t gk = (uint32_t)(g0 + u) << 16;
+            queue[o] = gk | i;
+            if (cu > 1) {
+              i = nxt[i];
+              queue[o + 1] = gk | i;
+#pragma unroll 1
+              for (int t = 2; t < cu; t++) {
+                i = nxt[i];
+                queue[o + t] = gk | i;
+              }
+            }
+            o += cu;
+          }
+        }
+        nq += total;
+      }
+      __syncwarp();
+      // B2: one lane per raw hit (two per trip): chain-start test, extension, ballot-compacted ordered writes
+#pragma unroll 1
+      for (int q0 = 0; q0 < nq && !bad; q0 += 64) {
+        bool em[2] = {false, false};
+        int gg[2], ii[2], ll[2] = {0, 0};
+        uint32_t e[2];
+        uint8_t ca[2], cb[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const int q = q0 + 32 * u + lane;
+          e[u] = (q < nq) ? queue[q] : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          gg[u] = (int)(e[u] >> 16);
+          ii[u] = (int)(e[u] & 0xFFFFu);
+          const bool ok = e[u] != 0xFFFFFFFFu;
+          ca[u] = (ok && ii[u] > 0) ? rd[ii[u] - 1] : 0;
+          cb[u] = (ok && gg[u] > 0) ? ref[gg[u] - 1] : 1;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          if (e[u] == 0xFFFFFFFFu) continue;
+          const int g = gg[u], i = ii[u];
+          const bool start = (i == 0) || (g == 0) || (ca[u] != cb[u]);
+          if (start) {
+            em[u] = true;
+            ll[u] = sd_extend(rd, ref, i, g, K, L, G);
+          } else if (poscode[g] & 0x8000u) {
+            em[u] = true;  // Q1: a chain passing through a twice-indexed position adds a zero-length hit
+          }
+        }
+        const unsigned m0 = __ballot_sync(VG_FULL, em[0]);
+        const unsigned m1 = __ballot_sync(VG_FULL, em[1]);
+        const int t0 = __popc(m0), total = t0 + __popc(m1);
+        if (nS + total > A.capS) {
+          bad = true;
+          break;
+        }
+        if (em[0]) S[nS + __popc(m0 & lt)] = ((uint64_t)gg[0] << 32) | ((uint64_t)ii[0] << 16) | (uint64_t)ll[0];
+        if (em[1]) S[nS + t0 + __popc(m1 & lt)] = ((uint64_t)gg[1] << 32) | ((uint64_t)ii[1] << 16) | (uint64_t)ll[1];
+        nS += total;
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      if (bad) sd2_fallback(A, it);
+      else A.nS[it] = nS;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 2: overlap resolution, window counts, pruning. One warp per read orientation.
+// Per-warp shared memory (winWarpBytes), two aliased uses:
+//   C   : win u64[SD_WIN + 32] (padded window over the stream) | pendL u64[32][SD_LPEND]
+//   E-G : hitG u16[capRs] | P u16[capRs] | bucket u16[nBuckets]   (bins int[256] of the sort overlay hitG)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
+  extern __shared__ __align__(16) uint8_t sd_smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warpSlot = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int K = A.K, G = A.G;
+  uint8_t* wbase = sd_smem + (size_t)warp * A.winWarpBytes;
+  uint64_t* win = (uint64_t*)wbase;
+  uint64_t* pend = (uint64_t*)(wbase + (SD_WIN + 32) * 8) + lane * SD_LPEND;
+  const int capRs = A.capRs;
+  uint16_t* bucket = (uint16_t*)(wbase + (size_t)capRs * 4);
+  int* bins = (int*)wbase;
+  const int capC = A.capC;
+  uint32_t* ckey = A.candKey + (size_t)warpSlot * 2 * capC;
+  uint32_t* cval = A.candVal + (size_t)warpSlot * 2 * capC;
+  const unsigned lt = (1u << lane) - 1u;
+
+#pragma unroll 1
+  for (;;) {
+    int it = 0;
+    if (lane == 0) it = atomicAdd(A.counters + 1, 1);
+    it = __shfl_sync(VG_FULL, it, 0);
+    if (it >= A.nItems) break;
+    const int64_t gi = A.itemBase + it;
+    int64_t off;
+    int L, rev;
+    sd2_item(A, it, off, L, rev);
+    const int nS = A.nS[it];
+    if (nS < 0) continue;  // redone by the general kernel
+    if (L > SD_MAXL && lane == 0) atomicOr(A.counters + 2, 16);
+    uint64_t* S = A.S + (size_t)it * A.capS;
+    int nWin = 0, nR = 0;
+    bool giveUp = false;
+    __syncwarp();
+    // ---- C: mergeHits phase 2 (KMerCounterBase.java:422-449); see seed.cuh for the decomposition into
+    // independent segments at synchronisation points. The LongHits that survive are written back to the front
+    // of the item's slot (never ahead of what has been read into the window).
+    if (nS > 0) {
+      constexpr int CH = SD_WIN / 32;  // entries per lane when flagging
+      int tbase = 0, runMaxE = -1;
+#pragma unroll 1
+      while (tbase < nS) {
+        const int cnt = min(SD_WIN, nS - tbase);
+#pragma unroll 4
+        for (int e = lane; e < cnt; e += 32) win[SD_WI(e)] = S[tbase + e];
+        __syncwarp();
+        const int lo = lane * CH, hi = min(lo + CH, cnt);
+        int locMax = -1;
+#pragma unroll 1
+        for (int j = lo; j < hi; j++) {
+          const uint64_t v = win[SD_WI(j)];
+          locMax = max(locMax, (int)(v >> 32) + (int)(v & 0xFFFFu) + K);
+        }
+        int incl = locMax;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(VG_FULL, incl, d);
+          if (lane >= d) incl = max(incl, t);
+        }
+        int excl = __shfl_up_sync(VG_FULL, incl, 1);
+        excl = (lane == 0) ? runMaxE : max(excl, runMaxE);
+        uint32_t fmask = 0;
+        {
+          int m = excl;
+#pragma unroll 1
+          for (int j = lo; j < hi; j++) {
+            const uint64_t v = win[SD_WI(j)];
+            const int g = (int)(v >> 32);
+            if (g > m) fmask |= 1u << (j - lo);
+            m = max(m, g + (int)(v & 0xFFFFu) + K);
+          }
+        }
+        // lane l sweeps the segments that START in its chunk: from its first flag to the first flag of the next
+        // flagged lane; the last segment of a window that is not the last one is carried over (tailStart)
+        const int nSeg = __reduce_add_sync(VG_FULL, __popc(fmask));
+        const int firstFlag = fmask ? lo + __ffs(fmask) - 1 : 0x7fff;
+        const int lastFlag = fmask ? lo + 31 - __clz(fmask) : -1;
+        const bool more = tbase + cnt < nS;
+        if ((more ? nSeg - 1 : nSeg) <= 0) {  // a single segment longer than the window
+          giveUp = true;
+          break;
+        }
+        const int tailStart = more ? __reduce_max_sync(VG_FULL, lastFlag) : cnt;
+        int nextFirst;
+        {
+          int v = firstFlag;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_down_sync(VG_FULL, v, d);
+            if (lane + d < 32) v = min(v, o);
+          }
+          nextFirst = __shfl_down_sync(VG_FULL, v, 1);
+          if (lane == 31) nextFirst = 0x7fff;
+        }
+        {  // running maximum end over the entries that are consumed now (original ends)
+          int m2 = -1;
+#pragma unroll 1
+          for (int j = lo; j < hi && j < tailStart; j++) {
+            const uint64_t v = win[SD_WI(j)];
+            m2 = max(m2, (int)(v >> 32) + (int)(v & 0xFFFFu) + K);
+          }
+          runMaxE = max(runMaxE, __reduce_max_sync(VG_FULL, m2));
+        }
+        const int s0 = min(firstFlag, tailStart), s1 = min(nextFirst, tailStart);  // s0 == s1: nothing to do
+        __syncwarp();
+        // all lanes step through their ranges in lock-step (one polled element per trip): the sweep of
+        // KMerCounterBase.java:422-449 verbatim, started afresh at a synchronisation point; results in place
+        bool ovf = false;
+        int si = s0, w = s0, np = 0;
+        bool have = false;
+        int pg = 0, pr = 0, pl = 0;
+#pragma unroll 1
+        for (;;) {
+          const bool act = si < s1 || np > 0;
+          if (!__any_sync(VG_FULL, act)) break;
+          if (act) {
+            uint64_t v;
+            if (np > 0 && (si >= s1 || (pend[0] >> 16) < (win[SD_WI(si)] >> 16))) {  // TreeSet.pollFirst
+              v = pend[0];
+#pragma unroll 1
+              for (int t = 1; t < np; t++) pend[t - 1] = pend[t];
+              np--;
+            } else {
+              v = win[SD_WI(si)];
+              si++;
+            }
+            int cg = (int)(v >> 32), cr = (int)((v >> 16) & 0xFFFFu), cl = (int)(v & 0xFFFFu);
+            if (!have) {
+              have = true;
+              pg = cg, pr = cr, pl = cl;
+            } else if (pg + pl + K - 1 >= cg) {
+              if (pl < cl) {
+                pl = cg - pg - K;
+                if (pl >= 0) {
+                  win[SD_WI(w)] = ((uint64_t)pg << 32) | ((uint64_t)pr << 16) | (uint64_t)pl;
+                  w++;
+                }
+                pg = cg, pr = cr, pl = cl;
+              } else {
+                const int lenDiff = pg + pl + K - cg;
+                cl -= lenDiff;
+                if (cl >= 0) {
+                  cg += lenDiff;
+                  cr += lenDiff;
+                  // TreeSet.add: dropped when an element with the same (genomePos, readPos) is present (Q2)
+                  const uint64_t key = ((uint64_t)cg << 16) | (uint64_t)cr;
+                  bool present = false;
+                  int ins = np;
+#pragma unroll 1
+                  for (int t = 0; t < np; t++) {
+                    const uint64_t pk = pend[t] >> 16;
+                    if (pk == key) present = true;
+                    if (pk > key && ins == np) ins = t;
+                  }
+                  if (!present)
+#pragma unroll 1
+                    for (int j = si; j < s1; j++) {  // the key lies before the next synchronisation point
+                      const uint64_t k = win[SD_WI(j)] >> 16;
+                      if (k >= key) {
+                        present = (k == key);
+                        break;
+                      }
+                    }
+                  if (!present) {
+                    if (np >= SD_LPEND) {
+                      ovf = true;
+                      np = 0;
+                      si = s1;
+                    } else {
+#pragma unroll 1
+                      for (int t = np; t > ins; t--) pend[t] = pend[t - 1];
+                      pend[ins] = (key << 16) | (uint64_t)cl;
+                      np++;
+                    }
+                  }
+                }
+              }
+            } else {
+              win[SD_WI(w)] = ((uint64_t)pg << 32) | ((uint64_t)pr << 16) | (uint64_t)pl;
+              w++;
+              pg = cg, pr = cr, pl = cl;
+            }
+          }
+          __syncwarp();
+        }
+        if (have) {
+          win[SD_WI(w)] = ((uint64_t)pg << 32) | ((uint64_t)pr << 16) | (uint64_t)pl;
+          w++;
+        }
+#pragma unroll 1
+        for (int t = w; t < s1; t++) win[SD_WI(t)] = ~0ull;  // consumed, not emitted
+        __syncwarp();
+        if (__any_sync(VG_FULL, ovf)) {
+          giveUp = true;
+          break;
+        }
+#pragma unroll 1
+        for (int e0 = 0; e0 < tailStart; e0 += 32) {  // ordered compaction
+          const int e = e0 + lane;
+          const uint64_t v = (e < tailStart) ? win[SD_WI(e)] : ~0ull;
+          const bool ok = v != ~0ull;
+          const unsigned m = __ballot_sync(VG_FULL, ok);
+          if (ok) S[nR + __popc(m & lt)] = v;
+          nR += __popc(m);
+        }
+        __syncwarp();
+        tbase += tailStart;
+      }
+    }
+    __syncwarp();
+    // ---- D: KMerCounter.splitLongHits (KMerCounter.java:142-185); hits are independent given their contig
+    if (!giveUp && A.nContigs > 1 && nR > 0) {
+      __threadfence_block();
+      int nOut = 0;
+      bool bad = false;
+#pragma unroll 1
+      for (int j0 = 0; j0 < nR; j0 += 32) {
+        const int j = j0 + lane;
+        int qg[3], qr[3], ql[3], np2 = 0;
+        if (j < nR) {
+          const uint64_t v = S[j];
+          int g = (int)(v >> 32), r = (int)((v >> 16) & 0xFFFFu), len = (int)(v & 0xFFFFu);
+          for (;;) {
+            int lo2 = 0, hi2 = A.nContigs - 1;
+#pragma unroll 1
+            while (lo2 < hi2) {
+              const int mid = (lo2 + hi2) >> 1;
+              if (A.contigEnds[mid] > g) hi2 = mid;
+              else lo2 = mid + 1;
+            }
+            const int contigEnd = A.contigEnds[lo2];
+            if (g + K + len > contigEnd) {
+              if (contigEnd - g >= K) {
+                if (np2 < 3) qg[np2] = g, qr[np2] = r, ql[np2] = contigEnd - g - K;
+                np2++;
+              }
+              if (g + K + len - contigEnd >= K) {
+                r += contigEnd - g;
+                len -= contigEnd - g;
+                g = contigEnd;
+                continue;
+              }
+              break;
+            }
+            if (np2 < 3) qg[np2] = g, qr[np2] = r, ql[np2] = len;
+            np2++;
+            break;
+          }
+          if (np2 > 3) bad = true, np2 = 3;  // a hit across > 2 contig boundaries (contigs shorter than K + 1)
+        }
+        const int ic = sd_warp_incl_scan(np2, lane);
+        int o = nOut + ic - np2;
+#pragma unroll 1
+        for (int t = 0; t < np2; t++, o++)
+          if (o < capC) ckey[o] = (uint32_t)qg[t] | ((uint32_t)qr[t] << 16), cval[o] = (uint32_t)ql[t];
+        nOut += __shfl_sync(VG_FULL, ic, 31);
+      }
+      __syncwarp();
+      __threadfence_block();
+      if (__any_sync(VG_FULL, bad) || nOut > capC || nOut > A.capS) {
+        giveUp = true;
+      } else {
+#pragma unroll 1
+        for (int j = lane; j < nOut; j += 32)
+          S[j] = ((uint64_t)(ckey[j] & 0xFFFFu) << 32) | ((uint64_t)(ckey[j] >> 16) << 16) | (uint64_t)cval[j];
+        nR = nOut;
+      }
+      __syncwarp();
+    }
+    if (giveUp || nR > A.capR) {
+      if (lane == 0) sd2_fallback(A, it);
+      continue;
+    }
+    __threadfence_block();
+    if (A.dbgHits && gi == 0) {
+#pragma unroll 1
+      for (int j = lane; j < nR; j += 32) {
+        const uint64_t v = S[j];
+        A.dbgHits[3 * j] = (int)(v >> 32);
+        A.dbgHits[3 * j + 1] = (int)((v >> 16) & 0xFFFFu);
+        A.dbgHits[3 * j + 2] = (int)(v & 0xFFFFu);
+      }
+      if (lane == 0) *A.dbgNHits = nR;
+    }
+    if (nR > 0) {
+      // ---- E: isAdjacent (IEEE binary32 division, Q3 coefficients verbatim) + prefix sums
+      //         P[j] = sum_{t<=j}(len_t + isAdjacent[t-1]) (mod 2^16); genomePos table + buckets for the searches
+      uint16_t* hitG = (uint16_t*)wbase;
+      uint16_t* Pp = hitG + capRs;
+      if (nR > capRs) {  // does not fit in shared memory: L2-resident per-warp scratch
+        hitG = A.scratchR + (size_t)warpSlot * 2 * A.capR;
+        Pp = hitG + A.capR;
+      }
+      int carry = 0, pgLast = 0, prLast = 0;
+#pragma unroll 1
+      for (int j0 = 0; j0 < nR; j0 += 32) {
+        const int j = j0 + lane;
+        int val = 0, g = 0, r = 0;
+        if (j < nR) {
+          const uint64_t v = S[j];
+          g = (int)(v >> 32), r = (int)((v >> 16) & 0xFFFFu);
+          val = (int)(v & 0xFFFFu);
+          hitG[j] = (uint16_t)g;
+        }
+        int pg = __shfl_up_sync(VG_FULL, g, 1), pr = __shfl_up_sync(VG_FULL, r, 1);
+        if (lane == 0) pg = pgLast, pr = prLast;
+        if (j < nR && j > 0) {
+          const float rate = __fdiv_rn((float)(g - pg), (float)(r - pr));
+          if (A.lowCoef <= rate && rate <= A.highCoef) val++;
+        }
+        const int incl = sd_warp_incl_scan(val, lane);
+        if (j < nR) Pp[j] = (uint16_t)(carry + incl);
+        carry += __shfl_sync(VG_FULL, incl, 31);
+        pgLast = __shfl_sync(VG_FULL, g, 31);
+        prLast = __shfl_sync(VG_FULL, r, 31);
+      }
+      // bucket[b] = first hit index with g >= 32 b
+      const int nb = A.nBuckets;
+#pragma unroll 1
+      for (int b = lane; b < nb; b += 32) bucket[b] = (uint16_t)nR;
+      __syncwarp();
+#pragma unroll 1
+      for (int j = lane; j < nR; j += 32) {
+        const int b = hitG[j] >> 5;
+        if (j == 0 || (hitG[j - 1] >> 5) != b) bucket[b] = (uint16_t)j;
+      }
+      __syncwarp();
+      {  // suffix fill of empty buckets (serial over chunks from the top, parallel inside a chunk)
+        int nextv = nR;
+#pragma unroll 1
+        for (int b0 = ((nb - 1) >> 5) << 5; b0 >= 0; b0 -= 32) {
+          const int b = b0 + lane;
+          int v = (b < nb) ? bucket[b] : nR;
+          const bool empty = (v == nR);
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_down_sync(VG_FULL, v, d);
+            if (lane + d < 32) v = min(v, o);
+          }
+          v = min(v, nextv);
+          if (b < nb && empty) bucket[b] = (uint16_t)v;
+          nextv = __shfl_sync(VG_FULL, v, 0);
+        }
+      }
+      __syncwarp();
+      // ---- F: every window independently (updateCount equals a direct recount on sorted non-overlapping
+      //         hits); candidates (count > cutoff, strict) compacted in hit order
+      const int cutoff = (L < A.nCutoffs) ? A.cutoffs[L] : 0x7fffffff;
+      int nC = 0;
+#pragma unroll 1
+      for (int j0 = 0; j0 < nR; j0 += 32) {
+        const int j = j0 + lane;
+        bool isCand = false;
+        uint32_t key = 0, cnt = 0;
+        if (j < nR) {
+          const uint64_t v = S[j];
+          const int g = (int)(v >> 32), r = (int)((v >> 16) & 0xFFFFu), len = (int)(v & 0xFFFFu);
+          int cs = 0, ce = G;
+          if (A.nContigs > 1) {
+            int lo = 0, hi = A.nContigs - 1;
+#pragma unroll 1
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (A.contigEnds[mid] > g) hi = mid;
+              else lo = mid + 1;
+            }
+            ce = A.contigEnds[lo];
+            cs = lo ? A.contigEnds[lo - 1] : 0;
+          }
+          const int start = max(cs, g - r * 3 / 2);
+          const int end = min(g + len + K + (L - r - len - K) * 3 / 2, ce);
+          int a = bucket[start >> 5];
+#pragma unroll 1
+          while (hitG[a] < start) a++;
+          int u = bucket[min(end, G) >> 5];
+#pragma unroll 1
+          while (u < nR && hitG[u] < end) u++;
+          int b = u - 1;
+          const uint64_t va = S[a], vb = S[b];
+          if ((int)(vb >> 32) + K + (int)(vb & 0xFFFFu) > end) b--;
+          cnt = (uint32_t)((uint16_t)(Pp[b] - Pp[a])) + (uint32_t)(va & 0xFFFFu);
+          isCand = (int)cnt > cutoff;
+          key = ((uint32_t)start << 16) | (uint32_t)(0xFFFF - end);
+        }
+        const unsigned m = __ballot_sync(VG_FULL, isCand);
+        if (isCand) {
+          const int o = nC + __popc(m & lt);
+          ckey[o] = key;
+          cval[o] = cnt;
+        }
+        nC += __popc(m);
+      }
+      __syncwarp();
+      // ---- G: stable sort by (start asc, end desc) + pruneWindows (KMerCounterBase.java:317-335). The pivot only
+      //         changes at the first later candidate that either does not overlap it (emit, new pivot) or overlaps
+      //         with a larger count (new pivot); the warp looks at 32 candidates at a time.
+      if (nC > 0) {
+        const int srcb = sd_radix_sort(ckey, cval, capC, nC, bins, lane, 32);
+        __threadfence_block();
+        const uint32_t* ks = ckey + (size_t)srcb * capC;
+        const uint32_t* vs = cval + (size_t)srcb * capC;
+        int32_t* W = A.windows + (size_t)gi * A.maxWin * 3;
+        int ps = ks[0] >> 16, pe = 0xFFFF - (ks[0] & 0xFFFF), pc = vs[0];
+#pragma unroll 1
+        for (int t0 = 1; t0 < nC; t0 += 32) {
+          const int idx = t0 + lane;
+          const bool valid = idx < nC;
+          const uint32_t k = valid ? ks[idx] : 0u;
+          const int cs_ = k >> 16, ce_ = 0xFFFF - (k & 0xFFFF), cc = valid ? (int)vs[idx] : 0;
+          int from = 0;  // lanes below `from` are already behind the pivot
+#pragma unroll 1
+          for (;;) {
+            const unsigned m = __ballot_sync(VG_FULL, valid && lane >= from && (pe <= cs_ || pc < cc));
+            if (!m) break;
+            const int f = __ffs(m) - 1;
+            const int ns = __shfl_sync(VG_FULL, cs_, f), ne = __shfl_sync(VG_FULL, ce_, f), nc = __shfl_sync(VG_FULL, cc, f);
+            if (pe <= ns) {
+              if (lane == 0 && nWin < A.maxWin) W[3 * nWin] = ps, W[3 * nWin + 1] = pe, W[3 * nWin + 2] = pc;
+              nWin++;
+            }
+            ps = ns, pe = ne, pc = nc;
+            from = f + 1;
+          }
+        }
+        if (lane == 0 && nWin < A.maxWin) W[3 * nWin] = ps, W[3 * nWin + 1] = pe, W[3 * nWin + 2] = pc;
+        nWin++;
+        if (nWin > A.maxWin) {
+          if (lane == 0) atomicOr(A.counters + 2, 8);
+          nWin = 0;
+        }
+      }
+    }
+    if (lane == 0) A.nWindows[gi] = nWin;
+    __syncwarp();
+  }
+}

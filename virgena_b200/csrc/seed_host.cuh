@@ -4,9 +4,14 @@
 
 #include "ctx.cuh"
 #include "seed.cuh"
+#include "seed2.cuh"
 
 struct SeedHostState {  // lives in vg_ctx via the DevBufs; plain helpers here
 };
+
+// blob = [ref padded to 16][poscode u16, padded with SD_NONE16 to a multiple of 128 entries]
+static inline int sdh_ref_pad(int G) { return (G + 15) & ~15; }
+static inline int sdh_code_pad(int G) { return std::max(128, (G + 127) & ~127) * 2; }
 
 static inline int sdh_code2(uint8_t b) { return b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : b == 'T' ? 3 : -1; }
 
@@ -82,12 +87,12 @@ static int seed_build_reference(vg_ctx* c, const uint8_t* keys, const int64_t* o
   if ((1u << (2 * K)) + exo.size() >= SD_NONE16)
     return vg_fail(c, VG_ERR_INVALID, "too many distinct k-mers for the 15-bit id table (K=%d, %zu exotic)", K, exo.size());
   // blob = [ref padded to 16][poscode u16 padded to 16]
-  const int refPad = (G + 15) & ~15;
-  const int codePad = (G * 2 + 15) & ~15;
+  const int refPad = sdh_ref_pad(G);
+  const int codePad = sdh_code_pad(G);
   std::vector<uint8_t> blob((size_t)refPad + codePad + 16, 0);
   memcpy(blob.data(), ref, G);
   uint16_t* pc = (uint16_t*)(blob.data() + refPad);
-  for (int p = 0; p < G; p++) {
+  for (int p = 0; p < codePad / 2; p++) {
     uint16_t v = SD_NONE16;
     if (p < nPos) {
       uint32_t code;
@@ -156,9 +161,10 @@ static int seed_build_msa(vg_ctx* c, const uint8_t* keys, const int64_t* offsets
 
 // Launches seed_kernel over nItems work items. Windows land in c->d_cand ([nItems][maxWin][3]) and
 // c->d_ncand ([nItems]).
-static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_t* d_off1, const int32_t* d_len1,
-                       const int64_t* d_off2, const int32_t* d_len2, const int64_t* d_pairIdx, int64_t nItems,
-                       bool singleReads, int maxReadLen, int maxWin, int32_t* dbgHits, int32_t* dbgNHits) {
+static int seed_launch_v1(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_t* d_off1, const int32_t* d_len1,
+                          const int64_t* d_off2, const int32_t* d_len2, const int64_t* d_pairIdx, int64_t nItems,
+                          bool singleReads, int maxReadLen, int maxWin, int32_t* dbgHits, int32_t* dbgNHits,
+                          const int32_t* d_itemList = nullptr) {
   const SeedConfig& sc = msa ? c->seedMsa : c->seed;
   const int K = sc.K;
   const int range = msa ? c->msaLength : c->G;
@@ -183,12 +189,12 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   g.capR = std::max(256, std::min(16384, range / K + nContigs + 16));
   g.nBuckets = (range >> 5) + 2;
   const int regAB = 2 * SD_HS * 4 + SD_MAXL * 2;  // table/hash + nxt
-  const int regCG = SD_PENDING * 8 + 1024 + ((g.nBuckets * 2 + 15) & ~15) + 32 * SD_LPEND * 8 + (2 * (SD_WIN + 2) + 4) * 2 + 16;
+  const int regCG = SD_PENDING * 8 + 1024 + ((g.nBuckets * 2 + 15) & ~15) + 32 * SD_LPEND * 8 + 16;
   g.regA = (std::max(regAB, regCG) + 15) & ~15;
-  g.warpBytes = (g.regA + SD_WIN * 8 + SD_MAXL + 16 + 15) & ~15;
+  g.warpBytes = (g.regA + (SD_WIN + 32) * 8 + SD_MAXL + 16 + 15) & ~15;
   g.refBytes = 0;
   if (!msa) {
-    const int refPad = (c->G + 15) & ~15, codePad = (c->G * 2 + 15) & ~15;
+    const int refPad = sdh_ref_pad(c->G), codePad = sdh_code_pad(c->G);
     A.blob = c->d_poscode.as<uint8_t>();
     A.blobRefBytes = refPad;
     A.blobBytes = refPad + codePad;
@@ -251,6 +257,7 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   A.len2 = d_len2;
   A.pairIdx = d_pairIdx;
   A.nItems = nItems;
+  A.itemList = d_itemList;  // when set: nItems entries, each the index of an item to (re)do
   A.singleReads = singleReads ? 1 : 0;
   A.dbgHits = dbgHits;
   A.dbgNHits = dbgNHits;
@@ -284,5 +291,130 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
                    (f & 1) ? " raw-hit buffer" : "", (f & 2) ? " LongHit buffer" : "", (f & 4) ? " re-insertion queue" : "",
                    (f & 8) ? " window list" : "", (f & 16) ? " read too long" : "");
   }
+  return VG_OK;
+}
+
+// Seeding entry point. Single-reference mode with a direct-addressed k-mer table (K <= 5, few exotic k-mers) and a
+// reference that fits in shared memory runs the two-kernel fast path (seed2.cuh) in sub-chunks of items; the items
+// it hands back, and every other mode (MSA, K > 5), run the general kernel. Windows land in c->d_cand
+// ([nItems][maxWin][3]) and c->d_ncand ([nItems]).
+static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_t* d_off1, const int32_t* d_len1,
+                       const int64_t* d_off2, const int32_t* d_len2, const int64_t* d_pairIdx, int64_t nItems,
+                       bool singleReads, int maxReadLen, int maxWin, int32_t* dbgHits, int32_t* dbgNHits) {
+  c->seedFallbacks = 0;
+  const SeedConfig& sc = c->seed;
+  const int K = sc.K, G = c->G;
+  const int smemMax = 227 * 1024;
+  bool fast = !msa && !getenv("VG_SEED_V1") && !getenv("VG_SEED_HASH") && !getenv("VG_SEED_PROF") && K >= 1 && K <= 7 &&
+              G < 65535 && G >= K && maxReadLen <= SD_MAXL && maxReadLen >= K && nItems > 0 && nItems <= 0x7fffffff &&
+              (maxReadLen < (int)sc.cutoffs.size());
+  Seed2Args A;
+  memset(&A, 0, sizeof A);
+  int genWarps = 0, winWarps = 0;
+  if (fast) {
+    A.emptyId = (1 << (2 * K)) + c->nExo;
+    A.tabBytes = ((A.emptyId + 1) * 2 + 15) & ~15;
+    A.nxtBytes = (maxReadLen * 2 + 15) & ~15;
+    A.qcap = 512;
+    A.rdBytes = (maxReadLen + 16 + 15) & ~15;
+    A.genWarpBytes = A.tabBytes + A.nxtBytes + A.qcap * 4 + A.rdBytes;
+    A.blobRefBytes = sdh_ref_pad(G);
+    A.blobBytes = A.blobRefBytes + sdh_code_pad(G);
+    genWarps = std::min(32, (smemMax - 64 - A.blobBytes) / A.genWarpBytes);
+    const int nContigs = (int)c->contigEnds.size();
+    A.capR = std::max(256, std::min(16384, G / K + nContigs + 16));
+    A.nBuckets = (G >> 5) + 2;
+    const int bucketBytes = (A.nBuckets * 2 + 15) & ~15;
+    const int cBytes = (SD_WIN + 32) * 8 + 32 * SD_LPEND * 8;
+    const int budget = (smemMax / 32) & ~15;  // per-warp bytes at 32 warps per SM
+    A.capRs = std::max(0, std::min(A.capR, (budget - bucketBytes) / 4)) & ~7;
+    A.winWarpBytes = std::max(std::max(cBytes, 1024), A.capRs * 4 + bucketBytes);
+    winWarps = std::min(32, smemMax / A.winWarpBytes);
+    if (A.emptyId >= SD_NONE16 || A.emptyId > 8191 || genWarps < 8 || winWarps < 8) fast = false;
+  }
+  if (!fast)
+    return seed_launch_v1(c, msa, d_bases, d_off1, d_len1, d_off2, d_len2, d_pairIdx, nItems, singleReads, maxReadLen, maxWin,
+                          dbgHits, dbgNHits);
+  if (const char* e = getenv("VG_SEED_WARPS")) {
+    genWarps = std::max(1, std::min(genWarps, atoi(e)));
+    winWarps = std::max(1, std::min(winWarps, atoi(e)));
+  }
+  A.blob = c->d_poscode.as<uint8_t>();
+  A.exoKeys = c->d_exoKeys.as<uint64_t>();
+  A.nExo = c->nExo;
+  A.contigEnds = c->d_contigEnds.as<int32_t>();
+  A.nContigs = (int)c->contigEnds.size();
+  A.G = G;
+  A.K = K;
+  A.lowCoef = sc.lowCoef;
+  A.highCoef = sc.highCoef;
+  A.cutoffs = sc.d_cutoffs.as<int32_t>();
+  A.nCutoffs = (int)sc.cutoffs.size();
+  A.bases = d_bases;
+  A.off1 = d_off1, A.len1 = d_len1, A.off2 = d_off2, A.len2 = d_len2;
+  A.pairIdx = d_pairIdx;
+  A.singleReads = singleReads ? 1 : 0;
+  A.maxWin = maxWin;
+  A.dbgHits = dbgHits;
+  A.dbgNHits = dbgNHits;
+  // per-item slot: 1.6 x the expected number of raw LongHits of a random read (0.75 of the raw k-mer hits start a
+  // chain) + slack; a read that needs more is redone by the general kernel
+  {
+    const double nk = std::max(1, maxReadLen - K + 1), nPos = G - K + 1;
+    const double expect = 0.75 * nk * nPos / (double)(1u << (2 * K));
+    A.capS = (int)std::min<double>(65536.0, std::max(1024.0, 1.6 * expect + 512.0));
+    A.capS = (A.capS + 255) & ~255;
+    if (const char* e = getenv("VG_SEED_CAPS2")) A.capS = std::max(64, atoi(e));
+  }
+  A.capC = A.capR;
+  const size_t sBudget = 4ull << 30;
+  const int64_t subItems = std::max<int64_t>(4096, std::min<int64_t>(nItems, (int64_t)(sBudget / ((size_t)A.capS * 8))));
+  const size_t genSmem = (size_t)A.blobBytes + (size_t)genWarps * A.genWarpBytes;
+  const size_t winSmem = (size_t)winWarps * A.winWarpBytes;
+  VG_CUDA(c, cudaFuncSetAttribute(seed_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmem));
+  VG_CUDA(c, cudaFuncSetAttribute(seed_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)winSmem));
+  const int64_t sub0 = std::min(subItems, nItems);
+  const int genBlocks = (int)std::max<int64_t>(1, std::min<int64_t>((sub0 + genWarps - 1) / genWarps, c->smCount));
+  const int winBlocks = (int)std::max<int64_t>(1, std::min<int64_t>((sub0 + winWarps - 1) / winWarps, c->smCount));
+  const int winSlots = winBlocks * winWarps;
+  VG_CUDA(c, c->d_seedS.reserve((size_t)sub0 * A.capS * 8));
+  VG_CUDA(c, c->d_seedNS.reserve((size_t)sub0 * 4));
+  VG_CUDA(c, c->d_seedFb.reserve((size_t)nItems * 4));
+  VG_CUDA(c, c->d_seqOff.reserve((size_t)winSlots * 2 * A.capC * 4 * 2));
+  VG_CUDA(c, c->d_scratchR.reserve((size_t)winSlots * 2 * A.capR * 2 + 64));
+  VG_CUDA(c, c->d_cand.reserve((size_t)nItems * maxWin * 3 * 4));
+  VG_CUDA(c, c->d_ncand.reserve((size_t)nItems * 4));
+  VG_CUDA(c, c->d_counter.reserve(64));
+  A.S = c->d_seedS.as<uint64_t>();
+  A.nS = c->d_seedNS.as<int32_t>();
+  A.fallback = c->d_seedFb.as<int32_t>();
+  A.candKey = c->d_seqOff.as<uint32_t>();
+  A.candVal = A.candKey + (size_t)winSlots * 2 * A.capC;
+  A.scratchR = c->d_scratchR.as<uint16_t>();
+  A.windows = c->d_cand.as<int32_t>();
+  A.nWindows = c->d_ncand.as<int32_t>();
+  A.counters = c->d_counter.as<int>() + 4;
+  VG_CUDA(c, cudaMemsetAsync(A.counters, 0, 16, c->stream));
+  for (int64_t s = 0; s < nItems; s += subItems) {
+    A.itemBase = s;
+    A.nItems = (int)std::min(subItems, nItems - s);
+    VG_CUDA(c, cudaMemsetAsync(A.counters, 0, 8, c->stream));
+    seed_gen_kernel<<<genBlocks, genWarps * 32, genSmem, c->stream>>>(A);
+    VG_LAUNCH_CHECK(c);
+    seed_win_kernel<<<winBlocks, winWarps * 32, winSmem, c->stream>>>(A);
+    VG_LAUNCH_CHECK(c);
+  }
+  int flags[4] = {0, 0, 0, 0};
+  VG_CUDA(c, cudaMemcpyAsync(flags, A.counters, 16, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (flags[2]) {
+    const int f = flags[2];
+    return vg_fail(c, VG_ERR_OVERFLOW, "seeding work buffer overflow (flags 0x%x:%s%s); shorten reads", f,
+                   (f & 8) ? " window list" : "", (f & 16) ? " read too long" : "");
+  }
+  c->seedFallbacks = flags[3];
+  if (flags[3] > 0)
+    VG_TRY(seed_launch_v1(c, msa, d_bases, d_off1, d_len1, d_off2, d_len2, d_pairIdx, flags[3], singleReads, maxReadLen, maxWin,
+                          dbgHits, dbgNHits, c->d_seedFb.as<int32_t>()));
   return VG_OK;
 }
