@@ -2,7 +2,10 @@
 --import-source on:  ncu_lines.py rep [top_n] [file_substr]"""
 import csv, subprocess, sys
 rep = sys.argv[1]; n = int(sys.argv[2]) if len(sys.argv) > 2 else 40; want = sys.argv[3] if len(sys.argv) > 3 else ""
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+extra = []
+for a in sys.argv:
+    if a.startswith("--kernel="): extra = ["--kernel-name", "regex:" + a.split("=", 1)[1]]
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"] + extra, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 cur = None; lines = []
 for r in rows:

@@ -68,6 +68,7 @@ struct vg_ctx {
   DevBuf d_poscode;   // u32 per reference position: k-mer id | dup flag
   DevBuf d_exoKeys;   // sorted 64-bit packed exotic k-mers (contain a non-ACGT byte)
   int nExo = 0;
+  double seedHitsPerKmer = 0;  // expected raw hits of one read k-mer (sizes the fast path's per-item slot)
   // MSA index
   bool haveMsa = false;
   int msaLength = 0;

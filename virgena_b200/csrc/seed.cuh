@@ -39,7 +39,7 @@
 #define SD_MAXL 512             // longest supported read
 #define SD_PENDING 32           // capacity of the re-insertion queue of phase C
 #define SD_WIN 512              // entries of the shared-memory window over the sorted LongHit stream
-#define SD_LPEND 6              // per-lane re-insertion queue of the segment-parallel sweep
+#define SD_LPEND 11             // per-lane re-insertion queue of the segment-parallel sweep
 // padded window index (one spare slot per 16 entries: no bank conflicts when every lane walks its own 16-entry chunk)
 __device__ __forceinline__ int SD_WI(int e) { return e + (e >> 4); }
 

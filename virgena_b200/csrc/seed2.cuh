@@ -52,14 +52,17 @@ struct Seed2Args {
   int32_t* windows;            // [all items][maxWin][3]
   int32_t* nWindows;
   int maxWin;
-  int* counters;               // [0] gen work counter, [1] window work counter, [2] error flags, [3] fallback count
+  int* counters;               // [0] gen work counter, [1] window work counter, [2] error flags, [3] fallback count,
+                               // [4..8] fallbacks by reason
   int32_t* fallback;           // global item indices to redo with seed_kernel
   int32_t* dbgHits;
   int32_t* dbgNHits;
+  unsigned long long* prof;    // optional: cycles per phase of the window kernel (VG_SEED_DEBUG=2)
   // geometry (host computed)
   int emptyId;                 // 4^K + nExo: a table slot that is never filled
   int tabBytes, nxtBytes, qcap, rdBytes, genWarpBytes;
   int capRs, nBuckets, winWarpBytes;
+  int key24;                   // G < 16384: candidates sort on a 24-bit key (start << 10 | 1023 - (end - start)), 3 passes
 };
 
 __device__ __forceinline__ void sd2_item(const Seed2Args& A, int local, int64_t& off, int& L, int& rev) {
@@ -78,7 +81,9 @@ __device__ __forceinline__ void sd2_item(const Seed2Args& A, int local, int64_t&
   }
 }
 
-__device__ __forceinline__ void sd2_fallback(const Seed2Args& A, int local) {
+// reasons: 0 k-mer count > 127 / queue, 1 slot full, 2 long segment, 3 re-insertion queue, 4 split / LongHit capacity
+__device__ __forceinline__ void sd2_fallback(const Seed2Args& A, int local, int reason) {
+  atomicAdd(A.counters + 4 + reason, 1);
   const int slot = atomicAdd(A.counters + 3, 1);
   A.fallback[slot] = (int32_t)(A.itemBase + local);
   A.nS[local] = -1;
@@ -86,7 +91,7 @@ __device__ __forceinline__ void sd2_fallback(const Seed2Args& A, int local) {
 
 // ------------------------------------------------------------------------------------------------
 // Kernel 1: LongHit stream. One warp per read orientation; blockDim = 32 * warps.
-// Dynamic shared memory: [staged blob][per warp: tab u16 | nxt u16 | queue u32[qcap] | rd]
+// Dynamic shared memory: [staged blob][per warp: tab u16 | nxt u16 | queue u32[qcap + 4] | rd]
 //   tab[id] = head | count << 9 (count 0 = the k-mer does not occur in the read), nxt = chain of ascending
 //   read positions, queue = flattened raw hits (g << 16 | i) of the current batch of genome positions.
 // ------------------------------------------------------------------------------------------------
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
   uint16_t* tab = (uint16_t*)wbase;
   uint16_t* nxt = (uint16_t*)(wbase + A.tabBytes);
   uint32_t* queue = (uint32_t*)(wbase + A.tabBytes + A.nxtBytes);
-  uint8_t* rd = (uint8_t*)(queue + A.qcap);
+  uint8_t* rd = (uint8_t*)(queue + A.qcap + 4);  // queue[qcap]: spare slot for predicated-off writes
   const int QCAP = A.qcap;
   const int emptyId = A.emptyId;
   const unsigned lt = (1u << lane) - 1u;
@@ -131,6 +136,7 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
     __syncwarp();
     // ---- A: read k-mer table, chains built from the last chunk down so that they ascend ------------
     bool bad = false;
+    int why = 0;
 #pragma unroll 1
     for (int base = ((nk - 1) >> 5) << 5; base >= 0; base -= 32) {
       const int i = base + lane;
@@ -196,23 +202,21 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
         }
         int o = nq + excl;
 #pragma unroll
-        for (int u = 0; u < 4; u++) {  // chains of 1 or 2 read positions are the rule: straight-line code
-          const int cu = hv[u] >> 9;
-          if (cu) {
-            uint32_t i = hv[u] & 511u;
-            const uint32_t gk = (uint32_t)(g0 + u) << 16;
-            queue[o] = gk | i;
-            if (cu > 1) {
-              i = nxt[i];
-              queue[o + 1] = gk | i;
+        for (int u = 0; u < 4; u++) {  // chains of 1 or 2 read positions are the rule: branch-free, misses go to a
+          const int cu = hv[u] >> 9;   // spare slot behind the queue
+          const uint32_t i0 = hv[u] & 511u;
+          const uint32_t gk = (uint32_t)(g0 + u) << 16;
+          queue[cu ? o : QCAP] = gk | i0;
+          uint32_t i = nxt[i0];
+          queue[cu > 1 ? o + 1 : QCAP] = gk | i;
+          if (cu > 2) {
 #pragma unroll 1
-              for (int t = 2; t < cu; t++) {
-                i = nxt[i];
-                queue[o + t] = gk | i;
-              }
+            for (int t = 2; t < cu; t++) {
+              i = nxt[i];
+              queue[o + t] = gk | i;
             }
-            o += cu;
           }
+          o += cu;
         }
         nq += total;
       }
@@ -254,6 +258,7 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
         const int t0 = __popc(m0), total = t0 + __popc(m1);
         if (nS + total > A.capS) {
           bad = true;
+          why = 1;
           break;
         }
         if (em[0]) S[nS + __popc(m0 & lt)] = ((uint64_t)gg[0] << 32) | ((uint64_t)ii[0] << 16) | (uint64_t)ll[0];
@@ -263,7 +268,7 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
       __syncwarp();
     }
     if (lane == 0) {
-      if (bad) sd2_fallback(A, it);
+      if (bad) sd2_fallback(A, it, why);
       else A.nS[it] = nS;
     }
   }
@@ -275,6 +280,13 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
 //   C   : win u64[SD_WIN + 32] (padded window over the stream) | pendL u64[32][SD_LPEND]
 //   E-G : hitG u16[capRs] | P u16[capRs] | bucket u16[nBuckets]   (bins int[256] of the sort overlay hitG)
 // ------------------------------------------------------------------------------------------------
+#define SD2_PH(k)                                                            \
+  if (A.prof) {                                                              \
+    __syncwarp();                                                            \
+    const long long t2 = clock64();                                          \
+    if (lane == 0) atomicAdd(A.prof + (k), (unsigned long long)(t2 - tph)); \
+    tph = t2;                                                                \
+  }
 __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
   extern __shared__ __align__(16) uint8_t sd_smem[];
   const int lane = threadIdx.x & 31;
@@ -298,16 +310,23 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
     if (lane == 0) it = atomicAdd(A.counters + 1, 1);
     it = __shfl_sync(VG_FULL, it, 0);
     if (it >= A.nItems) break;
+    long long tph = A.prof ? clock64() : 0;
     const int64_t gi = A.itemBase + it;
     int64_t off;
     int L, rev;
     sd2_item(A, it, off, L, rev);
     const int nS = A.nS[it];
     if (nS < 0) continue;  // redone by the general kernel
+    SD2_PH(0)
     if (L > SD_MAXL && lane == 0) atomicOr(A.counters + 2, 16);
     uint64_t* S = A.S + (size_t)it * A.capS;
+    // the stream was written by the other kernel and comes from HBM: pull all of it into L2 now, so that only the
+    // first window pays the DRAM latency
+#pragma unroll 1
+    for (int e = lane * 16; e < nS; e += 32 * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(S + e));
     int nWin = 0, nR = 0;
     bool giveUp = false;
+    int why = 4;
     __syncwarp();
     // ---- C: mergeHits phase 2 (KMerCounterBase.java:422-449); see seed.cuh for the decomposition into
     // independent segments at synchronisation points. The LongHits that survive are written back to the front
@@ -321,11 +340,12 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
 #pragma unroll 4
         for (int e = lane; e < cnt; e += 32) win[SD_WI(e)] = S[tbase + e];
         __syncwarp();
-        const int lo = lane * CH, hi = min(lo + CH, cnt);
+        const int lo = lane * CH, nOwn = max(0, min(CH, cnt - lo));
+        const uint64_t* wl = win + lane * (CH + 1);  // = win + SD_WI(lo): the lane's chunk is contiguous
         int locMax = -1;
-#pragma unroll 1
-        for (int j = lo; j < hi; j++) {
-          const uint64_t v = win[SD_WI(j)];
+#pragma unroll 4
+        for (int t = 0; t < nOwn; t++) {
+          const uint64_t v = wl[t];
           locMax = max(locMax, (int)(v >> 32) + (int)(v & 0xFFFFu) + K);
         }
         int incl = locMax;
@@ -337,13 +357,17 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
         int excl = __shfl_up_sync(VG_FULL, incl, 1);
         excl = (lane == 0) ? runMaxE : max(excl, runMaxE);
         uint32_t fmask = 0;
+        int mLast = excl;  // running maximum end in front of the lane's last flagged entry
         {
           int m = excl;
-#pragma unroll 1
-          for (int j = lo; j < hi; j++) {
-            const uint64_t v = win[SD_WI(j)];
+#pragma unroll 4
+          for (int t = 0; t < nOwn; t++) {
+            const uint64_t v = wl[t];
             const int g = (int)(v >> 32);
-            if (g > m) fmask |= 1u << (j - lo);
+            if (g > m) {
+              fmask |= 1u << t;
+              mLast = m;
+            }
             m = max(m, g + (int)(v & 0xFFFFu) + K);
           }
         }
@@ -355,6 +379,7 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
         const bool more = tbase + cnt < nS;
         if ((more ? nSeg - 1 : nSeg) <= 0) {  // a single segment longer than the window
           giveUp = true;
+          why = 2;
           break;
         }
         const int tailStart = more ? __reduce_max_sync(VG_FULL, lastFlag) : cnt;
@@ -369,19 +394,16 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
           nextFirst = __shfl_down_sync(VG_FULL, v, 1);
           if (lane == 31) nextFirst = 0x7fff;
         }
-        {  // running maximum end over the entries that are consumed now (original ends)
-          int m2 = -1;
-#pragma unroll 1
-          for (int j = lo; j < hi && j < tailStart; j++) {
-            const uint64_t v = win[SD_WI(j)];
-            m2 = max(m2, (int)(v >> 32) + (int)(v & 0xFFFFu) + K);
-          }
-          runMaxE = max(runMaxE, __reduce_max_sync(VG_FULL, m2));
-        }
+        // maximum end over the entries consumed now = what the owner of the carried-over flag saw in front of it
+        if (more) runMaxE = __shfl_sync(VG_FULL, mLast, tailStart / CH);
         const int s0 = min(firstFlag, tailStart), s1 = min(nextFirst, tailStart);  // s0 == s1: nothing to do
         __syncwarp();
-        // all lanes step through their ranges in lock-step (one polled element per trip): the sweep of
-        // KMerCounterBase.java:422-449 verbatim, started afresh at a synchronisation point; results in place
+        // All lanes step through their ranges in lock-step, one polled element per trip: the sweep of
+        // KMerCounterBase.java:422-449, started afresh at a synchronisation point; results in place. The common
+        // cases are branch-free: with prev = (pg, pr, pl) and the polled element (cg, cr, cl),
+        //   no overlap                      -> emit prev, prev = curr              (:443-446)
+        //   overlap, prev shorter           -> emit prev truncated to cg - pg - K if >= 0, prev = curr (:428-433)
+        //   overlap, prev at least as long  -> curr clipped on the left and re-inserted if it keeps >= K (:435-441)
         bool ovf = false;
         int si = s0, w = s0, np = 0;
         bool have = false;
@@ -402,60 +424,55 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
               si++;
             }
             int cg = (int)(v >> 32), cr = (int)((v >> 16) & 0xFFFFu), cl = (int)(v & 0xFFFFu);
-            if (!have) {
-              have = true;
+            const int pe = pg + pl + K;
+            const bool ov = have && pe - 1 >= cg;
+            const bool keepPrev = ov && pl >= cl;
+            const int tl = cg - pg - K;
+            if (have && !keepPrev && (!ov || tl >= 0)) {
+              win[SD_WI(w)] = ((uint64_t)pg << 32) | ((uint64_t)pr << 16) | (uint64_t)(ov ? tl : pl);
+              w++;
+            }
+            have = true;
+            if (!keepPrev) {
               pg = cg, pr = cr, pl = cl;
-            } else if (pg + pl + K - 1 >= cg) {
-              if (pl < cl) {
-                pl = cg - pg - K;
-                if (pl >= 0) {
-                  win[SD_WI(w)] = ((uint64_t)pg << 32) | ((uint64_t)pr << 16) | (uint64_t)pl;
-                  w++;
+            } else {
+              const int lenDiff = pe - cg;
+              cl -= lenDiff;
+              if (cl >= 0) {
+                cg += lenDiff;
+                cr += lenDiff;
+                // TreeSet.add: dropped when an element with the same (genomePos, readPos) is present (Q2)
+                const uint64_t key = ((uint64_t)cg << 16) | (uint64_t)cr;
+                bool present = false;
+                int ins = np;
+#pragma unroll 1
+                for (int t = 0; t < np; t++) {
+                  const uint64_t pk = pend[t] >> 16;
+                  if (pk == key) present = true;
+                  if (pk > key && ins == np) ins = t;
                 }
-                pg = cg, pr = cr, pl = cl;
-              } else {
-                const int lenDiff = pg + pl + K - cg;
-                cl -= lenDiff;
-                if (cl >= 0) {
-                  cg += lenDiff;
-                  cr += lenDiff;
-                  // TreeSet.add: dropped when an element with the same (genomePos, readPos) is present (Q2)
-                  const uint64_t key = ((uint64_t)cg << 16) | (uint64_t)cr;
-                  bool present = false;
-                  int ins = np;
+                if (!present)
 #pragma unroll 1
-                  for (int t = 0; t < np; t++) {
-                    const uint64_t pk = pend[t] >> 16;
-                    if (pk == key) present = true;
-                    if (pk > key && ins == np) ins = t;
+                  for (int j = si; j < s1; j++) {  // the key lies before the next synchronisation point
+                    const uint64_t k = win[SD_WI(j)] >> 16;
+                    if (k >= key) {
+                      present = (k == key);
+                      break;
+                    }
                   }
-                  if (!present)
+                if (!present) {
+                  if (np >= SD_LPEND) {
+                    ovf = true;
+                    np = 0;
+                    si = s1;
+                  } else {
 #pragma unroll 1
-                    for (int j = si; j < s1; j++) {  // the key lies before the next synchronisation point
-                      const uint64_t k = win[SD_WI(j)] >> 16;
-                      if (k >= key) {
-                        present = (k == key);
-                        break;
-                      }
-                    }
-                  if (!present) {
-                    if (np >= SD_LPEND) {
-                      ovf = true;
-                      np = 0;
-                      si = s1;
-                    } else {
-#pragma unroll 1
-                      for (int t = np; t > ins; t--) pend[t] = pend[t - 1];
-                      pend[ins] = (key << 16) | (uint64_t)cl;
-                      np++;
-                    }
+                    for (int t = np; t > ins; t--) pend[t] = pend[t - 1];
+                    pend[ins] = (key << 16) | (uint64_t)cl;
+                    np++;
                   }
                 }
               }
-            } else {
-              win[SD_WI(w)] = ((uint64_t)pg << 32) | ((uint64_t)pr << 16) | (uint64_t)pl;
-              w++;
-              pg = cg, pr = cr, pl = cl;
             }
           }
           __syncwarp();
@@ -464,27 +481,26 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
           win[SD_WI(w)] = ((uint64_t)pg << 32) | ((uint64_t)pr << 16) | (uint64_t)pl;
           w++;
         }
-#pragma unroll 1
-        for (int t = w; t < s1; t++) win[SD_WI(t)] = ~0ull;  // consumed, not emitted
         __syncwarp();
         if (__any_sync(VG_FULL, ovf)) {
           giveUp = true;
+          why = 3;
           break;
         }
+        {  // ordered copy-out: every lane appends its run of survivors behind those of the lanes below
+          const int c = w - s0;
+          const int ic = sd_warp_incl_scan(c, lane);
+          uint64_t* dst = S + nR + ic - c;
 #pragma unroll 1
-        for (int e0 = 0; e0 < tailStart; e0 += 32) {  // ordered compaction
-          const int e = e0 + lane;
-          const uint64_t v = (e < tailStart) ? win[SD_WI(e)] : ~0ull;
-          const bool ok = v != ~0ull;
-          const unsigned m = __ballot_sync(VG_FULL, ok);
-          if (ok) S[nR + __popc(m & lt)] = v;
-          nR += __popc(m);
+          for (int t = 0; t < c; t++) dst[t] = win[SD_WI(s0 + t)];
+          nR += __shfl_sync(VG_FULL, ic, 31);
         }
         __syncwarp();
         tbase += tailStart;
       }
     }
     __syncwarp();
+    SD2_PH(1)
     // ---- D: KMerCounter.splitLongHits (KMerCounter.java:142-185); hits are independent given their contig
     if (!giveUp && A.nContigs > 1 && nR > 0) {
       __threadfence_block();
@@ -545,7 +561,7 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
       __syncwarp();
     }
     if (giveUp || nR > A.capR) {
-      if (lane == 0) sd2_fallback(A, it);
+      if (lane == 0) sd2_fallback(A, it, why);
       continue;
     }
     __threadfence_block();
@@ -620,6 +636,7 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
         }
       }
       __syncwarp();
+      SD2_PH(2)
       // ---- F: every window independently (updateCount equals a direct recount on sorted non-overlapping
       //         hits); candidates (count > cutoff, strict) compacted in hit order
       const int cutoff = (L < A.nCutoffs) ? A.cutoffs[L] : 0x7fffffff;
@@ -657,7 +674,8 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
           if ((int)(vb >> 32) + K + (int)(vb & 0xFFFFu) > end) b--;
           cnt = (uint32_t)((uint16_t)(Pp[b] - Pp[a])) + (uint32_t)(va & 0xFFFFu);
           isCand = (int)cnt > cutoff;
-          key = ((uint32_t)start << 16) | (uint32_t)(0xFFFF - end);
+          // order (start asc, end desc); a window is at most 1.5 L <= 768 wide
+          key = A.key24 ? ((uint32_t)start << 10) | (uint32_t)(1023 - (end - start)) : ((uint32_t)start << 16) | (uint32_t)(0xFFFF - end);
         }
         const unsigned m = __ballot_sync(VG_FULL, isCand);
         if (isCand) {
@@ -668,22 +686,27 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
         nC += __popc(m);
       }
       __syncwarp();
+      SD2_PH(3)
       // ---- G: stable sort by (start asc, end desc) + pruneWindows (KMerCounterBase.java:317-335). The pivot only
       //         changes at the first later candidate that either does not overlap it (emit, new pivot) or overlaps
       //         with a larger count (new pivot); the warp looks at 32 candidates at a time.
       if (nC > 0) {
-        const int srcb = sd_radix_sort(ckey, cval, capC, nC, bins, lane, 32);
+        const int srcb = sd_radix_sort(ckey, cval, capC, nC, bins, lane, A.key24 ? 24 : 32);
         __threadfence_block();
+        SD2_PH(4)
         const uint32_t* ks = ckey + (size_t)srcb * capC;
         const uint32_t* vs = cval + (size_t)srcb * capC;
         int32_t* W = A.windows + (size_t)gi * A.maxWin * 3;
-        int ps = ks[0] >> 16, pe = 0xFFFF - (ks[0] & 0xFFFF), pc = vs[0];
+        const bool k24 = A.key24 != 0;
+        const uint32_t k0 = ks[0];
+        int ps = k24 ? k0 >> 10 : k0 >> 16, pe = k24 ? ps + 1023 - (int)(k0 & 1023u) : 0xFFFF - (int)(k0 & 0xFFFFu), pc = vs[0];
 #pragma unroll 1
         for (int t0 = 1; t0 < nC; t0 += 32) {
           const int idx = t0 + lane;
           const bool valid = idx < nC;
           const uint32_t k = valid ? ks[idx] : 0u;
-          const int cs_ = k >> 16, ce_ = 0xFFFF - (k & 0xFFFF), cc = valid ? (int)vs[idx] : 0;
+          const int cs_ = k24 ? k >> 10 : k >> 16, ce_ = k24 ? cs_ + 1023 - (int)(k & 1023u) : 0xFFFF - (int)(k & 0xFFFFu);
+          const int cc = valid ? (int)vs[idx] : 0;
           int from = 0;  // lanes below `from` are already behind the pivot
 #pragma unroll 1
           for (;;) {
@@ -709,5 +732,6 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
     }
     if (lane == 0) A.nWindows[gi] = nWin;
     __syncwarp();
+    SD2_PH(5)
   }
 }

@@ -105,6 +105,13 @@ static int seed_build_reference(vg_ctx* c, const uint8_t* keys, const int64_t* o
     }
     pc[p] = v;
   }
+  {  // expected raw hits per read k-mer when the read is drawn from this reference: sum_id count(id)^2 / positions
+    std::unordered_map<uint32_t, int> cnt;
+    for (int p = 0; p < nPos; p++) cnt[pc[p] & 0x7FFFu]++;
+    double ss = 0;
+    for (auto& kv : cnt) ss += (double)kv.second * kv.second;
+    c->seedHitsPerKmer = nPos > 0 ? ss / nPos : 0.0;
+  }
   VG_CUDA(c, c->d_poscode.reserve(blob.size()));
   VG_CUDA(c, cudaMemcpy(c->d_poscode.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
   VG_CUDA(c, c->d_exoKeys.reserve(exo.size() * 8 + 8));
@@ -317,7 +324,7 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     A.nxtBytes = (maxReadLen * 2 + 15) & ~15;
     A.qcap = 512;
     A.rdBytes = (maxReadLen + 16 + 15) & ~15;
-    A.genWarpBytes = A.tabBytes + A.nxtBytes + A.qcap * 4 + A.rdBytes;
+    A.genWarpBytes = A.tabBytes + A.nxtBytes + (A.qcap + 4) * 4 + A.rdBytes;
     A.blobRefBytes = sdh_ref_pad(G);
     A.blobBytes = A.blobRefBytes + sdh_code_pad(G);
     genWarps = std::min(32, (smemMax - 64 - A.blobBytes) / A.genWarpBytes);
@@ -357,17 +364,19 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   A.maxWin = maxWin;
   A.dbgHits = dbgHits;
   A.dbgNHits = dbgNHits;
-  // per-item slot: 1.6 x the expected number of raw LongHits of a random read (0.75 of the raw k-mer hits start a
-  // chain) + slack; a read that needs more is redone by the general kernel
+  // per-item slot: 1.25 x the expected number of raw LongHits of a read drawn from the reference (0.75 of the raw k-mer
+  // hits start a chain) + slack; a read that needs more is redone by the general kernel
   {
-    const double nk = std::max(1, maxReadLen - K + 1), nPos = G - K + 1;
-    const double expect = 0.75 * nk * nPos / (double)(1u << (2 * K));
-    A.capS = (int)std::min<double>(65536.0, std::max(1024.0, 1.6 * expect + 512.0));
+    const double nk = std::max(1, maxReadLen - K + 1);
+    const double expect = 0.75 * nk * c->seedHitsPerKmer;
+    A.capS = (int)std::min<double>(65536.0, std::max(1024.0, 1.25 * expect + 1024.0));
     A.capS = (A.capS + 255) & ~255;
     if (const char* e = getenv("VG_SEED_CAPS2")) A.capS = std::max(64, atoi(e));
   }
+  size_t sBudget = 8ull << 30;
+  if (const char* e = getenv("VG_SEED_SUBMB")) sBudget = (size_t)std::max(1, atoi(e)) << 20;
   A.capC = A.capR;
-  const size_t sBudget = 4ull << 30;
+  A.key24 = (G < 16384 && !getenv("VG_SEED_KEY32")) ? 1 : 0;
   const int64_t subItems = std::max<int64_t>(4096, std::min<int64_t>(nItems, (int64_t)(sBudget / ((size_t)A.capS * 8))));
   const size_t genSmem = (size_t)A.blobBytes + (size_t)genWarps * A.genWarpBytes;
   const size_t winSmem = (size_t)winWarps * A.winWarpBytes;
@@ -384,7 +393,7 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   VG_CUDA(c, c->d_scratchR.reserve((size_t)winSlots * 2 * A.capR * 2 + 64));
   VG_CUDA(c, c->d_cand.reserve((size_t)nItems * maxWin * 3 * 4));
   VG_CUDA(c, c->d_ncand.reserve((size_t)nItems * 4));
-  VG_CUDA(c, c->d_counter.reserve(64));
+  VG_CUDA(c, c->d_counter.reserve(512));
   A.S = c->d_seedS.as<uint64_t>();
   A.nS = c->d_seedNS.as<int32_t>();
   A.fallback = c->d_seedFb.as<int32_t>();
@@ -394,19 +403,46 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   A.windows = c->d_cand.as<int32_t>();
   A.nWindows = c->d_ncand.as<int32_t>();
   A.counters = c->d_counter.as<int>() + 4;
-  VG_CUDA(c, cudaMemsetAsync(A.counters, 0, 16, c->stream));
+  VG_CUDA(c, cudaMemsetAsync(A.counters, 0, 48, c->stream));
+  const bool dbg = getenv("VG_SEED_DEBUG") != nullptr;
+  float genMs = 0, winMs = 0;
+  if (dbg && atoi(getenv("VG_SEED_DEBUG")) >= 2) {
+    A.prof = (unsigned long long*)(c->d_counter.as<int>() + 32);
+    VG_CUDA(c, cudaMemsetAsync(A.prof, 0, 64, c->stream));
+  }
   for (int64_t s = 0; s < nItems; s += subItems) {
     A.itemBase = s;
     A.nItems = (int)std::min(subItems, nItems - s);
     VG_CUDA(c, cudaMemsetAsync(A.counters, 0, 8, c->stream));
+    if (dbg) cudaEventRecord(c->ev[4], c->stream);
     seed_gen_kernel<<<genBlocks, genWarps * 32, genSmem, c->stream>>>(A);
     VG_LAUNCH_CHECK(c);
+    if (dbg) cudaEventRecord(c->ev[5], c->stream);
     seed_win_kernel<<<winBlocks, winWarps * 32, winSmem, c->stream>>>(A);
     VG_LAUNCH_CHECK(c);
+    if (dbg) {
+      cudaEventRecord(c->ev[6], c->stream);
+      cudaEventSynchronize(c->ev[6]);
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, c->ev[4], c->ev[5]);
+      cudaEventElapsedTime(&b, c->ev[5], c->ev[6]);
+      genMs += a, winMs += b;
+    }
   }
-  int flags[4] = {0, 0, 0, 0};
-  VG_CUDA(c, cudaMemcpyAsync(flags, A.counters, 16, cudaMemcpyDeviceToHost, c->stream));
+  if (A.prof) {
+    unsigned long long ph[8];
+    cudaMemcpy(ph, A.prof, 64, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[seed] window kernel cycles/item: item+prefetch %.0f, C %.0f, D+E %.0f, F %.0f, sort %.0f, prune %.0f\n", ph[0] / (double)nItems,
+            ph[1] / (double)nItems, ph[2] / (double)nItems, ph[3] / (double)nItems, ph[4] / (double)nItems, ph[5] / (double)nItems);
+  }
+  if (dbg) fprintf(stderr, "[seed] gen %.2f ms, win %.2f ms over %lld items in sub-chunks of %lld\n", genMs, winMs, (long long)nItems, (long long)subItems);
+  int flags[12] = {0};
+  VG_CUDA(c, cudaMemcpyAsync(flags, A.counters, 48, cudaMemcpyDeviceToHost, c->stream));
   VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (getenv("VG_SEED_DEBUG"))
+    fprintf(stderr, "[seed] items=%lld capS=%d genWarps=%d winWarps=%d capRs=%d fallbacks=%d (count/queue %d, slot %d, long segment %d, "
+            "re-insertion %d, capacity %d)\n", (long long)nItems, A.capS, genWarps, winWarps, A.capRs, flags[3], flags[4], flags[5],
+            flags[6], flags[7], flags[8]);
   if (flags[2]) {
     const int f = flags[2];
     return vg_fail(c, VG_ERR_OVERFLOW, "seeding work buffer overflow (flags 0x%x:%s%s); shorten reads", f,
