@@ -193,6 +193,10 @@ int vg_seed_batch(vg_ctx* ctx, int32_t msa, const uint8_t* pool, const int64_t* 
  * (CUDA events on the context's stream): [0]=seeding+pair select, [1]=SW fill,
  * [2]=traceback, [3]=pileup, [4]=total, [5]=SW cells (as a double count). */
 int vg_last_timings(vg_ctx* ctx, double* out6);
+/* Seeding kernels of the last map call (summed over its chunks): [0]=LongHit-stream kernel ms, [1]=window kernel ms,
+ * [2]=general (fallback) kernel ms, [3]=LongHits produced by mergeHits phase 1, [4]=LongHits kept by phase 2,
+ * [5]=read orientations redone by the general kernel, [6]=sub-chunks, [7]=read orientations seeded. */
+int vg_seed_timings(vg_ctx* ctx, double* out8);
 
 /* Measurement helpers (bench.py): a DPX issue-rate microbenchmark that defines
  * the denominator of the SW roofline (packed s16x2 ops/s), and counters of the

@@ -72,6 +72,7 @@ _SIGS = {
     "vg_seed_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                 C.c_void_p]),
     "vg_last_timings": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vg_seed_timings": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vg_dpx_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "vg_kernel_launches": (C.c_int64, [C.c_void_p]),
     "vg_ctx_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

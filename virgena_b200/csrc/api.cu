@@ -68,6 +68,7 @@ void vg_ctx_destroy(vg_ctx* c) {
   for (DevBuf* b : bufs) b->release();
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : c->seedEv) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -79,6 +80,12 @@ int64_t vg_kernel_launches(const vg_ctx* c) { return c ? c->launches : 0; }
 int vg_ctx_stream(vg_ctx* c, void** stream) {
   if (!c || !stream) return VG_ERR_INVALID;
   *stream = (void*)c->stream;
+  return VG_OK;
+}
+
+int vg_seed_timings(vg_ctx* c, double* out8) {
+  if (!c || !out8) return VG_ERR_INVALID;
+  for (int i = 0; i < 8; i++) out8[i] = c->seedStats[i];
   return VG_OK;
 }
 

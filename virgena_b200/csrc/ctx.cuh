@@ -91,6 +91,9 @@ struct vg_ctx {
   DevBuf d_s1pool, d_s2pool, d_s1off, d_s2off, d_rowpool, d_rowLen, d_scratchR;
   DevBuf d_seedS, d_seedNS, d_seedFb;  // fast seeding path: per-item LongHit slots, counts, fallback list
   int64_t seedFallbacks = 0;           // items of the last seeding call redone by the general kernel
+  std::vector<cudaEvent_t> seedEv;     // 3 events per sub-chunk of the fast seeding path
+  double seedStats[8] = {0};           // last map call: gen ms, window ms, fallback ms, LongHits in, LongHits kept, fallback items,
+                                       // sub-chunks, items
   int64_t lastTasks = 0;
   // pileup
   DevBuf d_counts;

@@ -160,6 +160,7 @@ static int mh_map(vg_ctx* c, bool msa, const int64_t* pair_idx, int64_t n_idx, v
   c->seq1Bytes = 0;
   c->resultsMsa = msa;
   for (double& t : c->timings) t = 0;
+  for (double& t : c->seedStats) t = 0;
   if (stats) memset(stats, 0, sizeof *stats);
   VG_CUDA(c, c->d_pairIdx.reserve((size_t)std::max<int64_t>(n, 1) * 8));
   if (pair_idx) {

@@ -138,15 +138,19 @@ __device__ __forceinline__ uint32_t sd_load4(const uint8_t* base, int pos) {
 // number of further matching bases of the chain that starts with the K-mer hit (i, g): 4 bytes per trip
 __device__ __forceinline__ int sd_extend(const uint8_t* rd, const uint8_t* ref, int i, int g, int K, int L, int G) {
   const int maxLen = min(L - i - K, G - g - K);
-  int len = 0;
+  // the first 4 bytes decide almost every chain: straight-line; longer matches take the loop
+  const uint32_t x0 = sd_load4(rd, i + K) ^ sd_load4(ref, g + K);
+  int len = x0 ? (__ffs(x0) - 1) >> 3 : 4;
+  if (x0 == 0 && maxLen > 4) {
 #pragma unroll 1
-  while (len < maxLen) {
-    const uint32_t x = sd_load4(rd, i + K + len) ^ sd_load4(ref, g + K + len);
-    if (x) {
-      len += (__ffs(x) - 1) >> 3;
-      break;
+    while (len < maxLen) {
+      const uint32_t x = sd_load4(rd, i + K + len) ^ sd_load4(ref, g + K + len);
+      if (x) {
+        len += (__ffs(x) - 1) >> 3;
+        break;
+      }
+      len += 4;
     }
-    len += 4;
   }
   return min(len, maxLen);
 }

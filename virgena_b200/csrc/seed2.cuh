@@ -53,7 +53,7 @@ struct Seed2Args {
   int32_t* nWindows;
   int maxWin;
   int* counters;               // [0] gen work counter, [1] window work counter, [2] error flags, [3] fallback count,
-                               // [4..8] fallbacks by reason
+                               // [4..8] fallbacks by reason, [10..13] two u64: LongHits in, LongHits kept
   int32_t* fallback;           // global item indices to redo with seed_kernel
   int32_t* dbgHits;
   int32_t* dbgNHits;
@@ -277,9 +277,27 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
 // ------------------------------------------------------------------------------------------------
 // Kernel 2: overlap resolution, window counts, pruning. One warp per read orientation.
 // Per-warp shared memory (winWarpBytes), two aliased uses:
-//   C   : win u64[SD_WIN + 32] (padded window over the stream) | pendL u64[32][SD_LPEND]
-//   E-G : hitG u16[capRs] | P u16[capRs] | bucket u16[nBuckets]   (bins int[256] of the sort overlay hitG)
+//   C   : win u64[SD_WIN + 32] (padded window over the stream; re-inserted LongHits go back into it)
+//   E-G : hitG u16[capRs + 8] | P u16[capRs] | len u8[capRs] | bucket u16[nBuckets]   (bins int[256] of the sort
+//         overlay hitG); len saturates at 255 (then the exact value is re-read from the stream)
 // ------------------------------------------------------------------------------------------------
+// TreeSet.add of a clipped LongHit (KMerCounterBase.java:435-441) into the sorted window: it goes in front of the first
+// unpolled element with a larger (genomePos, readPos); dropped when that key is already there (Q2). The slot of the
+// element polled last is free (the in-place output is always at least two behind), so the elements in between move
+// down by one and the stream index steps back. Its genomePos is the end of prev, which lies before the next
+// synchronisation point, i.e. inside [si, s1]. Returns the new stream index.
+__device__ __noinline__ int sd2_reinsert(uint64_t* win, int si, int s1, int g, int r, int len) {
+  const uint64_t key = ((uint64_t)g << 16) | (uint64_t)r;
+  int p = si;
+#pragma unroll 1
+  while (p < s1 && (win[SD_WI(p)] >> 16) < key) p++;
+  if (p < s1 && (win[SD_WI(p)] >> 16) == key) return si;
+#pragma unroll 1
+  for (int j = si; j < p; j++) win[SD_WI(j - 1)] = win[SD_WI(j)];
+  win[SD_WI(p - 1)] = (key << 16) | (uint64_t)len;
+  return si - 1;
+}
+
 #define SD2_PH(k)                                                            \
   if (A.prof) {                                                              \
     __syncwarp();                                                            \
@@ -295,9 +313,8 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
   const int K = A.K, G = A.G;
   uint8_t* wbase = sd_smem + (size_t)warp * A.winWarpBytes;
   uint64_t* win = (uint64_t*)wbase;
-  uint64_t* pend = (uint64_t*)(wbase + (SD_WIN + 32) * 8) + lane * SD_LPEND;
   const int capRs = A.capRs;
-  uint16_t* bucket = (uint16_t*)(wbase + (size_t)capRs * 4);
+  uint16_t* bucket = (uint16_t*)(wbase + (size_t)capRs * 5 + 16);
   int* bins = (int*)wbase;
   const int capC = A.capC;
   uint32_t* ckey = A.candKey + (size_t)warpSlot * 2 * capC;
@@ -404,26 +421,17 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
         //   no overlap                      -> emit prev, prev = curr              (:443-446)
         //   overlap, prev shorter           -> emit prev truncated to cg - pg - K if >= 0, prev = curr (:428-433)
         //   overlap, prev at least as long  -> curr clipped on the left and re-inserted if it keeps >= K (:435-441)
-        bool ovf = false;
-        int si = s0, w = s0, np = 0;
+        int si = s0, w = s0;
         bool have = false;
         int pg = 0, pr = 0, pl = 0;
 #pragma unroll 1
         for (;;) {
-          const bool act = si < s1 || np > 0;
+          const bool act = si < s1;
           if (!__any_sync(VG_FULL, act)) break;
           if (act) {
-            uint64_t v;
-            if (np > 0 && (si >= s1 || (pend[0] >> 16) < (win[SD_WI(si)] >> 16))) {  // TreeSet.pollFirst
-              v = pend[0];
-#pragma unroll 1
-              for (int t = 1; t < np; t++) pend[t - 1] = pend[t];
-              np--;
-            } else {
-              v = win[SD_WI(si)];
-              si++;
-            }
-            int cg = (int)(v >> 32), cr = (int)((v >> 16) & 0xFFFFu), cl = (int)(v & 0xFFFFu);
+            const uint64_t v = win[SD_WI(si)];  // TreeSet.pollFirst
+            si++;
+            const int cg = (int)(v >> 32), cr = (int)((v >> 16) & 0xFFFFu), cl = (int)(v & 0xFFFFu);
             const int pe = pg + pl + K;
             const bool ov = have && pe - 1 >= cg;
             const bool keepPrev = ov && pl >= cl;
@@ -435,44 +443,8 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
             have = true;
             if (!keepPrev) {
               pg = cg, pr = cr, pl = cl;
-            } else {
-              const int lenDiff = pe - cg;
-              cl -= lenDiff;
-              if (cl >= 0) {
-                cg += lenDiff;
-                cr += lenDiff;
-                // TreeSet.add: dropped when an element with the same (genomePos, readPos) is present (Q2)
-                const uint64_t key = ((uint64_t)cg << 16) | (uint64_t)cr;
-                bool present = false;
-                int ins = np;
-#pragma unroll 1
-                for (int t = 0; t < np; t++) {
-                  const uint64_t pk = pend[t] >> 16;
-                  if (pk == key) present = true;
-                  if (pk > key && ins == np) ins = t;
-                }
-                if (!present)
-#pragma unroll 1
-                  for (int j = si; j < s1; j++) {  // the key lies before the next synchronisation point
-                    const uint64_t k = win[SD_WI(j)] >> 16;
-                    if (k >= key) {
-                      present = (k == key);
-                      break;
-                    }
-                  }
-                if (!present) {
-                  if (np >= SD_LPEND) {
-                    ovf = true;
-                    np = 0;
-                    si = s1;
-                  } else {
-#pragma unroll 1
-                    for (int t = np; t > ins; t--) pend[t] = pend[t - 1];
-                    pend[ins] = (key << 16) | (uint64_t)cl;
-                    np++;
-                  }
-                }
-              }
+            } else if (cl - (pe - cg) >= 0) {
+              si = sd2_reinsert(win, si, s1, pe, cr + (pe - cg), cl - (pe - cg));
             }
           }
           __syncwarp();
@@ -482,11 +454,6 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
           w++;
         }
         __syncwarp();
-        if (__any_sync(VG_FULL, ovf)) {
-          giveUp = true;
-          why = 3;
-          break;
-        }
         {  // ordered copy-out: every lane appends its run of survivors behind those of the lanes below
           const int c = w - s0;
           const int ic = sd_warp_incl_scan(c, lane);
@@ -579,11 +546,14 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
       // ---- E: isAdjacent (IEEE binary32 division, Q3 coefficients verbatim) + prefix sums
       //         P[j] = sum_{t<=j}(len_t + isAdjacent[t-1]) (mod 2^16); genomePos table + buckets for the searches
       uint16_t* hitG = (uint16_t*)wbase;
-      uint16_t* Pp = hitG + capRs;
+      uint16_t* Pp = hitG + capRs + 8;
+      uint8_t* hitL = (uint8_t*)(Pp + capRs);
       if (nR > capRs) {  // does not fit in shared memory: L2-resident per-warp scratch
-        hitG = A.scratchR + (size_t)warpSlot * 2 * A.capR;
-        Pp = hitG + A.capR;
+        hitG = A.scratchR + (size_t)warpSlot * 3 * (A.capR + 8);
+        Pp = hitG + A.capR + 8;
+        hitL = (uint8_t*)(Pp + A.capR + 8);
       }
+      if (lane < 8) hitG[nR + lane] = 0xFFFFu;  // sentinels for the branch-free searches of phase F
       int carry = 0, pgLast = 0, prLast = 0;
 #pragma unroll 1
       for (int j0 = 0; j0 < nR; j0 += 32) {
@@ -594,6 +564,7 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
           g = (int)(v >> 32), r = (int)((v >> 16) & 0xFFFFu);
           val = (int)(v & 0xFFFFu);
           hitG[j] = (uint16_t)g;
+          hitL[j] = (uint8_t)min(val, 255);
         }
         int pg = __shfl_up_sync(VG_FULL, g, 1), pr = __shfl_up_sync(VG_FULL, r, 1);
         if (lane == 0) pg = pgLast, pr = prLast;
@@ -663,16 +634,26 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
           }
           const int start = max(cs, g - r * 3 / 2);
           const int end = min(g + len + K + (L - r - len - K) * 3 / 2, ce);
+          // a = first hit with genomePos >= start, u = first with genomePos >= end: a 32-position bucket holds at most
+          // 32 / K + 1 hits (they do not overlap), three branch-free halving steps cover 8; the loops are the safety net
           int a = bucket[start >> 5];
+          a += (hitG[a + 3] < start) ? 4 : 0;
+          a += (hitG[a + 1] < start) ? 2 : 0;
+          a += (hitG[a] < start) ? 1 : 0;
 #pragma unroll 1
           while (hitG[a] < start) a++;
           int u = bucket[min(end, G) >> 5];
+          u += (hitG[u + 3] < end) ? 4 : 0;
+          u += (hitG[u + 1] < end) ? 2 : 0;
+          u += (hitG[u] < end) ? 1 : 0;
 #pragma unroll 1
-          while (u < nR && hitG[u] < end) u++;
+          while (hitG[u] < end) u++;  // stops at the sentinel at the latest
           int b = u - 1;
-          const uint64_t va = S[a], vb = S[b];
-          if ((int)(vb >> 32) + K + (int)(vb & 0xFFFFu) > end) b--;
-          cnt = (uint32_t)((uint16_t)(Pp[b] - Pp[a])) + (uint32_t)(va & 0xFFFFu);
+          int lenA = hitL[a], lenB = hitL[b];
+          if (lenA == 255) lenA = (int)(S[a] & 0xFFFFu);
+          if (lenB == 255) lenB = (int)(S[b] & 0xFFFFu);
+          if ((int)hitG[b] + K + lenB > end) b--;
+          cnt = (uint32_t)((uint16_t)(Pp[b] - Pp[a])) + (uint32_t)lenA;
           isCand = (int)cnt > cutoff;
           // order (start asc, end desc); a window is at most 1.5 L <= 768 wide
           key = A.key24 ? ((uint32_t)start << 10) | (uint32_t)(1023 - (end - start)) : ((uint32_t)start << 16) | (uint32_t)(0xFFFF - end);
@@ -730,7 +711,12 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
         }
       }
     }
-    if (lane == 0) A.nWindows[gi] = nWin;
+    if (lane == 0) {
+      A.nWindows[gi] = nWin;
+      unsigned long long* sums = (unsigned long long*)(A.counters + 10);
+      atomicAdd(sums, (unsigned long long)nS);
+      atomicAdd(sums + 1, (unsigned long long)nR);
+    }
     __syncwarp();
     SD2_PH(5)
   }

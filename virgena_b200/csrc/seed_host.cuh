@@ -332,10 +332,10 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     A.capR = std::max(256, std::min(16384, G / K + nContigs + 16));
     A.nBuckets = (G >> 5) + 2;
     const int bucketBytes = (A.nBuckets * 2 + 15) & ~15;
-    const int cBytes = (SD_WIN + 32) * 8 + 32 * SD_LPEND * 8;
+    const int cBytes = (SD_WIN + 32) * 8;
     const int budget = (smemMax / 32) & ~15;  // per-warp bytes at 32 warps per SM
-    A.capRs = std::max(0, std::min(A.capR, (budget - bucketBytes) / 4)) & ~7;
-    A.winWarpBytes = std::max(std::max(cBytes, 1024), A.capRs * 4 + bucketBytes);
+    A.capRs = std::max(0, std::min(A.capR, (budget - bucketBytes - 16) / 5)) & ~7;
+    A.winWarpBytes = (std::max(std::max(cBytes, 1024), A.capRs * 5 + 16 + bucketBytes) + 15) & ~15;
     winWarps = std::min(32, smemMax / A.winWarpBytes);
     if (A.emptyId >= SD_NONE16 || A.emptyId > 8191 || genWarps < 8 || winWarps < 8) fast = false;
   }
@@ -390,7 +390,7 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   VG_CUDA(c, c->d_seedNS.reserve((size_t)sub0 * 4));
   VG_CUDA(c, c->d_seedFb.reserve((size_t)nItems * 4));
   VG_CUDA(c, c->d_seqOff.reserve((size_t)winSlots * 2 * A.capC * 4 * 2));
-  VG_CUDA(c, c->d_scratchR.reserve((size_t)winSlots * 2 * A.capR * 2 + 64));
+  VG_CUDA(c, c->d_scratchR.reserve((size_t)winSlots * 3 * (A.capR + 8) * 2 + 64));
   VG_CUDA(c, c->d_cand.reserve((size_t)nItems * maxWin * 3 * 4));
   VG_CUDA(c, c->d_ncand.reserve((size_t)nItems * 4));
   VG_CUDA(c, c->d_counter.reserve(512));
@@ -403,54 +403,72 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   A.windows = c->d_cand.as<int32_t>();
   A.nWindows = c->d_ncand.as<int32_t>();
   A.counters = c->d_counter.as<int>() + 4;
-  VG_CUDA(c, cudaMemsetAsync(A.counters, 0, 48, c->stream));
+  VG_CUDA(c, cudaMemsetAsync(A.counters, 0, 64, c->stream));
   const bool dbg = getenv("VG_SEED_DEBUG") != nullptr;
-  float genMs = 0, winMs = 0;
   if (dbg && atoi(getenv("VG_SEED_DEBUG")) >= 2) {
     A.prof = (unsigned long long*)(c->d_counter.as<int>() + 32);
     VG_CUDA(c, cudaMemsetAsync(A.prof, 0, 64, c->stream));
   }
-  for (int64_t s = 0; s < nItems; s += subItems) {
+  const int nSub = (int)((nItems + subItems - 1) / subItems);
+  while ((int)c->seedEv.size() < 3 * nSub + 2) {
+    cudaEvent_t e;
+    VG_CUDA(c, cudaEventCreate(&e));
+    c->seedEv.push_back(e);
+  }
+  int sub = 0;
+  for (int64_t s = 0; s < nItems; s += subItems, sub++) {
     A.itemBase = s;
     A.nItems = (int)std::min(subItems, nItems - s);
     VG_CUDA(c, cudaMemsetAsync(A.counters, 0, 8, c->stream));
-    if (dbg) cudaEventRecord(c->ev[4], c->stream);
+    VG_CUDA(c, cudaEventRecord(c->seedEv[3 * sub], c->stream));
     seed_gen_kernel<<<genBlocks, genWarps * 32, genSmem, c->stream>>>(A);
     VG_LAUNCH_CHECK(c);
-    if (dbg) cudaEventRecord(c->ev[5], c->stream);
+    VG_CUDA(c, cudaEventRecord(c->seedEv[3 * sub + 1], c->stream));
     seed_win_kernel<<<winBlocks, winWarps * 32, winSmem, c->stream>>>(A);
     VG_LAUNCH_CHECK(c);
-    if (dbg) {
-      cudaEventRecord(c->ev[6], c->stream);
-      cudaEventSynchronize(c->ev[6]);
-      float a = 0, b = 0;
-      cudaEventElapsedTime(&a, c->ev[4], c->ev[5]);
-      cudaEventElapsedTime(&b, c->ev[5], c->ev[6]);
-      genMs += a, winMs += b;
-    }
+    VG_CUDA(c, cudaEventRecord(c->seedEv[3 * sub + 2], c->stream));
   }
+  int flags[16] = {0};
+  VG_CUDA(c, cudaMemcpyAsync(flags, A.counters, 64, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  float genMs = 0, winMs = 0;
+  for (int i = 0; i < nSub; i++) {
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, c->seedEv[3 * i], c->seedEv[3 * i + 1]);
+    cudaEventElapsedTime(&b, c->seedEv[3 * i + 1], c->seedEv[3 * i + 2]);
+    genMs += a, winMs += b;
+  }
+  unsigned long long sums[2];
+  memcpy(sums, flags + 10, 16);
+  c->seedStats[0] += genMs, c->seedStats[1] += winMs;
+  c->seedStats[3] += (double)sums[0], c->seedStats[4] += (double)sums[1];
+  c->seedStats[5] += flags[3], c->seedStats[6] += nSub, c->seedStats[7] += (double)nItems;
   if (A.prof) {
     unsigned long long ph[8];
     cudaMemcpy(ph, A.prof, 64, cudaMemcpyDeviceToHost);
     fprintf(stderr, "[seed] window kernel cycles/item: item+prefetch %.0f, C %.0f, D+E %.0f, F %.0f, sort %.0f, prune %.0f\n", ph[0] / (double)nItems,
             ph[1] / (double)nItems, ph[2] / (double)nItems, ph[3] / (double)nItems, ph[4] / (double)nItems, ph[5] / (double)nItems);
   }
-  if (dbg) fprintf(stderr, "[seed] gen %.2f ms, win %.2f ms over %lld items in sub-chunks of %lld\n", genMs, winMs, (long long)nItems, (long long)subItems);
-  int flags[12] = {0};
-  VG_CUDA(c, cudaMemcpyAsync(flags, A.counters, 48, cudaMemcpyDeviceToHost, c->stream));
-  VG_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (getenv("VG_SEED_DEBUG"))
-    fprintf(stderr, "[seed] items=%lld capS=%d genWarps=%d winWarps=%d capRs=%d fallbacks=%d (count/queue %d, slot %d, long segment %d, "
-            "re-insertion %d, capacity %d)\n", (long long)nItems, A.capS, genWarps, winWarps, A.capRs, flags[3], flags[4], flags[5],
-            flags[6], flags[7], flags[8]);
+  if (dbg)
+    fprintf(stderr, "[seed] items=%lld in %d sub-chunks of %lld: gen %.2f ms, win %.2f ms; capS=%d genWarps=%d winWarps=%d capRs=%d; LongHits "
+            "%.0f -> %.0f per item; fallbacks=%d (count/queue %d, slot %d, long segment %d, re-insertion %d, capacity %d)\n",
+            (long long)nItems, nSub, (long long)subItems, genMs, winMs, A.capS, genWarps, winWarps, A.capRs, sums[0] / (double)nItems,
+            sums[1] / (double)nItems, flags[3], flags[4], flags[5], flags[6], flags[7], flags[8]);
   if (flags[2]) {
     const int f = flags[2];
     return vg_fail(c, VG_ERR_OVERFLOW, "seeding work buffer overflow (flags 0x%x:%s%s); shorten reads", f,
                    (f & 8) ? " window list" : "", (f & 16) ? " read too long" : "");
   }
   c->seedFallbacks = flags[3];
-  if (flags[3] > 0)
+  if (flags[3] > 0) {
+    VG_CUDA(c, cudaEventRecord(c->seedEv[0], c->stream));
     VG_TRY(seed_launch_v1(c, msa, d_bases, d_off1, d_len1, d_off2, d_len2, d_pairIdx, flags[3], singleReads, maxReadLen, maxWin,
                           dbgHits, dbgNHits, c->d_seedFb.as<int32_t>()));
+    VG_CUDA(c, cudaEventRecord(c->seedEv[1], c->stream));
+    VG_CUDA(c, cudaEventSynchronize(c->seedEv[1]));
+    float f = 0;
+    cudaEventElapsedTime(&f, c->seedEv[0], c->seedEv[1]);
+    c->seedStats[2] += f;
+  }
   return VG_OK;
 }

@@ -315,6 +315,12 @@ class Context:
         self._chk(self.L.vg_last_timings(self.h, ptr(t)))
         return dict(seed_ms=t[0], sw_fill_ms=t[1], traceback_ms=t[2], pileup_ms=t[3], total_ms=t[4], sw_cells=t[5])
 
+    def seed_timings(self):
+        t = np.zeros(8, np.float64)
+        self._chk(self.L.vg_seed_timings(self.h, ptr(t)))
+        return dict(gen_ms=t[0], win_ms=t[1], fallback_ms=t[2], longhits_in=t[3], longhits_kept=t[4], fallback_items=t[5],
+                    sub_chunks=t[6], items=t[7])
+
     def dpx_peak(self):
         v = C.c_double()
         self._chk(self.L.vg_dpx_peak(self.h, C.byref(v)))
