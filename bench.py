@@ -279,6 +279,7 @@ def main():
     if rank == 0:
         sampler.start()
     stage_ms = np.zeros(6)
+    seed_acc = np.zeros(8)
     barrier()
     launches1 = ctx.kernel_launches()
     ev0 = torch.cuda.Event(enable_timing=True)
@@ -289,6 +290,9 @@ def main():
         stats = step_resident()
         t = ctx.timings()
         stage_ms += np.array([t["seed_ms"], t["sw_fill_ms"], t["traceback_ms"], t["pileup_ms"], t["total_ms"], t["sw_cells"]])
+        sd = ctx.seed_timings()
+        seed_acc += np.array([sd["gen_ms"], sd["win_ms"], sd["fallback_ms"], sd["longhits_in"], sd["longhits_kept"], sd["fallback_items"],
+                              sd["windows_out"], sd["items"]])
     ev1.record(ext_stream)
     barrier()
     wall_ms = (time.time() - t0) * 1e3
@@ -328,21 +332,32 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         seed_ms, fill_ms, tb_ms, pu_ms, tot_ms, cells = stage_ms / args.steps
         dpx = ctx.dpx_peak()
-        # dominant kernel: the seeding kernel. Algorithmic HBM bytes per pair = read bases in (2 x 250 B)
-        # + window records out (4 orientations x (nWindows x 12 B + 4 B)) ~ 0.5 KB + 0.8 KB.
-        alg_bytes_pair = 2 * L + 4 * (16 * 12 + 4)
-        seed_gbs = alg_bytes_pair * n / (seed_ms * 1e-3) / 1e9
+        # The seeding stage is two kernels: seed_gen_kernel (reads -> LongHit stream, 8 B per LongHit)
+        # and seed_win_kernel (stream -> windows). Algorithmic HBM bytes per launch:
+        #   gen: read bases in (every read is seeded in both orientations: 2 x (L1 + L2) per pair) + stream out
+        #   win: stream in + window records out (12 B per window + 4 B count per orientation)
+        gen_ms, win_ms, fb_ms, lh_in, lh_kept, fb_items, win_out, items = seed_acc / args.steps
+        gen_bytes = 4 * L * n + 8 * lh_in
+        win_bytes = 8 * lh_in + 12 * win_out + 4 * items
+        kern = {"seed_gen_kernel": (gen_ms, gen_bytes), "seed_win_kernel": (win_ms, win_bytes)}
+        traffic_all = {}
+        tp = os.path.join(ROOT, "profiles", "traffic_r1.json")
+        if os.path.exists(tp):
+            traffic_all = json.load(open(tp)).get("dram_bytes_per_pair", {})
+        rl = {}
+        for k, (kms, kb) in kern.items():
+            gbs = kb / (kms * 1e-3) / 1e9 if kms else None
+            rl[k] = {"bound": "hbm", "kernel": k, "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": gbs / hbm_peak if gbs else None,
+                     "traffic": traffic_all[k] * n if k in traffic_all else None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": kb, "ms_per_step": kms}
+        dominant = max(kern, key=lambda k: kern[k][0])
         # pileup: algorithmic bytes = aligned columns read once (1 B each) + 16 B per mapped read + G*5*4 B out
         n_res, seq1_bytes = ctx.result_sizes()
         pile_bytes = seq1_bytes + 16 * int(stats[3]) + G * 5 * 4
         pile = {"bound": "hbm", "achieved": pile_bytes / (pu_ms * 1e-3) / 1e9 if pu_ms else None, "peak": hbm_peak,
                 "unit": "GB/s", "frac": pile_bytes / (pu_ms * 1e-3) / 1e9 / hbm_peak if pu_ms else None,
                 "note": "all pileup kernels (list, bin, count, reduce); 5 ms per 10^6 pairs"}
-        # measured DRAM traffic of the dominant kernel from the committed ncu capture (bytes per pair)
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic_r1.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("seed_kernel_dram_bytes_per_pair")
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -354,20 +369,24 @@ def main():
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches2 - launches1),
             "clocks": clocks,
-            "stage_ms_per_step": {"seed_pairselect": seed_ms, "sw_fill": fill_ms, "sw_traceback": tb_ms, "pileup": pu_ms,
+            "stage_ms_per_step": {"seed_pairselect": seed_ms, "seed_gen_kernel": gen_ms, "seed_win_kernel": win_ms,
+                                  "seed_fallback_kernel": fb_ms, "sw_fill": fill_ms, "sw_traceback": tb_ms, "pileup": pu_ms,
                                   "map_total": tot_ms},
-            "roofline": {"bound": "hbm", "kernel": "seed_kernel", "achieved": seed_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": seed_gbs / hbm_peak, "traffic": (traffic * n if traffic else None), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes_pair * n,
-                         "note": "seeding is shared-memory / issue bound by construction (SURVEY 8d): "
-                                 "k-mer lookups/s = %.3e" % (4 * (L - 5 + 1) * n / (seed_ms * 1e-3))},
+            "roofline": dict(rl[dominant], note="dominant kernel of the step; the seeding kernels are issue / shared-memory bound by "
+                             "construction (SURVEY 8d): LongHits generated per second = %.3e, swept per second = %.3e; "
+                             "%d of %d read orientations took the general (fallback) kernel"
+                             % (lh_in / (gen_ms * 1e-3) if gen_ms else 0, lh_in / (win_ms * 1e-3) if win_ms else 0, int(fb_items), int(items))),
+            "seed_gen_roofline": rl["seed_gen_kernel"],
+            "seed_win_roofline": rl["seed_win_kernel"],
             "sw_roofline": {"bound": "dpx", "gcups_fill": cells / (fill_ms * 1e-3) / 1e9 if fill_ms else None,
                             "gcups_fill_traceback": cells / ((fill_ms + tb_ms) * 1e-3) / 1e9 if fill_ms else None,
                             "dpx_s16x2_ops_per_s_measured": dpx,
                             "gcups_peak_3ops_per_cellpair": dpx * 2 / 3 / 1e9,
                             "frac_of_3op_peak_fill": (cells / (fill_ms * 1e-3)) / (dpx * 2 / 3) if fill_ms else None,
+                            "dpx_ops_per_cellpair_issued": 7.5,
+                            "frac_of_dpx_issue_peak_fill": (cells / 2 * 7.5 / (fill_ms * 1e-3)) / dpx if fill_ms else None,
                             "cells_per_step": cells},
-            "pileup_roofline": {"bound": "hbm", "achieved_gbs": None},
+            "pileup_roofline": pile,
             "mapping_stats": [int(x) for x in stats],
         }
         if not args.no_cpu_baseline:

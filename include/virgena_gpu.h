@@ -195,7 +195,7 @@ int vg_seed_batch(vg_ctx* ctx, int32_t msa, const uint8_t* pool, const int64_t* 
 int vg_last_timings(vg_ctx* ctx, double* out6);
 /* Seeding kernels of the last map call (summed over its chunks): [0]=LongHit-stream kernel ms, [1]=window kernel ms,
  * [2]=general (fallback) kernel ms, [3]=LongHits produced by mergeHits phase 1, [4]=LongHits kept by phase 2,
- * [5]=read orientations redone by the general kernel, [6]=sub-chunks, [7]=read orientations seeded. */
+ * [5]=read orientations redone by the general kernel, [6]=windows written, [7]=read orientations seeded. */
 int vg_seed_timings(vg_ctx* ctx, double* out8);
 
 /* Measurement helpers (bench.py): a DPX issue-rate microbenchmark that defines

@@ -93,7 +93,7 @@ struct vg_ctx {
   int64_t seedFallbacks = 0;           // items of the last seeding call redone by the general kernel
   std::vector<cudaEvent_t> seedEv;     // 3 events per sub-chunk of the fast seeding path
   double seedStats[8] = {0};           // last map call: gen ms, window ms, fallback ms, LongHits in, LongHits kept, fallback items,
-                                       // sub-chunks, items
+                                       // windows out, items
   int64_t lastTasks = 0;
   // pileup
   DevBuf d_counts;

@@ -53,7 +53,7 @@ struct Seed2Args {
   int32_t* nWindows;
   int maxWin;
   int* counters;               // [0] gen work counter, [1] window work counter, [2] error flags, [3] fallback count,
-                               // [4..8] fallbacks by reason, [10..13] two u64: LongHits in, LongHits kept
+                               // [4..8] fallbacks by reason, [10..15] three u64: LongHits in, LongHits kept, windows out
   int32_t* fallback;           // global item indices to redo with seed_kernel
   int32_t* dbgHits;
   int32_t* dbgNHits;
@@ -716,6 +716,7 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
       unsigned long long* sums = (unsigned long long*)(A.counters + 10);
       atomicAdd(sums, (unsigned long long)nS);
       atomicAdd(sums + 1, (unsigned long long)nR);
+      atomicAdd(sums + 2, (unsigned long long)nWin);
     }
     __syncwarp();
     SD2_PH(5)

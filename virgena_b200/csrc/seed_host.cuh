@@ -438,11 +438,11 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     cudaEventElapsedTime(&b, c->seedEv[3 * i + 1], c->seedEv[3 * i + 2]);
     genMs += a, winMs += b;
   }
-  unsigned long long sums[2];
-  memcpy(sums, flags + 10, 16);
+  unsigned long long sums[3];
+  memcpy(sums, flags + 10, 24);
   c->seedStats[0] += genMs, c->seedStats[1] += winMs;
   c->seedStats[3] += (double)sums[0], c->seedStats[4] += (double)sums[1];
-  c->seedStats[5] += flags[3], c->seedStats[6] += nSub, c->seedStats[7] += (double)nItems;
+  c->seedStats[5] += flags[3], c->seedStats[6] += (double)sums[2], c->seedStats[7] += (double)nItems;
   if (A.prof) {
     unsigned long long ph[8];
     cudaMemcpy(ph, A.prof, 64, cudaMemcpyDeviceToHost);

@@ -319,7 +319,7 @@ class Context:
         t = np.zeros(8, np.float64)
         self._chk(self.L.vg_seed_timings(self.h, ptr(t)))
         return dict(gen_ms=t[0], win_ms=t[1], fallback_ms=t[2], longhits_in=t[3], longhits_kept=t[4], fallback_items=t[5],
-                    sub_chunks=t[6], items=t[7])
+                    windows_out=t[6], items=t[7])
 
     def dpx_peak(self):
         v = C.c_double()
