@@ -230,10 +230,19 @@ __device__ __forceinline__ void sw_tile_recompute(const SwTask& tk, const uint8_
     uint2 w = rowckP[(int64_t)(cl + k - 1) * 32 + (k - 1)];
     vtopPrev = hi ? vg_hi(w.x) : vg_lo(w.x);
   }
+  // the top boundary (bottom row of strip k-1) is one 8-byte checkpoint per column, 256 bytes apart, in HBM: the
+  // load of the next column is issued before this column is computed and the lines further ahead are pulled into L2
+  const uint2* topRow = rowckP + (k - 1);  // + (j + k - 1) * 32 per column (unused when k == 0)
+  uint2 wNext = make_uint2(0u, 0u);
+  if (k > 0 && cl + 1 <= jmax) wNext = topRow[(int64_t)(cl + 1 + k - 1) * 32];
+  if (k > 0)
+    for (int j = cl + 2; j <= min(jmax, cl + 5); j++) asm volatile("prefetch.global.L2 [%0];" ::"l"(topRow + (int64_t)(j + k - 1) * 32));
   for (int j = cl + 1; j <= jmax; j++) {
     int vtop = 0, es = SW_NEG;
     if (k > 0) {
-      uint2 w = rowckP[(int64_t)(j + k - 1) * 32 + (k - 1)];
+      const uint2 w = wNext;
+      if (j + 1 <= jmax) wNext = topRow[(int64_t)(j + 1 + k - 1) * 32];
+      if (j + 5 <= jmax) asm volatile("prefetch.global.L2 [%0];" ::"l"(topRow + (int64_t)(j + 5 + k - 1) * 32));
       vtop = hi ? vg_hi(w.x) : vg_lo(w.x);
       es = hi ? vg_hi(w.y) : vg_lo(w.y);
     }
@@ -282,7 +291,7 @@ __device__ __forceinline__ int sw_tile_left(int k, int j) {
 }
 
 template <int R>
-__global__ void __launch_bounds__(128) sw_traceback_kernel(const SwTask* __restrict__ tasks, int ntasks,
+__global__ void __launch_bounds__(128, 6) sw_traceback_kernel(const SwTask* __restrict__ tasks, int ntasks,
                                                            const uint8_t* __restrict__ s1pool,
                                                            const uint8_t* __restrict__ s2pool, SwParams prm,
                                                            const uint2* __restrict__ rowck,
