@@ -189,6 +189,24 @@ int vg_sw_max_score_batch(vg_ctx* ctx, const uint8_t* s1_pool, const int64_t* s1
 int vg_seed_batch(vg_ctx* ctx, int32_t msa, const uint8_t* pool, const int64_t* off, int64_t n, int32_t max_windows,
                   int32_t* windows, int32_t* n_windows);
 
+/* BAM record fields of the last single-reference mapping, replacing the per-read derivations of
+ * BamPrinter.setRecordFieldsMapped / setRecordFieldsUnmapped / setCigar (BamPrinter.java:16-171); serialisation stays with
+ * htsjdk. Two records per pair result, in (pair, mate) order. ref_index is the index into Reference.contigEnds of the
+ * contig holding the alignment start (the shim applies BamPrinter's contigToRefIndex for fragmented references). CIGAR
+ * elements are len << 4 | op with the BAM op codes M=0, I=1, D=2, S=4; like the Java, an alignment that starts with an
+ * insertion or deletion carries a leading 0M. Unmapped reads have n_cigar = 0 ("*"), ref_index = -1, pos = 0, mapq = 0. */
+typedef struct {
+  int32_t flag;            /* 0x1 paired | 0x2 proper pair | 0x4 unmapped | 0x8 mate unmapped | 0x10 reverse |
+                              0x20 mate reverse | 0x40 first | 0x80 second */
+  int32_t ref_index, pos;  /* pos is 1-based inside the contig (record.setAlignmentStart) */
+  int32_t mapq;            /* 255 mapped, 0 unmapped */
+  int32_t mate_ref_index, mate_pos;
+  int32_t xn;              /* XN attribute: aligned read bases - identity */
+  int32_t n_cigar;
+  int64_t cigar_offset;    /* first element in the pool */
+} vg_bam_record;
+int vg_bam_fields(vg_ctx* ctx, vg_bam_record* out, int64_t n_records, uint32_t* cigar_pool, int64_t pool_cap, int64_t* n_ops);
+
 /* Timing of the device stages of the last map / pileup call, in milliseconds
  * (CUDA events on the context's stream): [0]=seeding+pair select, [1]=SW fill,
  * [2]=traceback, [3]=pileup, [4]=total, [5]=SW cells (as a double count). */

@@ -218,6 +218,62 @@ def cigar(seq1, start1, end1, read_len, identity):
     return s, xn.value
 
 
+def cigar_ops(seq1, start1, end1, read_len, identity):
+    """setCigar (BamPrinter.java:121-171) as (array of len << 4 | op, XN)."""
+    seq1 = _u8(seq1)
+    ops = np.zeros(len(seq1) + 4, np.uint32)
+    xn = C.c_int(0)
+    n = lib().vo_cigar(_p(seq1 if len(seq1) else np.zeros(1, np.uint8)), len(seq1), start1, end1, read_len, identity, _p(ops),
+                       len(ops), C.byref(xn))
+    return ops[:n].copy(), xn.value
+
+
+def bam_records(recs, pool, len1, len2, contig_ends):
+    """BamPrinter.setRecordFieldsMapped / setRecordFieldsUnmapped (BamPrinter.java:16-115) + printBAM's proper-pair flag
+    (:259-317) for every pair result, two records per pair in (pair, mate) order. recs = the oracle's / library's pair
+    records, pool = sequence1 bytes, len1/len2 = read lengths per pair. Returns a list of dicts with the same fields as
+    vg_bam_record and the CIGAR elements as an array (empty = "*")."""
+    contig_ends = [int(x) for x in contig_ends]
+
+    def locate(s):  # BamPrinter.java:21-30 (runs off the end when s lies behind the last contig)
+        prev = 0
+        r = 0
+        while r < len(contig_ends):
+            if s < contig_ends[r]:
+                s -= prev
+                break
+            prev = contig_ends[r]
+            r += 1
+        return r, s + 1
+
+    out = []
+    for pi in range(len(recs)):
+        cls = int(recs["cls"][pi])
+        proper = cls in (0, 1)  # VG_CLS_CONCORDANT_FR / _RF
+        for mate in range(2):
+            me, other = recs["m"][pi][mate], recs["m"][pi][1 - mate]
+            d = dict(flag=0x1 | (0x80 if mate else 0x40) | (0x2 if proper else 0), ref_index=-1, pos=0, mapq=0, mate_ref_index=-1,
+                     mate_pos=0, xn=0, cigar=np.zeros(0, np.uint32))
+            if me["present"]:
+                d["ref_index"], d["pos"] = locate(int(me["start"]) + int(me["start2"]))
+                d["mapq"] = 255
+                if me["reverse"]:
+                    d["flag"] |= 0x10
+                off, ln = int(me["seq1_offset"]), int(me["length"])
+                rl = int(len2[pi] if mate else len1[pi])
+                d["cigar"], d["xn"] = cigar_ops(pool[off:off + ln], int(me["start1"]), int(me["end1"]), rl, int(me["identity"]))
+            else:
+                d["flag"] |= 0x4
+            if other["present"]:
+                d["mate_ref_index"], d["mate_pos"] = locate(int(other["start"]) + int(other["start2"]))
+                if other["reverse"]:
+                    d["flag"] |= 0x20
+            else:
+                d["flag"] |= 0x8
+            out.append(d)
+    return out
+
+
 def revcomp(seq):
     seq = _u8(seq)
     out = np.zeros(len(seq), np.uint8)

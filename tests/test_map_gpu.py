@@ -105,6 +105,7 @@ def test_map_reads_single_reference(hiv, cfg, n, threads):
     genome = vg.Reference(ref, K=5, thread_num=threads)
     md = mapper.mapReads(reads, genome)
     _compare(md, orec, opool, ostats)
+    _compare_bam(mapper, orec, opool, len1, len2, [len(ref)])
     # pileup + consensus (both flavours of saveUncovered)
     cb = vg.ConsensusBuilderSimple(mapper)
     cons = cb.getConsensusSimple(True, 0, genome.seqB)
@@ -127,6 +128,21 @@ def test_map_reads_single_reference(hiv, cfg, n, threads):
     for f in FIELDS:
         assert (md2.remapped.records["m"][f] == osub["m"][f]).all(), f
     assert (md2.remapped.records["cls"] == osub["cls"]).all()
+
+
+def _compare_bam(mapper, orec, opool, len1, len2, contig_ends):
+    """vg_bam_fields vs the oracle's restatement of BamPrinter (flags, positions, mate fields, CIGAR, XN)."""
+    import oracle
+    import virgena_b200 as vg
+    rec, pool = vg.BamPrinter(mapper).records()
+    want = oracle.bam_records(orec, opool, len1, len2, contig_ends)
+    assert len(rec) == len(want)
+    for i, w in enumerate(want):
+        for f in ("flag", "ref_index", "pos", "mapq", "mate_ref_index", "mate_pos", "xn"):
+            assert rec[f][i] == w[f], (i, f, rec[f][i], w[f])
+        got = pool[rec["cigar_offset"][i]:rec["cigar_offset"][i] + rec["n_cigar"][i]]
+        assert got.tolist() == w["cigar"].tolist(), (i, vg.cigar_string(got), vg.cigar_string(w["cigar"]))
+    assert rec["n_cigar"].sum() == len(pool)
 
 
 @pytest.mark.parametrize("cutv", [None, 30, 60])
@@ -158,6 +174,7 @@ def test_map_reads_fragmented_reference(built, cutv):
     _compare(md, orec, opool, ostats)
     if cutv is not None:
         assert len(md.discordant) > 0 and len(md.unmapped) > 0 and len(md.rightMateMapped) > 0
+    _compare_bam(mapper, orec, opool, len1, len2, ends)
     mapper.ctx.pileup()
     assert (mapper.ctx.counts() == oracle.pileup(orec, opool, len(ref))).all()
 

@@ -302,6 +302,34 @@ def test_cigar_and_xn():
     assert oracle.cigar(b"aCG", 0, 3, 3, 2)[0] == "0M1I2M"
 
 
+def test_bam_record_fields():
+    # BamPrinter.setRecordFieldsMapped / setRecordFieldsUnmapped (BamPrinter.java:16-115), hand-derived:
+    # contigs [0,100) [100,250); pair 0 concordant (mate1 forward at 95+8=103 -> contig 1, pos 4; mate2 reverse at 20+0),
+    # pair 1 left-mate-mapped, pair 2 unmapped.
+    import virgena_b200 as vg
+    rec = np.zeros(3, vg.PAIR_DTYPE)
+    rec["m"]["seq1_offset"] = -1
+    pool = np.frombuffer(b"ACGTaC-G" + b"TTTT", np.uint8)
+    rec["cls"] = [0, 3, 5]
+    m = rec["m"][0][0]
+    m["present"], m["start"], m["start2"], m["reverse"], m["start1"], m["end1"], m["identity"], m["length"], m["seq1_offset"] = 1, 95, 8, 0, 1, 8, 5, 8, 0
+    m = rec["m"][0][1]
+    m["present"], m["start"], m["start2"], m["reverse"], m["start1"], m["end1"], m["identity"], m["length"], m["seq1_offset"] = 1, 20, 0, 1, 0, 4, 4, 4, 8
+    m = rec["m"][1][0]
+    m["present"], m["start"], m["start2"], m["reverse"], m["start1"], m["end1"], m["identity"], m["length"], m["seq1_offset"] = 1, 240, 20, 0, 0, 4, 3, 4, 8
+    out = oracle.bam_records(rec, pool, [10, 4, 5], [4, 6, 5], [100, 250])
+    a, b, c, d, e, f = out
+    assert (a["flag"], a["ref_index"], a["pos"], a["mapq"], a["mate_ref_index"], a["mate_pos"], a["xn"]) == (0x1 | 0x2 | 0x20 | 0x40, 1, 4, 255, 0, 21, 1)
+    assert vg.cigar_string(a["cigar"]) == "1S4M1I1M1D1M2S"
+    assert (b["flag"], b["ref_index"], b["pos"], b["mate_ref_index"], b["mate_pos"], b["xn"]) == (0x1 | 0x2 | 0x10 | 0x80, 0, 21, 1, 4, 0)
+    assert vg.cigar_string(b["cigar"]) == "4M"
+    # position 260 lies behind the last contig: the Java loop runs off the end (refIndex = 2, no offset subtracted)
+    assert (c["flag"], c["ref_index"], c["pos"], c["mate_ref_index"], c["mate_pos"], c["xn"]) == (0x1 | 0x8 | 0x40, 2, 261, -1, 0, 1)
+    assert (d["flag"], d["ref_index"], d["pos"], d["mapq"], d["mate_ref_index"], d["mate_pos"]) == (0x1 | 0x4 | 0x80, -1, 0, 0, 2, 261)
+    assert vg.cigar_string(d["cigar"]) == "*"
+    assert (e["flag"], f["flag"]) == (0x1 | 0x4 | 0x8 | 0x40, 0x1 | 0x4 | 0x8 | 0x80)
+
+
 # --------------------------------------------------------------------------------------------------
 # Mapper.mapRead pairing (Mapper.java:92-390)
 # --------------------------------------------------------------------------------------------------

@@ -29,6 +29,9 @@ MATE_DTYPE = np.dtype(
 )
 PAIR_DTYPE = np.dtype([("cls", "<i4"), ("pad_", "<i4"), ("m", MATE_DTYPE, (2,))], align=True)
 assert MATE_DTYPE.itemsize == 64 and PAIR_DTYPE.itemsize == 136
+BAM_DTYPE = np.dtype([("flag", "<i4"), ("ref_index", "<i4"), ("pos", "<i4"), ("mapq", "<i4"), ("mate_ref_index", "<i4"),
+                      ("mate_pos", "<i4"), ("xn", "<i4"), ("n_cigar", "<i4"), ("cigar_offset", "<i8")], align=True)
+assert BAM_DTYPE.itemsize == 40
 
 
 class VgParams(C.Structure):
@@ -73,6 +76,7 @@ _SIGS = {
                                 C.c_void_p]),
     "vg_last_timings": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vg_seed_timings": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vg_bam_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "vg_dpx_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "vg_kernel_launches": (C.c_int64, [C.c_void_p]),
     "vg_ctx_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -3,6 +3,7 @@
 #pragma once
 #include "ctx.cuh"
 #include "pileup.cuh"
+#include "bam.cuh"
 #include "seed_host.cuh"
 #include "sw_host.cuh"
 
@@ -425,6 +426,56 @@ int vg_get_results(vg_ctx* c, vg_pair_result* out, int64_t n_out, uint8_t* seq1_
     if (!seq1_pool) return vg_fail(c, VG_ERR_INVALID, "null sequence1 pool");
     VG_CUDA(c, cudaMemcpyAsync(seq1_pool, c->d_seq1pool.p, (size_t)c->seq1Bytes, cudaMemcpyDeviceToHost, c->stream));
   }
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VG_OK;
+}
+
+int vg_bam_fields(vg_ctx* c, vg_bam_record* out, int64_t n_records, uint32_t* cigar_pool, int64_t pool_cap, int64_t* n_ops) {
+  if (!c) return VG_ERR_INVALID;
+  VG_CUDA(c, cudaSetDevice(c->device));
+  if (!c->haveRef) return vg_fail(c, VG_ERR_STATE, "vg_set_reference has not been called");
+  if (c->resultsMsa) return vg_fail(c, VG_ERR_STATE, "the last mapping was MSA mode (no alignments, no BAM records)");
+  const int64_t n = c->nResults;
+  if (n_ops) *n_ops = 0;
+  if (n_records < 2 * n) {
+    c->required = 2 * n;
+    return vg_fail(c, VG_ERR_CAPACITY, "record buffer too small (%lld records)", (long long)(2 * n));
+  }
+  if (n == 0) return VG_OK;
+  if (!out) return vg_fail(c, VG_ERR_INVALID, "null output");
+  BamArgs A;
+  memset(&A, 0, sizeof A);
+  A.res = c->d_results.as<vg_pair_result>();
+  A.nPairs = n;
+  A.seq1pool = c->d_seq1pool.as<uint8_t>();
+  A.pairIdx = c->d_pairIdx.as<int64_t>();
+  A.len1 = c->d_len1.as<int32_t>();
+  A.len2 = c->d_len2.as<int32_t>();
+  A.contigEnds = c->d_contigEnds.as<int32_t>();
+  A.nContigs = (int)c->contigEnds.size();
+  VG_CUDA(c, c->d_bamN.reserve((size_t)n * 2 * 4 + 64));
+  VG_CUDA(c, c->d_bamOff.reserve((size_t)n * 2 * 8 + 64));
+  VG_CUDA(c, c->d_bamRec.reserve((size_t)n * 2 * sizeof(vg_bam_record)));
+  A.nOps = c->d_bamN.as<int32_t>();
+  const unsigned blocks = (unsigned)((2 * n + 127) / 128);
+  bam_fields_kernel<false><<<blocks, 128, 0, c->stream>>>(A);
+  VG_LAUNCH_CHECK(c);
+  int64_t total = 0;
+  VG_TRY(mh_exclusive_scan(c, A.nOps, c->d_bamOff.as<int64_t>(), 2 * n, &total));
+  if (n_ops) *n_ops = total;
+  if (pool_cap < total) {
+    c->required = total;
+    return vg_fail(c, VG_ERR_CAPACITY, "CIGAR pool too small (%lld elements)", (long long)total);
+  }
+  if (total > 0 && !cigar_pool) return vg_fail(c, VG_ERR_INVALID, "null CIGAR pool");
+  VG_CUDA(c, c->d_bamOps.reserve((size_t)std::max<int64_t>(total, 1) * 4));
+  A.opOff = c->d_bamOff.as<int64_t>();
+  A.out = c->d_bamRec.as<vg_bam_record>();
+  A.ops = c->d_bamOps.as<uint32_t>();
+  bam_fields_kernel<true><<<blocks, 128, 0, c->stream>>>(A);
+  VG_LAUNCH_CHECK(c);
+  VG_CUDA(c, cudaMemcpyAsync(out, A.out, (size_t)n * 2 * sizeof(vg_bam_record), cudaMemcpyDeviceToHost, c->stream));
+  if (total > 0) VG_CUDA(c, cudaMemcpyAsync(cigar_pool, A.ops, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream));
   VG_CUDA(c, cudaStreamSynchronize(c->stream));
   return VG_OK;
 }

@@ -16,7 +16,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import PAIR_DTYPE, VgError, VgMapStats, VgParams, ptr
+from ._lib import BAM_DTYPE, PAIR_DTYPE, VgError, VgMapStats, VgParams, ptr
 
 NULL_SEQ = b"*"  # Constants.NULL_SEQ (Constants.java:8)
 
@@ -347,6 +347,39 @@ class Context:
 
     def kernel_launches(self):
         return int(self.L.vg_kernel_launches(self.h))
+
+    def bam_fields(self):
+        """vg_bam_fields: (records BAM_DTYPE[2 * n_results], CIGAR pool uint32) of the last single-reference mapping."""
+        n = C.c_int64()
+        self._chk(self.L.vg_result_sizes(self.h, C.byref(n), None))
+        rec = np.zeros(2 * n.value, BAM_DTYPE)
+        nops = C.c_int64()
+        pool = np.zeros(max(1, 2 * n.value * 8), np.uint32)
+        rc = self.L.vg_bam_fields(self.h, ptr(rec), len(rec), ptr(pool), len(pool), C.byref(nops))
+        if rc == -4:  # VG_ERR_CAPACITY: n_ops now holds the size
+            pool = np.zeros(max(1, nops.value), np.uint32)
+            rc = self.L.vg_bam_fields(self.h, ptr(rec), len(rec), ptr(pool), len(pool), C.byref(nops))
+        self._chk(rc)
+        return rec, pool[:nops.value]
+
+
+CIGAR_OPS = "MID?S"
+
+
+def cigar_string(ops):
+    """CIGAR text of a run of len << 4 | op elements ('*' when empty)."""
+    return "".join("%d%s" % (int(o) >> 4, CIGAR_OPS[int(o) & 15]) for o in ops) or "*"
+
+
+class BamPrinter:
+    """The per-record derivations of BamPrinter (BamPrinter.java:16-171) for the last mapping of `mapper`: flags,
+    positions inside the contig, mate fields, CIGAR and XN, computed on the device. Serialisation stays with the host."""
+
+    def __init__(self, mapper):
+        self.mapper = mapper
+
+    def records(self):
+        return self.mapper.ctx.bam_fields()
 
 
 class Mapper:
