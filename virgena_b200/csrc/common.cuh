@@ -59,8 +59,8 @@ struct SwTask {
 struct SwFillOut {
   int32_t score;   // S = max V
   int32_t strip;   // smallest strip index whose maximum equals S
-  int32_t col;     // first column at which that strip reached S
-  int32_t tie;     // 1: the strip reached S again at a later column (end cell needs a scan)
+  int32_t col;     // last column of the group of 4 wavefront steps in which that strip first reached S
+  int32_t tie;     // 1: the strip reached S again in a later group (end cell needs a scan of the strip)
 };
 
 // Alignment record written by the traceback kernel (Alignment.java:4-35).

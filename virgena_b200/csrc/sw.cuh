@@ -41,6 +41,21 @@ __device__ __forceinline__ uint8_t sw_s1_byte(const uint8_t* s1, int m, int rc, 
 //   rowck[p][t][lane]  = uint2{V, Es} of lane's bottom row at wavefront step t (column j = t - lane)
 //   colck[p][tb][row]  = uint2{V, Fs} of row (0-based) at step t = 32*tb           (column j = 32*tb - row/R)
 // Indexing by the wavefront step makes every store warp-uniform and fully coalesced.
+// colA/colB = last column of the group of 4 wavefront steps in which the strip first reached its maximum (the group
+// (4q, 4q+4] lies inside one checkpoint tile because the column checkpoints are taken at steps that are multiples of 32)
+#define SW_MAX_BOOKKEEPING(JEND)                                              \
+  {                                                                           \
+    bool ph, pl, qh, ql;                                                      \
+    const uint32_t nm = __vibmax_s16x2(lanemax, cm4, &ph, &pl); /* p = lanemax >= cm4 */ \
+    (void)__vibmax_s16x2(cm4, lanemax, &qh, &ql);              /* q = cm4 >= lanemax */ \
+    tieA = pl ? (tieA | ql) : false;                                          \
+    colA = pl ? colA : (JEND);                                                \
+    tieB = ph ? (tieB | qh) : false;                                          \
+    colB = ph ? colB : (JEND);                                                \
+    lanemax = nm;                                                             \
+    cm4 = 0;                                                                  \
+  }
+
 template <int R, bool STORE>
 __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__ tasks, int ntasks,
                                                       const uint8_t* __restrict__ s1pool,
@@ -94,13 +109,13 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
       int idx = lane * R + r;
       uint32_t ca = (idx < ta.m) ? ((uint32_t)sw_s1_byte(a1, ta.m, ta.rc, idx) << 8) : SW_PAD_S1;
       uint32_t cb = (idx < tb.m) ? ((uint32_t)sw_s1_byte(b1, tb.m, tb.rc, idx) << 8) : SW_PAD_S1;
-      a[r] = ca | (cb << 16);
+      a[r] = ~(ca | (cb << 16));  // complemented: a[r] ^ b is the XNOR of the codes in one LOP3
       V[r] = 0;
       F[r] = NEGp;
     }
     __syncwarp();
 
-    uint32_t vup_prev = 0, vbot = 0, ebot = NEGp, lanemax = 0;
+    uint32_t vup_prev = 0, vbot = 0, ebot = NEGp, lanemax = 0, cm4 = 0;
     int colA = 0, colB = 0;
     bool tieA = false, tieB = false;
     // lanes whose strip starts beyond both reads never influence a result
@@ -120,10 +135,10 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
       const bool active = (j >= 1 && j <= nmax && lane <= lastLane);
       if (active) {
         const uint32_t b = wsym[j];
-        uint32_t vd = vup_prev, vu = vin, e = ein, cm = 0;
+        uint32_t vd = vup_prev, vu = vin, e = ein, cm = cm4;  // running maximum of the current group of 4 steps
 #pragma unroll
         for (int r = 0; r < R; r++) {
-          uint32_t nx = ~(a[r] ^ b);
+          uint32_t nx = a[r] ^ b;  // 0xFFFF in a lane whose symbols are equal, negative and < -256 otherwise
           uint32_t sim = __viaddmax_s16x2(nx, MATCH1p, MISp);  // equal: match, else mismatch
           uint32_t f = __vadd2(vd, sim);
           e = __viaddmax_s16x2(e, NGEPp, vu);
@@ -141,17 +156,11 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
         vbot = vu;
         ebot = e;
         vup_prev = vin;
-        {  // exact maximum: value per strip, first column reaching it, and whether it was reached again
-          bool ph, pl, qh, ql;
-          uint32_t nm = __vibmax_s16x2(lanemax, cm, &ph, &pl);  // p = lanemax >= cm
-          (void)__vibmax_s16x2(cm, lanemax, &qh, &ql);          // q = cm >= lanemax
-          tieA = pl ? (tieA | ql) : false;
-          colA = pl ? colA : j;
-          tieB = ph ? (tieB | qh) : false;
-          colB = ph ? colB : j;
-          lanemax = nm;
-        }
+        cm4 = cm;
         if (STORE) rowp[(int64_t)t * 32] = make_uint2(vbot, ebot);
+      }
+      if ((t & 3) == 0) {  // warp-uniform, every 4th step: exact maximum of the strip, the group of 4 columns that reached
+        SW_MAX_BOOKKEEPING(t - lane)  // it first, and whether a later group reached it again
       }
       if (STORE && (t & (SW_TC - 1)) == 0) {  // warp-uniform: every lane checkpoints its rows at this step
         if (active) {
@@ -161,7 +170,10 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
         }
       }
     }
-    // warp reduction: S, the smallest strip holding it, its first column and tie flag
+    if (tEnd & 3) {
+      SW_MAX_BOOKKEEPING(((tEnd + 3) & ~3) - lane)
+    }
+    // warp reduction: S, the smallest strip holding it, its first column group and tie flag
     int sA = __reduce_max_sync(VG_FULL, vg_lo(lanemax));
     int sB = __reduce_max_sync(VG_FULL, vg_hi(lanemax));
     unsigned candA = __ballot_sync(VG_FULL, vg_lo(lanemax) == sA);
@@ -271,7 +283,7 @@ __device__ __forceinline__ void sw_tile_recompute(const SwTask& tk, const uint8_
       word[r >> 3] |= nib << ((r & 7) * 4);
       v[r] = V;
       vu = V;
-      if (V == probeS && i <= tk.m && (probeCol < 0 || probeCol == j)) {
+      if (V == probeS && i <= tk.m && (probeCol < 0 || (j <= probeCol && j + 3 >= probeCol))) {
         if (i < bestI || (i == bestI && j < bestJ)) {
           bestI = i;
           bestJ = j;
@@ -331,8 +343,9 @@ __global__ void __launch_bounds__(128, 6) sw_traceback_kernel(const SwTask* __re
   if (!done) {
     int bi = 1 << 30, bj = 1 << 30;
     if (!fo.tie) {
-      int cl = sw_tile_left(fo.strip, fo.col);
-      sw_tile_recompute<R>(tk, s1, s2, prm, rowckP, colckP, hi, fo.strip, cl, fo.col, flags, 128, fo.score, fo.col, bi, bj);
+      const int jEnd = min(fo.col, tk.n);  // fo.col = last column of the group of 4 that reached the maximum
+      int cl = sw_tile_left(fo.strip, jEnd);
+      sw_tile_recompute<R>(tk, s1, s2, prm, rowckP, colckP, hi, fo.strip, cl, jEnd, flags, 128, fo.score, fo.col, bi, bj);
       haveK = fo.strip, haveCl = cl;
     } else {
       for (int jj = tk.n; jj >= 1;) {  // rare: the strip reached S at several columns
