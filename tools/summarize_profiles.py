@@ -30,10 +30,17 @@ with open(os.path.join(root, "profiles", "launches_%s.md" % tag), "w") as f:
     f.write("\nTotal %.1f ms over %d launches.\n" % (tot / 1e3, sum(a[0] for a in agg.values())))
 
 # ---- per-kernel metrics -------------------------------------------------------------------------------
+def load(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    return list(csv.reader(out.splitlines()))
+
+
 rep = os.path.join(root, "gpurun_out", "prof_%s.ncu-rep" % tag)
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(out.splitlines()))
+rows = load(rep)
 hdr = rows[0]
+# seed_win_kernel rewrites its input in place: captured separately under application replay
+rep_win = os.path.join(root, "gpurun_out", "prof_win_%s.ncu-rep" % tag)
+rows_win = load(rep_win) if os.path.exists(rep_win) else []
 want = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
         ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "ALU(DPX) pipe active %"),
         ("sm__inst_executed_pipe_alu.sum", "ALU-pipe instr"), ("smsp__inst_executed.sum", "warp instr"),
@@ -51,14 +58,19 @@ units = rows[1]
 seen = set()
 with open(os.path.join(root, "profiles", "kernels_%s.md" % tag), "w") as f:
     f.write("# Per-kernel ncu --set full summary (%s)\n\nFrom `gpurun_out/prof_%s.ncu-rep` (`ncu --set full --clock-control none --import-source on`, "
-            "bench.py at 100k pairs/step). Times under ncu are not bench values.\n" % (tag, tag))
-    for r in rows[2:]:
-        name = r[hdr.index("Kernel Name")].split("(")[0]
-        if name in seen:
+            "tools/map_probe.py 100000 2: the mapping pipeline at 100k pairs). Times under ncu are not bench values.\n" % (tag, tag))
+    for rws, note in ((rows, ""), (rows_win, " (`--replay-mode application`, tools/map_probe.py 20000 2: the kernel rewrites its "
+                                               "multi-GB input slot in place, which kernel replay does not restore)")):
+        if not rws:
             continue
-        seen.add(name)
-        f.write("\n## `%s`\n\n| metric | value |\n|---|---|\n" % name)
-        for m, label in want:
-            if m in hdr:
-                f.write("| %s (`%s`) | %s %s |\n" % (label, m, r[hdr.index(m)], units[hdr.index(m)]))
+        h, un = rws[0], rws[1]
+        for r in rws[2:]:
+            name = r[h.index("Kernel Name")].split("(")[0]
+            if name in seen:
+                continue
+            seen.add(name)
+            f.write("\n## `%s`%s\n\n| metric | value |\n|---|---|\n" % (name, note))
+            for m, label in want:
+                if m in h:
+                    f.write("| %s (`%s`) | %s %s |\n" % (label, m, r[h.index(m)], un[h.index(m)]))
 print(open(os.path.join(root, "profiles", "launches_%s.md" % tag)).read())
