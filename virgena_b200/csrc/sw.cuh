@@ -38,9 +38,10 @@ __device__ __forceinline__ uint8_t sw_s1_byte(const uint8_t* s1, int m, int rc, 
 
 // Checkpoint layout (written by the fill kernel, read by the traceback kernel), per *pair* p of tasks
 // (2p, 2p+1) whose values sit in the lo / hi s16 lanes:
-//   rowck[p][t][lane]  = uint2{V, Es} of lane's bottom row at wavefront step t (column j = t - lane)
+//   rowck[p][lane][t-1] = uint2{V, Es} of lane's bottom row at wavefront step t (column j = t - lane); nT entries per lane
 //   colck[p][tb][row]  = uint2{V, Fs} of row (0-based) at step t = 32*tb           (column j = 32*tb - row/R)
-// Indexing by the wavefront step makes every store warp-uniform and fully coalesced.
+// Indexing by the wavefront step makes every store warp-uniform; the row checkpoints go out as whole 32-byte sectors
+// (4 steps per lane) and come back to the traceback as contiguous runs.
 // colA/colB = last column of the group of 4 wavefront steps in which the strip first reached its maximum (the group
 // (4q, 4q+4] lies inside one checkpoint tile because the column checkpoints are taken at steps that are multiples of 32)
 #define SW_MAX_BOOKKEEPING(JEND)                                              \
@@ -121,57 +122,69 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
     // lanes whose strip starts beyond both reads never influence a result
     const int lastLane = min(31, (mmax - 1) / R);
     const int tEnd = nmax + lastLane;
-    uint2* rowp = rowck + ((int64_t)pi * nT) * 32 + lane;
+    // checkpoints of the lane's bottom row: nT entries per lane, entry t - 1 = wavefront step t, written 4 steps
+    // (one 32-byte sector) at a time so that the traceback reads the boundary of a tile as one contiguous run
+    uint2* rowp = rowck + ((int64_t)pi * 32 + lane) * nT;
     uint2* colp = colck + ((int64_t)pi * nTb) * (32 * R) + lane * R;
+    const int tEnd4 = (tEnd + 3) & ~3;  // steps beyond tEnd find every lane inactive
 
-    for (int t = 1; t <= tEnd; t++) {
-      uint32_t vin = __shfl_up_sync(VG_FULL, vbot, 1);
-      uint32_t ein = __shfl_up_sync(VG_FULL, ebot, 1);
-      if (lane == 0) {
-        vin = 0;
-        ein = NEGp;
-      }
-      const int j = t - lane;
-      const bool active = (j >= 1 && j <= nmax && lane <= lastLane);
-      if (active) {
-        const uint32_t b = wsym[j];
-        uint32_t vd = vup_prev, vu = vin, e = ein, cm = cm4;  // running maximum of the current group of 4 steps
+#pragma unroll 1
+    for (int tg = 0; tg < tEnd4; tg += 4) {
+      uint2 rb[4];
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-          uint32_t nx = a[r] ^ b;  // 0xFFFF in a lane whose symbols are equal, negative and < -256 otherwise
-          uint32_t sim = __viaddmax_s16x2(nx, MATCH1p, MISp);  // equal: match, else mismatch
-          uint32_t f = __vadd2(vd, sim);
-          e = __viaddmax_s16x2(e, NGEPp, vu);
-          F[r] = __viaddmax_s16x2(F[r], NGEPp, V[r]);
-          uint32_t tm = __vmaxs2(e, F[r]);
-          vd = V[r];
-          uint32_t v = __viaddmax_s16x2_relu(tm, NGOPp, f);
-          V[r] = v;
-          vu = v;
-          if (r & 1)
-            cm = __vimax3_s16x2(cm, V[r - 1], v);
-          else if (r == R - 1)
-            cm = __vmaxs2(cm, v);
+      for (int s4 = 1; s4 <= 4; s4++) {
+        const int t = tg + s4;
+        uint32_t vin = __shfl_up_sync(VG_FULL, vbot, 1);
+        uint32_t ein = __shfl_up_sync(VG_FULL, ebot, 1);
+        if (lane == 0) {
+          vin = 0;
+          ein = NEGp;
         }
-        vbot = vu;
-        ebot = e;
-        vup_prev = vin;
-        cm4 = cm;
-        if (STORE) rowp[(int64_t)t * 32] = make_uint2(vbot, ebot);
-      }
-      if ((t & 3) == 0) {  // warp-uniform, every 4th step: exact maximum of the strip, the group of 4 columns that reached
-        SW_MAX_BOOKKEEPING(t - lane)  // it first, and whether a later group reached it again
-      }
-      if (STORE && (t & (SW_TC - 1)) == 0) {  // warp-uniform: every lane checkpoints its rows at this step
+        const int j = t - lane;
+        const bool active = (j >= 1 && j <= nmax && lane <= lastLane);
         if (active) {
-          uint2* dst = colp + (int64_t)(t / SW_TC) * (32 * R);
+          const uint32_t b = wsym[j];
+          uint32_t vd = vup_prev, vu = vin, e = ein, cm = cm4;  // running maximum of the current group of 4 steps
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            uint32_t nx = a[r] ^ b;  // 0xFFFF in a lane whose symbols are equal, negative and < -256 otherwise
+            uint32_t sim = __viaddmax_s16x2(nx, MATCH1p, MISp);  // equal: match, else mismatch
+            uint32_t f = __vadd2(vd, sim);
+            e = __viaddmax_s16x2(e, NGEPp, vu);
+            F[r] = __viaddmax_s16x2(F[r], NGEPp, V[r]);
+            uint32_t tm = __vmaxs2(e, F[r]);
+            vd = V[r];
+            uint32_t v = __viaddmax_s16x2_relu(tm, NGOPp, f);
+            V[r] = v;
+            vu = v;
+            if (r & 1)
+              cm = __vimax3_s16x2(cm, V[r - 1], v);
+            else if (r == R - 1)
+              cm = __vmaxs2(cm, v);
+          }
+          vbot = vu;
+          ebot = e;
+          vup_prev = vin;
+          cm4 = cm;
+        }
+        rb[s4 - 1] = make_uint2(vbot, ebot);
+      }
+      // once per group of 4 steps (warp-uniform): exact maximum of the strip, the group of 4 columns that reached it
+      // first, and whether a later group reached it again
+      SW_MAX_BOOKKEEPING(tg + 4 - lane)
+      if (STORE) {
+        const int j1 = tg + 1 - lane, j4 = tg + 4 - lane;
+        if (lane <= lastLane && j4 >= 1 && j1 <= nmax) {
+          uint4* dst = (uint4*)(rowp + tg);
+          dst[0] = make_uint4(rb[0].x, rb[0].y, rb[1].x, rb[1].y);
+          dst[1] = make_uint4(rb[2].x, rb[2].y, rb[3].x, rb[3].y);
+        }
+        if (((tg + 4) & (SW_TC - 1)) == 0 && lane <= lastLane && j4 >= 1 && j4 <= nmax) {  // column checkpoint of the rows
+          uint2* dst = colp + (int64_t)((tg + 4) / SW_TC) * (32 * R);
 #pragma unroll
           for (int r = 0; r < R; r++) dst[r] = make_uint2(V[r], F[r]);
         }
       }
-    }
-    if (tEnd & 3) {
-      SW_MAX_BOOKKEEPING(((tEnd + 3) & ~3) - lane)
     }
     // warp reduction: S, the smallest strip holding it, its first column group and tie flag
     int sA = __reduce_max_sync(VG_FULL, vg_lo(lanemax));
@@ -213,7 +226,7 @@ template <int R>
 __device__ __forceinline__ void sw_tile_recompute(const SwTask& tk, const uint8_t* __restrict__ s1,
                                                   const uint8_t* __restrict__ s2, const SwParams& prm,
                                                   const uint2* __restrict__ rowckP, const uint2* __restrict__ colckP,
-                                                  int hi, int k, int cl, int jmax, uint32_t* __restrict__ flags,
+                                                  int nT, int hi, int k, int cl, int jmax, uint32_t* __restrict__ flags,
                                                   int fstride, int probeS, int probeCol, int& bestI, int& bestJ) {
   constexpr int WPC = SwTb<R>::WPC;
   const int r0 = k * R;
@@ -237,24 +250,25 @@ __device__ __forceinline__ void sw_tile_recompute(const SwTask& tk, const uint8_
     }
   }
   // V(r0, cl): corner for the first diagonal
+  // top boundary = bottom row of strip k-1 (lane k-1): column j was computed at step j + k - 1, entry j + k - 2
+  const uint2* topRow = rowckP + (int64_t)(k - 1) * nT + (k - 2);  // [j] (unused when k == 0)
   int vtopPrev = 0;
   if (k > 0 && cl > 0) {
-    uint2 w = rowckP[(int64_t)(cl + k - 1) * 32 + (k - 1)];
+    uint2 w = topRow[cl];
     vtopPrev = hi ? vg_hi(w.x) : vg_lo(w.x);
   }
-  // the top boundary (bottom row of strip k-1) is one 8-byte checkpoint per column, 256 bytes apart, in HBM: the
-  // load of the next column is issued before this column is computed and the lines further ahead are pulled into L2
-  const uint2* topRow = rowckP + (k - 1);  // + (j + k - 1) * 32 per column (unused when k == 0)
+  // the boundary of the tile is one contiguous run of 8-byte checkpoints in HBM: both of its lines are requested up
+  // front and the load of the next column is issued before this column is computed
   uint2 wNext = make_uint2(0u, 0u);
-  if (k > 0 && cl + 1 <= jmax) wNext = topRow[(int64_t)(cl + 1 + k - 1) * 32];
-  if (k > 0)
-    for (int j = cl + 2; j <= min(jmax, cl + 5); j++) asm volatile("prefetch.global.L2 [%0];" ::"l"(topRow + (int64_t)(j + k - 1) * 32));
+  if (k > 0 && cl + 1 <= jmax) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(topRow + min(jmax, cl + 17)));
+    wNext = topRow[cl + 1];
+  }
   for (int j = cl + 1; j <= jmax; j++) {
     int vtop = 0, es = SW_NEG;
     if (k > 0) {
       const uint2 w = wNext;
-      if (j + 1 <= jmax) wNext = topRow[(int64_t)(j + 1 + k - 1) * 32];
-      if (j + 5 <= jmax) asm volatile("prefetch.global.L2 [%0];" ::"l"(topRow + (int64_t)(j + 5 + k - 1) * 32));
+      if (j + 1 <= jmax) wNext = topRow[j + 1];
       vtop = hi ? vg_hi(w.x) : vg_lo(w.x);
       es = hi ? vg_hi(w.y) : vg_lo(w.y);
     }
@@ -330,7 +344,7 @@ __global__ void __launch_bounds__(128, 6) sw_traceback_kernel(const SwTask* __re
   const uint8_t* s1 = s1pool + tk.s1_off;
   const uint8_t* s2 = s2pool + tk.s2_off;
   const int hi = ti & 1;
-  const uint2* rowckP = rowck + ((int64_t)(ti >> 1) * nT) * 32;
+  const uint2* rowckP = rowck + ((int64_t)(ti >> 1) * 32) * nT;
   const uint2* colckP = colck + ((int64_t)(ti >> 1) * nTb) * (32 * R);
   uint32_t* flags = flagS + tid;
   uint8_t* out = rev + (int64_t)tk.out * revStride;
@@ -345,12 +359,12 @@ __global__ void __launch_bounds__(128, 6) sw_traceback_kernel(const SwTask* __re
     if (!fo.tie) {
       const int jEnd = min(fo.col, tk.n);  // fo.col = last column of the group of 4 that reached the maximum
       int cl = sw_tile_left(fo.strip, jEnd);
-      sw_tile_recompute<R>(tk, s1, s2, prm, rowckP, colckP, hi, fo.strip, cl, jEnd, flags, 128, fo.score, fo.col, bi, bj);
+      sw_tile_recompute<R>(tk, s1, s2, prm, rowckP, colckP, nT, hi, fo.strip, cl, jEnd, flags, 128, fo.score, fo.col, bi, bj);
       haveK = fo.strip, haveCl = cl;
     } else {
       for (int jj = tk.n; jj >= 1;) {  // rare: the strip reached S at several columns
         int cl = sw_tile_left(fo.strip, jj);
-        sw_tile_recompute<R>(tk, s1, s2, prm, rowckP, colckP, hi, fo.strip, cl, jj, flags, 128, fo.score, -1, bi, bj);
+        sw_tile_recompute<R>(tk, s1, s2, prm, rowckP, colckP, nT, hi, fo.strip, cl, jj, flags, 128, fo.score, -1, bi, bj);
         jj = cl;
       }
     }
@@ -365,7 +379,7 @@ __global__ void __launch_bounds__(128, 6) sw_traceback_kernel(const SwTask* __re
       k = (i - 1) / R;
       cl = sw_tile_left(k, j);
       if (k != haveK || cl != haveCl)
-        sw_tile_recompute<R>(tk, s1, s2, prm, rowckP, colckP, hi, k, cl, j, flags, 128, -1, -1, no1, no2);
+        sw_tile_recompute<R>(tk, s1, s2, prm, rowckP, colckP, nT, hi, k, cl, j, flags, 128, -1, -1, no1, no2);
       haveK = -1;
     }
     while (!done) {

@@ -30,7 +30,7 @@ static int sw_launch_R(vg_ctx* c, const SwTask* d_tasks, int ntasks, const uint8
                        int nmax, bool traceback, SwFillOut* d_fill, SwAln* d_alns, uint8_t* d_rev, int64_t revStride,
                        double* msFill, double* msTb) {
   const int nW = nmax + 1;
-  const int nT = nmax + 32;           // wavefront steps 1 .. nmax + 31
+  const int nT = (nmax + 32 + 3) & ~3;  // wavefront steps 1 .. nmax + 31, rounded to whole groups of 4
   const int nTb = nT / SW_TC + 1;     // column checkpoints at t = 32, 64, ...
   const size_t perPair = ((size_t)nT * 32 + (size_t)nTb * 32 * R) * sizeof(uint2);
   const size_t perTask = perPair / 2;
