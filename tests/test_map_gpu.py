@@ -63,6 +63,48 @@ def test_seed_hits_and_windows(hiv):
         ctx.close()
 
 
+@pytest.mark.parametrize("K,caps", [(5, None), (5, "64"), (4, None), (3, None), (6, None)])
+def test_seed_paths_and_long_reads(built, K, caps, monkeypatch):
+    """The fast seeding path (seed2.cuh) and everything it hands to the general kernel: reads up to 512 bases with exact
+    matches longer than 255 (the shared-memory hit length saturates there), low-complexity reads (a k-mer more than 127
+    times in the read), a per-item slot that is too small for every read (VG_SEED_CAPS2), and K = 3, 4 (direct table) / 6
+    (hash path of the general kernel). Windows must equal the oracle's for every read."""
+    import oracle
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    if caps is not None:
+        monkeypatch.setenv("VG_SEED_CAPS2", caps)
+    ref, _ = synth.config_reference(1)
+    cut = np.full(600, 40 if K >= 5 else 60, np.int32)
+    rng = np.random.default_rng(11)
+    reads = []
+    for L in (300, 400, 512, 511, 257, 261):
+        p = int(rng.integers(0, len(ref) - L))
+        reads.append(ref[p:p + L].tobytes())                                   # exact copy: one LongHit of len L - K
+        reads.append(synth.revcomp(ref[p:p + L]).tobytes())                    # wrong orientation: noise only
+        r = ref[p:p + L].copy()
+        r[L // 2] = ord("N")
+        r[L // 3] = ord("A") if r[L // 3] != ord("A") else ord("C")
+        reads.append(r.tobytes())
+    reads += [b"A" * 250, b"A" * 512, b"AT" * 200, b"ACGTN" * 60, b"N" * 300, b"ACGTACG", b"AC"]
+    m1, m2 = synth.config_pairs(3, 40)
+    reads += [m1[i].tobytes() for i in range(40)] + [synth.revcomp(m2[i]).tobytes() for i in range(40)]
+    o = oracle.Oracle(K=K, cutoffs=cut)
+    o.set_reference(ref, index_thread_num=8)
+    ctx = vg.Context(K=K, cutoffs=cut)
+    ctx.set_reference(vg.Reference(ref, K=K, thread_num=8))
+    win, nwin = ctx.seed_batch(b"".join(reads), _offs(reads), max_windows=128)
+    for i, r in enumerate(reads):
+        ow = o.seed(r)
+        assert nwin[i] == len(ow), (K, caps, i, len(r), nwin[i], len(ow))
+        assert (win[i, :nwin[i]] == ow).all(), (K, caps, i)
+    for r in reads[:6]:
+        h = ctx.debug_seed_hits(r)
+        oh = o.get_hits(r)
+        assert h.shape == oh.shape and (h == oh).all(), (K, caps, len(r))
+    ctx.close()
+
+
 def test_seed_host_csr_index(hiv):
     """The host-built CSR index (with its duplicated boundary positions, Q1) gives the same result as
     letting the library rebuild it from the thread count."""

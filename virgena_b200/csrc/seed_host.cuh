@@ -238,7 +238,9 @@ static int seed_launch_v1(vg_ctx* c, bool msa, const uint8_t* d_bases, const int
   if (perSm < 1) return vg_fail(c, VG_ERR_INVALID, "seeding kernel does not fit on the device");
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((nItems + warps - 1) / warps, (int64_t)c->smCount * perSm));
   const int warpSlots = blocks * warps;
-  A.capS = 1 << 16;
+  // raw LongHits per read: 64k entries per resident warp, more when few warps run (the fallback list of the fast path
+  // is where the low-complexity reads end up), within 2 GB of scratch
+  A.capS = (int)std::max<int64_t>(1 << 16, std::min<int64_t>(1 << 22, ((int64_t)1 << 28) / warpSlots));
   if (const char* e = getenv("VG_SEED_CAPS")) A.capS = atoi(e);
   VG_CUDA(c, c->d_scratch.reserve((size_t)warpSlots * A.capS * 8));
   A.capC = msa ? std::max(g.capR, 16384) : g.capR;
