@@ -74,6 +74,7 @@ struct vg_ctx {
   int msaLength = 0;
   DevBuf d_msaOff, d_msaCols, d_msaExoKeys;  // CSR: 4^K + nExo keys
   int nMsaExo = 0;
+  double msaHitsPerKmer = 0;  // expected raw hits of one read k-mer against the MSA index
 
   // resident reads
   bool haveReads = false;

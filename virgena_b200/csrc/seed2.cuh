@@ -62,6 +62,12 @@ struct Seed2Args {
   int emptyId;                 // 4^K + nExo: a table slot that is never filled
   int tabBytes, nxtBytes, qcap, rdBytes, genWarpBytes;
   int capRs, nBuckets, winWarpBytes;
+  // MSA mode (seed_gen_msa_kernel): CSR index id -> sorted distinct alignment columns, per-warp sort scratch
+  const int32_t* msaOff;
+  const int32_t* msaCols;
+  uint32_t* rawBuf;            // [warpSlots][4][capRaw]
+  int capRaw;
+  int msaWarpBytes, idsBytes;
   int key24;                   // G < 16384: candidates sort on a 24-bit key (start << 10 | 1023 - (end - start)), 3 passes
 };
 
@@ -270,6 +276,199 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
     if (lane == 0) {
       if (bad) sd2_fallback(A, it, why);
       else A.nS[it] = nS;
+    }
+  }
+}
+
+// Stable LSD radix sort on the low `keyBits` bits of the keys (8 bits per pass), values optional (v0 == nullptr).
+// Ping-pongs between (k0, v0) and (k1, v1); returns 0 / 1 = which pair holds the result. bins = 256 ints of shared memory.
+__device__ __noinline__ int sd2_radix_sort(uint32_t* k0, uint32_t* k1, uint32_t* v0, uint32_t* v1, int n, int* bins, int lane,
+                                           int keyBits) {
+  int src = 0;
+  for (int shift = 0; shift < keyBits; shift += 8) {
+    const uint32_t* ks = src ? k1 : k0;
+    const uint32_t* vs = src ? v1 : v0;
+    uint32_t* kd = src ? k0 : k1;
+    uint32_t* vd = src ? v0 : v1;
+    for (int b = lane; b < 256; b += 32) bins[b] = 0;
+    __syncwarp();
+#pragma unroll 4
+    for (int e = lane; e < n; e += 32) atomicAdd(&bins[(ks[e] >> shift) & 255], 1);
+    __syncwarp();
+    {
+      int loc[8], sum = 0;
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        loc[t] = bins[lane * 8 + t];
+        sum += loc[t];
+      }
+      int run = sd_warp_incl_scan(sum, lane) - sum;
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        bins[lane * 8 + t] = run;
+        run += loc[t];
+      }
+    }
+    __syncwarp();
+#pragma unroll 2
+    for (int e0 = 0; e0 < n; e0 += 32) {
+      const int e = e0 + lane;
+      const bool ok = e < n;
+      const uint32_t k = ok ? ks[e] : 0;
+      const uint32_t v = (ok && v0) ? vs[e] : 0;
+      const uint32_t d = ok ? ((k >> shift) & 255u) : (256u + lane);
+      const unsigned grp = __match_any_sync(VG_FULL, d);
+      const int rank = __popc(grp & ((1u << lane) - 1));
+      const int leader = __ffs(grp) - 1;
+      int base = 0;
+      if (ok && lane == leader) {
+        base = bins[d];
+        bins[d] = base + __popc(grp);
+      }
+      base = __shfl_sync(VG_FULL, base, leader);
+      if (ok) {
+        kd[base + rank] = k;
+        if (v0) vd[base + rank] = v;
+      }
+      __syncwarp();
+    }
+    src ^= 1;
+    __threadfence_block();
+    __syncwarp();
+  }
+  return src;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 1, MSA flavour (KMerCounterMSA.getNBestRegions, KMerCounterMSA.java:71): the index maps a k-mer to the
+// sorted distinct alignment columns where it starts in some reference (ReferenceAlignment.java:104-209), so a
+// column holds many k-mers and the genome-ordered scan of seed_gen_kernel does not apply. Instead:
+//   1. every raw hit (i, c) is listed read position by read position (lane = read position, its list is contiguous);
+//   2. stable sort by diagonal c - i (descending, see 4.): a chain of mergeHits phase 1 (KMerCounterBase.java:341-421,
+//      hits on one diagonal at consecutive read positions) is now a run of consecutive i inside one diagonal;
+//   3. run starts -> LongHits (c, i, len = run length - 1);
+//   4. stable sort by c: LongHits with equal c come in descending-diagonal = ascending-i order, the TreeSet order.
+// Dynamic shared memory per warp: ids u16[idsBytes / 2] | bins int[256] | rd.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
+  extern __shared__ __align__(16) uint8_t sd_smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warpSlot = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int K = A.K, G = A.G;
+  uint8_t* wbase = sd_smem + (size_t)warp * A.msaWarpBytes;
+  uint16_t* ids = (uint16_t*)wbase;
+  int* bins = (int*)(wbase + A.idsBytes);
+  uint8_t* rd = (uint8_t*)(bins + 256);
+  const int capRaw = A.capRaw;
+  uint32_t* K0 = A.rawBuf + (size_t)warpSlot * 4 * capRaw;
+  uint32_t* K1 = K0 + capRaw;
+  uint32_t* V0 = K1 + capRaw;
+  uint32_t* V1 = V0 + capRaw;
+  const unsigned lt = (1u << lane) - 1u;
+  const uint32_t dBias = (uint32_t)(G - 1);  // key = dBias - (c - i) in [0, G + L): larger diagonal first
+
+#pragma unroll 1
+  for (;;) {
+    int it = 0;
+    if (lane == 0) it = atomicAdd(A.counters, 1);
+    it = __shfl_sync(VG_FULL, it, 0);
+    if (it >= A.nItems) break;
+    int64_t off;
+    int L, rev;
+    sd2_item(A, it, off, L, rev);
+    const int nk = L - K + 1;
+    if (nk < 1 || L > SD_MAXL) {  // NULL_SEQ / shorter than K: no k-mer (MapperMSA.java:57)
+      if (lane == 0) A.nS[it] = 0;
+      continue;
+    }
+    const uint8_t* src = A.bases + off;
+    __syncwarp();
+#pragma unroll 1
+    for (int i = lane; i < L; i += 32) rd[i] = rev ? vg_complement(src[L - 1 - i]) : src[i];
+    __syncwarp();
+#pragma unroll 1
+    for (int i = lane; i < nk; i += 32) ids[i] = (uint16_t)sd_kmer_id(rd + i, K, A.exoKeys, A.nExo);
+    __syncwarp();
+    // 1. raw hits, read position by read position
+    int nRaw = 0, why = 0;
+    bool bad = false;
+#pragma unroll 1
+    for (int base = 0; base < nk; base += 32) {
+      const int i = base + lane;
+      int lo = 0, hi = 0;
+      if (i < nk && ids[i] != SD_NONE16) {
+        lo = A.msaOff[ids[i]];
+        hi = A.msaOff[ids[i] + 1];
+      }
+      const int cnt = hi - lo;
+      const int incl = sd_warp_incl_scan(cnt, lane);
+      const int total = __shfl_sync(VG_FULL, incl, 31);
+      if (nRaw + total > capRaw) {
+        bad = true;
+        break;
+      }
+      uint32_t* dst = K0 + nRaw + incl - cnt;
+      const uint32_t kk = ((uint32_t)i << 16) + dBias + (uint32_t)i;  // low half: dBias - (c - i)
+#pragma unroll 2
+      for (int q = 0; q < cnt; q++) dst[q] = kk - (uint32_t)A.msaCols[lo + q];
+      nRaw += total;
+    }
+    __syncwarp();
+    int nSt = 0;
+    uint64_t* S = A.S + (size_t)it * A.capS;
+    if (!bad && nRaw > 0) {
+      __threadfence_block();
+      // 2. stable sort by diagonal (16-bit key in the low half, read position rides in the high half)
+      const int sb = sd2_radix_sort(K0, K1, nullptr, nullptr, nRaw, bins, lane, 16);
+      const uint32_t* ks = sb ? K1 : K0;
+      uint32_t* stPos = sb ? K0 : K1;
+      // 3. chain starts: first hit of a diagonal, or read position not the successor of the previous hit's
+#pragma unroll 1
+      for (int e0 = 0; e0 < nRaw; e0 += 32) {
+        const int e = e0 + lane;
+        bool st = false;
+        if (e < nRaw) {
+          const uint32_t k = ks[e], kp = e ? ks[e - 1] : ~k;
+          st = !(((k ^ kp) & 0xFFFFu) == 0 && (k >> 16) == (kp >> 16) + 1);
+        }
+        const unsigned m = __ballot_sync(VG_FULL, st);
+        if (st) stPos[nSt + __popc(m & lt)] = (uint32_t)e;
+        nSt += __popc(m);
+      }
+      __syncwarp();
+      __threadfence_block();
+      if (nSt > A.capS) {
+        bad = true;
+        why = 1;
+      } else {
+#pragma unroll 1
+        for (int s0 = lane; s0 < nSt; s0 += 32) {
+          const int e = (int)stPos[s0];
+          const int en = (s0 + 1 < nSt) ? (int)stPos[s0 + 1] : nRaw;
+          const uint32_t k = ks[e];
+          const int i = (int)(k >> 16);
+          const int c = (int)dBias - (int)(k & 0xFFFFu) + i;
+          V0[s0] = ((uint32_t)i << 16) | (uint32_t)c;
+          V1[s0] = (uint32_t)(en - e - 1);
+        }
+        __syncwarp();
+        __threadfence_block();
+        // 4. stable sort by column; K0 / K1 are free again and serve as the other halves
+        const int sb2 = sd2_radix_sort(V0, K0, V1, K1, nSt, bins, lane, 16);
+        const uint32_t* k2 = sb2 ? K0 : V0;
+        const uint32_t* v2 = sb2 ? K1 : V1;
+#pragma unroll 2
+        for (int e = lane; e < nSt; e += 32) {
+          const uint32_t k = k2[e];
+          S[e] = ((uint64_t)(k & 0xFFFFu) << 32) | ((uint64_t)(k >> 16) << 16) | (uint64_t)v2[e];
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      if (bad) sd2_fallback(A, it, why);
+      else A.nS[it] = nSt;
     }
   }
 }

@@ -154,6 +154,11 @@ static int seed_build_msa(vg_ctx* c, const uint8_t* keys, const int64_t* offsets
       }
   }
   off[nIds] = (int32_t)cols.size();
+  {  // expected raw hits of one read k-mer when the read is drawn from the aligned references: sum |list|^2 / sum |list|
+    double ss = 0;
+    for (size_t id = 0; id < nIds; id++) ss += (double)(off[id + 1] - off[id]) * (off[id + 1] - off[id]);
+    c->msaHitsPerKmer = cols.empty() ? 0.0 : ss / (double)cols.size();
+  }
   std::vector<uint64_t> exoKeys(exo.size());
   for (size_t e = 0; e < exo.size(); e++) exoKeys[e] = exo[e].first;
   VG_CUDA(c, c->d_msaOff.reserve(off.size() * 4));
@@ -311,26 +316,33 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
                        const int64_t* d_off2, const int32_t* d_len2, const int64_t* d_pairIdx, int64_t nItems,
                        bool singleReads, int maxReadLen, int maxWin, int32_t* dbgHits, int32_t* dbgNHits) {
   c->seedFallbacks = 0;
-  const SeedConfig& sc = c->seed;
-  const int K = sc.K, G = c->G;
+  const SeedConfig& sc = msa ? c->seedMsa : c->seed;
+  const int K = sc.K, G = msa ? c->msaLength : c->G;
   const int smemMax = 227 * 1024;
-  bool fast = !msa && !getenv("VG_SEED_V1") && !getenv("VG_SEED_HASH") && !getenv("VG_SEED_PROF") && K >= 1 && K <= 7 &&
-              G < 65535 && G >= K && maxReadLen <= SD_MAXL && maxReadLen >= K && nItems > 0 && nItems <= 0x7fffffff &&
+  bool fast = !getenv("VG_SEED_V1") && !getenv("VG_SEED_HASH") && !getenv("VG_SEED_PROF") && K >= 1 && K <= 7 && G >= K &&
+              G + maxReadLen < 65535 && maxReadLen <= SD_MAXL && maxReadLen >= K && nItems > 0 && nItems <= 0x7fffffff &&
               (maxReadLen < (int)sc.cutoffs.size());
   Seed2Args A;
   memset(&A, 0, sizeof A);
   int genWarps = 0, winWarps = 0;
   if (fast) {
-    A.emptyId = (1 << (2 * K)) + c->nExo;
-    A.tabBytes = ((A.emptyId + 1) * 2 + 15) & ~15;
-    A.nxtBytes = (maxReadLen * 2 + 15) & ~15;
-    A.qcap = 512;
     A.rdBytes = (maxReadLen + 16 + 15) & ~15;
-    A.genWarpBytes = A.tabBytes + A.nxtBytes + (A.qcap + 4) * 4 + A.rdBytes;
-    A.blobRefBytes = sdh_ref_pad(G);
-    A.blobBytes = A.blobRefBytes + sdh_code_pad(G);
-    genWarps = std::min(32, (smemMax - 64 - A.blobBytes) / A.genWarpBytes);
-    const int nContigs = (int)c->contigEnds.size();
+    if (!msa) {
+      A.emptyId = (1 << (2 * K)) + c->nExo;
+      A.tabBytes = ((A.emptyId + 1) * 2 + 15) & ~15;
+      A.nxtBytes = (maxReadLen * 2 + 15) & ~15;
+      A.qcap = 512;
+      A.genWarpBytes = A.tabBytes + A.nxtBytes + (A.qcap + 4) * 4 + A.rdBytes;
+      A.blobRefBytes = sdh_ref_pad(G);
+      A.blobBytes = A.blobRefBytes + sdh_code_pad(G);
+      genWarps = std::min(32, (smemMax - 64 - A.blobBytes) / A.genWarpBytes);
+      if (A.emptyId >= SD_NONE16 || A.emptyId > 8191) fast = false;
+    } else {
+      A.idsBytes = (maxReadLen * 2 + 15) & ~15;
+      A.msaWarpBytes = A.idsBytes + 1024 + A.rdBytes;
+      genWarps = std::min(32, smemMax / A.msaWarpBytes);
+    }
+    const int nContigs = msa ? 1 : (int)c->contigEnds.size();
     A.capR = std::max(256, std::min(16384, G / K + nContigs + 16));
     A.nBuckets = (G >> 5) + 2;
     const int bucketBytes = (A.nBuckets * 2 + 15) & ~15;
@@ -339,7 +351,7 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     A.capRs = std::max(0, std::min(A.capR, (budget - bucketBytes - 16) / 5)) & ~7;
     A.winWarpBytes = (std::max(std::max(cBytes, 1024), A.capRs * 5 + 16 + bucketBytes) + 15) & ~15;
     winWarps = std::min(32, smemMax / A.winWarpBytes);
-    if (A.emptyId >= SD_NONE16 || A.emptyId > 8191 || genWarps < 8 || winWarps < 8) fast = false;
+    if (genWarps < 8 || winWarps < 8) fast = false;
   }
   if (!fast)
     return seed_launch_v1(c, msa, d_bases, d_off1, d_len1, d_off2, d_len2, d_pairIdx, nItems, singleReads, maxReadLen, maxWin,
@@ -348,11 +360,22 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     genWarps = std::max(1, std::min(genWarps, atoi(e)));
     winWarps = std::max(1, std::min(winWarps, atoi(e)));
   }
-  A.blob = c->d_poscode.as<uint8_t>();
-  A.exoKeys = c->d_exoKeys.as<uint64_t>();
-  A.nExo = c->nExo;
-  A.contigEnds = c->d_contigEnds.as<int32_t>();
-  A.nContigs = (int)c->contigEnds.size();
+  double hitsPerKmer = c->seedHitsPerKmer;
+  if (!msa) {
+    A.blob = c->d_poscode.as<uint8_t>();
+    A.exoKeys = c->d_exoKeys.as<uint64_t>();
+    A.nExo = c->nExo;
+    A.contigEnds = c->d_contigEnds.as<int32_t>();
+    A.nContigs = (int)c->contigEnds.size();
+  } else {
+    A.exoKeys = c->d_msaExoKeys.as<uint64_t>();
+    A.nExo = c->nMsaExo;
+    A.msaOff = c->d_msaOff.as<int32_t>();
+    A.msaCols = c->d_msaCols.as<int32_t>();
+    A.contigEnds = nullptr;  // one "contig" = the whole alignment: never looked up
+    A.nContigs = 1;
+    hitsPerKmer = c->msaHitsPerKmer;
+  }
   A.G = G;
   A.K = K;
   A.lowCoef = sc.lowCoef;
@@ -368,9 +391,9 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   A.dbgNHits = dbgNHits;
   // per-item slot: 1.25 x the expected number of raw LongHits of a read drawn from the reference (0.75 of the raw k-mer
   // hits start a chain) + slack; a read that needs more is redone by the general kernel
+  const double nkMax = std::max(1, maxReadLen - K + 1);
   {
-    const double nk = std::max(1, maxReadLen - K + 1);
-    const double expect = 0.75 * nk * c->seedHitsPerKmer;
+    const double expect = (msa ? 1.0 : 0.75) * nkMax * hitsPerKmer;
     A.capS = (int)std::min<double>(65536.0, std::max(1024.0, 1.25 * expect + 1024.0));
     A.capS = (A.capS + 255) & ~255;
     if (const char* e = getenv("VG_SEED_CAPS2")) A.capS = std::max(64, atoi(e));
@@ -380,9 +403,10 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   A.capC = A.capR;
   A.key24 = (G < 16384 && !getenv("VG_SEED_KEY32")) ? 1 : 0;
   const int64_t subItems = std::max<int64_t>(4096, std::min<int64_t>(nItems, (int64_t)(sBudget / ((size_t)A.capS * 8))));
-  const size_t genSmem = (size_t)A.blobBytes + (size_t)genWarps * A.genWarpBytes;
+  const size_t genSmem = msa ? (size_t)genWarps * A.msaWarpBytes : (size_t)A.blobBytes + (size_t)genWarps * A.genWarpBytes;
   const size_t winSmem = (size_t)winWarps * A.winWarpBytes;
-  VG_CUDA(c, cudaFuncSetAttribute(seed_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmem));
+  if (msa) VG_CUDA(c, cudaFuncSetAttribute(seed_gen_msa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmem));
+  else VG_CUDA(c, cudaFuncSetAttribute(seed_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmem));
   VG_CUDA(c, cudaFuncSetAttribute(seed_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)winSmem));
   const int64_t sub0 = std::min(subItems, nItems);
   const int genBlocks = (int)std::max<int64_t>(1, std::min<int64_t>((sub0 + genWarps - 1) / genWarps, c->smCount));
@@ -396,6 +420,15 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   VG_CUDA(c, c->d_cand.reserve((size_t)nItems * maxWin * 3 * 4));
   VG_CUDA(c, c->d_ncand.reserve((size_t)nItems * 4));
   VG_CUDA(c, c->d_counter.reserve(512));
+  if (msa) {  // raw-hit sort scratch of the MSA stream kernel: 4 arrays per resident warp, within 4 GB
+    const int genSlots = genBlocks * genWarps;
+    const double want = 2.0 * nkMax * hitsPerKmer + 4096.0;
+    const int64_t fit = (int64_t)(((size_t)4 << 30) / ((size_t)genSlots * 16));
+    A.capRaw = (int)std::max<int64_t>(A.capS, std::min<int64_t>(std::min<int64_t>((int64_t)want, 1 << 18), fit)) & ~255;
+    if (const char* e = getenv("VG_SEED_CAPRAW")) A.capRaw = std::max(256, atoi(e)) & ~255;
+    VG_CUDA(c, c->d_scratch.reserve((size_t)genSlots * 4 * A.capRaw * 4));
+    A.rawBuf = c->d_scratch.as<uint32_t>();
+  }
   A.S = c->d_seedS.as<uint64_t>();
   A.nS = c->d_seedNS.as<int32_t>();
   A.fallback = c->d_seedFb.as<int32_t>();
@@ -423,7 +456,8 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     A.nItems = (int)std::min(subItems, nItems - s);
     VG_CUDA(c, cudaMemsetAsync(A.counters, 0, 8, c->stream));
     VG_CUDA(c, cudaEventRecord(c->seedEv[3 * sub], c->stream));
-    seed_gen_kernel<<<genBlocks, genWarps * 32, genSmem, c->stream>>>(A);
+    if (msa) seed_gen_msa_kernel<<<genBlocks, genWarps * 32, genSmem, c->stream>>>(A);
+    else seed_gen_kernel<<<genBlocks, genWarps * 32, genSmem, c->stream>>>(A);
     VG_LAUNCH_CHECK(c);
     VG_CUDA(c, cudaEventRecord(c->seedEv[3 * sub + 1], c->stream));
     seed_win_kernel<<<winBlocks, winWarps * 32, winSmem, c->stream>>>(A);
