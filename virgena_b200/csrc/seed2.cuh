@@ -280,63 +280,79 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
   }
 }
 
-// Stable LSD radix sort on the low `keyBits` bits of the keys (8 bits per pass), values optional (v0 == nullptr).
-// Ping-pongs between (k0, v0) and (k1, v1); returns 0 / 1 = which pair holds the result. bins = 256 ints of shared memory.
-__device__ __noinline__ int sd2_radix_sort(uint32_t* k0, uint32_t* k1, uint32_t* v0, uint32_t* v1, int n, int* bins, int lane,
-                                           int keyBits) {
-  int src = 0;
-  for (int shift = 0; shift < keyBits; shift += 8) {
-    const uint32_t* ks = src ? k1 : k0;
-    const uint32_t* vs = src ? v1 : v0;
-    uint32_t* kd = src ? k0 : k1;
-    uint32_t* vd = src ? v0 : v1;
-    for (int b = lane; b < 256; b += 32) bins[b] = 0;
-    __syncwarp();
-#pragma unroll 4
-    for (int e = lane; e < n; e += 32) atomicAdd(&bins[(ks[e] >> shift) & 255], 1);
-    __syncwarp();
-    {
-      int loc[8], sum = 0;
+#define SD2_PH(k)                                                            \
+  if (A.prof) {                                                              \
+    __syncwarp();                                                            \
+    const long long t2 = clock64();                                          \
+    if (lane == 0) atomicAdd(A.prof + (k), (unsigned long long)(t2 - tph)); \
+    tph = t2;                                                                \
+  }
+// Stable LSD radix sort on the low 16 bits of the keys (two 8-bit passes), values optional (v0 == nullptr). The caller
+// has already counted the two digits of every key into binsLo / binsHi (256 ints of shared memory each) while it produced
+// the keys, so the buffers — which live in L2 / HBM — are read only by the two scatter passes, eight chunks of keys in
+// flight per lane. Ping-pongs (k0, v0) -> (k1, v1) -> (k0, v0): the result is back in (k0, v0).
+__device__ __forceinline__ void sd2_scan_bins(int* bins, int lane) {
+  int loc[8], sum = 0;
 #pragma unroll
-      for (int t = 0; t < 8; t++) {
-        loc[t] = bins[lane * 8 + t];
-        sum += loc[t];
+  for (int t = 0; t < 8; t++) {
+    loc[t] = bins[lane * 8 + t];
+    sum += loc[t];
+  }
+  int run = sd_warp_incl_scan(sum, lane) - sum;
+#pragma unroll
+  for (int t = 0; t < 8; t++) {
+    bins[lane * 8 + t] = run;
+    run += loc[t];
+  }
+}
+
+__device__ __noinline__ void sd2_radix_sort16(uint32_t* k0, uint32_t* k1, uint32_t* v0, uint32_t* v1, int n, int* binsLo,
+                                              int* binsHi, int lane) {
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    const uint32_t* ks = pass ? k1 : k0;
+    const uint32_t* vs = pass ? v1 : v0;
+    uint32_t* kd = pass ? k0 : k1;
+    uint32_t* vd = pass ? v0 : v1;
+    int* bins = pass ? binsHi : binsLo;
+    const int shift = pass * 8;
+    __syncwarp();
+    sd2_scan_bins(bins, lane);
+    __syncwarp();
+#pragma unroll 1
+    for (int e0 = 0; e0 < n; e0 += 256) {
+      uint32_t kk[8], vv[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int e = e0 + 32 * u + lane;
+        kk[u] = (e < n) ? ks[e] : 0;
+        vv[u] = (e < n && v0) ? vs[e] : 0;
       }
-      int run = sd_warp_incl_scan(sum, lane) - sum;
 #pragma unroll
-      for (int t = 0; t < 8; t++) {
-        bins[lane * 8 + t] = run;
-        run += loc[t];
+      for (int u = 0; u < 8; u++) {
+        if (e0 + 32 * u >= n) break;
+        const int e = e0 + 32 * u + lane;
+        const bool ok = e < n;
+        const uint32_t d = ok ? ((kk[u] >> shift) & 255u) : (256u + lane);
+        const unsigned grp = __match_any_sync(VG_FULL, d);
+        const int rank = __popc(grp & ((1u << lane) - 1));
+        const int leader = __ffs(grp) - 1;
+        int base = 0;
+        if (ok && lane == leader) {
+          base = bins[d];
+          bins[d] = base + __popc(grp);
+        }
+        base = __shfl_sync(VG_FULL, base, leader);
+        if (ok) {
+          kd[base + rank] = kk[u];
+          if (v0) vd[base + rank] = vv[u];
+        }
+        __syncwarp();
       }
     }
-    __syncwarp();
-#pragma unroll 2
-    for (int e0 = 0; e0 < n; e0 += 32) {
-      const int e = e0 + lane;
-      const bool ok = e < n;
-      const uint32_t k = ok ? ks[e] : 0;
-      const uint32_t v = (ok && v0) ? vs[e] : 0;
-      const uint32_t d = ok ? ((k >> shift) & 255u) : (256u + lane);
-      const unsigned grp = __match_any_sync(VG_FULL, d);
-      const int rank = __popc(grp & ((1u << lane) - 1));
-      const int leader = __ffs(grp) - 1;
-      int base = 0;
-      if (ok && lane == leader) {
-        base = bins[d];
-        bins[d] = base + __popc(grp);
-      }
-      base = __shfl_sync(VG_FULL, base, leader);
-      if (ok) {
-        kd[base + rank] = k;
-        if (v0) vd[base + rank] = v;
-      }
-      __syncwarp();
-    }
-    src ^= 1;
     __threadfence_block();
     __syncwarp();
   }
-  return src;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -348,7 +364,7 @@ __device__ __noinline__ int sd2_radix_sort(uint32_t* k0, uint32_t* k1, uint32_t*
 //      hits on one diagonal at consecutive read positions) is now a run of consecutive i inside one diagonal;
 //   3. run starts -> LongHits (c, i, len = run length - 1);
 //   4. stable sort by c: LongHits with equal c come in descending-diagonal = ascending-i order, the TreeSet order.
-// Dynamic shared memory per warp: ids u16[idsBytes / 2] | bins int[256] | rd.
+// Dynamic shared memory per warp: ids u16[idsBytes / 2] | binsLo int[256] | binsHi int[256] | rd.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
   extern __shared__ __align__(16) uint8_t sd_smem[];
@@ -358,8 +374,9 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
   const int K = A.K, G = A.G;
   uint8_t* wbase = sd_smem + (size_t)warp * A.msaWarpBytes;
   uint16_t* ids = (uint16_t*)wbase;
-  int* bins = (int*)(wbase + A.idsBytes);
-  uint8_t* rd = (uint8_t*)(bins + 256);
+  int* binsLo = (int*)(wbase + A.idsBytes);
+  int* binsHi = binsLo + 256;
+  uint8_t* rd = (uint8_t*)(binsHi + 256);
   const int capRaw = A.capRaw;
   uint32_t* K0 = A.rawBuf + (size_t)warpSlot * 4 * capRaw;
   uint32_t* K1 = K0 + capRaw;
@@ -382,6 +399,7 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
       if (lane == 0) A.nS[it] = 0;
       continue;
     }
+    long long tph = A.prof ? clock64() : 0;
     const uint8_t* src = A.bases + off;
     __syncwarp();
 #pragma unroll 1
@@ -390,7 +408,10 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
 #pragma unroll 1
     for (int i = lane; i < nk; i += 32) ids[i] = (uint16_t)sd_kmer_id(rd + i, K, A.exoKeys, A.nExo);
     __syncwarp();
-    // 1. raw hits, read position by read position
+#pragma unroll 1
+    for (int b = lane; b < 512; b += 32) binsLo[b] = 0;
+    __syncwarp();
+    // 1. raw hits, read position by read position (the two digits of every sort key are counted on the way)
     int nRaw = 0, why = 0;
     bool bad = false;
 #pragma unroll 1
@@ -410,39 +431,57 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
       }
       uint32_t* dst = K0 + nRaw + incl - cnt;
       const uint32_t kk = ((uint32_t)i << 16) + dBias + (uint32_t)i;  // low half: dBias - (c - i)
-#pragma unroll 2
-      for (int q = 0; q < cnt; q++) dst[q] = kk - (uint32_t)A.msaCols[lo + q];
+#pragma unroll 4
+      for (int q = 0; q < cnt; q++) {
+        const uint32_t key = kk - (uint32_t)A.msaCols[lo + q];
+        dst[q] = key;
+        atomicAdd(&binsLo[key & 255u], 1);
+        atomicAdd(&binsHi[(key >> 8) & 255u], 1);
+      }
       nRaw += total;
     }
     __syncwarp();
+    SD2_PH(8)
+    if (A.prof && lane == 0) atomicAdd(A.prof + 13, (unsigned long long)nRaw);
     int nSt = 0;
     uint64_t* S = A.S + (size_t)it * A.capS;
     if (!bad && nRaw > 0) {
       __threadfence_block();
       // 2. stable sort by diagonal (16-bit key in the low half, read position rides in the high half)
-      const int sb = sd2_radix_sort(K0, K1, nullptr, nullptr, nRaw, bins, lane, 16);
-      const uint32_t* ks = sb ? K1 : K0;
-      uint32_t* stPos = sb ? K0 : K1;
+      sd2_radix_sort16(K0, K1, nullptr, nullptr, nRaw, binsLo, binsHi, lane);
+      const uint32_t* ks = K0;
+      uint32_t* stPos = K1;
+#pragma unroll 1
+      for (int b = lane; b < 512; b += 32) binsLo[b] = 0;  // for the second sort
+      __syncwarp();
+      SD2_PH(9)
       // 3. chain starts: first hit of a diagonal, or read position not the successor of the previous hit's
 #pragma unroll 1
-      for (int e0 = 0; e0 < nRaw; e0 += 32) {
-        const int e = e0 + lane;
-        bool st = false;
-        if (e < nRaw) {
-          const uint32_t k = ks[e], kp = e ? ks[e - 1] : ~k;
-          st = !(((k ^ kp) & 0xFFFFu) == 0 && (k >> 16) == (kp >> 16) + 1);
+      for (int e0 = 0; e0 < nRaw; e0 += 128) {
+        uint32_t kc[4], kp[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int e = e0 + 32 * u + lane;
+          kc[u] = (e < nRaw) ? ks[e] : 0;
+          kp[u] = (e < nRaw && e > 0) ? ks[e - 1] : ~kc[u];
         }
-        const unsigned m = __ballot_sync(VG_FULL, st);
-        if (st) stPos[nSt + __popc(m & lt)] = (uint32_t)e;
-        nSt += __popc(m);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int e = e0 + 32 * u + lane;
+          const bool st = e < nRaw && !(((kc[u] ^ kp[u]) & 0xFFFFu) == 0 && (kc[u] >> 16) == (kp[u] >> 16) + 1);
+          const unsigned m = __ballot_sync(VG_FULL, st);
+          if (st) stPos[nSt + __popc(m & lt)] = (uint32_t)e;
+          nSt += __popc(m);
+        }
       }
       __syncwarp();
       __threadfence_block();
+      SD2_PH(10)
       if (nSt > A.capS) {
         bad = true;
         why = 1;
       } else {
-#pragma unroll 1
+#pragma unroll 4
         for (int s0 = lane; s0 < nSt; s0 += 32) {
           const int e = (int)stPos[s0];
           const int en = (s0 + 1 < nSt) ? (int)stPos[s0 + 1] : nRaw;
@@ -451,14 +490,17 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
           const int c = (int)dBias - (int)(k & 0xFFFFu) + i;
           V0[s0] = ((uint32_t)i << 16) | (uint32_t)c;
           V1[s0] = (uint32_t)(en - e - 1);
+          atomicAdd(&binsLo[c & 255], 1);
+          atomicAdd(&binsHi[(c >> 8) & 255], 1);
         }
         __syncwarp();
         __threadfence_block();
+        SD2_PH(11)
         // 4. stable sort by column; K0 / K1 are free again and serve as the other halves
-        const int sb2 = sd2_radix_sort(V0, K0, V1, K1, nSt, bins, lane, 16);
-        const uint32_t* k2 = sb2 ? K0 : V0;
-        const uint32_t* v2 = sb2 ? K1 : V1;
-#pragma unroll 2
+        sd2_radix_sort16(V0, K0, V1, K1, nSt, binsLo, binsHi, lane);
+        const uint32_t* k2 = V0;
+        const uint32_t* v2 = V1;
+#pragma unroll 4
         for (int e = lane; e < nSt; e += 32) {
           const uint32_t k = k2[e];
           S[e] = ((uint64_t)(k & 0xFFFFu) << 32) | ((uint64_t)(k >> 16) << 16) | (uint64_t)v2[e];
@@ -466,6 +508,7 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
       }
     }
     __syncwarp();
+    SD2_PH(12)
     if (lane == 0) {
       if (bad) sd2_fallback(A, it, why);
       else A.nS[it] = nSt;
@@ -497,13 +540,6 @@ __device__ __noinline__ int sd2_reinsert(uint64_t* win, int si, int s1, int g, i
   return si - 1;
 }
 
-#define SD2_PH(k)                                                            \
-  if (A.prof) {                                                              \
-    __syncwarp();                                                            \
-    const long long t2 = clock64();                                          \
-    if (lane == 0) atomicAdd(A.prof + (k), (unsigned long long)(t2 - tph)); \
-    tph = t2;                                                                \
-  }
 __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
   extern __shared__ __align__(16) uint8_t sd_smem[];
   const int lane = threadIdx.x & 31;

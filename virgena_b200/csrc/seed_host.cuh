@@ -339,7 +339,7 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
       if (A.emptyId >= SD_NONE16 || A.emptyId > 8191) fast = false;
     } else {
       A.idsBytes = (maxReadLen * 2 + 15) & ~15;
-      A.msaWarpBytes = A.idsBytes + 1024 + A.rdBytes;
+      A.msaWarpBytes = A.idsBytes + 2048 + A.rdBytes;
       genWarps = std::min(32, smemMax / A.msaWarpBytes);
     }
     const int nContigs = msa ? 1 : (int)c->contigEnds.size();
@@ -442,7 +442,7 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   const bool dbg = getenv("VG_SEED_DEBUG") != nullptr;
   if (dbg && atoi(getenv("VG_SEED_DEBUG")) >= 2) {
     A.prof = (unsigned long long*)(c->d_counter.as<int>() + 32);
-    VG_CUDA(c, cudaMemsetAsync(A.prof, 0, 64, c->stream));
+    VG_CUDA(c, cudaMemsetAsync(A.prof, 0, 128, c->stream));
   }
   const int nSub = (int)((nItems + subItems - 1) / subItems);
   while ((int)c->seedEv.size() < 3 * nSub + 2) {
@@ -480,8 +480,12 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   c->seedStats[3] += (double)sums[0], c->seedStats[4] += (double)sums[1];
   c->seedStats[5] += flags[3], c->seedStats[6] += (double)sums[2], c->seedStats[7] += (double)nItems;
   if (A.prof) {
-    unsigned long long ph[8];
-    cudaMemcpy(ph, A.prof, 64, cudaMemcpyDeviceToHost);
+    unsigned long long ph[16];
+    cudaMemcpy(ph, A.prof, 128, cudaMemcpyDeviceToHost);
+    if (msa)
+      fprintf(stderr, "[seed] MSA stream kernel cycles/item: list %.0f, sort by diagonal %.0f, chain starts %.0f, LongHits %.0f, sort by column + "
+              "write %.0f; raw hits/item %.0f\n", ph[8] / (double)nItems, ph[9] / (double)nItems, ph[10] / (double)nItems,
+              ph[11] / (double)nItems, ph[12] / (double)nItems, ph[13] / (double)nItems);
     fprintf(stderr, "[seed] window kernel cycles/item: item+prefetch %.0f, C %.0f, D+E %.0f, F %.0f, sort %.0f, prune %.0f\n", ph[0] / (double)nItems,
             ph[1] / (double)nItems, ph[2] / (double)nItems, ph[3] / (double)nItems, ph[4] / (double)nItems, ph[5] / (double)nItems);
   }
