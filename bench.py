@@ -138,6 +138,30 @@ def cpu_baseline(ref, cut, m1, m2, n_sample, threads, index_threads):
     return n_sample / dt, dt
 
 
+def msa_arm(vg, synth, device, n_pairs):
+    """Secondary line: BASELINE.json configs[1], MapperMSA.mapAllReads (seeding + pair selection against the reference
+    MSA, no alignment) on synthetic cfg2 reads, device-resident, CUDA events inside the library. Rank 0 only."""
+    cut, _ = load_cutoffs(2)
+    rows = synth.config_msa()
+    m1, m2 = synth.config_pairs(2, min(n_pairs, 5000))
+    k = (n_pairs + len(m1) - 1) // len(m1)
+    m1 = np.tile(m1, (k, 1))[:n_pairs]
+    m2 = np.tile(m2, (k, 1))[:n_pairs]
+    aln = vg.ReferenceAlignment(rows, K=7)
+    mapper = vg.MapperMSA(K=7, indel_tolerance=1.5, cutoffs=cut, device=device)
+    reads = vg.PairedReads(*synth.pack_pairs(m1, m2))
+    best = None
+    for _ in range(4):
+        md = mapper.mapAllReads(reads, aln)
+        t = mapper.ctx.timings()["total_ms"]
+        best = t if best is None else min(best, t)
+    sd = mapper.ctx.seed_timings()
+    return {"metric": "read_pairs_mapped_per_s (MapperMSA.mapAllReads)", "value": n_pairs / (best * 1e-3), "unit": UNIT,
+            "ms": best, "pairs": n_pairs, "workload": "cfg2: synthetic 2x250 reads against a %d-sequence MSA (%d columns), K=7, 1.5"
+            % (rows.shape[0], rows.shape[1]), "seed_gen_msa_kernel_ms": sd["gen_ms"], "seed_win_kernel_ms": sd["win_ms"],
+            "fallback_items": int(sd["fallback_items"]), "mapping_stats": [int(x) for x in md.stats]}
+
+
 def run_reference(args):
     """--impl reference: the CPU path on all host cores. Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -178,6 +202,7 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=0, help="pairs per step of the CPU reference arm (0: 1000 x host threads)")
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs of the cpu_baseline sample (0: 3000 x host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-msa", action="store_true", help="skip the secondary MapperMSA.mapAllReads measurement (configs[1])")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -433,6 +458,8 @@ def main():
             "pileup_roofline": pile,
             "mapping_stats": [int(x) for x in stats],
         }
+        if not args.no_msa:
+            out["msa_mode"] = msa_arm(vg, synth, local, min(n, 200000))
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             ncpu = min(n, args.cpu_pairs or 3000 * threads)
