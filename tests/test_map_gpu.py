@@ -67,8 +67,8 @@ def test_seed_hits_and_windows(hiv):
 def test_seed_paths_and_long_reads(built, K, caps, monkeypatch):
     """The fast seeding path (seed2.cuh) and everything it hands to the general kernel: reads up to 512 bases with exact
     matches longer than 255 (the shared-memory hit length saturates there), low-complexity reads (a k-mer more than 127
-    times in the read), a per-item slot that is too small for every read (VG_SEED_CAPS2), and K = 3, 4 (direct table) / 6
-    (hash path of the general kernel). Windows must equal the oracle's for every read."""
+    times in the read), a per-item slot that is too small for every read (VG_SEED_CAPS2), and K = 3, 4, 6 (direct tables of 64 .. 4096
+    ids). Windows must equal the oracle's for every read."""
     import oracle
     import virgena_b200 as vg
     from virgena_b200 import synth
