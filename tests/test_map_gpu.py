@@ -63,7 +63,7 @@ def test_seed_hits_and_windows(hiv):
         ctx.close()
 
 
-@pytest.mark.parametrize("K,caps", [(5, None), (5, "64"), (4, None), (3, None), (6, None)])
+@pytest.mark.parametrize("K,caps", [(5, None), (5, "64"), (4, None), (3, None), (6, None), (7, None)])
 def test_seed_paths_and_long_reads(built, K, caps, monkeypatch):
     """The fast seeding path (seed2.cuh) and everything it hands to the general kernel: reads up to 512 bases with exact
     matches longer than 255 (the shared-memory hit length saturates there), low-complexity reads (a k-mer more than 127

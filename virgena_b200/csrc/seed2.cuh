@@ -289,8 +289,8 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
   }
 // Stable LSD radix sort on the low 16 bits of the keys (two 8-bit passes), values optional (v0 == nullptr). The caller
 // has already counted the two digits of every key into binsLo / binsHi (256 ints of shared memory each) while it produced
-// the keys, so the buffers — which live in L2 / HBM — are read only by the two scatter passes, eight chunks of keys in
-// flight per lane. Ping-pongs (k0, v0) -> (k1, v1) -> (k0, v0): the result is back in (k0, v0).
+// the keys, so the buffers — which live in L2 / HBM — are read only by the two scatter passes, with the next four chunks
+// of keys in flight while four are ranked. Ping-pongs (k0, v0) -> (k1, v1) -> (k0, v0): the result is back in (k0, v0).
 __device__ __forceinline__ void sd2_scan_bins(int* bins, int lane) {
   int loc[8], sum = 0;
 #pragma unroll
@@ -319,17 +319,25 @@ __device__ __noinline__ void sd2_radix_sort16(uint32_t* k0, uint32_t* k1, uint32
     __syncwarp();
     sd2_scan_bins(bins, lane);
     __syncwarp();
-#pragma unroll 1
-    for (int e0 = 0; e0 < n; e0 += 256) {
-      uint32_t kk[8], vv[8];
+    uint32_t kn[4], vn[4];  // the next four chunks are requested while the current four are ranked (serial part)
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const int e = e0 + 32 * u + lane;
-        kk[u] = (e < n) ? ks[e] : 0;
-        vv[u] = (e < n && v0) ? vs[e] : 0;
+    for (int u = 0; u < 4; u++) {
+      const int e = 32 * u + lane;
+      kn[u] = (e < n) ? ks[e] : 0;
+      vn[u] = (e < n && v0) ? vs[e] : 0;
+    }
+#pragma unroll 1
+    for (int e0 = 0; e0 < n; e0 += 128) {
+      uint32_t kk[4], vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        kk[u] = kn[u], vv[u] = vn[u];
+        const int e = e0 + 128 + 32 * u + lane;
+        kn[u] = (e < n) ? ks[e] : 0;
+        vn[u] = (e < n && v0) ? vs[e] : 0;
       }
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
+      for (int u = 0; u < 4; u++) {
         if (e0 + 32 * u >= n) break;
         const int e = e0 + 32 * u + lane;
         const bool ok = e < n;
@@ -429,14 +437,28 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
         bad = true;
         break;
       }
-      uint32_t* dst = K0 + nRaw + incl - cnt;
-      const uint32_t kk = ((uint32_t)i << 16) + dBias + (uint32_t)i;  // low half: dBias - (c - i)
-#pragma unroll 4
-      for (int q = 0; q < cnt; q++) {
-        const uint32_t key = kk - (uint32_t)A.msaCols[lo + q];
-        dst[q] = key;
-        atomicAdd(&binsLo[key & 255u], 1);
-        atomicAdd(&binsHi[(key >> 8) & 255u], 1);
+      // the lists are of very different lengths: the entries of the 32 lists are dealt out evenly, entry t of the
+      // round to lane t mod 32 (its read position = the last lane whose exclusive offset is <= t, by bisection over the
+      // lanes), so that loads and stores are coalesced and no lane waits for the longest list
+      const int excl = incl - cnt;
+      const int src0 = lo - excl;  // msaCols index of round entry t when this lane owns it: src0 + t
+#pragma unroll 1
+      for (int t0 = 0; t0 < total; t0 += 32) {
+        const int t = t0 + lane;
+        int owner = 0;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+          const int ex = __shfl_sync(VG_FULL, excl, owner + d);  // owner + d <= 31
+          if (ex <= t) owner += d;
+        }
+        const int oSrc = __shfl_sync(VG_FULL, src0, owner);
+        if (t < total) {
+          const uint32_t io = (uint32_t)(base + owner);
+          const uint32_t key = (io << 16) + dBias + io - (uint32_t)A.msaCols[oSrc + t];  // low half: dBias - (c - i)
+          K0[nRaw + t] = key;
+          atomicAdd(&binsLo[key & 255u], 1);
+          atomicAdd(&binsHi[(key >> 8) & 255u], 1);
+        }
       }
       nRaw += total;
     }
