@@ -189,6 +189,14 @@ int vg_sw_max_score_batch(vg_ctx* ctx, const uint8_t* s1_pool, const int64_t* s1
 int vg_seed_batch(vg_ctx* ctx, int32_t msa, const uint8_t* pool, const int64_t* off, int64_t n, int32_t max_windows,
                   int32_t* windows, int32_t* n_windows);
 
+/* KMerCounter.mapReadToRegion over the whole reference (KMerCounter.java:119-140; from = 0, to = reference / MSA length)
+ * and KMerCounterBase.computeKMerCount (:468-487, what RandomModel.java:122-128 scores its random reads with) for a
+ * batch of reads in their given orientation: windows[i] = {start, end, count} of the first window of maximal count
+ * (no cutoff, no splitLongHits, no pruning), found[i] = 0 when the read has no k-mer hit (mapReadToRegion returns
+ * null, computeKMerCount returns 0). SURVEY 8f N1 (seeding part) / N3. */
+int vg_best_window_batch(vg_ctx* ctx, int32_t msa, const uint8_t* pool, const int64_t* off, int64_t n, int32_t* windows,
+                         int32_t* found);
+
 /* BAM record fields of the last single-reference mapping, replacing the per-read derivations of
  * BamPrinter.setRecordFieldsMapped / setRecordFieldsUnmapped / setCigar (BamPrinter.java:16-171); serialisation stays with
  * htsjdk. Two records per pair result, in (pair, mate) order. ref_index is the index into Reference.contigEnds of the

@@ -140,6 +140,15 @@ class Oracle:
         assert n <= len(out)
         return out[:n].copy()
 
+    def map_read_to_region(self, read, msa=False):
+        """KMerCounter.mapReadToRegion(read, index, 0, length): (start, end, count) or None; count = computeKMerCount."""
+        read = _u8(read)
+        out = np.zeros(3, np.int32)
+        lib().vo_map_read_to_region.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        n = lib().vo_map_read_to_region(self.h, int(msa), _p(read if len(read) else np.zeros(1, np.uint8)), len(read), _p(out))
+        assert n >= 0, "mapReadToRegion and computeKMerCount disagree"
+        return tuple(int(x) for x in out) if n else None
+
     def seed(self, read, msa=False):
         read = _u8(read)
         out = np.zeros((4096, 3), np.int32)

@@ -1273,6 +1273,26 @@ int vo_seed(OracleCtx* c, int msa, const uint8_t* read, int L, int32_t* out, int
   return (int)v.size();
 }
 
+// KMerCounter.mapReadToRegion (KMerCounter.java:119-140) with from = 0, to = reference / MSA length: the first window of
+// maximal count over all hits (no cutoff, no splitLongHits, no pruning). Returns 0 when the read has no hit (null).
+// out = {start, end, count}; count equals KMerCounterBase.computeKMerCount (:468-487).
+int vo_map_read_to_region(OracleCtx* c, int msa, const uint8_t* read, int L, int32_t* out) {
+  const KMerCounter& kc = msa ? c->mapperMSA.counterRF : c->mapper.counter;
+  const int to = msa ? c->msaLength : (int)c->genome.seq.size();
+  std::string r((const char*)read, L);
+  std::vector<LongHit> h = kc.getHits(r, msa ? c->msaIndex : c->genome.index);
+  if (h.empty()) return 0;
+  std::vector<uint8_t> adj = kc.concordanceArray(h);
+  Location st = kc.getInitState(0, to, L, h, adj);
+  out[0] = st.start, out[1] = st.end, out[2] = st.count;
+  for (int i = 1; i < (int)h.size(); i++) {
+    kc.computeCount(0, to, L, h, i, st, adj);
+    if (st.count > out[2]) out[0] = st.start, out[1] = st.end, out[2] = st.count;
+  }
+  if (out[2] != kc.computeKMerCount(r, msa ? c->msaIndex : c->genome.index, 0, to)) return -1;
+  return 1;
+}
+
 // Walk the windows of one read with the exact incremental state machine and,
 // beside it, a direct recount: per hit i writes (start,end,count_incremental,count_direct).
 int vo_window_walk(OracleCtx* c, int msa, const uint8_t* read, int L, int32_t* out, int cap) {

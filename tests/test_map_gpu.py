@@ -105,6 +105,47 @@ def test_seed_paths_and_long_reads(built, K, caps, monkeypatch):
     ctx.close()
 
 
+def test_best_window_batch(built):
+    """vg_best_window_batch = KMerCounter.mapReadToRegion over the whole reference / computeKMerCount (SURVEY 8f N1
+    seeding part, N3): single contig, fragmented reference (no splitLongHits, windows not clipped to contigs) and MSA."""
+    import oracle
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    cut = np.full(400, 40, np.int32)
+    for cfg in (1, 4):
+        ref, ends = synth.config_reference(cfg)
+        m1, m2 = synth.config_pairs(cfg, 150)
+        reads = [m1[i].tobytes() for i in range(150)] + [synth.revcomp(m2[i]).tobytes() for i in range(150)]
+        reads += [b"ACGTACG", b"AC", b"N" * 40, ref[50:200].tobytes()]
+        if cfg == 4:
+            reads += [ref[e - 60:e + 60].tobytes() for e in ends[:-1]]  # across segment boundaries
+        o = oracle.Oracle(K=5, cutoffs=cut)
+        o.set_reference(ref, contig_ends=ends, fragment_ends=ends, is_fragmented=len(ends) > 1, index_thread_num=8)
+        ctx = vg.Context(K=5, cutoffs=cut)
+        ctx.set_reference(vg.Reference(ref, K=5, contig_ends=ends, fragment_ends=ends, is_fragmented=len(ends) > 1, thread_num=8))
+        win, found = ctx.best_window_batch(b"".join(reads), _offs(reads))
+        for i, r in enumerate(reads):
+            w = o.map_read_to_region(r)
+            assert (found[i] != 0) == (w is not None), (cfg, i)
+            if w is not None:
+                assert tuple(win[i]) == w, (cfg, i, tuple(win[i]), w)
+        ctx.close()
+    rows = synth.config_msa(n_refs=12)
+    cut7 = np.full(400, 30, np.int32)
+    m1, m2 = synth.config_pairs(2, 150)
+    reads = [m1[i].tobytes() for i in range(150)] + [synth.revcomp(m2[i]).tobytes() for i in range(150)] + [b"ACGTACG", b"*"]
+    o = oracle.Oracle(K=5)
+    o.set_msa(rows, K=7, low_coef=float(np.float32(1) / np.float32(1.5)), high_coef=1.5, cutoffs=cut7)
+    mapper = vg.MapperMSA(K=7, indel_tolerance=1.5, cutoffs=cut7)
+    mapper.ctx.set_msa(vg.ReferenceAlignment(rows, K=7), float(mapper.low), float(mapper.high), cut7)
+    win, found = mapper.ctx.best_window_batch(b"".join(reads), _offs(reads), msa=True)
+    for i, r in enumerate(reads):
+        w = o.map_read_to_region(r, msa=True)
+        assert (found[i] != 0) == (w is not None), ("msa", i)
+        if w is not None:
+            assert tuple(win[i]) == w, ("msa", i, tuple(win[i]), w)
+
+
 def test_seed_host_csr_index(hiv):
     """The host-built CSR index (with its duplicated boundary positions, Q1) gives the same result as
     letting the library rebuild it from the thread count."""

@@ -302,6 +302,21 @@ def test_cigar_and_xn():
     assert oracle.cigar(b"aCG", 0, 3, 3, 2)[0] == "0M1I2M"
 
 
+def test_map_read_to_region_hand_derived():
+    # KMerCounter.mapReadToRegion (KMerCounter.java:119-140) / computeKMerCount (KMerCounterBase.java:468-487).
+    # ref = AAAAACCCCCGGGGGTTTTT, K = 5, read = CCCCCGGGGG: read k-mer i occurs only at reference position 5 + i, i.e. one
+    # chain LongHit(g=5, r=0, len=5); window start = max(0, 5 - 0*3/2) = 5, end = min(5 + 5 + 5 + (10-0-5-5)*3/2, 20) = 15,
+    # count = len = 5.
+    o = oracle.Oracle(K=5, cutoffs=np.zeros(64, np.int32))
+    o.set_reference(b"AAAAACCCCCGGGGGTTTTT", index_thread_num=1)
+    assert o.map_read_to_region(b"CCCCCGGGGG") == (5, 15, 5)
+    # CCCCCTTTTT: two isolated zero-length hits (5, 0) and (15, 5). Hit 0: start 5, end = min(5 + 0 + 5 + (10-0-0-5)*3/2, 20)
+    # = 17 (integer 15/2 = 7), hit 1 ends at 20 > 17: count 0. Hit 1: window [8, 20) holds only itself: count 0, not
+    # strictly greater: the first window stays.
+    assert o.map_read_to_region(b"CCCCCTTTTT") == (5, 17, 0)
+    assert o.map_read_to_region(b"ACGTACGTAC") is None         # no k-mer of the read occurs in the reference
+
+
 def test_bam_record_fields():
     # BamPrinter.setRecordFieldsMapped / setRecordFieldsUnmapped (BamPrinter.java:16-115), hand-derived:
     # contigs [0,100) [100,250); pair 0 concordant (mate1 forward at 95+8=103 -> contig 1, pos 4; mate2 reverse at 20+0),

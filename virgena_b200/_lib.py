@@ -76,6 +76,7 @@ _SIGS = {
                                 C.c_void_p]),
     "vg_last_timings": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vg_seed_timings": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vg_best_window_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "vg_bam_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "vg_dpx_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "vg_kernel_launches": (C.c_int64, [C.c_void_p]),

@@ -586,7 +586,7 @@ int vg_consensus(vg_ctx* c, int32_t save_uncovered, int32_t coverage_threshold, 
 }
 
 static int mh_seed_batch(vg_ctx* c, int32_t msa, const uint8_t* pool, const int64_t* off, int64_t n, int32_t max_windows,
-                         int32_t* windows, int32_t* n_windows, int32_t* dbgHits, int32_t dbgCap, int32_t* dbgN) {
+                         int32_t* windows, int32_t* n_windows, int32_t* dbgHits, int32_t dbgCap, int32_t* dbgN, bool bestOnly = false) {
   if (!c) return VG_ERR_INVALID;
   VG_CUDA(c, cudaSetDevice(c->device));
   if (msa ? !c->haveMsa : !c->haveRef) return vg_fail(c, VG_ERR_STATE, "reference / MSA index not set");
@@ -617,7 +617,7 @@ static int mh_seed_batch(vg_ctx* c, int32_t msa, const uint8_t* pool, const int6
     VG_CUDA(c, cudaMemsetAsync(d_dbgN, 0, 16, c->stream));
   }
   VG_TRY(seed_launch(c, msa != 0, c->d_s1pool.as<uint8_t>(), c->d_s1off.as<int64_t>(), c->d_s2off.as<int32_t>(), nullptr,
-                     nullptr, nullptr, n, true, maxLen, max_windows, d_dbg, d_dbgN));
+                     nullptr, nullptr, n, true, maxLen, max_windows, d_dbg, d_dbgN, bestOnly));
   VG_CUDA(c, cudaMemcpyAsync(windows, c->d_cand.p, (size_t)n * max_windows * 3 * 4, cudaMemcpyDeviceToHost, c->stream));
   VG_CUDA(c, cudaMemcpyAsync(n_windows, c->d_ncand.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
   if (dbgHits) {
@@ -634,6 +634,11 @@ static int mh_seed_batch(vg_ctx* c, int32_t msa, const uint8_t* pool, const int6
 int vg_seed_batch(vg_ctx* c, int32_t msa, const uint8_t* pool, const int64_t* off, int64_t n, int32_t max_windows,
                   int32_t* windows, int32_t* n_windows) {
   return mh_seed_batch(c, msa, pool, off, n, max_windows, windows, n_windows, nullptr, 0, nullptr);
+}
+
+int vg_best_window_batch(vg_ctx* c, int32_t msa, const uint8_t* pool, const int64_t* off, int64_t n, int32_t* windows,
+                         int32_t* found) {
+  return mh_seed_batch(c, msa, pool, off, n, 1, windows, found, nullptr, 0, nullptr, true);
 }
 
 // Test hook (not part of the reference-facing ABI): LongHits of one read after mergeHits + splitLongHits.

@@ -68,6 +68,8 @@ struct Seed2Args {
   uint32_t* rawBuf;            // [warpSlots][4][capRaw]
   int capRaw;
   int msaWarpBytes, idsBytes;
+  int bestOnly;                // 1: mapReadToRegion / computeKMerCount over [0, G): the first window of maximal count, no cutoff,
+                               //    no splitLongHits, no pruning (KMerCounter.java:119-140, KMerCounterBase.java:468-487)
   int key24;                   // G < 16384: candidates sort on a 24-bit key (start << 10 | 1023 - (end - start)), 3 passes
 };
 
@@ -726,7 +728,7 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
     __syncwarp();
     SD2_PH(1)
     // ---- D: KMerCounter.splitLongHits (KMerCounter.java:142-185); hits are independent given their contig
-    if (!giveUp && A.nContigs > 1 && nR > 0) {
+    if (!giveUp && A.nContigs > 1 && nR > 0 && !A.bestOnly) {
       __threadfence_block();
       int nOut = 0;
       bool bad = false;
@@ -867,8 +869,9 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
       SD2_PH(2)
       // ---- F: every window independently (updateCount equals a direct recount on sorted non-overlapping
       //         hits); candidates (count > cutoff, strict) compacted in hit order
-      const int cutoff = (L < A.nCutoffs) ? A.cutoffs[L] : 0x7fffffff;
+      const int cutoff = A.bestOnly ? -1 : (L < A.nCutoffs) ? A.cutoffs[L] : 0x7fffffff;
       int nC = 0;
+      int bestCnt = -1, bestJ = 0x7fffffff, bestS = 0, bestE = 0;  // bestOnly: per lane, first maximum in hit order
 #pragma unroll 1
       for (int j0 = 0; j0 < nR; j0 += 32) {
         const int j = j0 + lane;
@@ -878,7 +881,7 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
           const uint64_t v = S[j];
           const int g = (int)(v >> 32), r = (int)((v >> 16) & 0xFFFFu), len = (int)(v & 0xFFFFu);
           int cs = 0, ce = G;
-          if (A.nContigs > 1) {
+          if (A.nContigs > 1 && !A.bestOnly) {
             int lo = 0, hi = A.nContigs - 1;
 #pragma unroll 1
             while (lo < hi) {
@@ -912,6 +915,10 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
           if ((int)hitG[b] + K + lenB > end) b--;
           cnt = (uint32_t)((uint16_t)(Pp[b] - Pp[a])) + (uint32_t)lenA;
           isCand = (int)cnt > cutoff;
+          if (A.bestOnly) {
+            if ((int)cnt > bestCnt) bestCnt = (int)cnt, bestJ = j, bestS = start, bestE = end;
+            isCand = false;
+          }
           // order (start asc, end desc); a window is at most 1.5 L <= 768 wide
           key = A.key24 ? ((uint32_t)start << 10) | (uint32_t)(1023 - (end - start)) : ((uint32_t)start << 16) | (uint32_t)(0xFFFF - end);
         }
@@ -924,6 +931,15 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
         nC += __popc(m);
       }
       __syncwarp();
+      if (A.bestOnly) {  // strict '>' in hit order: the first hit that reaches the maximum wins
+        const int mx = __reduce_max_sync(VG_FULL, bestCnt);
+        const int jw = __reduce_min_sync(VG_FULL, bestCnt == mx ? bestJ : 0x7fffffff);
+        if (bestCnt == mx && bestJ == jw) {
+          int32_t* W = A.windows + (size_t)gi * A.maxWin * 3;
+          W[0] = bestS, W[1] = bestE, W[2] = mx;
+        }
+        nWin = 1;
+      }
       SD2_PH(3)
       // ---- G: stable sort by (start asc, end desc) + pruneWindows (KMerCounterBase.java:317-335). The pivot only
       //         changes at the first later candidate that either does not overlap it (emit, new pivot) or overlaps

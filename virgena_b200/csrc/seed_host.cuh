@@ -314,7 +314,7 @@ static int seed_launch_v1(vg_ctx* c, bool msa, const uint8_t* d_bases, const int
 // ([nItems][maxWin][3]) and c->d_ncand ([nItems]).
 static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_t* d_off1, const int32_t* d_len1,
                        const int64_t* d_off2, const int32_t* d_len2, const int64_t* d_pairIdx, int64_t nItems,
-                       bool singleReads, int maxReadLen, int maxWin, int32_t* dbgHits, int32_t* dbgNHits) {
+                       bool singleReads, int maxReadLen, int maxWin, int32_t* dbgHits, int32_t* dbgNHits, bool bestOnly = false) {
   c->seedFallbacks = 0;
   const SeedConfig& sc = msa ? c->seedMsa : c->seed;
   const int K = sc.K, G = msa ? c->msaLength : c->G;
@@ -353,6 +353,9 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     winWarps = std::min(32, smemMax / A.winWarpBytes);
     if (genWarps < 8 || winWarps < 8) fast = false;
   }
+  if (!fast && bestOnly)
+    return vg_fail(c, VG_ERR_INVALID, "best-window seeding needs the fast path (K <= 6 in single-reference mode, reference + read length "
+                                      "< 65535, cutoffs covering the read length)");
   if (!fast)
     return seed_launch_v1(c, msa, d_bases, d_off1, d_len1, d_off2, d_len2, d_pairIdx, nItems, singleReads, maxReadLen, maxWin,
                           dbgHits, dbgNHits);
@@ -386,6 +389,7 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   A.off1 = d_off1, A.len1 = d_len1, A.off2 = d_off2, A.len2 = d_len2;
   A.pairIdx = d_pairIdx;
   A.singleReads = singleReads ? 1 : 0;
+  A.bestOnly = bestOnly ? 1 : 0;
   A.maxWin = maxWin;
   A.dbgHits = dbgHits;
   A.dbgNHits = dbgNHits;
@@ -500,6 +504,9 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
                    (f & 8) ? " window list" : "", (f & 16) ? " read too long" : "");
   }
   c->seedFallbacks = flags[3];
+  if (flags[3] > 0 && bestOnly)
+    return vg_fail(c, VG_ERR_OVERFLOW, "%d reads need the general seeding kernel (low-complexity reads), which has no best-window mode",
+                   flags[3]);
   if (flags[3] > 0) {
     VG_CUDA(c, cudaEventRecord(c->seedEv[0], c->stream));
     VG_TRY(seed_launch_v1(c, msa, d_bases, d_off1, d_len1, d_off2, d_len2, d_pairIdx, flags[3], singleReads, maxReadLen, maxWin,

@@ -299,6 +299,17 @@ class Context:
         self._chk(self.L.vg_seed_batch(self.h, int(msa), ptr(pool), ptr(off), n, max_windows, ptr(win), ptr(nwin)))
         return win, nwin
 
+    def best_window_batch(self, pool, off, msa=False):
+        """vg_best_window_batch: KMerCounter.mapReadToRegion(read, index, 0, length) / computeKMerCount for every read.
+        Returns (windows int32[n, 3] = start, end, count; found int32[n])."""
+        pool = _u8(pool)
+        off = np.ascontiguousarray(off, np.int64)
+        n = len(off) - 1
+        win = np.zeros((max(n, 1), 3), np.int32)
+        found = np.zeros(max(n, 1), np.int32)
+        self._chk(self.L.vg_best_window_batch(self.h, int(msa), ptr(pool), ptr(off), n, ptr(win), ptr(found)))
+        return win[:n], found[:n]
+
     def debug_seed_hits(self, read, msa=False):
         """Test hook: LongHits (genomePos, readPos, len) of one read after mergeHits + splitLongHits."""
         read = _u8(read)
