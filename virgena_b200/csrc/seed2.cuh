@@ -579,6 +579,14 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
   uint32_t* ckey = A.candKey + (size_t)warpSlot * 2 * capC;
   uint32_t* cval = A.candVal + (size_t)warpSlot * 2 * capC;
   const unsigned lt = (1u << lane) - 1u;
+  // contig ends: binary-searched per hit in phases D and F; a copy in shared memory when there are few of them
+  __shared__ int32_t sd_contigs[64];
+  const int32_t* cEnds = A.contigEnds;
+  if (A.nContigs > 1 && A.nContigs <= 64) {
+    if (threadIdx.x < A.nContigs) sd_contigs[threadIdx.x] = A.contigEnds[threadIdx.x];
+    __syncthreads();
+    cEnds = sd_contigs;
+  }
 
 #pragma unroll 1
   for (;;) {
@@ -730,10 +738,13 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
     // ---- D: KMerCounter.splitLongHits (KMerCounter.java:142-185); hits are independent given their contig
     if (!giveUp && A.nContigs > 1 && nR > 0 && !A.bestOnly) {
       __threadfence_block();
+      // the pieces go to the upper half of the item's slot (a hit yields at most 3), which then replaces the lower half
+      const int half = A.capS >> 1;
+      uint64_t* S2 = S + half;
       int nOut = 0;
-      bool bad = false;
+      bool bad = nR > half;
 #pragma unroll 1
-      for (int j0 = 0; j0 < nR; j0 += 32) {
+      for (int j0 = 0; j0 < nR && !bad; j0 += 32) {
         const int j = j0 + lane;
         int qg[3], qr[3], ql[3], np2 = 0;
         if (j < nR) {
@@ -744,10 +755,10 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
 #pragma unroll 1
             while (lo2 < hi2) {
               const int mid = (lo2 + hi2) >> 1;
-              if (A.contigEnds[mid] > g) hi2 = mid;
+              if (cEnds[mid] > g) hi2 = mid;
               else lo2 = mid + 1;
             }
-            const int contigEnd = A.contigEnds[lo2];
+            const int contigEnd = cEnds[lo2];
             if (g + K + len > contigEnd) {
               if (contigEnd - g >= K) {
                 if (np2 < 3) qg[np2] = g, qr[np2] = r, ql[np2] = contigEnd - g - K;
@@ -767,24 +778,25 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
           }
           if (np2 > 3) bad = true, np2 = 3;  // a hit across > 2 contig boundaries (contigs shorter than K + 1)
         }
-        const int ic = sd_warp_incl_scan(np2, lane);
-        int o = nOut + ic - np2;
-#pragma unroll 1
-        for (int t = 0; t < np2; t++, o++)
-          if (o < capC) ckey[o] = (uint32_t)qg[t] | ((uint32_t)qr[t] << 16), cval[o] = (uint32_t)ql[t];
-        nOut += __shfl_sync(VG_FULL, ic, 31);
+        const unsigned m1 = __ballot_sync(VG_FULL, np2 >= 1), m2 = __ballot_sync(VG_FULL, np2 >= 2), m3 = __ballot_sync(VG_FULL, np2 >= 3);
+        int o = nOut + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt);
+        nOut += __popc(m1) + __popc(m2) + __popc(m3);
+        if (__any_sync(VG_FULL, bad) || nOut > half) {
+          bad = true;
+          break;
+        }
+#pragma unroll
+        for (int t = 0; t < 3; t++)
+          if (t < np2) S2[o + t] = ((uint64_t)qg[t] << 32) | ((uint64_t)qr[t] << 16) | (uint64_t)ql[t];
       }
       __syncwarp();
       __threadfence_block();
-      if (__any_sync(VG_FULL, bad) || nOut > capC || nOut > A.capS) {
+      if (__any_sync(VG_FULL, bad)) {
         giveUp = true;
       } else {
-#pragma unroll 1
-        for (int j = lane; j < nOut; j += 32)
-          S[j] = ((uint64_t)(ckey[j] & 0xFFFFu) << 32) | ((uint64_t)(ckey[j] >> 16) << 16) | (uint64_t)cval[j];
+        S = S2;
         nR = nOut;
       }
-      __syncwarp();
     }
     if (giveUp || nR > A.capR) {
       if (lane == 0) sd2_fallback(A, it, why);
@@ -886,11 +898,11 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
 #pragma unroll 1
             while (lo < hi) {
               const int mid = (lo + hi) >> 1;
-              if (A.contigEnds[mid] > g) hi = mid;
+              if (cEnds[mid] > g) hi = mid;
               else lo = mid + 1;
             }
-            ce = A.contigEnds[lo];
-            cs = lo ? A.contigEnds[lo - 1] : 0;
+            ce = cEnds[lo];
+            cs = lo ? cEnds[lo - 1] : 0;
           }
           const int start = max(cs, g - r * 3 / 2);
           const int end = min(g + len + K + (L - r - len - K) * 3 / 2, ce);
