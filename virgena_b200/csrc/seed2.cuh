@@ -289,10 +289,9 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
     if (lane == 0) atomicAdd(A.prof + (k), (unsigned long long)(t2 - tph)); \
     tph = t2;                                                                \
   }
-// Stable LSD radix sort on the low 16 bits of the keys (two 8-bit passes), values optional (v0 == nullptr). The caller
-// has already counted the two digits of every key into binsLo / binsHi (256 ints of shared memory each) while it produced
-// the keys, so the buffers — which live in L2 / HBM — are read only by the two scatter passes, with the next four chunks
-// of keys in flight while four are ranked. Ping-pongs (k0, v0) -> (k1, v1) -> (k0, v0): the result is back in (k0, v0).
+// Stable LSD radix sort on the low 8 x passes bits of the keys, values optional (v0 == nullptr). The caller has already
+// counted the digits of every key into binsAll[pass][256] (shared memory), e.g. while it produced the keys, so the buffers — which live in L2 / HBM — are read only by the two scatter passes, with the next four chunks
+// of keys in flight while four are ranked. Ping-pongs between (k0, v0) and (k1, v1); returns which pair holds the result.
 __device__ __forceinline__ void sd2_scan_bins(int* bins, int lane) {
   int loc[8], sum = 0;
 #pragma unroll
@@ -308,15 +307,15 @@ __device__ __forceinline__ void sd2_scan_bins(int* bins, int lane) {
   }
 }
 
-__device__ __noinline__ void sd2_radix_sort16(uint32_t* k0, uint32_t* k1, uint32_t* v0, uint32_t* v1, int n, int* binsLo,
-                                              int* binsHi, int lane) {
+__device__ __noinline__ int sd2_radix_sort_counted(uint32_t* k0, uint32_t* k1, uint32_t* v0, uint32_t* v1, int n, int* binsAll,
+                                                   int passes, int lane) {
 #pragma unroll 1
-  for (int pass = 0; pass < 2; pass++) {
-    const uint32_t* ks = pass ? k1 : k0;
-    const uint32_t* vs = pass ? v1 : v0;
-    uint32_t* kd = pass ? k0 : k1;
-    uint32_t* vd = pass ? v0 : v1;
-    int* bins = pass ? binsHi : binsLo;
+  for (int pass = 0; pass < passes; pass++) {
+    const uint32_t* ks = (pass & 1) ? k1 : k0;
+    const uint32_t* vs = (pass & 1) ? v1 : v0;
+    uint32_t* kd = (pass & 1) ? k0 : k1;
+    uint32_t* vd = (pass & 1) ? v0 : v1;
+    int* bins = binsAll + 256 * pass;
     const int shift = pass * 8;
     __syncwarp();
     sd2_scan_bins(bins, lane);
@@ -363,6 +362,7 @@ __device__ __noinline__ void sd2_radix_sort16(uint32_t* k0, uint32_t* k1, uint32
     __threadfence_block();
     __syncwarp();
   }
+  return passes & 1;  // 0: result in (k0, v0), 1: in (k1, v1)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
     if (!bad && nRaw > 0) {
       __threadfence_block();
       // 2. stable sort by diagonal (16-bit key in the low half, read position rides in the high half)
-      sd2_radix_sort16(K0, K1, nullptr, nullptr, nRaw, binsLo, binsHi, lane);
+      sd2_radix_sort_counted(K0, K1, nullptr, nullptr, nRaw, binsLo, 2, lane);
       const uint32_t* ks = K0;
       uint32_t* stPos = K1;
 #pragma unroll 1
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
         __threadfence_block();
         SD2_PH(11)
         // 4. stable sort by column; K0 / K1 are free again and serve as the other halves
-        sd2_radix_sort16(V0, K0, V1, K1, nSt, binsLo, binsHi, lane);
+        sd2_radix_sort_counted(V0, K0, V1, K1, nSt, binsLo, 2, lane);
         const uint32_t* k2 = V0;
         const uint32_t* v2 = V1;
 #pragma unroll 4
@@ -957,8 +957,21 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
       //         changes at the first later candidate that either does not overlap it (emit, new pivot) or overlaps
       //         with a larger count (new pivot); the warp looks at 32 candidates at a time.
       if (nC > 0) {
-        const int srcb = sd_radix_sort(ckey, cval, capC, nC, bins, lane, A.key24 ? 24 : 32);
+        const int passes = A.key24 ? 3 : 4;
         __threadfence_block();
+#pragma unroll 1
+        for (int b = lane; b < 256 * passes; b += 32) bins[b] = 0;  // hitG / P / len are dead now
+        __syncwarp();
+#pragma unroll 4
+        for (int e = lane; e < nC; e += 32) {  // all digits counted in one pass over the keys
+          const uint32_t k = ckey[e];
+          atomicAdd(&bins[k & 255u], 1);
+          atomicAdd(&bins[256 + ((k >> 8) & 255u)], 1);
+          atomicAdd(&bins[512 + ((k >> 16) & 255u)], 1);
+          if (passes == 4) atomicAdd(&bins[768 + (k >> 24)], 1);
+        }
+        __syncwarp();
+        const int srcb = sd2_radix_sort_counted(ckey, ckey + capC, cval, cval + capC, nC, bins, passes, lane);
         SD2_PH(4)
         const uint32_t* ks = ckey + (size_t)srcb * capC;
         const uint32_t* vs = cval + (size_t)srcb * capC;
