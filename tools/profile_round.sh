@@ -4,7 +4,7 @@
 # 3. seed_win_kernel under application replay (it rewrites its multi-GB input in place, kernel replay is wrong).
 tag=${1:-r1}
 out=gpurun_out
-cmd="python bench.py --steps 2 --warmup 3 --pairs 100000 --no-cpu-baseline"
+cmd="python bench.py --steps 2 --warmup 3 --pairs 100000 --no-cpu-baseline --no-msa"
 $cmd > $out/plain_$tag.log 2>&1 || { tail -5 $out/plain_$tag.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches_$tag.csv $cmd > $out/ncu_launch_$tag.log 2>&1
 probe="python tools/map_probe.py 100000 2"

@@ -23,7 +23,7 @@ for r in rows:
 tot = sum(a[1] for a in agg.values())
 with open(os.path.join(root, "profiles", "launches_%s.md" % tag), "w") as f:
     f.write("# Kernel launch list (%s)\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` over\n"
-            "`python bench.py --steps 2 --warmup 3 --pairs 100000 --no-cpu-baseline` (cold-cache, serialised: compare shares).\n\n"
+            "`python bench.py --steps 2 --warmup 3 --pairs 100000 --no-cpu-baseline --no-msa` (cold-cache, serialised: compare shares).\n\n"
             "| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n" % tag)
     for k, (n, us) in sorted(agg.items(), key=lambda x: -x[1][1]):
         f.write("| `%s` | %d | %.3f | %.1f%% |\n" % (k, n, us / 1e3, 100 * us / tot))
