@@ -197,6 +197,23 @@ int vg_seed_batch(vg_ctx* ctx, int32_t msa, const uint8_t* pool, const int64_t* 
 int vg_best_window_batch(vg_ctx* ctx, int32_t msa, const uint8_t* pool, const int64_t* off, int64_t n, int32_t* windows,
                          int32_t* found);
 
+/* KMerCounter.mapReadToRegion (KMerCounter.java:119-140) for (read, region) pairs where every region is its own small
+ * reference with its own StringIndexer.buildIndex index: ContigBuilder.countReads against cluster centroids
+ * (ContigBuilder.java:72-104, 219-227), Graph.SWScore against reference sub-sequences (Graph.java:493-550). Regions and
+ * reads are byte pools + offsets (n+1 entries); read_region[i] names the region of read i; windows[i] = {start, end,
+ * count} inside that region, found[i] = 0 when mapReadToRegion returns null. The alignment of the read against
+ * region[start, end) is vg_sw_align_batch. SURVEY 8f N1. Uses K and the coefficients of vg_ctx_create. */
+int vg_map_to_regions(vg_ctx* ctx, const uint8_t* region_pool, const int64_t* region_off, int64_t n_regions,
+                      const uint8_t* read_pool, const int64_t* read_off, int64_t n_reads, const int32_t* read_region,
+                      int32_t* windows, int32_t* found);
+
+/* The pileup loop of ContigBuilder.countReads (ContigBuilder.java:93-99) for a batch of alignments: alignment i (sequence1 at
+ * seq1_pool + seq1_off[i], `length[i]` columns) starts at position pos[i] (= region base + MappedRead.start +
+ * Alignment.start2 when the regions are laid out back to back); counts = int32[total_positions][5] (A, T, G, C, gap),
+ * zeroed by the call. */
+int vg_pileup_alignments(vg_ctx* ctx, const uint8_t* seq1_pool, const int64_t* seq1_off, const int32_t* length,
+                         const int64_t* pos, int64_t n, int64_t total_positions, int32_t* counts);
+
 /* BAM record fields of the last single-reference mapping, replacing the per-read derivations of
  * BamPrinter.setRecordFieldsMapped / setRecordFieldsUnmapped / setCigar (BamPrinter.java:16-171); serialisation stays with
  * htsjdk. Two records per pair result, in (pair, mate) order. ref_index is the index into Reference.contigEnds of the

@@ -146,6 +146,65 @@ def test_best_window_batch(built):
             assert tuple(win[i]) == w, ("msa", i, tuple(win[i]), w)
 
 
+def test_contig_builder_count_reads(built):
+    """ContigBuilder.countReads (ContigBuilder.java:72-104) = mapReadToRegion against the centroid's own index
+    (vg_map_to_regions) + align against the window (vg_sw_align_batch) + pileup into the centroid's counts
+    (vg_pileup_alignments), for many clusters in one call."""
+    import oracle
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    ref, _ = synth.config_reference(1)
+    rng = np.random.default_rng(5)
+    cut = np.full(400, 40, np.int32)
+    centroids, reads, rc = [], [], []
+    for cidx in range(12):
+        ln = int(rng.integers(180, 1600))
+        p = int(rng.integers(0, len(ref) - ln))
+        cen = ref[p:p + ln].copy()
+        if cidx % 4 == 1:
+            cen[ln // 2:ln // 2 + 3] = ord("N")
+        if cidx % 4 == 2:
+            cen[10:14] = ord("-")
+        centroids.append(cen.tobytes())
+        for _ in range(25):
+            L = int(rng.integers(40, 251))
+            q = int(rng.integers(0, max(1, ln - L)))
+            r = cen[q:q + L].copy()
+            mut = rng.random(len(r)) < 0.08
+            r[mut] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(mut.sum()))]
+            if rng.random() < 0.2:
+                r = np.delete(r, int(rng.integers(5, len(r) - 5)))
+            reads.append(r.tobytes())
+            rc.append(cidx)
+        reads += [b"ACG", bytes(rng.integers(65, 85, 80).astype(np.uint8)), ref[(p + 4000) % 9000:(p + 4000) % 9000 + 120].tobytes()]
+        rc += [cidx] * 3
+    mapper = vg.Mapper(K=5, cutoffs=cut)
+    win, found, aln, seqs, counts = vg.ContigBuilder(mapper).countReads(centroids, reads, rc)
+    want_counts = [np.zeros((len(c), 5), np.int32) for c in centroids]
+    n_found = 0
+    for cidx, cen in enumerate(centroids):
+        o = oracle.Oracle(K=5, cutoffs=cut)
+        o.set_reference(cen, index_thread_num=1)  # StringIndexer.buildIndex: single-threaded, no duplicated positions
+        for i in [t for t in range(len(reads)) if rc[t] == cidx]:
+            w = o.map_read_to_region(reads[i])
+            assert (found[i] != 0) == (w is not None), (cidx, i)
+            if w is None:
+                continue
+            n_found += 1
+            assert tuple(win[i]) == w, (cidx, i, tuple(win[i]), w)
+            rec, s1 = o.sw_align(reads[i], cen[w[0]:w[1]])
+            assert tuple(aln[i]) == tuple(int(x) for x in rec), (cidx, i)
+            assert seqs[i] == s1
+            k = w[0] + int(rec[3])
+            for ch in s1:
+                if ch < ord("a"):
+                    want_counts[cidx][k, {ord("T"): 1, ord("G"): 2, ord("C"): 3, ord("-"): 4}.get(ch, 0)] += 1
+                    k += 1
+    assert n_found > 250
+    for cidx in range(len(centroids)):
+        assert (counts[cidx] == want_counts[cidx]).all(), cidx
+
+
 def test_seed_host_csr_index(hiv):
     """The host-built CSR index (with its duplicated boundary positions, Q1) gives the same result as
     letting the library rebuild it from the thread count."""

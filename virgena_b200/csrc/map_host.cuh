@@ -641,6 +641,145 @@ int vg_best_window_batch(vg_ctx* c, int32_t msa, const uint8_t* pool, const int6
   return mh_seed_batch(c, msa, pool, off, n, 1, windows, found, nullptr, 0, nullptr, true);
 }
 
+// ContigBuilder.countReads / Graph.SWScore seeding step: KMerCounter.mapReadToRegion(read, index of the
+// region, 0, |region|) for (read, region) pairs, every region with its own StringIndexer.buildIndex index (single-threaded:
+// no duplicated positions). The per-region tables are built here and live in global memory.
+int vg_map_to_regions(vg_ctx* c, const uint8_t* region_pool, const int64_t* region_off, int64_t n_regions,
+                      const uint8_t* read_pool, const int64_t* read_off, int64_t n_reads, const int32_t* read_region,
+                      int32_t* windows, int32_t* found) {
+  if (!c) return VG_ERR_INVALID;
+  VG_CUDA(c, cudaSetDevice(c->device));
+  if (n_regions < 0 || n_reads < 0 || (n_regions > 0 && (!region_pool || !region_off)) ||
+      (n_reads > 0 && (!read_pool || !read_off || !read_region || !windows || !found)))
+    return vg_fail(c, VG_ERR_INVALID, "bad arguments");
+  if (n_reads == 0) return VG_OK;
+  const int K = c->seed.K;
+  if (K < 1 || K > 6) return vg_fail(c, VG_ERR_INVALID, "region seeding supports K = 1..6 (got %d)", K);
+  // layout: region bytes padded by 16, codes padded to a multiple of 128 entries
+  std::vector<int64_t> refOff(n_regions + 1, 0), codeOff(n_regions + 1, 0);
+  std::vector<int32_t> rlen(std::max<int64_t>(n_regions, 1), 0);
+  int maxLen = 0;
+  for (int64_t r = 0; r < n_regions; r++) {
+    const int64_t l = region_off[r + 1] - region_off[r];
+    if (l < 0 || l >= 65000) return vg_fail(c, VG_ERR_INVALID, "region %lld has unsupported length %lld", (long long)r, (long long)l);
+    rlen[r] = (int32_t)l;
+    maxLen = std::max(maxLen, (int)l);
+    refOff[r + 1] = refOff[r] + ((l + 15) & ~(int64_t)15) + 16;
+    codeOff[r + 1] = codeOff[r] + std::max<int64_t>(128, (l + 127) & ~(int64_t)127);
+  }
+  for (int64_t i = 0; i < region_off[n_regions]; i++)
+    if (region_pool[i] >= 127) return vg_fail(c, VG_ERR_ALPHABET, "region byte >= 127");
+  std::vector<int32_t> len(n_reads);
+  int maxRead = 0;
+  for (int64_t i = 0; i < n_reads; i++) {
+    const int64_t l = read_off[i + 1] - read_off[i];
+    if (l < 0 || l > (1 << 20)) return vg_fail(c, VG_ERR_INVALID, "bad read offsets");
+    if (read_region[i] < 0 || read_region[i] >= n_regions) return vg_fail(c, VG_ERR_INVALID, "read %lld names region %d", (long long)i, read_region[i]);
+    len[i] = (int32_t)l;
+    maxRead = std::max(maxRead, (int)l);
+  }
+  for (int64_t i = 0; i < read_off[n_reads]; i++)
+    if (read_pool[i] >= 127) return vg_fail(c, VG_ERR_ALPHABET, "read byte >= 127");
+  // exotic k-mers (a byte outside ACGT) of all regions: one sorted list, ids 4^K + rank
+  std::vector<uint64_t> exo;
+  for (int64_t r = 0; r < n_regions; r++) {
+    const uint8_t* p = region_pool + region_off[r];
+    for (int g = 0; g + K <= rlen[r]; g++) {
+      uint32_t code;
+      uint64_t key;
+      if (!sdh_pack(p + g, K, &code, &key)) exo.push_back(key);
+    }
+  }
+  std::sort(exo.begin(), exo.end());
+  exo.erase(std::unique(exo.begin(), exo.end()), exo.end());
+  std::vector<uint8_t> hRef((size_t)refOff[n_regions] + 16, 0);
+  std::vector<uint16_t> hCode((size_t)codeOff[n_regions] + 128, (uint16_t)SD_NONE16);
+  for (int64_t r = 0; r < n_regions; r++) {
+    const uint8_t* p = region_pool + region_off[r];
+    memcpy(hRef.data() + refOff[r], p, rlen[r]);
+    for (int g = 0; g + K <= rlen[r]; g++) {
+      uint32_t code;
+      uint64_t key;
+      hCode[codeOff[r] + g] = sdh_pack(p + g, K, &code, &key)
+                                  ? (uint16_t)code
+                                  : (uint16_t)((1u << (2 * K)) + (std::lower_bound(exo.begin(), exo.end(), key) - exo.begin()));
+    }
+  }
+  // device copies (scratch buffers that no mapping result depends on)
+  VG_CUDA(c, c->d_s1pool.reserve((size_t)read_off[n_reads] + 64));
+  VG_CUDA(c, c->d_s1off.reserve((size_t)(n_reads + 1) * 8));
+  VG_CUDA(c, c->d_s2off.reserve((size_t)n_reads * 4 + 64));
+  VG_CUDA(c, c->d_s2pool.reserve(hRef.size() + hCode.size() * 2 + (size_t)(n_regions + 1) * 20 + (size_t)n_reads * 4 + exo.size() * 8 + 1024));
+  uint8_t* base = c->d_s2pool.as<uint8_t>();
+  size_t o = 0;
+  auto put = [&](const void* src, size_t bytes) -> uint8_t* {
+    uint8_t* d = base + o;
+    if (bytes) cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, c->stream);
+    o = (o + bytes + 255) & ~(size_t)255;
+    return d;
+  };
+  SeedRegions R;
+  R.d_ref = put(hRef.data(), hRef.size());
+  R.d_code = (const uint16_t*)put(hCode.data(), hCode.size() * 2);
+  R.d_refOff = (const int64_t*)put(refOff.data(), refOff.size() * 8);
+  R.d_codeOff = (const int64_t*)put(codeOff.data(), codeOff.size() * 8);
+  R.d_len = (const int32_t*)put(rlen.data(), rlen.size() * 4);
+  R.d_itemRegion = (const int32_t*)put(read_region, (size_t)n_reads * 4);
+  R.d_exo = (const uint64_t*)put(exo.data(), exo.size() * 8);
+  R.nExo = (int)exo.size();
+  R.maxLen = maxLen;
+  VG_CUDA(c, cudaMemcpyAsync(c->d_s1pool.p, read_pool, (size_t)read_off[n_reads], cudaMemcpyHostToDevice, c->stream));
+  VG_CUDA(c, cudaMemcpyAsync(c->d_s1off.p, read_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  VG_CUDA(c, cudaMemcpyAsync(c->d_s2off.p, len.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, c->stream));
+  VG_CUDA(c, cudaGetLastError());
+  VG_TRY(seed_launch(c, false, c->d_s1pool.as<uint8_t>(), c->d_s1off.as<int64_t>(), c->d_s2off.as<int32_t>(), nullptr, nullptr,
+                     nullptr, n_reads, true, maxRead, 1, nullptr, nullptr, true, &R));
+  VG_CUDA(c, cudaMemcpyAsync(windows, c->d_cand.p, (size_t)n_reads * 3 * 4, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaMemcpyAsync(found, c->d_ncand.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VG_OK;
+}
+
+int vg_pileup_alignments(vg_ctx* c, const uint8_t* seq1_pool, const int64_t* seq1_off, const int32_t* length, const int64_t* pos,
+                         int64_t n, int64_t total_positions, int32_t* counts) {
+  if (!c) return VG_ERR_INVALID;
+  VG_CUDA(c, cudaSetDevice(c->device));
+  if (n < 0 || total_positions < 0 || (n > 0 && (!seq1_pool || !seq1_off || !length || !pos)) || (total_positions > 0 && !counts))
+    return vg_fail(c, VG_ERR_INVALID, "bad arguments");
+  if (total_positions == 0) return VG_OK;
+  int64_t bytes = 0;
+  for (int64_t i = 0; i < n; i++) {
+    if (length[i] < 0 || seq1_off[i] < 0) return vg_fail(c, VG_ERR_INVALID, "bad alignment %lld", (long long)i);
+    bytes = std::max(bytes, seq1_off[i] + length[i]);
+  }
+  VG_CUDA(c, c->d_s1pool.reserve((size_t)bytes + 64));
+  VG_CUDA(c, c->d_s1off.reserve((size_t)std::max<int64_t>(n, 1) * 8));
+  VG_CUDA(c, c->d_s2off.reserve((size_t)std::max<int64_t>(n, 1) * 4));
+  VG_CUDA(c, c->d_s2pool.reserve((size_t)std::max<int64_t>(n, 1) * 8 + (size_t)total_positions * 20 + 256));
+  int64_t* d_pos = c->d_s2pool.as<int64_t>();
+  int32_t* d_counts = (int32_t*)(c->d_s2pool.as<uint8_t>() + (((size_t)std::max<int64_t>(n, 1) * 8 + 255) & ~(size_t)255));
+  VG_CUDA(c, c->d_counter.reserve(512));
+  int* d_err = c->d_counter.as<int>();
+  VG_CUDA(c, cudaMemsetAsync(d_err, 0, 4, c->stream));
+  VG_CUDA(c, cudaMemsetAsync(d_counts, 0, (size_t)total_positions * 20, c->stream));
+  if (n > 0) {
+    VG_CUDA(c, cudaMemcpyAsync(c->d_s1pool.p, seq1_pool, (size_t)bytes, cudaMemcpyHostToDevice, c->stream));
+    VG_CUDA(c, cudaMemcpyAsync(c->d_s1off.p, seq1_off, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    VG_CUDA(c, cudaMemcpyAsync(c->d_s2off.p, length, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    VG_CUDA(c, cudaMemcpyAsync(d_pos, pos, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    pu_alignments_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->d_s1pool.as<uint8_t>(), c->d_s1off.as<int64_t>(),
+                                                                           c->d_s2off.as<int32_t>(), d_pos, n, total_positions,
+                                                                           d_counts, d_err);
+    VG_LAUNCH_CHECK(c);
+  }
+  int err = 0;
+  VG_CUDA(c, cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaMemcpyAsync(counts, d_counts, (size_t)total_positions * 20, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (err) return vg_fail(c, VG_ERR_ALPHABET, "an aligned byte lies in ('T', 'a') or an alignment runs past the last position (the Java would throw)");
+  return VG_OK;
+}
+
 // Test hook (not part of the reference-facing ABI): LongHits of one read after mergeHits + splitLongHits.
 int vg_debug_seed_hits(vg_ctx* c, int32_t msa, const uint8_t* read, int32_t L, int32_t* hits, int32_t cap, int32_t* n_hits) {
   int64_t off[2] = {0, L};

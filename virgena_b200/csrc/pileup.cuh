@@ -194,3 +194,25 @@ __global__ void pu_consensus_kernel(const int32_t* __restrict__ counts, int G, i
     r = maxIdx == 0 ? 'A' : maxIdx == 1 ? 'T' : maxIdx == 2 ? 'G' : 'C';  // Constants.iToN
   out[i] = r;
 }
+
+// ContigBuilder.countReads pileup (ContigBuilder.java:93-99; the same loop as ConsensusBuilderSimple.java:56-75) for a batch
+// of alignments against many small regions laid out back to back: alignment i starts at position pos[i] of the
+// concatenated coordinate system. One thread per alignment; integer atomics (the result does not depend on their order).
+__global__ void pu_alignments_kernel(const uint8_t* __restrict__ seq1, const int64_t* __restrict__ off,
+                                     const int32_t* __restrict__ len, const int64_t* __restrict__ pos, int64_t n,
+                                     int64_t total, int32_t* __restrict__ counts, int* __restrict__ err) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t k = pos[i];
+  const uint8_t* s = seq1 + off[i];
+  for (int j = 0; j < len[i]; j++) {
+    const uint8_t ch = s[j];
+    if (ch >= 'a') continue;               // insertion in the read: no reference position
+    if (ch > 'T' || k < 0 || k >= total) {  // nToI has 'T' + 1 entries / counts[k] out of range: the Java throws
+      *err = 1;
+      return;
+    }
+    atomicAdd(&counts[k * 5 + pu_ntoi(ch)], 1);
+    k++;
+  }
+}

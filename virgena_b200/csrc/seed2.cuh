@@ -68,6 +68,15 @@ struct Seed2Args {
   uint32_t* rawBuf;            // [warpSlots][4][capRaw]
   int capRaw;
   int msaWarpBytes, idsBytes;
+  // region mode (vg_map_to_regions): every work item has its own small reference (cluster centroid / reference
+  // sub-sequence); tables live in global memory, nothing is staged
+  int regions;
+  const uint8_t* regRef;       // region bytes, each region padded by >= 16
+  const uint16_t* regCode;     // per-position k-mer ids, each region padded with SD_NONE16 to a multiple of 128 entries
+  const int64_t* regRefOff;
+  const int64_t* regCodeOff;
+  const int32_t* regLen;
+  const int32_t* itemRegion;   // [all items]
   int bestOnly;                // 1: mapReadToRegion / computeKMerCount over [0, G): the first window of maximal count, no cutoff,
                                //    no splitLongHits, no pruning (KMerCounter.java:119-140, KMerCounterBase.java:468-487)
   int key24;                   // G < 16384: candidates sort on a 24-bit key (start << 10 | 1023 - (end - start)), 3 passes
@@ -108,8 +117,9 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
   __shared__ uint64_t sd_mbar;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int K = A.K, G = A.G;
-  sd_tma_stage(sd_smem, A.blob, A.blobBytes, &sd_mbar);
+  const int K = A.K;
+  int G = A.G;
+  if (A.blobBytes > 0) sd_tma_stage(sd_smem, A.blob, A.blobBytes, &sd_mbar);
   const uint8_t* ref = sd_smem;
   const uint16_t* poscode = (const uint16_t*)(sd_smem + A.blobRefBytes);
   uint8_t* wbase = sd_smem + A.blobBytes + (size_t)warp * A.genWarpBytes;
@@ -130,6 +140,12 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
     int64_t off;
     int L, rev;
     sd2_item(A, it, off, L, rev);
+    if (A.regions) {
+      const int rg = A.itemRegion[A.itemBase + it];
+      ref = A.regRef + A.regRefOff[rg];
+      poscode = A.regCode + A.regCodeOff[rg];
+      G = A.regLen[rg];
+    }
     const int nk = L - K + 1;
     if (nk < 1 || L > SD_MAXL) {  // L < K: no k-mer (Q6); too long: reported by the window kernel
       if (lane == 0) A.nS[it] = 0;
@@ -569,7 +585,8 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int warpSlot = blockIdx.x * (blockDim.x >> 5) + warp;
-  const int K = A.K, G = A.G;
+  const int K = A.K;
+  int G = A.G;
   uint8_t* wbase = sd_smem + (size_t)warp * A.winWarpBytes;
   uint64_t* win = (uint64_t*)wbase;
   const int capRs = A.capRs;
@@ -601,6 +618,7 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
     sd2_item(A, it, off, L, rev);
     const int nS = A.nS[it];
     if (nS < 0) continue;  // redone by the general kernel
+    if (A.regions) G = A.regLen[A.itemRegion[gi]];
     SD2_PH(0)
     if (L > SD_MAXL && lane == 0) atomicOr(A.counters + 2, 16);
     uint64_t* S = A.S + (size_t)it * A.capS;

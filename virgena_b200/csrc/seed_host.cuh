@@ -308,33 +308,48 @@ static int seed_launch_v1(vg_ctx* c, bool msa, const uint8_t* d_bases, const int
   return VG_OK;
 }
 
+// Region mode (vg_map_to_regions): per-item references prepared by the caller on the device.
+struct SeedRegions {
+  const uint8_t* d_ref;
+  const uint16_t* d_code;
+  const int64_t* d_refOff;
+  const int64_t* d_codeOff;
+  const int32_t* d_len;
+  const int32_t* d_itemRegion;
+  const uint64_t* d_exo;
+  int nExo;
+  int maxLen;
+};
+
 // Seeding entry point. Single-reference mode with a direct-addressed k-mer table (K <= 5, few exotic k-mers) and a
 // reference that fits in shared memory runs the two-kernel fast path (seed2.cuh) in sub-chunks of items; the items
 // it hands back, and every other mode (MSA, K > 5), run the general kernel. Windows land in c->d_cand
 // ([nItems][maxWin][3]) and c->d_ncand ([nItems]).
 static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_t* d_off1, const int32_t* d_len1,
                        const int64_t* d_off2, const int32_t* d_len2, const int64_t* d_pairIdx, int64_t nItems,
-                       bool singleReads, int maxReadLen, int maxWin, int32_t* dbgHits, int32_t* dbgNHits, bool bestOnly = false) {
+                       bool singleReads, int maxReadLen, int maxWin, int32_t* dbgHits, int32_t* dbgNHits, bool bestOnly = false,
+                       const SeedRegions* regs = nullptr) {
   c->seedFallbacks = 0;
   const SeedConfig& sc = msa ? c->seedMsa : c->seed;
-  const int K = sc.K, G = msa ? c->msaLength : c->G;
+  const int K = sc.K, G = regs ? regs->maxLen : msa ? c->msaLength : c->G;
+  const int nExoRef = regs ? regs->nExo : c->nExo;
   const int smemMax = 227 * 1024;
   bool fast = !getenv("VG_SEED_V1") && !getenv("VG_SEED_HASH") && !getenv("VG_SEED_PROF") && K >= 1 && K <= 7 && G >= K &&
               G + maxReadLen < 65535 && maxReadLen <= SD_MAXL && maxReadLen >= K && nItems > 0 && nItems <= 0x7fffffff &&
-              (maxReadLen < (int)sc.cutoffs.size());
+              (bestOnly || maxReadLen < (int)sc.cutoffs.size());
   Seed2Args A;
   memset(&A, 0, sizeof A);
   int genWarps = 0, winWarps = 0;
   if (fast) {
     A.rdBytes = (maxReadLen + 16 + 15) & ~15;
     if (!msa) {
-      A.emptyId = (1 << (2 * K)) + c->nExo;
+      A.emptyId = (1 << (2 * K)) + nExoRef;
       A.tabBytes = ((A.emptyId + 1) * 2 + 15) & ~15;
       A.nxtBytes = (maxReadLen * 2 + 15) & ~15;
       A.qcap = 512;
       A.genWarpBytes = A.tabBytes + A.nxtBytes + (A.qcap + 4) * 4 + A.rdBytes;
-      A.blobRefBytes = sdh_ref_pad(G);
-      A.blobBytes = A.blobRefBytes + sdh_code_pad(G);
+      A.blobRefBytes = regs ? 0 : sdh_ref_pad(G);
+      A.blobBytes = regs ? 0 : A.blobRefBytes + sdh_code_pad(G);
       genWarps = std::min(32, (smemMax - 64 - A.blobBytes) / A.genWarpBytes);
       if (A.emptyId >= SD_NONE16 || A.emptyId > 8191) fast = false;
     } else {
@@ -342,7 +357,7 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
       A.msaWarpBytes = A.idsBytes + 2048 + A.rdBytes;
       genWarps = std::min(32, smemMax / A.msaWarpBytes);
     }
-    const int nContigs = msa ? 1 : (int)c->contigEnds.size();
+    const int nContigs = (msa || regs) ? 1 : (int)c->contigEnds.size();
     A.capR = std::max(256, std::min(16384, G / K + nContigs + 16));
     A.nBuckets = (G >> 5) + 2;
     const int bucketBytes = (A.nBuckets * 2 + 15) & ~15;
@@ -365,7 +380,16 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     winWarps = std::max(1, std::min(winWarps, atoi(e)));
   }
   double hitsPerKmer = c->seedHitsPerKmer;
-  if (!msa) {
+  if (regs) {
+    A.regions = 1;
+    A.regRef = regs->d_ref, A.regCode = regs->d_code, A.regRefOff = regs->d_refOff, A.regCodeOff = regs->d_codeOff;
+    A.regLen = regs->d_len, A.itemRegion = regs->d_itemRegion;
+    A.exoKeys = regs->d_exo;
+    A.nExo = regs->nExo;
+    A.contigEnds = nullptr;
+    A.nContigs = 1;
+    hitsPerKmer = 4.0 * (double)G / (double)(1u << (2 * K)) + 1.0;  // no spectrum at hand: 4 x the uniform expectation
+  } else if (!msa) {
     A.blob = c->d_poscode.as<uint8_t>();
     A.exoKeys = c->d_exoKeys.as<uint64_t>();
     A.nExo = c->nExo;

@@ -310,6 +310,30 @@ class Context:
         self._chk(self.L.vg_best_window_batch(self.h, int(msa), ptr(pool), ptr(off), n, ptr(win), ptr(found)))
         return win[:n], found[:n]
 
+    def map_to_regions(self, region_pool, region_off, read_pool, read_off, read_region):
+        """vg_map_to_regions: mapReadToRegion of read i against region read_region[i] (each region its own index).
+        Returns (windows int32[n, 3], found int32[n])."""
+        region_pool, read_pool = _u8(region_pool), _u8(read_pool)
+        region_off = np.ascontiguousarray(region_off, np.int64)
+        read_off = np.ascontiguousarray(read_off, np.int64)
+        read_region = np.ascontiguousarray(read_region, np.int32)
+        n = len(read_off) - 1
+        win = np.zeros((max(n, 1), 3), np.int32)
+        found = np.zeros(max(n, 1), np.int32)
+        self._chk(self.L.vg_map_to_regions(self.h, ptr(region_pool), ptr(region_off), len(region_off) - 1, ptr(read_pool),
+                                           ptr(read_off), n, ptr(read_region), ptr(win), ptr(found)))
+        return win[:n], found[:n]
+
+    def pileup_alignments(self, seq1_pool, seq1_off, length, pos, total_positions):
+        seq1_pool = _u8(seq1_pool)
+        seq1_off = np.ascontiguousarray(seq1_off, np.int64)
+        length = np.ascontiguousarray(length, np.int32)
+        pos = np.ascontiguousarray(pos, np.int64)
+        counts = np.zeros((max(int(total_positions), 1), 5), np.int32)
+        self._chk(self.L.vg_pileup_alignments(self.h, ptr(seq1_pool), ptr(seq1_off), ptr(length), ptr(pos), len(length),
+                                              int(total_positions), ptr(counts)))
+        return counts[:int(total_positions)]
+
     def debug_seed_hits(self, read, msa=False):
         """Test hook: LongHits (genomePos, readPos, len) of one read after mergeHits + splitLongHits."""
         read = _u8(read)
@@ -380,6 +404,48 @@ CIGAR_OPS = "MID?S"
 def cigar_string(ops):
     """CIGAR text of a run of len << 4 | op elements ('*' when empty)."""
     return "".join("%d%s" % (int(o) >> 4, CIGAR_OPS[int(o) & 15]) for o in ops) or "*"
+
+
+class ContigBuilder:
+    """The read-counting step of ContigBuilder (ContigBuilder.java:72-104, rebuilt at :219-227): every read of a cluster is
+    seeded against the cluster's centroid (mapReadToRegion with the centroid's own index), aligned against the window
+    and piled up into the centroid's counts. One call handles all clusters."""
+
+    def __init__(self, mapper):
+        self.ctx = mapper.ctx
+
+    def countReads(self, centroids, reads, read_cluster):
+        """centroids, reads: lists of byte strings; read_cluster[i] = cluster of read i. Returns (windows int32[n, 3],
+        found int32[n], alignments int32[n, 7], sequence1 list, counts per centroid list of int32[len, 5])."""
+        cpool = np.frombuffer(b"".join(bytes(c) for c in centroids), np.uint8) if centroids else np.zeros(0, np.uint8)
+        coff = np.zeros(len(centroids) + 1, np.int64)
+        np.cumsum([len(c) for c in centroids], out=coff[1:])
+        rpool = np.frombuffer(b"".join(bytes(r) for r in reads), np.uint8) if reads else np.zeros(0, np.uint8)
+        roff = np.zeros(len(reads) + 1, np.int64)
+        np.cumsum([len(r) for r in reads], out=roff[1:])
+        read_cluster = np.ascontiguousarray(read_cluster, np.int32)
+        win, found = self.ctx.map_to_regions(cpool, coff, rpool, roff, read_cluster)
+        idx = np.nonzero(found)[0]
+        # aligner.align(read.seq, centroid[start:end]) (ContigBuilder.java:85-89)
+        s2 = [bytes(centroids[read_cluster[i]][win[i, 0]:win[i, 1]]) for i in idx]
+        s1 = [bytes(reads[i]) for i in idx]
+        s1off = np.zeros(len(idx) + 1, np.int64)
+        np.cumsum([len(x) for x in s1], out=s1off[1:])
+        s2off = np.zeros(len(idx) + 1, np.int64)
+        np.cumsum([len(x) for x in s2], out=s2off[1:])
+        aln = np.zeros((len(reads), 7), np.int32)
+        seqs = [b""] * len(reads)
+        total = int(coff[-1])
+        if len(idx):
+            rec, pool, soff = self.ctx.sw_align_batch(b"".join(s1), s1off, b"".join(s2), s2off)
+            aln[idx] = rec
+            for t, i in enumerate(idx):
+                seqs[i] = pool[soff[t]:soff[t] + rec[t, 6]].tobytes()
+            pos = coff[read_cluster[idx]] + win[idx, 0] + rec[:, 3]  # centroid base + mRead.start + alignment.start2
+            counts = self.ctx.pileup_alignments(pool, soff[:-1], rec[:, 6], pos, total)
+        else:
+            counts = np.zeros((total, 5), np.int32)
+        return win, found, aln, seqs, [counts[coff[c]:coff[c + 1]] for c in range(len(centroids))]
 
 
 class BamPrinter:
