@@ -32,6 +32,18 @@ final class VirgenaGpu implements AutoCloseable {
   native long[] mapPairs(long ctx, long[] pairIdxOrNull, boolean msa, ByteBuffer records, ByteBuffer seq1Pool);
   // vg_pileup + vg_consensus
   native byte[] consensus(long ctx, boolean saveUncovered, int coverageThreshold, byte[] genome);
+  // vg_bam_fields: records = direct buffer of vg_bam_record (40 B: flag, refIndex, pos, mapq, mateRefIndex, matePos, xn,
+  // nCigar, cigarOffset), cigar = len << 4 | op elements; BamPrinter keeps the htsjdk serialisation (BamPrinter.java:256-326)
+  native long bamFields(long ctx, ByteBuffer records, ByteBuffer cigarPool);
+  // vg_best_window_batch: mapReadToRegion over the whole reference / computeKMerCount (RandomModel.java:122-128)
+  native void bestWindows(long ctx, boolean msa, ByteBuffer reads, long[] readOff, int[] windows, int[] found);
+  // vg_map_to_regions + vg_sw_align_batch + vg_pileup_alignments: ContigBuilder.countReads (ContigBuilder.java:72-104)
+  native void mapToRegions(long ctx, ByteBuffer regions, long[] regionOff, ByteBuffer reads, long[] readOff, int[] readRegion,
+                           int[] windows, int[] found);
+  native void alignBatch(long ctx, ByteBuffer s1, long[] s1Off, ByteBuffer s2, long[] s2Off, int[] rec, ByteBuffer seq1,
+                         long[] seq1Off);
+  native void pileupAlignments(long ctx, ByteBuffer seq1, long[] seq1Off, int[] length, long[] pos, long totalPositions,
+                               int[] counts);
 
   long handle() { return ctx; }
 
