@@ -112,6 +112,9 @@ __device__ __forceinline__ void sd2_fallback(const Seed2Args& A, int local, int 
 //   tab[id] = head | count << 9 (count 0 = the k-mer does not occur in the read), nxt = chain of ascending
 //   read positions, queue = flattened raw hits (g << 16 | i) of the current batch of genome positions.
 // ------------------------------------------------------------------------------------------------
+// REGIONS: every work item has its own reference in global memory (vg_map_to_regions); otherwise the one reference is
+// staged in shared memory and addressed as such.
+template <bool REGIONS>
 __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
   extern __shared__ __align__(16) uint8_t sd_smem[];
   __shared__ uint64_t sd_mbar;
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
   const int warp = threadIdx.x >> 5;
   const int K = A.K;
   int G = A.G;
-  if (A.blobBytes > 0) sd_tma_stage(sd_smem, A.blob, A.blobBytes, &sd_mbar);
+  if (!REGIONS) sd_tma_stage(sd_smem, A.blob, A.blobBytes, &sd_mbar);
   const uint8_t* ref = sd_smem;
   const uint16_t* poscode = (const uint16_t*)(sd_smem + A.blobRefBytes);
   uint8_t* wbase = sd_smem + A.blobBytes + (size_t)warp * A.genWarpBytes;
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
     int64_t off;
     int L, rev;
     sd2_item(A, it, off, L, rev);
-    if (A.regions) {
+    if (REGIONS) {
       const int rg = A.itemRegion[A.itemBase + it];
       ref = A.regRef + A.regRefOff[rg];
       poscode = A.regCode + A.regCodeOff[rg];

@@ -435,7 +435,8 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   const size_t genSmem = msa ? (size_t)genWarps * A.msaWarpBytes : (size_t)A.blobBytes + (size_t)genWarps * A.genWarpBytes;
   const size_t winSmem = (size_t)winWarps * A.winWarpBytes;
   if (msa) VG_CUDA(c, cudaFuncSetAttribute(seed_gen_msa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmem));
-  else VG_CUDA(c, cudaFuncSetAttribute(seed_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmem));
+  else if (regs) VG_CUDA(c, cudaFuncSetAttribute(seed_gen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmem));
+  else VG_CUDA(c, cudaFuncSetAttribute(seed_gen_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmem));
   VG_CUDA(c, cudaFuncSetAttribute(seed_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)winSmem));
   const int64_t sub0 = std::min(subItems, nItems);
   const int genBlocks = (int)std::max<int64_t>(1, std::min<int64_t>((sub0 + genWarps - 1) / genWarps, c->smCount));
@@ -486,7 +487,8 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     VG_CUDA(c, cudaMemsetAsync(A.counters, 0, 8, c->stream));
     VG_CUDA(c, cudaEventRecord(c->seedEv[3 * sub], c->stream));
     if (msa) seed_gen_msa_kernel<<<genBlocks, genWarps * 32, genSmem, c->stream>>>(A);
-    else seed_gen_kernel<<<genBlocks, genWarps * 32, genSmem, c->stream>>>(A);
+    else if (regs) seed_gen_kernel<true><<<genBlocks, genWarps * 32, genSmem, c->stream>>>(A);
+    else seed_gen_kernel<false><<<genBlocks, genWarps * 32, genSmem, c->stream>>>(A);
     VG_LAUNCH_CHECK(c);
     VG_CUDA(c, cudaEventRecord(c->seedEv[3 * sub + 1], c->stream));
     seed_win_kernel<<<winBlocks, winWarps * 32, winSmem, c->stream>>>(A);
