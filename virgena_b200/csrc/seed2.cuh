@@ -14,6 +14,8 @@
 // slot, a sweep segment longer than the shared-memory window, a full re-insertion queue) is not an error: the
 // item is appended to a fallback list and redone by seed_kernel, which has the general (hash / serial) paths.
 #pragma once
+#include <type_traits>
+
 #include "seed.cuh"
 
 struct Seed2Args {
@@ -600,12 +602,11 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
   uint32_t* cval = A.candVal + (size_t)warpSlot * 2 * capC;
   const unsigned lt = (1u << lane) - 1u;
   // contig ends: binary-searched per hit in phases D and F; a copy in shared memory when there are few of them
-  __shared__ int32_t sd_contigs[64];
-  const int32_t* cEnds = A.contigEnds;
-  if (A.nContigs > 1 && A.nContigs <= 64) {
+  __shared__ int32_t sd_contigs[64];  // the host takes references with more than 64 contigs to the general kernel
+  const int32_t* cEnds = sd_contigs;
+  if (A.nContigs > 1) {
     if (threadIdx.x < A.nContigs) sd_contigs[threadIdx.x] = A.contigEnds[threadIdx.x];
     __syncthreads();
-    cEnds = sd_contigs;
   }
 
 #pragma unroll 1
@@ -837,131 +838,135 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
     if (nR > 0) {
       // ---- E: isAdjacent (IEEE binary32 division, Q3 coefficients verbatim) + prefix sums
       //         P[j] = sum_{t<=j}(len_t + isAdjacent[t-1]) (mod 2^16); genomePos table + buckets for the searches
-      uint16_t* hitG = (uint16_t*)wbase;
-      uint16_t* Pp = hitG + capRs + 8;
-      uint8_t* hitL = (uint8_t*)(Pp + capRs);
-      if (nR > capRs) {  // does not fit in shared memory: L2-resident per-warp scratch
-        hitG = A.scratchR + (size_t)warpSlot * 3 * (A.capR + 8);
-        Pp = hitG + A.capR + 8;
-        hitL = (uint8_t*)(Pp + A.capR + 8);
-      }
-      if (lane < 8) hitG[nR + lane] = 0xFFFFu;  // sentinels for the branch-free searches of phase F
-      int carry = 0, pgLast = 0, prLast = 0;
-#pragma unroll 1
-      for (int j0 = 0; j0 < nR; j0 += 32) {
-        const int j = j0 + lane;
-        int val = 0, g = 0, r = 0;
-        if (j < nR) {
-          const uint64_t v = S[j];
-          g = (int)(v >> 32), r = (int)((v >> 16) & 0xFFFFu);
-          val = (int)(v & 0xFFFFu);
-          hitG[j] = (uint16_t)g;
-          hitL[j] = (uint8_t)min(val, 255);
-        }
-        int pg = __shfl_up_sync(VG_FULL, g, 1), pr = __shfl_up_sync(VG_FULL, r, 1);
-        if (lane == 0) pg = pgLast, pr = prLast;
-        if (j < nR && j > 0) {
-          const float rate = __fdiv_rn((float)(g - pg), (float)(r - pr));
-          if (A.lowCoef <= rate && rate <= A.highCoef) val++;
-        }
-        const int incl = sd_warp_incl_scan(val, lane);
-        if (j < nR) Pp[j] = (uint16_t)(carry + incl);
-        carry += __shfl_sync(VG_FULL, incl, 31);
-        pgLast = __shfl_sync(VG_FULL, g, 31);
-        prLast = __shfl_sync(VG_FULL, r, 31);
-      }
-      // bucket[b] = first hit index with g >= 32 b
-      const int nb = A.nBuckets;
-#pragma unroll 1
-      for (int b = lane; b < nb; b += 32) bucket[b] = (uint16_t)nR;
-      __syncwarp();
-#pragma unroll 1
-      for (int j = lane; j < nR; j += 32) {
-        const int b = hitG[j] >> 5;
-        if (j == 0 || (hitG[j - 1] >> 5) != b) bucket[b] = (uint16_t)j;
-      }
-      __syncwarp();
-      {  // suffix fill of empty buckets (serial over chunks from the top, parallel inside a chunk)
-        int nextv = nR;
-#pragma unroll 1
-        for (int b0 = ((nb - 1) >> 5) << 5; b0 >= 0; b0 -= 32) {
-          const int b = b0 + lane;
-          int v = (b < nb) ? bucket[b] : nR;
-          const bool empty = (v == nR);
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_down_sync(VG_FULL, v, d);
-            if (lane + d < 32) v = min(v, o);
-          }
-          v = min(v, nextv);
-          if (b < nb && empty) bucket[b] = (uint16_t)v;
-          nextv = __shfl_sync(VG_FULL, v, 0);
-        }
-      }
-      __syncwarp();
-      SD2_PH(2)
-      // ---- F: every window independently (updateCount equals a direct recount on sorted non-overlapping
-      //         hits); candidates (count > cutoff, strict) compacted in hit order
       const int cutoff = A.bestOnly ? -1 : (L < A.nCutoffs) ? A.cutoffs[L] : 0x7fffffff;
       int nC = 0;
       int bestCnt = -1, bestJ = 0x7fffffff, bestS = 0, bestE = 0;  // bestOnly: per lane, first maximum in hit order
-#pragma unroll 1
-      for (int j0 = 0; j0 < nR; j0 += 32) {
-        const int j = j0 + lane;
-        bool isCand = false;
-        uint32_t key = 0, cnt = 0;
-        if (j < nR) {
-          const uint64_t v = S[j];
-          const int g = (int)(v >> 32), r = (int)((v >> 16) & 0xFFFFu), len = (int)(v & 0xFFFFu);
-          int cs = 0, ce = G;
-          if (A.nContigs > 1 && !A.bestOnly) {
-            int lo = 0, hi = A.nContigs - 1;
-#pragma unroll 1
-            while (lo < hi) {
-              const int mid = (lo + hi) >> 1;
-              if (cEnds[mid] > g) hi = mid;
-              else lo = mid + 1;
+      // The arrays live in shared memory when the LongHits fit (the rule) and in L2-resident per-warp scratch otherwise;
+      // the phases are instantiated once per address space so that the common case is compiled to LDS, not generic loads.
+      auto phaseEF = [&](auto inShared, uint16_t* hitG, uint16_t* Pp, uint8_t* hitL) {
+        (void)inShared;
+        if (lane < 8) hitG[nR + lane] = 0xFFFFu;  // sentinels for the branch-free searches of phase F
+        int carry = 0, pgLast = 0, prLast = 0;
+  #pragma unroll 1
+        for (int j0 = 0; j0 < nR; j0 += 32) {
+          const int j = j0 + lane;
+          int val = 0, g = 0, r = 0;
+          if (j < nR) {
+            const uint64_t v = S[j];
+            g = (int)(v >> 32), r = (int)((v >> 16) & 0xFFFFu);
+            val = (int)(v & 0xFFFFu);
+            hitG[j] = (uint16_t)g;
+            hitL[j] = (uint8_t)min(val, 255);
+          }
+          int pg = __shfl_up_sync(VG_FULL, g, 1), pr = __shfl_up_sync(VG_FULL, r, 1);
+          if (lane == 0) pg = pgLast, pr = prLast;
+          if (j < nR && j > 0) {
+            const float rate = __fdiv_rn((float)(g - pg), (float)(r - pr));
+            if (A.lowCoef <= rate && rate <= A.highCoef) val++;
+          }
+          const int incl = sd_warp_incl_scan(val, lane);
+          if (j < nR) Pp[j] = (uint16_t)(carry + incl);
+          carry += __shfl_sync(VG_FULL, incl, 31);
+          pgLast = __shfl_sync(VG_FULL, g, 31);
+          prLast = __shfl_sync(VG_FULL, r, 31);
+        }
+        // bucket[b] = first hit index with g >= 32 b
+        const int nb = A.nBuckets;
+  #pragma unroll 1
+        for (int b = lane; b < nb; b += 32) bucket[b] = (uint16_t)nR;
+        __syncwarp();
+  #pragma unroll 1
+        for (int j = lane; j < nR; j += 32) {
+          const int b = hitG[j] >> 5;
+          if (j == 0 || (hitG[j - 1] >> 5) != b) bucket[b] = (uint16_t)j;
+        }
+        __syncwarp();
+        {  // suffix fill of empty buckets (serial over chunks from the top, parallel inside a chunk)
+          int nextv = nR;
+  #pragma unroll 1
+          for (int b0 = ((nb - 1) >> 5) << 5; b0 >= 0; b0 -= 32) {
+            const int b = b0 + lane;
+            int v = (b < nb) ? bucket[b] : nR;
+            const bool empty = (v == nR);
+  #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const int o = __shfl_down_sync(VG_FULL, v, d);
+              if (lane + d < 32) v = min(v, o);
             }
-            ce = cEnds[lo];
-            cs = lo ? cEnds[lo - 1] : 0;
+            v = min(v, nextv);
+            if (b < nb && empty) bucket[b] = (uint16_t)v;
+            nextv = __shfl_sync(VG_FULL, v, 0);
           }
-          const int start = max(cs, g - r * 3 / 2);
-          const int end = min(g + len + K + (L - r - len - K) * 3 / 2, ce);
-          // a = first hit with genomePos >= start, u = first with genomePos >= end: a 32-position bucket holds at most
-          // 32 / K + 1 hits (they do not overlap), three branch-free halving steps cover 8; the loops are the safety net
-          int a = bucket[start >> 5];
-          a += (hitG[a + 3] < start) ? 4 : 0;
-          a += (hitG[a + 1] < start) ? 2 : 0;
-          a += (hitG[a] < start) ? 1 : 0;
-#pragma unroll 1
-          while (hitG[a] < start) a++;
-          int u = bucket[min(end, G) >> 5];
-          u += (hitG[u + 3] < end) ? 4 : 0;
-          u += (hitG[u + 1] < end) ? 2 : 0;
-          u += (hitG[u] < end) ? 1 : 0;
-#pragma unroll 1
-          while (hitG[u] < end) u++;  // stops at the sentinel at the latest
-          int b = u - 1;
-          int lenA = hitL[a], lenB = hitL[b];
-          if (lenA == 255) lenA = (int)(S[a] & 0xFFFFu);
-          if (lenB == 255) lenB = (int)(S[b] & 0xFFFFu);
-          if ((int)hitG[b] + K + lenB > end) b--;
-          cnt = (uint32_t)((uint16_t)(Pp[b] - Pp[a])) + (uint32_t)lenA;
-          isCand = (int)cnt > cutoff;
-          if (A.bestOnly) {
-            if ((int)cnt > bestCnt) bestCnt = (int)cnt, bestJ = j, bestS = start, bestE = end;
-            isCand = false;
+        }
+        __syncwarp();
+        SD2_PH(2)
+        // ---- F: every window independently (updateCount equals a direct recount on sorted non-overlapping
+        //         hits); candidates (count > cutoff, strict) compacted in hit order
+  #pragma unroll 1
+        for (int j0 = 0; j0 < nR; j0 += 32) {
+          const int j = j0 + lane;
+          bool isCand = false;
+          uint32_t key = 0, cnt = 0;
+          if (j < nR) {
+            const uint64_t v = S[j];
+            const int g = (int)(v >> 32), r = (int)((v >> 16) & 0xFFFFu), len = (int)(v & 0xFFFFu);
+            int cs = 0, ce = G;
+            if (A.nContigs > 1 && !A.bestOnly) {
+              int lo = 0, hi = A.nContigs - 1;
+  #pragma unroll 1
+              while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (cEnds[mid] > g) hi = mid;
+                else lo = mid + 1;
+              }
+              ce = cEnds[lo];
+              cs = lo ? cEnds[lo - 1] : 0;
+            }
+            const int start = max(cs, g - r * 3 / 2);
+            const int end = min(g + len + K + (L - r - len - K) * 3 / 2, ce);
+            // a = first hit with genomePos >= start, u = first with genomePos >= end: a 32-position bucket holds at most
+            // 32 / K + 1 hits (they do not overlap), three branch-free halving steps cover 8; the loops are the safety net
+            int a = bucket[start >> 5];
+            a += (hitG[a + 3] < start) ? 4 : 0;
+            a += (hitG[a + 1] < start) ? 2 : 0;
+            a += (hitG[a] < start) ? 1 : 0;
+  #pragma unroll 1
+            while (hitG[a] < start) a++;
+            int u = bucket[min(end, G) >> 5];
+            u += (hitG[u + 3] < end) ? 4 : 0;
+            u += (hitG[u + 1] < end) ? 2 : 0;
+            u += (hitG[u] < end) ? 1 : 0;
+  #pragma unroll 1
+            while (hitG[u] < end) u++;  // stops at the sentinel at the latest
+            int b = u - 1;
+            int lenA = hitL[a], lenB = hitL[b];
+            if (lenA == 255) lenA = (int)(S[a] & 0xFFFFu);
+            if (lenB == 255) lenB = (int)(S[b] & 0xFFFFu);
+            if ((int)hitG[b] + K + lenB > end) b--;
+            cnt = (uint32_t)((uint16_t)(Pp[b] - Pp[a])) + (uint32_t)lenA;
+            isCand = (int)cnt > cutoff;
+            if (A.bestOnly) {
+              if ((int)cnt > bestCnt) bestCnt = (int)cnt, bestJ = j, bestS = start, bestE = end;
+              isCand = false;
+            }
+            // order (start asc, end desc); a window is at most 1.5 L <= 768 wide
+            key = A.key24 ? ((uint32_t)start << 10) | (uint32_t)(1023 - (end - start)) : ((uint32_t)start << 16) | (uint32_t)(0xFFFF - end);
           }
-          // order (start asc, end desc); a window is at most 1.5 L <= 768 wide
-          key = A.key24 ? ((uint32_t)start << 10) | (uint32_t)(1023 - (end - start)) : ((uint32_t)start << 16) | (uint32_t)(0xFFFF - end);
+          const unsigned m = __ballot_sync(VG_FULL, isCand);
+          if (isCand) {
+            const int o = nC + __popc(m & lt);
+            ckey[o] = key;
+            cval[o] = cnt;
+          }
+          nC += __popc(m);
         }
-        const unsigned m = __ballot_sync(VG_FULL, isCand);
-        if (isCand) {
-          const int o = nC + __popc(m & lt);
-          ckey[o] = key;
-          cval[o] = cnt;
-        }
-        nC += __popc(m);
+      };
+      if (nR <= capRs) {
+        uint16_t* hs = (uint16_t*)wbase;
+        phaseEF(std::true_type{}, hs, hs + capRs + 8, (uint8_t*)(hs + 2 * capRs + 8));
+      } else {
+        uint16_t* hg = A.scratchR + (size_t)warpSlot * 3 * (A.capR + 8);
+        phaseEF(std::false_type{}, hg, hg + A.capR + 8, (uint8_t*)(hg + 2 * (A.capR + 8)));
       }
       __syncwarp();
       if (A.bestOnly) {  // strict '>' in hit order: the first hit that reaches the maximum wins

@@ -367,7 +367,7 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     A.capRs = std::max(0, std::min(A.capR, (budget - bucketBytes - 16) / 5)) & ~7;
     A.winWarpBytes = (std::max(std::max(cBytes, 1024), A.capRs * 5 + 16 + bucketBytes) + 15) & ~15;
     winWarps = std::min(32, winMax / A.winWarpBytes);
-    if (genWarps < 8 || winWarps < 8) fast = false;
+    if (genWarps < 8 || winWarps < 8 || nContigs > 64) fast = false;
   }
   if (!fast && bestOnly)
     return vg_fail(c, VG_ERR_INVALID, "best-window seeding needs the fast path (K <= 6 in single-reference mode, reference + read length "
