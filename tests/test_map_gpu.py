@@ -63,7 +63,7 @@ def test_seed_hits_and_windows(hiv):
         ctx.close()
 
 
-@pytest.mark.parametrize("K,caps", [(5, None), (5, "64"), (4, None), (3, None), (6, None), (7, None)])
+@pytest.mark.parametrize("K,caps", [(5, None), (5, "64"), (5, "wide"), (4, None), (3, None), (6, None), (7, None)])
 def test_seed_paths_and_long_reads(built, K, caps, monkeypatch):
     """The fast seeding path (seed2.cuh) and everything it hands to the general kernel: reads up to 512 bases with exact
     matches longer than 255 (the shared-memory hit length saturates there), low-complexity reads (a k-mer more than 127
@@ -72,7 +72,9 @@ def test_seed_paths_and_long_reads(built, K, caps, monkeypatch):
     import oracle
     import virgena_b200 as vg
     from virgena_b200 import synth
-    if caps is not None:
+    if caps == "wide":
+        monkeypatch.setenv("VG_SEED_WIDE", "1")  # 64-bit sweep window (what references of 16384 and more use)
+    elif caps is not None:
         monkeypatch.setenv("VG_SEED_CAPS2", caps)
     ref, _ = synth.config_reference(1)
     cut = np.full(600, 40 if K >= 5 else 60, np.int32)

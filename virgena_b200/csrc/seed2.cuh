@@ -564,27 +564,69 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
 // ------------------------------------------------------------------------------------------------
 // Kernel 2: overlap resolution, window counts, pruning. One warp per read orientation.
 // Per-warp shared memory (winWarpBytes), two aliased uses:
-//   C   : win u64[SD_WIN + 32] (padded window over the stream; re-inserted LongHits go back into it)
+//   C   : win (SdWin: 512 x u64 or 1024 x u32, + 32 spare slots; re-inserted LongHits go back into it)
 //   E-G : hitG u16[capRs + 8] | P u16[capRs] | len u8[capRs] | bucket u16[nBuckets]   (bins int[256] of the sort
 //         overlay hitG); len saturates at 255 (then the exact value is re-read from the stream)
 // ------------------------------------------------------------------------------------------------
+// The sweep window of phase C. Wide: the stream's own 64-bit entries, 512 of them (16 per lane). Packed (reference
+// shorter than 16384, reads up to 512): genomePos << 18 | readPos << 9 | len in 32 bits, 1024 entries in the same shared
+// memory (32 per lane): half as many windows per read, 32-bit shared-memory traffic. One spare slot per lane chunk keeps
+// the lanes' chunks on different banks.
+template <bool P32>
+struct SdWin;
+template <>
+struct SdWin<false> {
+  using E = uint64_t;
+  static constexpr int N = SD_WIN, CH = SD_WIN / 32, SH = 4;
+  static __device__ __forceinline__ E fromS(uint64_t v) { return v; }
+  static __device__ __forceinline__ uint64_t toS(E v) { return v; }
+  static __device__ __forceinline__ E pack(int g, int r, int l) { return ((uint64_t)g << 32) | ((uint64_t)r << 16) | (uint64_t)l; }
+  static __device__ __forceinline__ int g(E v) { return (int)(v >> 32); }
+  static __device__ __forceinline__ int r(E v) { return (int)((v >> 16) & 0xFFFFu); }
+  static __device__ __forceinline__ int l(E v) { return (int)(v & 0xFFFFu); }
+  static __device__ __forceinline__ uint64_t key(E v) { return v >> 16; }  // (genomePos, readPos): the TreeSet order
+  static __device__ __forceinline__ uint64_t mkkey(int g, int r) { return ((uint64_t)g << 16) | (uint64_t)r; }
+};
+template <>
+struct SdWin<true> {
+  using E = uint32_t;
+  static constexpr int N = 2 * SD_WIN, CH = 2 * SD_WIN / 32, SH = 5;
+  static __device__ __forceinline__ E fromS(uint64_t v) {
+    return ((uint32_t)(v >> 32) << 18) | (((uint32_t)v >> 16) << 9) | ((uint32_t)v & 0x1FFu);
+  }
+  static __device__ __forceinline__ uint64_t toS(E v) {
+    return ((uint64_t)(v >> 18) << 32) | ((uint64_t)((v >> 9) & 0x1FFu) << 16) | (uint64_t)(v & 0x1FFu);
+  }
+  static __device__ __forceinline__ E pack(int g, int r, int l) { return ((uint32_t)g << 18) | ((uint32_t)r << 9) | (uint32_t)l; }
+  static __device__ __forceinline__ int g(E v) { return (int)(v >> 18); }
+  static __device__ __forceinline__ int r(E v) { return (int)((v >> 9) & 0x1FFu); }
+  static __device__ __forceinline__ int l(E v) { return (int)(v & 0x1FFu); }
+  static __device__ __forceinline__ uint32_t key(E v) { return v >> 9; }
+  static __device__ __forceinline__ uint32_t mkkey(int g, int r) { return ((uint32_t)g << 9) | (uint32_t)r; }
+};
+template <bool P32>
+__device__ __forceinline__ int sd2_wi(int e) { return e + (e >> SdWin<P32>::SH); }
+
 // TreeSet.add of a clipped LongHit (KMerCounterBase.java:435-441) into the sorted window: it goes in front of the first
 // unpolled element with a larger (genomePos, readPos); dropped when that key is already there (Q2). The slot of the
 // element polled last is free (the in-place output is always at least two behind), so the elements in between move
 // down by one and the stream index steps back. Its genomePos is the end of prev, which lies before the next
 // synchronisation point, i.e. inside [si, s1]. Returns the new stream index.
-__device__ __noinline__ int sd2_reinsert(uint64_t* win, int si, int s1, int g, int r, int len) {
-  const uint64_t key = ((uint64_t)g << 16) | (uint64_t)r;
+template <bool P32>
+__device__ __noinline__ int sd2_reinsert(typename SdWin<P32>::E* win, int si, int s1, int g, int r, int len) {
+  using W = SdWin<P32>;
+  const auto key = W::mkkey(g, r);
   int p = si;
 #pragma unroll 1
-  while (p < s1 && (win[SD_WI(p)] >> 16) < key) p++;
-  if (p < s1 && (win[SD_WI(p)] >> 16) == key) return si;
+  while (p < s1 && W::key(win[sd2_wi<P32>(p)]) < key) p++;
+  if (p < s1 && W::key(win[sd2_wi<P32>(p)]) == key) return si;
 #pragma unroll 1
-  for (int j = si; j < p; j++) win[SD_WI(j - 1)] = win[SD_WI(j)];
-  win[SD_WI(p - 1)] = (key << 16) | (uint64_t)len;
+  for (int j = si; j < p; j++) win[sd2_wi<P32>(j - 1)] = win[sd2_wi<P32>(j)];
+  win[sd2_wi<P32>(p - 1)] = W::pack(g, r, len);
   return si - 1;
 }
 
+template <bool P32>
 __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
   extern __shared__ __align__(16) uint8_t sd_smem[];
   const int lane = threadIdx.x & 31;
@@ -593,7 +635,8 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
   const int K = A.K;
   int G = A.G;
   uint8_t* wbase = sd_smem + (size_t)warp * A.winWarpBytes;
-  uint64_t* win = (uint64_t*)wbase;
+  using W = SdWin<P32>;
+  typename W::E* win = (typename W::E*)wbase;
   const int capRs = A.capRs;
   uint16_t* bucket = (uint16_t*)(wbase + (size_t)capRs * 5 + 16);
   int* bins = (int*)wbase;
@@ -638,21 +681,21 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
     // independent segments at synchronisation points. The LongHits that survive are written back to the front
     // of the item's slot (never ahead of what has been read into the window).
     if (nS > 0) {
-      constexpr int CH = SD_WIN / 32;  // entries per lane when flagging
+      constexpr int CH = W::CH;  // entries per lane when flagging
       int tbase = 0, runMaxE = -1;
 #pragma unroll 1
       while (tbase < nS) {
-        const int cnt = min(SD_WIN, nS - tbase);
+        const int cnt = min(W::N, nS - tbase);
 #pragma unroll 4
-        for (int e = lane; e < cnt; e += 32) win[SD_WI(e)] = S[tbase + e];
+        for (int e = lane; e < cnt; e += 32) win[sd2_wi<P32>(e)] = W::fromS(S[tbase + e]);
         __syncwarp();
         const int lo = lane * CH, nOwn = max(0, min(CH, cnt - lo));
-        const uint64_t* wl = win + lane * (CH + 1);  // = win + SD_WI(lo): the lane's chunk is contiguous
+        const typename W::E* wl = win + lane * (CH + 1);  // = win + sd2_wi(lo): the lane's chunk is contiguous
         int locMax = -1;
 #pragma unroll 4
         for (int t = 0; t < nOwn; t++) {
-          const uint64_t v = wl[t];
-          locMax = max(locMax, (int)(v >> 32) + (int)(v & 0xFFFFu) + K);
+          const typename W::E v = wl[t];
+          locMax = max(locMax, W::g(v) + W::l(v) + K);
         }
         int incl = locMax;
 #pragma unroll
@@ -668,13 +711,13 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
           int m = excl;
 #pragma unroll 4
           for (int t = 0; t < nOwn; t++) {
-            const uint64_t v = wl[t];
-            const int g = (int)(v >> 32);
+            const typename W::E v = wl[t];
+            const int g = W::g(v);
             if (g > m) {
               fmask |= 1u << t;
               mLast = m;
             }
-            m = max(m, g + (int)(v & 0xFFFFu) + K);
+            m = max(m, g + W::l(v) + K);
           }
         }
         // lane l sweeps the segments that START in its chunk: from its first flag to the first flag of the next
@@ -718,28 +761,28 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
           const bool act = si < s1;
           if (!__any_sync(VG_FULL, act)) break;
           if (act) {
-            const uint64_t v = win[SD_WI(si)];  // TreeSet.pollFirst
+            const typename W::E v = win[sd2_wi<P32>(si)];  // TreeSet.pollFirst
             si++;
-            const int cg = (int)(v >> 32), cr = (int)((v >> 16) & 0xFFFFu), cl = (int)(v & 0xFFFFu);
+            const int cg = W::g(v), cr = W::r(v), cl = W::l(v);
             const int pe = pg + pl + K;
             const bool ov = have && pe - 1 >= cg;
             const bool keepPrev = ov && pl >= cl;
             const int tl = cg - pg - K;
             if (have && !keepPrev && (!ov || tl >= 0)) {
-              win[SD_WI(w)] = ((uint64_t)pg << 32) | ((uint64_t)pr << 16) | (uint64_t)(ov ? tl : pl);
+              win[sd2_wi<P32>(w)] = W::pack(pg, pr, ov ? tl : pl);
               w++;
             }
             have = true;
             if (!keepPrev) {
               pg = cg, pr = cr, pl = cl;
             } else if (cl - (pe - cg) >= 0) {
-              si = sd2_reinsert(win, si, s1, pe, cr + (pe - cg), cl - (pe - cg));
+              si = sd2_reinsert<P32>(win, si, s1, pe, cr + (pe - cg), cl - (pe - cg));
             }
           }
           __syncwarp();
         }
         if (have) {
-          win[SD_WI(w)] = ((uint64_t)pg << 32) | ((uint64_t)pr << 16) | (uint64_t)pl;
+          win[sd2_wi<P32>(w)] = W::pack(pg, pr, pl);
           w++;
         }
         __syncwarp();
@@ -748,7 +791,7 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
           const int ic = sd_warp_incl_scan(c, lane);
           uint64_t* dst = S + nR + ic - c;
 #pragma unroll 1
-          for (int t = 0; t < c; t++) dst[t] = win[SD_WI(s0 + t)];
+          for (int t = 0; t < c; t++) dst[t] = W::toS(win[sd2_wi<P32>(s0 + t)]);
           nR += __shfl_sync(VG_FULL, ic, 31);
         }
         __syncwarp();

@@ -437,7 +437,10 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   if (msa) VG_CUDA(c, cudaFuncSetAttribute(seed_gen_msa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmem));
   else if (regs) VG_CUDA(c, cudaFuncSetAttribute(seed_gen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmem));
   else VG_CUDA(c, cudaFuncSetAttribute(seed_gen_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmem));
-  VG_CUDA(c, cudaFuncSetAttribute(seed_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)winSmem));
+  // packed 32-bit sweep window (genomePos 14 bits, readPos 9, len 9) when the coordinates fit
+  const bool p32 = G < 16384 && maxReadLen <= 512 && !getenv("VG_SEED_WIDE");
+  if (p32) VG_CUDA(c, cudaFuncSetAttribute(seed_win_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)winSmem));
+  else VG_CUDA(c, cudaFuncSetAttribute(seed_win_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)winSmem));
   const int64_t sub0 = std::min(subItems, nItems);
   const int genBlocks = (int)std::max<int64_t>(1, std::min<int64_t>((sub0 + genWarps - 1) / genWarps, c->smCount));
   const int winBlocks = (int)std::max<int64_t>(1, std::min<int64_t>((sub0 + winWarps - 1) / winWarps, c->smCount));
@@ -491,7 +494,8 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     else seed_gen_kernel<false><<<genBlocks, genWarps * 32, genSmem, c->stream>>>(A);
     VG_LAUNCH_CHECK(c);
     VG_CUDA(c, cudaEventRecord(c->seedEv[3 * sub + 1], c->stream));
-    seed_win_kernel<<<winBlocks, winWarps * 32, winSmem, c->stream>>>(A);
+    if (p32) seed_win_kernel<true><<<winBlocks, winWarps * 32, winSmem, c->stream>>>(A);
+    else seed_win_kernel<false><<<winBlocks, winWarps * 32, winSmem, c->stream>>>(A);
     VG_LAUNCH_CHECK(c);
     VG_CUDA(c, cudaEventRecord(c->seedEv[3 * sub + 2], c->stream));
   }
