@@ -61,6 +61,29 @@ def test_reads_vs_windows(env):
     assert rec[:, 0].max() > 200
 
 
+def test_wide_checkpoints(env, monkeypatch):
+    """The 8-byte checkpoint format (scores >= 4096 or gop - gep > 15) on the inputs that normally take the 4-byte one."""
+    from virgena_b200 import synth
+    monkeypatch.setenv("VG_SW_WIDE", "1")
+    ctx, o = env
+    ref, _ = synth.config_reference(1)
+    m1, _ = synth.config_pairs(1, 300)
+    rng = np.random.default_rng(8)
+    s1, s2 = [], []
+    for i in range(300):
+        st = int(rng.integers(0, len(ref) - 380))
+        w = ref[st:st + int(rng.integers(250, 376))].copy()
+        r = w[10:10 + 240].copy() if i % 2 else m1[i]
+        mut = rng.random(len(r)) < 0.12
+        r = r.copy()
+        r[mut] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(mut.sum()))]
+        if i % 3 == 0:
+            r = np.delete(r, slice(100, 104))
+        s1.append(r.tobytes())
+        s2.append(w.tobytes())
+    _check(ctx, o, s1, s2)
+
+
 def test_ragged_random(env):
     ctx, o = env
     rng = np.random.default_rng(11)

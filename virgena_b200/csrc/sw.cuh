@@ -42,6 +42,36 @@ __device__ __forceinline__ uint8_t sw_s1_byte(const uint8_t* s1, int m, int rc, 
 //   colck[p][tb][row]  = uint2{V, Fs} of row (0-based) at step t = 32*tb           (column j = 32*tb - row/R)
 // Indexing by the wavefront step makes every store warp-uniform; the row checkpoints go out as whole 32-byte sectors
 // (4 steps per lane) and come back to the traceback as contiguous runs.
+// Checkpoint element. Wide: uint2{V, Xs} (Xs = Es or Fs, the gap state shifted by +gop), both s16x2 for the two
+// alignments of the pair. Compact (scores < 4096 and 0 <= gop - gep <= 15): one 32-bit word, per 16-bit lane V in the low
+// 12 bits and d = max(Xs - gep - V, 0) in the top 4. That is all the traceback needs of Xs: the cell below / to the right
+// extends the gap iff Xs - gep > V, i.e. iff d > 0, and then continues with Xs - gep = V + d; otherwise it restarts from V.
+// (Xs <= V + gop because E, F <= V, hence d <= gop - gep.) Xs is handed back as V + d + gep.
+template <bool COMPACT>
+struct SwCk;
+template <>
+struct SwCk<false> {
+  using T = uint2;
+  static __device__ __forceinline__ T make(uint32_t v, uint32_t xs, uint32_t) { return make_uint2(v, xs); }
+  static __device__ __forceinline__ void get(T w, int hi, int, int& v, int& xs) {
+    v = hi ? vg_hi(w.x) : vg_lo(w.x);
+    xs = hi ? vg_hi(w.y) : vg_lo(w.y);
+  }
+};
+template <>
+struct SwCk<true> {
+  using T = uint32_t;
+  static __device__ __forceinline__ T make(uint32_t v, uint32_t xs, uint32_t ngepP) {
+    const uint32_t d = __vsub2(__viaddmax_s16x2(xs, ngepP, v), v);  // max(Xs - gep, V) - V per lane, 0 .. 15
+    return v | (d << 12);
+  }
+  static __device__ __forceinline__ void get(T w, int hi, int gep, int& v, int& xs) {
+    const uint32_t h = hi ? (w >> 16) : (w & 0xFFFFu);
+    v = (int)(h & 0xFFFu);
+    xs = v + (int)(h >> 12) + gep;
+  }
+};
+
 // colA/colB = last column of the group of 4 wavefront steps in which the strip first reached its maximum (the group
 // (4q, 4q+4] lies inside one checkpoint tile because the column checkpoints are taken at steps that are multiples of 32)
 #define SW_MAX_BOOKKEEPING(JEND)                                              \
@@ -57,11 +87,12 @@ __device__ __forceinline__ uint8_t sw_s1_byte(const uint8_t* s1, int m, int rc, 
     cm4 = 0;                                                                  \
   }
 
-template <int R, bool STORE>
+template <int R, bool STORE, bool COMPACT>
 __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__ tasks, int ntasks,
                                                       const uint8_t* __restrict__ s1pool,
                                                       const uint8_t* __restrict__ s2pool, SwParams prm,
-                                                      uint2* __restrict__ rowck, uint2* __restrict__ colck,
+                                                      typename SwCk<COMPACT>::T* __restrict__ rowck,
+                                                      typename SwCk<COMPACT>::T* __restrict__ colck,
                                                       int nT, int nTb, SwFillOut* __restrict__ out,
                                                       int* __restrict__ counter, int smemWordsPerWarp) {
   extern __shared__ uint32_t sw_smem[];
@@ -124,13 +155,14 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
     const int tEnd = nmax + lastLane;
     // checkpoints of the lane's bottom row: nT entries per lane, entry t - 1 = wavefront step t, written 4 steps
     // (one 32-byte sector) at a time so that the traceback reads the boundary of a tile as one contiguous run
-    uint2* rowp = rowck + ((int64_t)pi * 32 + lane) * nT;
-    uint2* colp = colck + ((int64_t)pi * nTb) * (32 * R) + lane * R;
+    using CK = SwCk<COMPACT>;
+    typename CK::T* rowp = rowck + ((int64_t)pi * 32 + lane) * nT;
+    typename CK::T* colp = colck + ((int64_t)pi * nTb) * (32 * R) + lane * R;
     const int tEnd4 = (tEnd + 3) & ~3;  // steps beyond tEnd find every lane inactive
 
 #pragma unroll 1
     for (int tg = 0; tg < tEnd4; tg += 4) {
-      uint2 rb[4];
+      typename CK::T rb[4];
 #pragma unroll
       for (int s4 = 1; s4 <= 4; s4++) {
         const int t = tg + s4;
@@ -167,7 +199,7 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
           vup_prev = vin;
           cm4 = cm;
         }
-        rb[s4 - 1] = make_uint2(vbot, ebot);
+        if (STORE) rb[s4 - 1] = CK::make(vbot, ebot, NGEPp);
       }
       // once per group of 4 steps (warp-uniform): exact maximum of the strip, the group of 4 columns that reached it
       // first, and whether a later group reached it again
@@ -176,13 +208,17 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
         const int j1 = tg + 1 - lane, j4 = tg + 4 - lane;
         if (lane <= lastLane && j4 >= 1 && j1 <= nmax) {
           uint4* dst = (uint4*)(rowp + tg);
-          dst[0] = make_uint4(rb[0].x, rb[0].y, rb[1].x, rb[1].y);
-          dst[1] = make_uint4(rb[2].x, rb[2].y, rb[3].x, rb[3].y);
+          if constexpr (COMPACT) {
+            dst[0] = make_uint4(rb[0], rb[1], rb[2], rb[3]);
+          } else {
+            dst[0] = make_uint4(rb[0].x, rb[0].y, rb[1].x, rb[1].y);
+            dst[1] = make_uint4(rb[2].x, rb[2].y, rb[3].x, rb[3].y);
+          }
         }
         if (((tg + 4) & (SW_TC - 1)) == 0 && lane <= lastLane && j4 >= 1 && j4 <= nmax) {  // column checkpoint of the rows
-          uint2* dst = colp + (int64_t)((tg + 4) / SW_TC) * (32 * R);
+          typename CK::T* dst = colp + (int64_t)((tg + 4) / SW_TC) * (32 * R);
 #pragma unroll
-          for (int r = 0; r < R; r++) dst[r] = make_uint2(V[r], F[r]);
+          for (int r = 0; r < R; r++) dst[r] = CK::make(V[r], F[r], NGEPp);
         }
       }
     }
@@ -222,10 +258,11 @@ struct SwTb {
   static constexpr int WPC = (R + 7) / 8;  // flag words per column
 };
 
-template <int R>
+template <int R, bool COMPACT>
 __device__ __forceinline__ void sw_tile_recompute(const SwTask& tk, const uint8_t* __restrict__ s1,
                                                   const uint8_t* __restrict__ s2, const SwParams& prm,
-                                                  const uint2* __restrict__ rowckP, const uint2* __restrict__ colckP,
+                                                  const typename SwCk<COMPACT>::T* __restrict__ rowckP,
+                                                  const typename SwCk<COMPACT>::T* __restrict__ colckP,
                                                   int nT, int hi, int k, int cl, int jmax, uint32_t* __restrict__ flags,
                                                   int fstride, int probeS, int probeCol, int& bestI, int& bestJ) {
   constexpr int WPC = SwTb<R>::WPC;
@@ -243,23 +280,22 @@ __device__ __forceinline__ void sw_tile_recompute(const SwTask& tk, const uint8_
     if (i <= tk.m) {
       asym[r] = sw_s1_byte(s1, tk.m, tk.rc, i - 1);
       if (cl > 0) {
-        uint2 w = colckP[(int64_t)tb * (32 * R) + (i - 1)];
-        v[r] = hi ? vg_hi(w.x) : vg_lo(w.x);
-        hs[r] = hi ? vg_hi(w.y) : vg_lo(w.y);
+        SwCk<COMPACT>::get(colckP[(int64_t)tb * (32 * R) + (i - 1)], hi, prm.gep, v[r], hs[r]);
       }
     }
   }
   // V(r0, cl): corner for the first diagonal
   // top boundary = bottom row of strip k-1 (lane k-1): column j was computed at step j + k - 1, entry j + k - 2
-  const uint2* topRow = rowckP + (int64_t)(k - 1) * nT + (k - 2);  // [j] (unused when k == 0)
+  using CK = SwCk<COMPACT>;
+  const typename CK::T* topRow = rowckP + (int64_t)(k - 1) * nT + (k - 2);  // [j] (unused when k == 0)
   int vtopPrev = 0;
   if (k > 0 && cl > 0) {
-    uint2 w = topRow[cl];
-    vtopPrev = hi ? vg_hi(w.x) : vg_lo(w.x);
+    int unusedXs;
+    CK::get(topRow[cl], hi, prm.gep, vtopPrev, unusedXs);
   }
   // the boundary of the tile is one contiguous run of 8-byte checkpoints in HBM: both of its lines are requested up
   // front and the load of the next column is issued before this column is computed
-  uint2 wNext = make_uint2(0u, 0u);
+  typename CK::T wNext = typename CK::T();
   if (k > 0 && cl + 1 <= jmax) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(topRow + min(jmax, cl + 17)));
     wNext = topRow[cl + 1];
@@ -267,10 +303,9 @@ __device__ __forceinline__ void sw_tile_recompute(const SwTask& tk, const uint8_
   for (int j = cl + 1; j <= jmax; j++) {
     int vtop = 0, es = SW_NEG;
     if (k > 0) {
-      const uint2 w = wNext;
+      const typename CK::T w = wNext;
       if (j + 1 <= jmax) wNext = topRow[j + 1];
-      vtop = hi ? vg_hi(w.x) : vg_lo(w.x);
-      es = hi ? vg_hi(w.y) : vg_lo(w.y);
+      CK::get(w, hi, prm.gep, vtop, es);
     }
     const uint8_t bsym = s2[j - 1];
     int vd = vtopPrev, vu = vtop;
@@ -316,12 +351,12 @@ __device__ __forceinline__ int sw_tile_left(int k, int j) {
   return cl < 1 ? 0 : cl;
 }
 
-template <int R>
+template <int R, bool COMPACT>
 __global__ void __launch_bounds__(128, 6) sw_traceback_kernel(const SwTask* __restrict__ tasks, int ntasks,
                                                            const uint8_t* __restrict__ s1pool,
                                                            const uint8_t* __restrict__ s2pool, SwParams prm,
-                                                           const uint2* __restrict__ rowck,
-                                                           const uint2* __restrict__ colck, int nT, int nTb,
+                                                           const typename SwCk<COMPACT>::T* __restrict__ rowck,
+                                                           const typename SwCk<COMPACT>::T* __restrict__ colck, int nT, int nTb,
                                                            const SwFillOut* __restrict__ fill,
                                                            SwAln* __restrict__ alns, uint8_t* __restrict__ rev,
                                                            int64_t revStride) {
@@ -344,8 +379,8 @@ __global__ void __launch_bounds__(128, 6) sw_traceback_kernel(const SwTask* __re
   const uint8_t* s1 = s1pool + tk.s1_off;
   const uint8_t* s2 = s2pool + tk.s2_off;
   const int hi = ti & 1;
-  const uint2* rowckP = rowck + ((int64_t)(ti >> 1) * 32) * nT;
-  const uint2* colckP = colck + ((int64_t)(ti >> 1) * nTb) * (32 * R);
+  const typename SwCk<COMPACT>::T* rowckP = rowck + ((int64_t)(ti >> 1) * 32) * nT;
+  const typename SwCk<COMPACT>::T* colckP = colck + ((int64_t)(ti >> 1) * nTb) * (32 * R);
   uint32_t* flags = flagS + tid;
   uint8_t* out = rev + (int64_t)tk.out * revStride;
   int no1 = 1 << 30, no2 = 1 << 30;
@@ -359,12 +394,12 @@ __global__ void __launch_bounds__(128, 6) sw_traceback_kernel(const SwTask* __re
     if (!fo.tie) {
       const int jEnd = min(fo.col, tk.n);  // fo.col = last column of the group of 4 that reached the maximum
       int cl = sw_tile_left(fo.strip, jEnd);
-      sw_tile_recompute<R>(tk, s1, s2, prm, rowckP, colckP, nT, hi, fo.strip, cl, jEnd, flags, 128, fo.score, fo.col, bi, bj);
+      sw_tile_recompute<R, COMPACT>(tk, s1, s2, prm, rowckP, colckP, nT, hi, fo.strip, cl, jEnd, flags, 128, fo.score, fo.col, bi, bj);
       haveK = fo.strip, haveCl = cl;
     } else {
       for (int jj = tk.n; jj >= 1;) {  // rare: the strip reached S at several columns
         int cl = sw_tile_left(fo.strip, jj);
-        sw_tile_recompute<R>(tk, s1, s2, prm, rowckP, colckP, nT, hi, fo.strip, cl, jj, flags, 128, fo.score, -1, bi, bj);
+        sw_tile_recompute<R, COMPACT>(tk, s1, s2, prm, rowckP, colckP, nT, hi, fo.strip, cl, jj, flags, 128, fo.score, -1, bi, bj);
         jj = cl;
       }
     }
@@ -379,7 +414,7 @@ __global__ void __launch_bounds__(128, 6) sw_traceback_kernel(const SwTask* __re
       k = (i - 1) / R;
       cl = sw_tile_left(k, j);
       if (k != haveK || cl != haveCl)
-        sw_tile_recompute<R>(tk, s1, s2, prm, rowckP, colckP, nT, hi, k, cl, j, flags, 128, -1, -1, no1, no2);
+        sw_tile_recompute<R, COMPACT>(tk, s1, s2, prm, rowckP, colckP, nT, hi, k, cl, j, flags, 128, -1, -1, no1, no2);
       haveK = -1;
     }
     while (!done) {

@@ -25,14 +25,15 @@ static inline int sw_validate(vg_ctx* c, int mmax, int nmax) {
   return VG_OK;
 }
 
-template <int R>
+template <int R, bool COMPACT>
 static int sw_launch_R(vg_ctx* c, const SwTask* d_tasks, int ntasks, const uint8_t* d_s1, const uint8_t* d_s2,
                        int nmax, bool traceback, SwFillOut* d_fill, SwAln* d_alns, uint8_t* d_rev, int64_t revStride,
                        double* msFill, double* msTb) {
+  using CkT = typename SwCk<COMPACT>::T;
   const int nW = nmax + 1;
   const int nT = (nmax + 32 + 3) & ~3;  // wavefront steps 1 .. nmax + 31, rounded to whole groups of 4
   const int nTb = nT / SW_TC + 1;     // column checkpoints at t = 32, 64, ...
-  const size_t perPair = ((size_t)nT * 32 + (size_t)nTb * 32 * R) * sizeof(uint2);
+  const size_t perPair = ((size_t)nT * 32 + (size_t)nTb * 32 * R) * sizeof(CkT);
   const size_t perTask = perPair / 2;
   size_t budget = (size_t)24 << 30;
   if (const char* e = getenv("VG_CKPT_BYTES")) budget = (size_t)atoll(e);
@@ -41,19 +42,19 @@ static int sw_launch_R(vg_ctx* c, const SwTask* d_tasks, int ntasks, const uint8
     chunk = std::min<int64_t>(ntasks, std::max<int64_t>(2, (int64_t)(budget / perTask)));
     chunk &= ~(int64_t)1;
     if (chunk < 2) chunk = 2;
-    VG_CUDA(c, c->d_rowck.reserve((size_t)(chunk / 2) * nT * 32 * sizeof(uint2)));
-    VG_CUDA(c, c->d_colck.reserve((size_t)(chunk / 2) * nTb * 32 * R * sizeof(uint2)));
+    VG_CUDA(c, c->d_rowck.reserve((size_t)(chunk / 2) * nT * 32 * sizeof(CkT)));
+    VG_CUDA(c, c->d_colck.reserve((size_t)(chunk / 2) * nTb * 32 * R * sizeof(CkT)));
   }
   VG_CUDA(c, c->d_counter.reserve(sizeof(int)));
   const int threads = 256, warps = threads / 32;
   const size_t smem = (size_t)warps * nW * sizeof(uint32_t);
   int perSm = 1;
   if (traceback) {
-    VG_CUDA(c, cudaFuncSetAttribute(sw_fill_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, sw_fill_kernel<R, true>, threads, smem));
+    VG_CUDA(c, cudaFuncSetAttribute(sw_fill_kernel<R, true, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, sw_fill_kernel<R, true, COMPACT>, threads, smem));
   } else {
-    VG_CUDA(c, cudaFuncSetAttribute(sw_fill_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, sw_fill_kernel<R, false>, threads, smem));
+    VG_CUDA(c, cudaFuncSetAttribute(sw_fill_kernel<R, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, sw_fill_kernel<R, false, false>, threads, smem));
   }
   if (perSm < 1) return vg_fail(c, VG_ERR_INVALID, "window length %d needs too much shared memory", nmax);
   float fms = 0, tms = 0;
@@ -64,18 +65,19 @@ static int sw_launch_R(vg_ctx* c, const SwTask* d_tasks, int ntasks, const uint8
     VG_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(int), c->stream));
     VG_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
     if (traceback)
-      sw_fill_kernel<R, true><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw,
-                                                                    c->d_rowck.as<uint2>(), c->d_colck.as<uint2>(),
-                                                                    nT, nTb, d_fill + s, c->d_counter.as<int>(), nW);
+      sw_fill_kernel<R, true, COMPACT><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw,
+                                                                             c->d_rowck.as<CkT>(), c->d_colck.as<CkT>(), nT,
+                                                                             nTb, d_fill + s, c->d_counter.as<int>(), nW);
     else
-      sw_fill_kernel<R, false><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw, nullptr, nullptr,
-                                                                     nT, nTb, d_fill + s, c->d_counter.as<int>(), nW);
+      sw_fill_kernel<R, false, false><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw, nullptr,
+                                                                            nullptr, nT, nTb, d_fill + s,
+                                                                            c->d_counter.as<int>(), nW);
     VG_LAUNCH_CHECK(c);
     VG_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
     if (traceback) {
-      sw_traceback_kernel<R><<<(nt + 127) / 128, 128, 0, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw,
-                                                                      c->d_rowck.as<uint2>(), c->d_colck.as<uint2>(),
-                                                                      nT, nTb, d_fill + s, d_alns, d_rev, revStride);
+      sw_traceback_kernel<R, COMPACT><<<(nt + 127) / 128, 128, 0, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw,
+                                                                               c->d_rowck.as<CkT>(), c->d_colck.as<CkT>(), nT,
+                                                                               nTb, d_fill + s, d_alns, d_rev, revStride);
       VG_LAUNCH_CHECK(c);
     }
     VG_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
@@ -99,10 +101,16 @@ static int sw_run(vg_ctx* c, const SwTask* d_tasks, int64_t ntasks, const uint8_
   if (ntasks > 0x7fffffff) return vg_fail(c, VG_ERR_INVALID, "too many alignment tasks in one call");
   VG_TRY(sw_validate(c, mmax, nmax));
   const int R = sw_pick_R(mmax);
+  // 4-byte checkpoints (V in 12 bits + the 4 bits of the gap state that matter, see SwCk) when the scores and the
+  // penalties allow it, else 8-byte ones
+  const bool compact = traceback && (int64_t)c->sw.match * std::min(mmax, nmax) + c->sw.match + 1 < 4096 && c->sw.gop >= c->sw.gep &&
+                       c->sw.gop - c->sw.gep <= 15 && !getenv("VG_SW_WIDE");
 #define SW_CASE(RR)                                                                                                   \
   case RR:                                                                                                            \
-    return sw_launch_R<RR>(c, d_tasks, (int)ntasks, d_s1, d_s2, nmax, traceback, d_fill, d_alns, d_rev, revStride,    \
-                           msFill, msTb);
+    return compact ? sw_launch_R<RR, true>(c, d_tasks, (int)ntasks, d_s1, d_s2, nmax, traceback, d_fill, d_alns, d_rev,  \
+                                           revStride, msFill, msTb)                                                    \
+                   : sw_launch_R<RR, false>(c, d_tasks, (int)ntasks, d_s1, d_s2, nmax, traceback, d_fill, d_alns, d_rev, \
+                                            revStride, msFill, msTb);
   switch (R) {
     SW_CASE(2)
     SW_CASE(3)
