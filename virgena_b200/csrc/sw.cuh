@@ -27,7 +27,7 @@
 #pragma once
 #include "common.cuh"
 
-#define SW_TC 32          // checkpoint column-block width
+#define SW_TC 16          // checkpoint column-block width (wavefront steps between column checkpoints)
 #define SW_NEG (-16384)   // stands in for Float.NEGATIVE_INFINITY (consumed only in row 1 / column 1)
 #define SW_PAD_S1 0x7F00  // symbol code of a padded row (never equals a real code or SW_PAD_S2)
 #define SW_PAD_S2 0x00FF  // symbol code of a padded column
@@ -39,7 +39,7 @@ __device__ __forceinline__ uint8_t sw_s1_byte(const uint8_t* s1, int m, int rc, 
 // Checkpoint layout (written by the fill kernel, read by the traceback kernel), per *pair* p of tasks
 // (2p, 2p+1) whose values sit in the lo / hi s16 lanes:
 //   rowck[p][lane][t-1] = uint2{V, Es} of lane's bottom row at wavefront step t (column j = t - lane); nT entries per lane
-//   colck[p][tb][row]  = uint2{V, Fs} of row (0-based) at step t = 32*tb           (column j = 32*tb - row/R)
+//   colck[p][tb][row]  = {V, Fs} of row (0-based) at step t = SW_TC*tb             (column j = SW_TC*tb - row/R)
 // Indexing by the wavefront step makes every store warp-uniform; the row checkpoints go out as whole 32-byte sectors
 // (4 steps per lane) and come back to the traceback as contiguous runs.
 // Checkpoint element. Wide: uint2{V, Xs} (Xs = Es or Fs, the gap state shifted by +gop), both s16x2 for the two
@@ -297,7 +297,7 @@ __device__ __forceinline__ void sw_tile_recompute(const SwTask& tk, const uint8_
   // front and the load of the next column is issued before this column is computed
   typename CK::T wNext = typename CK::T();
   if (k > 0 && cl + 1 <= jmax) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(topRow + min(jmax, cl + 17)));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(topRow + min(jmax, cl + SW_TC)));
     wNext = topRow[cl + 1];
   }
   for (int j = cl + 1; j <= jmax; j++) {

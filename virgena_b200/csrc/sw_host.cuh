@@ -32,7 +32,7 @@ static int sw_launch_R(vg_ctx* c, const SwTask* d_tasks, int ntasks, const uint8
   using CkT = typename SwCk<COMPACT>::T;
   const int nW = nmax + 1;
   const int nT = (nmax + 32 + 3) & ~3;  // wavefront steps 1 .. nmax + 31, rounded to whole groups of 4
-  const int nTb = nT / SW_TC + 1;     // column checkpoints at t = 32, 64, ...
+  const int nTb = nT / SW_TC + 1;     // column checkpoints at t = SW_TC, 2 SW_TC, ...
   const size_t perPair = ((size_t)nT * 32 + (size_t)nTb * 32 * R) * sizeof(CkT);
   const size_t perTask = perPair / 2;
   size_t budget = (size_t)24 << 30;
