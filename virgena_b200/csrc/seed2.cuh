@@ -890,12 +890,14 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
         (void)inShared;
         if (lane < 8) hitG[nR + lane] = 0xFFFFu;  // sentinels for the branch-free searches of phase F
         int carry = 0, pgLast = 0, prLast = 0;
+        uint64_t vNext = (lane < nR) ? S[lane] : 0;  // the slot is in L2: the next chunk is requested one trip ahead
   #pragma unroll 1
         for (int j0 = 0; j0 < nR; j0 += 32) {
           const int j = j0 + lane;
           int val = 0, g = 0, r = 0;
+          const uint64_t v = vNext;
+          if (j + 32 < nR) vNext = S[j + 32];
           if (j < nR) {
-            const uint64_t v = S[j];
             g = (int)(v >> 32), r = (int)((v >> 16) & 0xFFFFu);
             val = (int)(v & 0xFFFFu);
             hitG[j] = (uint16_t)g;
@@ -945,13 +947,15 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
         SD2_PH(2)
         // ---- F: every window independently (updateCount equals a direct recount on sorted non-overlapping
         //         hits); candidates (count > cutoff, strict) compacted in hit order
+        uint64_t vNextF = (lane < nR) ? S[lane] : 0;
   #pragma unroll 1
         for (int j0 = 0; j0 < nR; j0 += 32) {
           const int j = j0 + lane;
           bool isCand = false;
           uint32_t key = 0, cnt = 0;
+          const uint64_t v = vNextF;
+          if (j + 32 < nR) vNextF = S[j + 32];
           if (j < nR) {
-            const uint64_t v = S[j];
             const int g = (int)(v >> 32), r = (int)((v >> 16) & 0xFFFFu), len = (int)(v & 0xFFFFu);
             int cs = 0, ce = G;
             if (A.nContigs > 1 && !A.bestOnly) {
