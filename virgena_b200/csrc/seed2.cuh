@@ -1052,13 +1052,15 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
         const bool k24 = A.key24 != 0;
         const uint32_t k0 = ks[0];
         int ps = k24 ? k0 >> 10 : k0 >> 16, pe = k24 ? ps + 1023 - (int)(k0 & 1023u) : 0xFFFF - (int)(k0 & 0xFFFFu), pc = vs[0];
+        uint32_t kNext = (1 + lane < nC) ? ks[1 + lane] : 0u, cNext = (1 + lane < nC) ? vs[1 + lane] : 0u;
 #pragma unroll 1
         for (int t0 = 1; t0 < nC; t0 += 32) {
           const int idx = t0 + lane;
           const bool valid = idx < nC;
-          const uint32_t k = valid ? ks[idx] : 0u;
+          const uint32_t k = kNext;
+          const int cc = (int)cNext;
+          if (idx + 32 < nC) kNext = ks[idx + 32], cNext = vs[idx + 32];  // the next batch is requested one trip ahead
           const int cs_ = k24 ? k >> 10 : k >> 16, ce_ = k24 ? cs_ + 1023 - (int)(k & 1023u) : 0xFFFF - (int)(k & 0xFFFFu);
-          const int cc = valid ? (int)vs[idx] : 0;
           int from = 0;  // lanes below `from` are already behind the pivot
 #pragma unroll 1
           for (;;) {
