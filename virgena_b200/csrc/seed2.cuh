@@ -495,12 +495,25 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
       // 2. stable sort by diagonal (16-bit key in the low half, read position rides in the high half)
       sd2_radix_sort_counted(K0, K1, nullptr, nullptr, nRaw, binsLo, 2, lane);
       const uint32_t* ks = K0;
-      uint32_t* stPos = K1;
 #pragma unroll 1
       for (int b = lane; b < 512; b += 32) binsLo[b] = 0;  // for the second sort
       __syncwarp();
       SD2_PH(9)
-      // 3. chain starts: first hit of a diagonal, or read position not the successor of the previous hit's
+      // 3. chain starts (first hit of a diagonal, or read position not the successor of the previous hit's) -> LongHits
+      //    in one pass: a start is closed by the next start (len = distance - 1); the last start of a chunk of 32 stays
+      //    open (warp-uniform) until a later chunk, or the end of the list, closes it. (The digits of the second sort's
+      //    keys are counted on the way.)
+      auto emit = [&](int idx, uint32_t k, int len) {
+        const int i = (int)(k >> 16);
+        const int c = (int)dBias - (int)(k & 0xFFFFu) + i;
+        V0[idx] = ((uint32_t)i << 16) | (uint32_t)c;
+        V1[idx] = (uint32_t)len;
+        atomicAdd(&binsLo[c & 255], 1);
+        atomicAdd(&binsHi[(c >> 8) & 255], 1);
+      };
+      bool haveOpen = false;
+      uint32_t openKey = 0;
+      int openE = 0;
 #pragma unroll 1
       for (int e0 = 0; e0 < nRaw; e0 += 128) {
         uint32_t kc[4], kp[4];
@@ -512,12 +525,25 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-          const int e = e0 + 32 * u + lane;
+          const int eb = e0 + 32 * u, e = eb + lane;
           const bool st = e < nRaw && !(((kc[u] ^ kp[u]) & 0xFFFFu) == 0 && (kc[u] >> 16) == (kp[u] >> 16) + 1);
           const unsigned m = __ballot_sync(VG_FULL, st);
-          if (st) stPos[nSt + __popc(m & lt)] = (uint32_t)e;
-          nSt += __popc(m);
+          if (m) {
+            if (haveOpen && lane == 0) emit(nSt, openKey, eb + __ffs(m) - 1 - openE - 1);
+            const int base = nSt + (haveOpen ? 1 : 0);
+            const unsigned higher = m & ~((2u << lane) - 1u);
+            if (st && higher) emit(base + __popc(m & lt), kc[u], __ffs(higher) - 1 - lane - 1);
+            nSt = base + __popc(m) - 1;
+            const int lastLane = 31 - __clz(m);
+            openKey = __shfl_sync(VG_FULL, kc[u], lastLane);
+            openE = eb + lastLane;
+            haveOpen = true;
+          }
         }
+      }
+      if (haveOpen) {
+        if (lane == 0) emit(nSt, openKey, nRaw - openE - 1);
+        nSt++;
       }
       __syncwarp();
       __threadfence_block();
@@ -526,20 +552,6 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
         bad = true;
         why = 1;
       } else {
-#pragma unroll 4
-        for (int s0 = lane; s0 < nSt; s0 += 32) {
-          const int e = (int)stPos[s0];
-          const int en = (s0 + 1 < nSt) ? (int)stPos[s0 + 1] : nRaw;
-          const uint32_t k = ks[e];
-          const int i = (int)(k >> 16);
-          const int c = (int)dBias - (int)(k & 0xFFFFu) + i;
-          V0[s0] = ((uint32_t)i << 16) | (uint32_t)c;
-          V1[s0] = (uint32_t)(en - e - 1);
-          atomicAdd(&binsLo[c & 255], 1);
-          atomicAdd(&binsHi[(c >> 8) & 255], 1);
-        }
-        __syncwarp();
-        __threadfence_block();
         SD2_PH(11)
         // 4. stable sort by column; K0 / K1 are free again and serve as the other halves
         sd2_radix_sort_counted(V0, K0, V1, K1, nSt, binsLo, 2, lane);
