@@ -1,5 +1,7 @@
 """GPU parity: seeding, pair selection, full Mapper.mapReads / MapperMSA.mapAllReads, pileup and
 consensus vs the oracle, through the C ABI. Everything is bit-exact (integer / byte / index work)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -205,6 +207,76 @@ def test_contig_builder_count_reads(built):
     assert n_found > 250
     for cidx in range(len(centroids)):
         assert (counts[cidx] == want_counts[cidx]).all(), cidx
+
+
+_FUZZ_SEEDS = list(range(16))
+if os.environ.get("VG_FUZZ_SEEDS"):  # e.g. VG_FUZZ_SEEDS=16:100 for a longer one-off run
+    _a, _b = os.environ["VG_FUZZ_SEEDS"].split(":")
+    _FUZZ_SEEDS = list(range(int(_a), int(_b)))
+
+
+@pytest.mark.parametrize("seed", _FUZZ_SEEDS)
+def test_seed_fuzz_references(built, seed):
+    """Differential fuzz of the seeding path: random references (300 .. 24000 bases: the longer ones take the 64-bit sweep
+    window and the 32-bit sort key), low-complexity stretches, N runs, random contig cuts, K = 3 .. 6, random cutoffs, reads
+    that are mutated substrings / junk / repeats; seeds >= 10 also cut clusters of contigs shorter than a read (LongHits
+    split at several boundaries). Windows and LongHits must equal the oracle's."""
+    import oracle
+    import virgena_b200 as vg
+    rng = np.random.default_rng(1000 + seed)
+    G = int(rng.choice([300, 1200, 5000, 9000, 17000, 24000]))
+    K = int(rng.choice([3, 4, 5, 5, 6]))
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    ref = acgt[rng.choice(4, G, p=[0.36, 0.18, 0.24, 0.22])].copy()
+    for _ in range(int(rng.integers(0, 4))):  # low-complexity stretches and N runs
+        p, ln = int(rng.integers(0, G - 60)), int(rng.integers(8, 60))
+        ref[p:p + ln] = acgt[rng.integers(0, 4)] if rng.random() < 0.6 else ord("N")
+    if rng.random() < 0.5:  # a repeat
+        ln = int(rng.integers(30, 120))
+        a, b = int(rng.integers(0, G - ln)), int(rng.integers(0, G - ln))
+        ref[b:b + ln] = ref[a:a + ln]
+    ends = [G]
+    if rng.random() < 0.5:
+        cuts = sorted(set(int(x) for x in rng.integers(50, G - 50, int(rng.integers(1, 6)))))
+        ends = cuts + [G]
+    if seed >= 10 and rng.random() < 0.7:  # a cluster of very short contigs
+        c0 = int(rng.integers(10, G - 200))
+        extra = [c0 + int(x) for x in np.cumsum(rng.integers(2, 40, int(rng.integers(2, 6))))]
+        ends = sorted(set(ends[:-1] + [e for e in extra if e < G])) + [G]
+    threads = int(rng.choice([1, 2, 8]))
+    cut = np.full(600, int(rng.integers(0, 60)), np.int32)
+    reads = []
+    for _ in range(120):
+        L = int(rng.integers(K, min(400, G)))
+        p = int(rng.integers(0, G - L + 1))
+        r = ref[p:p + L].copy()
+        mut = rng.random(L) < rng.choice([0.0, 0.05, 0.2])
+        r[mut] = acgt[rng.integers(0, 4, int(mut.sum()))]
+        if rng.random() < 0.2 and L > 20:
+            r = np.delete(r, int(rng.integers(5, L - 5)))
+        if rng.random() < 0.1:
+            r = acgt[rng.integers(0, 4, L)]
+        if rng.random() < 0.05:
+            r = np.full(L, acgt[rng.integers(0, 4)], np.uint8)
+        reads.append(r.tobytes())
+    o = oracle.Oracle(K=K, cutoffs=cut)
+    o.set_reference(ref, contig_ends=ends, fragment_ends=ends, is_fragmented=len(ends) > 1, index_thread_num=threads)
+    ctx = vg.Context(K=K, cutoffs=cut)
+    ctx.set_reference(vg.Reference(ref, K=K, contig_ends=ends, fragment_ends=ends, is_fragmented=len(ends) > 1, thread_num=threads))
+    # pruned windows do not overlap and are at least as wide as the read (at least K): G / K + 2 per contig bounds them
+    win, nwin = ctx.seed_batch(b"".join(reads), _offs(reads), max_windows=G // K + 2 * len(ends) + 8)
+    for i, r in enumerate(reads):
+        ow = o.seed(r)
+        assert nwin[i] == len(ow), (seed, G, K, i, len(r), nwin[i], len(ow))
+        assert (win[i, :nwin[i]] == ow).all(), (seed, G, K, i)
+    bw, found = ctx.best_window_batch(b"".join(reads), _offs(reads))
+    for i, r in enumerate(reads[:40]):
+        w = o.map_read_to_region(r)
+        assert (found[i] != 0) == (w is not None) and (w is None or tuple(bw[i]) == w), (seed, G, K, i)
+    for r in reads[:4]:
+        h, oh = ctx.debug_seed_hits(r), o.get_hits(r)
+        assert h.shape == oh.shape and (h == oh).all(), (seed, G, K, len(r))
+    ctx.close()
 
 
 def test_seed_host_csr_index(hiv):

@@ -80,6 +80,7 @@ struct vg_ctx {
   bool haveReads = false;
   int64_t nPairs = 0, nBases = 0;
   int maxReadLen = 0;
+  int minReadLenGe[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // shortest read of at least k bases (sizes the window lists)
   DevBuf d_bases, d_off1, d_off2, d_len1, d_len2;
   std::vector<uint8_t> h_exist;  // per pair: bit0 mate1 exists, bit1 mate2 exists
 

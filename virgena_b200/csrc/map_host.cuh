@@ -190,7 +190,14 @@ static int mh_map(vg_ctx* c, bool msa, const int64_t* pair_idx, int64_t n_idx, v
   VG_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
   // ---- seeding + pair selection, in chunks of pairs -------------------------------------------------
   int maxWin = 64;
-  if (c->maxReadLen > 0) maxWin = std::max(8, std::min(256, range / std::max(1, c->maxReadLen / 2) + (int)c->contigEnds.size() + 4));
+  // pruned windows do not overlap and an unclipped window is at least as wide as its read: at most range / L + 2 per
+  // contig. Sized for the shortest read that can be seeded (the batch's windows buffer is chunked accordingly).
+  if (c->maxReadLen > 0) {
+    const int K = sc.K;
+    const int lmin = std::max(std::max(K, 1), std::min(c->minReadLenGe[std::min(std::max(K, 0), 8)], c->maxReadLen));
+    const int nCont = msa ? 1 : (int)c->contigEnds.size();
+    maxWin = std::max(8, std::min(8192, std::max(range / std::max(1, c->maxReadLen / 2), range / lmin) + 2 * nCont + 4));
+  }
   const int64_t chunkPairs = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)((size_t)(3ull << 30) / ((size_t)maxWin * 48 + 64))));
   const int nf = (int)c->fragmentEnds.size();
   if (emptyRef) {
@@ -362,11 +369,16 @@ int vg_upload_reads(vg_ctx* c, const uint8_t* bases, int64_t n_bases, const int6
     return vg_fail(c, VG_ERR_INVALID, "bad read arrays");
   c->haveReads = false;
   int maxLen = 0;
+  int minGe[9];  // shortest read of at least k bases, k = 0 .. 8 (a read shorter than K seeds nothing)
+  for (int& m : minGe) m = 0x7fffffff;
   for (int64_t i = 0; i < n_pairs; i++) {
     if (len1[i] < 0 || len2[i] < 0 || off1[i] < 0 || off2[i] < 0 || off1[i] + len1[i] > n_bases || off2[i] + len2[i] > n_bases)
       return vg_fail(c, VG_ERR_INVALID, "read %lld lies outside the byte pool", (long long)i);
     maxLen = std::max(maxLen, std::max(len1[i], len2[i]));
+    for (int l : {len1[i], len2[i]})
+      for (int k = std::min(l, 8); k >= 0 && minGe[k] > l; k--) minGe[k] = l;
   }
+  for (int k = 0; k < 9; k++) c->minReadLenGe[k] = minGe[k];
   VG_CUDA(c, c->d_bases.reserve((size_t)n_bases + 64));
   VG_CUDA(c, c->d_off1.reserve((size_t)n_pairs * 8 + 8));
   VG_CUDA(c, c->d_off2.reserve((size_t)n_pairs * 8 + 8));
@@ -611,7 +623,7 @@ static int mh_seed_batch(vg_ctx* c, int32_t msa, const uint8_t* pool, const int6
   int32_t* d_dbg = nullptr;
   int32_t* d_dbgN = nullptr;
   if (dbgHits) {
-    VG_CUDA(c, c->d_rev.reserve((size_t)4096 * 3 * 4 + 64));
+    VG_CUDA(c, c->d_rev.reserve((size_t)16384 * 3 * 4 + 64));
     d_dbgN = c->d_rev.as<int32_t>();
     d_dbg = d_dbgN + 4;
     VG_CUDA(c, cudaMemsetAsync(d_dbgN, 0, 16, c->stream));
@@ -783,9 +795,13 @@ int vg_pileup_alignments(vg_ctx* c, const uint8_t* seq1_pool, const int64_t* seq
 // Test hook (not part of the reference-facing ABI): LongHits of one read after mergeHits + splitLongHits.
 int vg_debug_seed_hits(vg_ctx* c, int32_t msa, const uint8_t* read, int32_t L, int32_t* hits, int32_t cap, int32_t* n_hits) {
   int64_t off[2] = {0, L};
-  std::vector<int32_t> win(64 * 3);
+  if (!c) return VG_ERR_INVALID;
+  // room for every window the read can have: pruned windows do not overlap and are at least K wide
+  const int K = std::max(1, msa ? c->seedMsa.K : c->seed.K);
+  const int mw = (msa ? c->msaLength : c->G) / K + 2 * (int)c->contigEnds.size() + 8;
+  std::vector<int32_t> win((size_t)mw * 3);
   int32_t nw = 0;
-  return mh_seed_batch(c, msa, read, off, 1, 64, win.data(), &nw, hits, cap, n_hits);
+  return mh_seed_batch(c, msa, read, off, 1, mw, win.data(), &nw, hits, cap, n_hits);
 }
 
 }  // extern "C"

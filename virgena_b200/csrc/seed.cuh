@@ -82,6 +82,8 @@ struct SeedArgs {
   int64_t nItems;              // 4 x pairs (pair mode) or number of single reads
   const int32_t* itemList;     // optional: nItems indices of the items to do (fallback of the fast path)
   int singleReads;             // 1: items are single forward reads (vg_seed_batch)
+  int bestOnly;                // 1: mapReadToRegion / computeKMerCount over [0, G): first window of maximal count, no cutoff,
+                               //    no splitLongHits, no pruning (see seed2.cuh)
   // scratch + outputs
   uint64_t* scratchS;          // [warpSlots][capS]
   uint16_t* scratchR;          // [warpSlots][4][capR]: hitG, hitR, hitL, P
@@ -870,7 +872,11 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
 #pragma unroll 1
         for (int e = lane; e < SD_WIN && e < nS; e += 32) win[e] = S[e];
         __syncwarp();
-        // lane-0 state of the sweep
+        // lane-0 state of the sweep. The re-insertion queue of this path lives in the (idle) candidate scratch: low-
+        // complexity reads against low-complexity stretches re-insert hundreds of clipped hits. Sorted, popped at `ph`.
+        uint64_t* pq = (uint64_t*)ckey;
+        const int PCAP = capC;
+        int ph = 0;
         int si = 0, np = 0;
         int pg = 0, pr = 0, pl = 0;
         bool started = false, done = false;
@@ -893,10 +899,9 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
               }
               // TreeSet.pollFirst: the smaller of the stream head and the re-insertion queue head
               uint64_t v;
-              if (np > 0 && (si >= nS || (pending[0] >> 16) < (win[si - wbase] >> 16))) {
-                v = pending[0];
-#pragma unroll 1
-                for (int t = 1; t < np; t++) pending[t - 1] = pending[t];
+              if (np > 0 && (si >= nS || (pq[ph] >> 16) < (win[si - wbase] >> 16))) {
+                v = pq[ph];
+                ph++;
                 np--;
               } else {
                 v = win[si - wbase];
@@ -921,14 +926,17 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
                     cr += lenDiff;
                     // TreeSet.add: dropped when an element with the same (genomePos, readPos) is present
                     const uint64_t key = ((uint64_t)cg << 16) | (uint64_t)cr;
-                    bool present = false;
-                    int ins = np;
+                    int ins = ph;
+                    {
+                      int hi2 = ph + np;
 #pragma unroll 1
-                    for (int t = 0; t < np; t++) {
-                      const uint64_t pk = pending[t] >> 16;
-                      if (pk == key) present = true;
-                      if (pk > key && ins == np) ins = t;
+                      while (ins < hi2) {
+                        const int mid = (ins + hi2) >> 1;
+                        if ((pq[mid] >> 16) < key) ins = mid + 1;
+                        else hi2 = mid;
+                      }
                     }
+                    bool present = ins < ph + np && (pq[ins] >> 16) == key;
                     if (!present) {
                       bool resolved = false;
                       const int wend = min(nS, wbase + SD_WIN);
@@ -953,12 +961,18 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
                       }
                     }
                     if (!present) {
-                      if (np >= SD_PENDING) {
+                      if (ph + np >= PCAP && ph > 0) {  // out of room at the top: move the queue down
+#pragma unroll 1
+                        for (int t = 0; t < np; t++) pq[t] = pq[ph + t];
+                        ins -= ph;
+                        ph = 0;
+                      }
+                      if (ph + np >= PCAP) {
                         err |= 4;
                       } else {
 #pragma unroll 1
-                        for (int t = np; t > ins; t--) pending[t] = pending[t - 1];
-                        pending[ins] = (key << 16) | (uint64_t)cl;
+                        for (int t = ph + np; t > ins; t--) pq[t] = pq[t - 1];
+                        pq[ins] = (key << 16) | (uint64_t)cl;
                         np++;
                       }
                     }
@@ -991,54 +1005,51 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
       if (nS > 0) {
         __syncwarp();
         // ---- D: KMerCounter.splitLongHits (KMerCounter.java:142-185); hits are independent given their contig
-        if (!err && nR <= capR && A.nContigs > 1 && nR > 0) {
+        if (!err && nR <= capR && A.nContigs > 1 && nR > 0 && !A.bestOnly) {
           uint32_t* tg = ckey;   // pieces: g | (r << 16) in ckey, len in cval
           uint32_t* tl = cval;
           int nOut = 0;
-          bool bad = false;
+          // the pieces of one hit, walking from contig to contig (any number of boundaries); counted first, then written
+          auto pieces = [&](int j, bool write, int o) -> int {
+            int g = hitG[j], r = hitR[j], len = hitL[j], n = 0;
+            for (;;) {
+              int lo2 = 0, hi2 = A.nContigs - 1;
+#pragma unroll 1
+              while (lo2 < hi2) {
+                const int mid = (lo2 + hi2) >> 1;
+                if (A.contigEnds[mid] > g) hi2 = mid;
+                else lo2 = mid + 1;
+              }
+              const int contigEnd = A.contigEnds[lo2];
+              if (g + K + len > contigEnd) {
+                if (contigEnd - g >= K) {
+                  if (write && o + n < capC) tg[o + n] = (uint32_t)g | ((uint32_t)r << 16), tl[o + n] = (uint32_t)(contigEnd - g - K);
+                  n++;
+                }
+                if (g + K + len - contigEnd >= K) {
+                  r += contigEnd - g;
+                  len -= contigEnd - g;
+                  g = contigEnd;
+                  continue;
+                }
+                break;
+              }
+              if (write && o + n < capC) tg[o + n] = (uint32_t)g | ((uint32_t)r << 16), tl[o + n] = (uint32_t)len;
+              n++;
+              break;
+            }
+            return n;
+          };
 #pragma unroll 1
           for (int j0 = 0; j0 < nR; j0 += 32) {
             const int j = j0 + lane;
-            int pg[3], pr[3], pl[3], np2 = 0;
-            if (j < nR) {
-              int g = hitG[j], r = hitR[j], len = hitL[j];
-              for (;;) {
-                int lo2 = 0, hi2 = A.nContigs - 1;
-#pragma unroll 1
-                while (lo2 < hi2) {
-                  const int mid = (lo2 + hi2) >> 1;
-                  if (A.contigEnds[mid] > g) hi2 = mid;
-                  else lo2 = mid + 1;
-                }
-                const int contigEnd = A.contigEnds[lo2];
-                if (g + K + len > contigEnd) {
-                  if (contigEnd - g >= K) {
-                    if (np2 < 3) pg[np2] = g, pr[np2] = r, pl[np2] = contigEnd - g - K;
-                    np2++;
-                  }
-                  if (g + K + len - contigEnd >= K) {
-                    r += contigEnd - g;
-                    len -= contigEnd - g;
-                    g = contigEnd;
-                    continue;
-                  }
-                  break;
-                }
-                if (np2 < 3) pg[np2] = g, pr[np2] = r, pl[np2] = len;
-                np2++;
-                break;
-              }
-              if (np2 > 3) bad = true, np2 = 3;  // a hit across > 2 contig boundaries (contigs shorter than K + 1)
-            }
+            const int np2 = (j < nR) ? pieces(j, false, 0) : 0;
             const int ic = sd_warp_incl_scan(np2, lane);
-            int o = nOut + ic - np2;
-#pragma unroll 1
-            for (int t = 0; t < np2; t++, o++)
-              if (o < capC) tg[o] = (uint32_t)pg[t] | ((uint32_t)pr[t] << 16), tl[o] = (uint32_t)pl[t];
+            if (j < nR) pieces(j, true, nOut + ic - np2);
             nOut += __shfl_sync(VG_FULL, ic, 31);
           }
           __syncwarp();
-          if (__any_sync(VG_FULL, bad) || nOut > capR) {
+          if (nOut > capR) {
             err |= 2;
           } else {
 #pragma unroll 1
@@ -1127,8 +1138,9 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
         __syncwarp();
         SD_PH(4)
         // ---- F: every window independently; candidates (count > cutoff) compacted in hit order ------
-        const int cutoff = (L < A.nCutoffs) ? A.cutoffs[L] : 0x7fffffff;
+        const int cutoff = A.bestOnly ? -1 : (L < A.nCutoffs) ? A.cutoffs[L] : 0x7fffffff;
         int nC = 0;
+        int bestCnt = -1, bestJ = 0x7fffffff, bestS = 0, bestE = 0;  // bestOnly: per lane, first maximum in hit order
 #pragma unroll 2
         for (int j0 = 0; j0 < nR; j0 += 32) {
           const int j = j0 + lane;
@@ -1137,7 +1149,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
           if (j < nR) {
             const int g = hitG[j], r = hitR[j], len = hitL[j];
             int cs = 0, ce = G;
-            if (A.nContigs > 1) {
+            if (A.nContigs > 1 && !A.bestOnly) {
               int lo = 0, hi = A.nContigs - 1;
 #pragma unroll 1
               while (lo < hi) {
@@ -1161,6 +1173,10 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
             cnt = (uint32_t)((uint16_t)(Pp[b] - Pp[a])) + hitL[a];
             isCand = (int)cnt > cutoff;
             key = ((uint32_t)start << 16) | (uint32_t)(0xFFFF - end);
+            if (A.bestOnly) {
+              if ((int)cnt > bestCnt) bestCnt = (int)cnt, bestJ = j, bestS = start, bestE = end;
+              isCand = false;
+            }
           }
           const unsigned m = __ballot_sync(VG_FULL, isCand);
           if (isCand) {
@@ -1171,6 +1187,15 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
           nC += __popc(m);
         }
         __syncwarp();
+        if (A.bestOnly) {  // strict '>' in hit order: the first hit that reaches the maximum wins
+          const int mx = __reduce_max_sync(VG_FULL, bestCnt);
+          const int jw = __reduce_min_sync(VG_FULL, bestCnt == mx ? bestJ : 0x7fffffff);
+          if (bestCnt == mx && bestJ == jw) {
+            int32_t* W = A.windows + (size_t)wi * A.maxWin * 3;
+            W[0] = bestS, W[1] = bestE, W[2] = mx;
+          }
+          nWin = 1;
+        }
         SD_PH(5)
         // ---- G: stable sort by (start asc, end desc) + pruneWindows (serial, lane 0) ----------------
         if (nC > 0) {

@@ -176,14 +176,14 @@ static int seed_build_msa(vg_ctx* c, const uint8_t* keys, const int64_t* offsets
 static int seed_launch_v1(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_t* d_off1, const int32_t* d_len1,
                           const int64_t* d_off2, const int32_t* d_len2, const int64_t* d_pairIdx, int64_t nItems,
                           bool singleReads, int maxReadLen, int maxWin, int32_t* dbgHits, int32_t* dbgNHits,
-                          const int32_t* d_itemList = nullptr) {
+                          const int32_t* d_itemList = nullptr, bool bestOnly = false) {
   const SeedConfig& sc = msa ? c->seedMsa : c->seed;
   const int K = sc.K;
   const int range = msa ? c->msaLength : c->G;
   if (K < 1 || K > 7) return vg_fail(c, VG_ERR_INVALID, "K=%d outside the supported range 1..7", K);
   if (range >= 65535) return vg_fail(c, VG_ERR_INVALID, "reference longer than 65534 is not supported by the 16-bit seeding tables");
   if (maxReadLen > SD_MAXL) return vg_fail(c, VG_ERR_INVALID, "read length %d exceeds the supported %d", maxReadLen, SD_MAXL);
-  if (maxReadLen >= K && maxReadLen >= (int)sc.cutoffs.size())
+  if (!bestOnly && maxReadLen >= K && maxReadLen >= (int)sc.cutoffs.size())
     return vg_fail(c, VG_ERR_INVALID, "cutoffs has %zu entries but a read has length %d (the Java would throw)",
                    sc.cutoffs.size(), maxReadLen);
   if (nItems > 0x7fffffff) return vg_fail(c, VG_ERR_INVALID, "too many reads in one call");
@@ -248,7 +248,7 @@ static int seed_launch_v1(vg_ctx* c, bool msa, const uint8_t* d_bases, const int
   A.capS = (int)std::max<int64_t>(1 << 16, std::min<int64_t>(1 << 22, ((int64_t)1 << 28) / warpSlots));
   if (const char* e = getenv("VG_SEED_CAPS")) A.capS = atoi(e);
   VG_CUDA(c, c->d_scratch.reserve((size_t)warpSlots * A.capS * 8));
-  A.capC = msa ? std::max(g.capR, 16384) : g.capR;
+  A.capC = msa ? std::max(g.capR, 16384) : std::max(g.capR, 4096);  // also the serial sweep's re-insertion queue (u64 x capC)
   VG_CUDA(c, c->d_seqOff.reserve((size_t)warpSlots * 2 * A.capC * 4 * 2));
   VG_CUDA(c, c->d_scratchR.reserve((size_t)warpSlots * 4 * g.capR * 2 + 64));
   A.scratchR = c->d_scratchR.as<uint16_t>();
@@ -273,6 +273,7 @@ static int seed_launch_v1(vg_ctx* c, bool msa, const uint8_t* d_bases, const int
   A.nItems = nItems;
   A.itemList = d_itemList;  // when set: nItems entries, each the index of an item to (re)do
   A.singleReads = singleReads ? 1 : 0;
+  A.bestOnly = bestOnly ? 1 : 0;
   A.dbgHits = dbgHits;
   A.dbgNHits = dbgNHits;
   A.geom = g;
@@ -369,12 +370,11 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     winWarps = std::min(32, winMax / A.winWarpBytes);
     if (genWarps < 8 || winWarps < 8 || nContigs > 64) fast = false;
   }
-  if (!fast && bestOnly)
-    return vg_fail(c, VG_ERR_INVALID, "best-window seeding needs the fast path (K <= 6 in single-reference mode, reference + read length "
-                                      "< 65535, cutoffs covering the read length)");
+  if (!fast && regs)
+    return vg_fail(c, VG_ERR_INVALID, "region seeding needs the fast path (K <= 6, region + read length < 65535)");
   if (!fast)
     return seed_launch_v1(c, msa, d_bases, d_off1, d_len1, d_off2, d_len2, d_pairIdx, nItems, singleReads, maxReadLen, maxWin,
-                          dbgHits, dbgNHits);
+                          dbgHits, dbgNHits, nullptr, bestOnly);
   if (const char* e = getenv("VG_SEED_WARPS")) {
     genWarps = std::max(1, std::min(genWarps, atoi(e)));
     winWarps = std::max(1, std::min(winWarps, atoi(e)));
@@ -535,13 +535,13 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
                    (f & 8) ? " window list" : "", (f & 16) ? " read too long" : "");
   }
   c->seedFallbacks = flags[3];
-  if (flags[3] > 0 && bestOnly)
-    return vg_fail(c, VG_ERR_OVERFLOW, "%d reads need the general seeding kernel (low-complexity reads), which has no best-window mode",
+  if (flags[3] > 0 && regs)
+    return vg_fail(c, VG_ERR_OVERFLOW, "%d reads need the general seeding kernel (low-complexity reads), which has no region mode",
                    flags[3]);
   if (flags[3] > 0) {
     VG_CUDA(c, cudaEventRecord(c->seedEv[0], c->stream));
     VG_TRY(seed_launch_v1(c, msa, d_bases, d_off1, d_len1, d_off2, d_len2, d_pairIdx, flags[3], singleReads, maxReadLen, maxWin,
-                          dbgHits, dbgNHits, c->d_seedFb.as<int32_t>()));
+                          dbgHits, dbgNHits, c->d_seedFb.as<int32_t>(), bestOnly));
     VG_CUDA(c, cudaEventRecord(c->seedEv[1], c->stream));
     VG_CUDA(c, cudaEventSynchronize(c->seedEv[1]));
     float f = 0;

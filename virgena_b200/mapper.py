@@ -340,7 +340,7 @@ class Context:
         fn = self.L.vg_debug_seed_hits
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
-        out = np.zeros((4096, 3), np.int32)
+        out = np.zeros((16384, 3), np.int32)
         n = C.c_int32()
         self._chk(fn(self.h, int(msa), ptr(read), len(read), ptr(out), len(out), C.byref(n)))
         return out[:n.value].copy()
