@@ -279,6 +279,164 @@ def test_seed_fuzz_references(built, seed):
     ctx.close()
 
 
+_MSA_FUZZ_SEEDS = list(range(8))
+if os.environ.get("VG_FUZZ_SEEDS"):
+    _MSA_FUZZ_SEEDS = _FUZZ_SEEDS
+
+
+@pytest.mark.parametrize("seed", _MSA_FUZZ_SEEDS)
+def test_seed_fuzz_msa(built, seed):
+    """Differential fuzz of MSA-mode seeding: random alignments (2 .. 10 rows, 150 .. 6000 columns, gap runs, divergent
+    and identical rows, N and low-complexity stretches), K = 3 .. 7, random cutoffs; reads are mutated ungapped row
+    substrings, chimeras of two rows, junk and homopolymers."""
+    import oracle
+    import virgena_b200 as vg
+    rng = np.random.default_rng(5000 + seed)
+    W = int(rng.choice([150, 600, 2500, 6000]))
+    R = int(rng.integers(2, 11))
+    K = int(rng.choice([3, 4, 5, 6, 7]))
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    base = acgt[rng.choice(4, W, p=[0.36, 0.18, 0.24, 0.22])].copy()
+    if rng.random() < 0.5:
+        p, ln = int(rng.integers(0, W - 40)), int(rng.integers(8, 40))
+        base[p:p + ln] = acgt[rng.integers(0, 4)]
+    rows = np.empty((R, W), np.uint8)
+    for r in range(R):
+        row = base.copy()
+        mut = rng.random(W) < rng.choice([0.0, 0.03, 0.15])
+        row[mut] = acgt[rng.integers(0, 4, int(mut.sum()))]
+        for _ in range(int(rng.integers(0, 5))):  # gap runs
+            p, ln = int(rng.integers(0, W - 30)), int(rng.integers(1, 30))
+            row[p:p + ln] = ord("-")
+        if rng.random() < 0.2:
+            p, ln = int(rng.integers(0, W - 20)), int(rng.integers(1, 20))
+            row[p:p + ln] = ord("N")
+        rows[r] = row
+    cut = np.full(600, int(rng.integers(0, 40)), np.int32)
+    ungapped = [row[row != ord("-")] for row in rows]
+    reads = []
+    for _ in range(100):
+        u = ungapped[int(rng.integers(0, R))]
+        L = int(rng.integers(K, max(K + 1, min(400, len(u)))))
+        p = int(rng.integers(0, max(1, len(u) - L + 1)))
+        r = u[p:p + L].copy()
+        if rng.random() < 0.2:  # chimera of two rows
+            u2 = ungapped[int(rng.integers(0, R))]
+            p2 = int(rng.integers(0, max(1, len(u2) - L + 1)))
+            r = np.concatenate([r[:L // 2], u2[p2:p2 + L - L // 2]])
+        mut = rng.random(len(r)) < rng.choice([0.0, 0.05, 0.2])
+        r[mut] = acgt[rng.integers(0, 4, int(mut.sum()))]
+        if rng.random() < 0.1:
+            r = acgt[rng.integers(0, 4, L)]
+        if rng.random() < 0.05:
+            r = np.full(L, acgt[rng.integers(0, 4)], np.uint8)
+        if len(r) >= K:
+            reads.append(r.tobytes())
+    low, high = float(np.float32(1) / np.float32(1.5)), 1.5
+    o = oracle.Oracle(K=5)
+    o.set_msa(rows, K=K, low_coef=low, high_coef=high, cutoffs=cut)
+    ctx = vg.Context(K=K, cutoffs=cut)
+    ctx.set_msa(vg.ReferenceAlignment(rows, K=K), low, high, cut)
+    win, nwin = ctx.seed_batch(b"".join(reads), _offs(reads), max_windows=W // K + 10, msa=True)
+    for i, r in enumerate(reads):
+        ow = o.seed(r, msa=True)
+        assert nwin[i] == len(ow), (seed, W, R, K, i, len(r), nwin[i], len(ow))
+        assert (win[i, :nwin[i]] == ow).all(), (seed, W, R, K, i)
+    bw, found = ctx.best_window_batch(b"".join(reads), _offs(reads), msa=True)
+    for i, r in enumerate(reads[:40]):
+        w = o.map_read_to_region(r, msa=True)
+        assert (found[i] != 0) == (w is not None) and (w is None or tuple(bw[i]) == w), (seed, W, R, K, i)
+    for r in reads[:4]:
+        h, oh = ctx.debug_seed_hits(r, msa=True), o.get_hits(r, msa=True)
+        assert h.shape == oh.shape and (h == oh).all(), (seed, W, R, K, len(r))
+    ctx.close()
+
+
+_PIPE_FUZZ_SEEDS = list(range(8))
+if os.environ.get("VG_FUZZ_SEEDS"):
+    _PIPE_FUZZ_SEEDS = _FUZZ_SEEDS
+
+
+@pytest.mark.parametrize("seed", _PIPE_FUZZ_SEEDS)
+def test_map_fuzz_pipeline(built, seed):
+    """Differential fuzz of the whole Mapper.mapReads path + pileup: random (possibly fragmented) references, K, cutoffs,
+    coefficients, insert length and aligner penalties (both checkpoint formats), ragged pairs with substitutions, indels,
+    N, absent and junk mates, mates on the same strand or from other contigs."""
+    import oracle
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    rng = np.random.default_rng(9000 + seed)
+    G = int(rng.choice([800, 3000, 9000, 15000]))
+    K = int(rng.choice([4, 5, 5, 6]))
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    ref = acgt[rng.choice(4, G, p=[0.36, 0.18, 0.24, 0.22])].copy()
+    if rng.random() < 0.5:
+        ln = int(rng.integers(30, 200))
+        a, b = int(rng.integers(0, G - ln)), int(rng.integers(0, G - ln))
+        ref[b:b + ln] = ref[a:a + ln]
+    if rng.random() < 0.3:
+        p = int(rng.integers(0, G - 40))
+        ref[p:p + int(rng.integers(5, 40))] = ord("N")
+    ends, frag = [G], False
+    if rng.random() < 0.5:
+        ends = sorted(set(int(x) for x in rng.integers(100, G - 100, int(rng.integers(1, 5))))) + [G]
+        frag = bool(rng.random() < 0.7)
+    threads = int(rng.choice([1, 4, 8]))
+    match, mismatch = int(rng.integers(1, 4)), -int(rng.integers(1, 5))
+    gop, gep = int(rng.integers(2, 13)), int(rng.integers(0, 4))
+    if rng.random() < 0.2:
+        gop = gep + 20  # forces the 8-byte checkpoints
+    high = float(rng.choice([1.25, 1.5]))
+    insert_len = int(rng.choice([300, 1000]))
+    cut = np.full(600, int(rng.integers(0, 50)), np.int32)
+    r1, r2 = [], []
+    for _ in range(300):
+        ins = int(rng.integers(60, min(700, G)))
+        p = int(rng.integers(0, G - ins + 1))
+        la, lb = int(rng.integers(20, min(300, ins) + 1)), int(rng.integers(20, min(300, ins) + 1))
+        a = ref[p:p + la].copy()
+        b = synth.revcomp(ref[p + ins - lb:p + ins])
+        if rng.random() < 0.1:  # mate from somewhere else
+            q = int(rng.integers(0, G - lb + 1))
+            b = synth.revcomp(ref[q:q + lb])
+        if rng.random() < 0.1:  # same strand
+            b = synth.revcomp(b)
+        if rng.random() < 0.5:
+            a, b = b, a
+        out = []
+        for r in (a, b):
+            r = r.copy()
+            mut = rng.random(len(r)) < rng.choice([0.0, 0.03, 0.12])
+            r[mut] = acgt[rng.integers(0, 4, int(mut.sum()))]
+            if rng.random() < 0.15 and len(r) > 30:
+                q = int(rng.integers(10, len(r) - 10))
+                r = np.delete(r, slice(q, q + int(rng.integers(1, 4)))) if rng.random() < 0.5 else \
+                    np.insert(r, q, acgt[rng.integers(0, 4, int(rng.integers(1, 4)))])
+            if rng.random() < 0.05:
+                r[int(rng.integers(0, len(r)))] = ord("N")
+            if rng.random() < 0.04:
+                r = acgt[rng.integers(0, 4, len(r))]
+            r = r.tobytes()
+            if rng.random() < 0.04:
+                r = b"*"
+            out.append(r)
+        r1.append(out[0])
+        r2.append(out[1])
+    bases, off1, len1, off2, len2 = synth.pack_ragged(r1, r2)
+    o = oracle.Oracle(K=K, high_coef=high, cutoffs=cut, insert_len=insert_len, match=match, mismatch=mismatch, gop=gop, gep=gep)
+    o.set_reference(ref, contig_ends=ends, fragment_ends=ends, is_fragmented=frag, index_thread_num=threads)
+    orec, opool, ostats = o.map_pairs(bases, off1, len1, off2, len2, n_threads=8)
+    mapper = vg.Mapper(K=K, indel_tolerance=high, cutoffs=cut, insert_len=insert_len, match=match, mismatch=mismatch,
+                       gop=gop, gep=gep)
+    genome = vg.Reference(ref, K=K, contig_ends=ends, fragment_ends=ends, is_fragmented=frag, thread_num=threads)
+    md = mapper.mapReads(vg.PairedReads(bases, off1, len1, off2, len2), genome)
+    _compare(md, orec, opool, ostats)
+    _compare_bam(mapper, orec, opool, len1, len2, ends)
+    mapper.ctx.pileup()
+    assert (mapper.ctx.counts() == oracle.pileup(orec, opool, len(ref))).all()
+    mapper.ctx.close()
+
+
 def test_seed_host_csr_index(hiv):
     """The host-built CSR index (with its duplicated boundary positions, Q1) gives the same result as
     letting the library rebuild it from the thread count."""

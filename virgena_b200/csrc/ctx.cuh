@@ -1,5 +1,6 @@
 // Host-side context of libvirgena_gpu.so.
 #pragma once
+#include <stdlib.h>
 #include <stdarg.h>
 
 #include <algorithm>
@@ -128,10 +129,16 @@ static inline int vg_fail(vg_ctx* c, int code, const char* fmt, ...) {
     if (rc__ != VG_OK) return rc__; \
   } while (0)
 
+// VG_SYNC_DEBUG=1 synchronises after every launch so that a faulting kernel is reported at its own launch site
+static inline bool vg_sync_debug() {
+  static const bool on = getenv("VG_SYNC_DEBUG") != nullptr;
+  return on;
+}
 #define VG_LAUNCH_CHECK(c)                                                                              \
   do {                                                                                                  \
     (c)->launches++;                                                                                    \
     cudaError_t e__ = cudaGetLastError();                                                               \
+    if (e__ == cudaSuccess && vg_sync_debug()) e__ = cudaStreamSynchronize((c)->stream);                \
     if (e__ != cudaSuccess)                                                                             \
       return vg_fail((c), VG_ERR_CUDA, "kernel launch failed at %s:%d: %s", __FILE__, __LINE__,         \
                      cudaGetErrorString(e__));                                                          \

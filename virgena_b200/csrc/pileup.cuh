@@ -109,10 +109,10 @@ __global__ void pu_scan_kernel(const int32_t* __restrict__ tileCount, int nTiles
 // scatter the reads into tile order (order inside a tile is irrelevant: integer sums)
 __global__ void pu_scatter_kernel(const PuRead* __restrict__ reads, const int32_t* __restrict__ tileOf, int64_t n,
                                   int nTiles, unsigned long long* __restrict__ cursor, PuRead* __restrict__ sorted) {
-  extern __shared__ int pu_sm[];
+  extern __shared__ __align__(16) int pu_sm[];
   int* hist = pu_sm;                // per-block count per tile
   int* base = pu_sm + nTiles;       // reserved global base per tile (low 32 bits of a 64-bit offset pair)
-  unsigned long long* base64 = (unsigned long long*)(pu_sm + 2 * nTiles + (nTiles & 1));
+  unsigned long long* base64 = (unsigned long long*)(pu_sm + 2 * nTiles + 2);  // 8-byte aligned whatever nTiles is
   for (int t = threadIdx.x; t < nTiles; t += blockDim.x) hist[t] = 0;
   __syncthreads();
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

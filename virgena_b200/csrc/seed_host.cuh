@@ -248,7 +248,10 @@ static int seed_launch_v1(vg_ctx* c, bool msa, const uint8_t* d_bases, const int
   A.capS = (int)std::max<int64_t>(1 << 16, std::min<int64_t>(1 << 22, ((int64_t)1 << 28) / warpSlots));
   if (const char* e = getenv("VG_SEED_CAPS")) A.capS = atoi(e);
   VG_CUDA(c, c->d_scratch.reserve((size_t)warpSlots * A.capS * 8));
-  A.capC = msa ? std::max(g.capR, 16384) : std::max(g.capR, 4096);  // also the serial sweep's re-insertion queue (u64 x capC)
+  // candidate sort buffers; also the serial sweep's re-insertion queue (u64 x capC) and, in MSA mode, the chain starts
+  // before the sweep (short k-mers on a long alignment give tens of thousands per read): within 2 GB
+  A.capC = msa ? (int)std::max<int64_t>(std::max(g.capR, 16384), std::min<int64_t>(A.capS, ((int64_t)1 << 27) / warpSlots))
+               : std::max(g.capR, 4096);
   VG_CUDA(c, c->d_seqOff.reserve((size_t)warpSlots * 2 * A.capC * 4 * 2));
   VG_CUDA(c, c->d_scratchR.reserve((size_t)warpSlots * 4 * g.capR * 2 + 64));
   A.scratchR = c->d_scratchR.as<uint16_t>();
