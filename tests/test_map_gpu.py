@@ -209,6 +209,85 @@ def test_contig_builder_count_reads(built):
         assert (counts[cidx] == want_counts[cidx]).all(), cidx
 
 
+def test_graph_sw_score_and_reference_finder(built):
+    """SURVEY 8f N1, the other two users of the same primitives: Graph.SWScore (Graph.java:493-586: contig vs every
+    candidate reference sub-sequence, mapReadToRegion + align, float32 score / identity / coverage, best reference and
+    those within delta) and ReferenceFinder.SWScoreCounter (ReferenceFinder.java:291-322: alignment score matrix)."""
+    import oracle
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    ref, _ = synth.config_reference(1)
+    rng = np.random.default_rng(11)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    cut = np.full(600, 0, np.int32)
+    contigs, subs = [], []
+    for c in range(10):
+        ln = int(rng.integers(120, 480))
+        p = int(rng.integers(0, len(ref) - 2000))
+        seq = ref[p:p + ln].copy()
+        mut = rng.random(ln) < 0.04
+        seq[mut] = acgt[rng.integers(0, 4, int(mut.sum()))]
+        gapped = np.insert(seq, sorted(rng.integers(0, ln, 5)), ord("-"))  # contig rows carry alignment gaps
+        contigs.append(gapped.tobytes())
+        cand = []
+        for j in range(int(rng.integers(1, 6))):
+            a = max(0, p - int(rng.integers(0, 80)))
+            sub = ref[a:a + ln + int(rng.integers(0, 160))].copy()
+            m2 = rng.random(len(sub)) < rng.choice([0.0, 0.05, 0.2])
+            sub[m2] = acgt[rng.integers(0, 4, int(m2.sum()))]
+            if j == 3:
+                sub = ref[(p + 5000) % 7000:(p + 5000) % 7000 + ln].copy()  # unrelated
+            if j == 4:
+                sub = cand[0]                                                # equal scores: the first one stays the best
+            cand.append(sub.tobytes() if not isinstance(sub, bytes) else sub)
+        subs.append(cand)
+    contigs.append(b"-----")  # nothing left after removing gaps: no reference can be scored
+    subs.append([ref[:300].tobytes()])
+    delta = 0.05
+    mapper = vg.Mapper(K=5, cutoffs=cut)
+    got = vg.Graph(mapper, delta=delta).SWScore(contigs, subs)
+    n_scored = 0
+    for c, (contig, cand) in enumerate(zip(contigs, subs)):
+        seq = bytes(b for b in contig if b != ord("-"))
+        scored = []
+        cov = np.float32(0)
+        for j, sub in enumerate(cand):
+            o = oracle.Oracle(K=5, cutoffs=cut)
+            o.set_reference(sub, index_thread_num=1)
+            w = o.map_read_to_region(seq)
+            e = got[c]["per_ref"][j]
+            assert e["found"] == (w is not None), (c, j)
+            if w is None:
+                continue
+            assert e["window"] == w, (c, j)
+            rec, _ = o.sw_align(seq, sub[w[0]:w[1]])
+            assert tuple(e["alignment"]) == tuple(int(x) for x in rec), (c, j)
+            sc = np.float32(rec[0]) / np.float32(len(seq) * 2)
+            ident = np.float32(rec[5]) / np.float32(rec[6])
+            cov = np.float32(rec[2] - rec[1]) / np.float32(len(seq))
+            assert e["scores"] == (sc, ident, cov)
+            scored.append((j, sc, ident))
+        assert got[c]["markedForDeletion"] == (not scored)
+        assert got[c]["coverage"] == cov
+        if scored:
+            n_scored += 1
+            best = max(sc for _, sc, _ in scored)
+            first = next(t for t in scored if t[1] == best)
+            assert got[c]["best"] == first[0] and got[c]["score"] == best and got[c]["identity"] == first[2]
+            assert sorted(j for j, _ in got[c]["refs"]) == sorted(j for j, sc, _ in scored if np.float32(best - sc) <= np.float32(delta))
+            assert [sc for _, sc in got[c]["refs"]] == sorted((sc for _, sc in got[c]["refs"]), reverse=True)
+    assert n_scored == 10 and got[-1]["markedForDeletion"]
+    # ReferenceFinder.SWScoreCounter
+    vseqs = [bytes(b for b in c if b != ord("-")) for c in contigs[:10]]
+    wins = [[s if (v + j) % 4 else None for j, s in enumerate(subs[v])] for v in range(10)]
+    sc = vg.ReferenceFinder(mapper).SWScoreCounter(vseqs, wins)
+    o = oracle.Oracle(K=5, cutoffs=cut)
+    for v in range(10):
+        for j, w in enumerate(wins[v]):
+            assert sc[v, j] == (0 if w is None else int(o.sw_align(vseqs[v], w)[0][0])), (v, j)
+    mapper.ctx.close()
+
+
 _FUZZ_SEEDS = list(range(16))
 if os.environ.get("VG_FUZZ_SEEDS"):  # e.g. VG_FUZZ_SEEDS=16:100 for a longer one-off run
     _a, _b = os.environ["VG_FUZZ_SEEDS"].split(":")

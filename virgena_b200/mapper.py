@@ -165,6 +165,7 @@ class Context:
             raise VgError(rc, msg)
         self.n_pairs = 0
         self.G = 0
+        self.sw_params = (match, mismatch, gop, gep)
 
     def close(self):
         if getattr(self, "h", None):
@@ -446,6 +447,112 @@ class ContigBuilder:
         else:
             counts = np.zeros((total, 5), np.int32)
         return win, found, aln, seqs, [counts[coff[c]:coff[c + 1]] for c in range(len(centroids))]
+
+
+class Graph:
+    """The reference-scoring step of Graph (Graph.java:493-586): every cluster contig (gaps removed) is seeded
+    against each candidate reference sub-sequence with that sub-sequence's own index (mapReadToRegion), aligned against
+    the window, and scored; the best reference and those within `delta` of it are kept. One call handles all clusters."""
+
+    def __init__(self, mapper, delta=0.0):
+        self.ctx = mapper.ctx
+        self.match = mapper.ctx.sw_params[0]
+        self.delta = np.float32(delta)
+
+    def SWScore(self, contigs, ref_subseqs):
+        """contigs[c]: gapped contig bytes; ref_subseqs[c]: list of byte strings (reference.seq.substring(ref.start, ref.end)
+        for every RefSubseq of the cluster's window). Returns one dict per cluster: markedForDeletion, score, identity,
+        coverage (float32, as SWScore's fields), best (index of the best reference or -1), refs [(index, score)] kept, and
+        per reference: found, window, alignment (7 ints), scores (score, identity, coverage as float32)."""
+        seqs = [bytes(b for b in bytes(c) if b != ord("-")) for c in contigs]
+        regions, reads, read_region, owner = [], [], [], []
+        for c, subs in enumerate(ref_subseqs):
+            for j, sub in enumerate(subs):
+                read_region.append(len(regions))
+                regions.append(bytes(sub))
+                reads.append(seqs[c])
+                owner.append((c, j))
+        n = len(reads)
+        goff = np.zeros(len(regions) + 1, np.int64)
+        np.cumsum([len(x) for x in regions], out=goff[1:])
+        roff = np.zeros(n + 1, np.int64)
+        np.cumsum([len(x) for x in reads], out=roff[1:])
+        win = np.zeros((max(n, 1), 3), np.int32)
+        found = np.zeros(max(n, 1), np.int32)
+        if n:
+            win, found = self.ctx.map_to_regions(np.frombuffer(b"".join(regions), np.uint8), goff,
+                                                 np.frombuffer(b"".join(reads), np.uint8), roff,
+                                                 np.asarray(read_region, np.int32))
+        idx = [i for i in range(n) if found[i]]
+        aln = np.zeros((max(n, 1), 7), np.int32)
+        if idx:
+            s1 = [reads[i] for i in idx]
+            s2 = [regions[i][win[i, 0]:win[i, 1]] for i in idx]
+            s1off = np.zeros(len(idx) + 1, np.int64)
+            np.cumsum([len(x) for x in s1], out=s1off[1:])
+            s2off = np.zeros(len(idx) + 1, np.int64)
+            np.cumsum([len(x) for x in s2], out=s2off[1:])
+            rec, _, _ = self.ctx.sw_align_batch(b"".join(s1), s1off, b"".join(s2), s2off)
+            aln[idx] = rec
+        out = []
+        k = 0
+        for c, subs in enumerate(ref_subseqs):
+            ln = len(seqs[c])
+            full = ln * self.match
+            per, scored = [], []
+            coverage = np.float32(0)
+            for j in range(len(subs)):
+                i = k + j
+                entry = dict(found=bool(found[i]), window=tuple(int(x) for x in win[i]), alignment=aln[i].copy(), scores=None)
+                if found[i]:
+                    with np.errstate(divide="ignore", invalid="ignore"):
+                        sc = np.float32(aln[i, 0]) / np.float32(full)
+                        ident = np.float32(aln[i, 5]) / np.float32(aln[i, 6])
+                        coverage = np.float32(aln[i, 2] - aln[i, 1]) / np.float32(ln)  # RefScore's ctor writes SWScore.coverage
+                    entry["scores"] = (sc, ident, coverage)
+                    scored.append((j, sc, ident))
+                per.append(entry)
+            k += len(subs)
+            res = dict(markedForDeletion=not scored, score=np.float32(0), identity=np.float32(0), coverage=coverage, best=-1,
+                       refs=[], per_ref=per)
+            if scored:
+                # Collections.sort by descending score, stable (Graph.java:521-527, :562)
+                order = sorted(range(len(scored)), key=lambda t: -float(scored[t][1]))
+                bj, bs, bi = scored[order[0]]
+                if bs > 0:
+                    res["refs"] = [(scored[t][0], scored[t][1]) for t in order if np.float32(bs - scored[t][1]) <= self.delta]
+                    res["score"], res["identity"], res["best"] = bs, bi, bj
+            out.append(res)
+        return out
+
+
+class ReferenceFinder:
+    """ReferenceFinder.SWScoreCounter (ReferenceFinder.java:291-322): clusterIDToScores[v][j] = align(vertex contig,
+    reference j's sub-sequence under the contig's alignment columns).score; 0 where the reference has no such columns."""
+
+    def __init__(self, mapper):
+        self.ctx = mapper.ctx
+
+    def SWScoreCounter(self, vertex_seqs, ref_windows):
+        """ref_windows[v][j]: bytes (ref.seq.substring(start, end)) or None (alnToSeqStart/End gave -1). Returns int32[v, j]."""
+        nref = max((len(r) for r in ref_windows), default=0)
+        scores = np.zeros((len(vertex_seqs), nref), np.int32)
+        s1, s2, where = [], [], []
+        for v, refs in enumerate(ref_windows):
+            for j, w in enumerate(refs):
+                if w is not None:
+                    s1.append(bytes(vertex_seqs[v]))
+                    s2.append(bytes(w))
+                    where.append((v, j))
+        if where:
+            s1off = np.zeros(len(s1) + 1, np.int64)
+            np.cumsum([len(x) for x in s1], out=s1off[1:])
+            s2off = np.zeros(len(s2) + 1, np.int64)
+            np.cumsum([len(x) for x in s2], out=s2off[1:])
+            rec, _, _ = self.ctx.sw_align_batch(b"".join(s1), s1off, b"".join(s2), s2off)
+            for (v, j), r in zip(where, rec):
+                scores[v, j] = r[0]
+        return scores
 
 
 class BamPrinter:
