@@ -214,6 +214,14 @@ int vg_map_to_regions(vg_ctx* ctx, const uint8_t* region_pool, const int64_t* re
 int vg_pileup_alignments(vg_ctx* ctx, const uint8_t* seq1_pool, const int64_t* seq1_off, const int32_t* length,
                          const int64_t* pos, int64_t n, int64_t total_positions, int32_t* counts);
 
+/* ProblemIntervalBuilder.countIdentity (ProblemIntervalBuilder.java:35-160): for every mapped read of the
+ * last vg_map_pairs call (mappedData.mappedReads = r1, r2 of every pair in order) whose length is at least window_size,
+ * the identity of every window of window_size read bases against the reference the reads were mapped to, added as
+ * (float)identity/len to identity[window start] with coverage[window start]++. The sums are binary32 and keep the
+ * reference's order: thread t of thread_num sums reads [t*size, (t+1)*size) (size = nReads / thread_num, the last thread
+ * takes the rest) in list order, and the per-thread arrays are added in thread order. identity / coverage: G entries. */
+int vg_identity_counting(vg_ctx* ctx, int32_t window_size, int32_t thread_num, float* identity, int32_t* coverage);
+
 /* BAM record fields of the last single-reference mapping, replacing the per-read derivations of
  * BamPrinter.setRecordFieldsMapped / setRecordFieldsUnmapped / setCigar (BamPrinter.java:16-171); serialisation stays with
  * htsjdk. Two records per pair result, in (pair, mate) order. ref_index is the index into Reference.contigEnds of the

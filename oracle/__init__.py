@@ -210,6 +210,24 @@ def pileup(recs, pool, G, counts=None):
     return counts
 
 
+def identity_counting(recs, pool, len1, len2, genome, window_size, thread_num):
+    """ProblemIntervalBuilder.countIdentity: (identity float32[G], coverage int32[G]) over the mapped reads of `recs`."""
+    genome = _u8(genome)
+    G = len(genome)
+    ident = np.zeros(max(G, 1), np.float32)
+    cov = np.zeros(max(G, 1), np.int32)
+    L = lib()
+    L.vo_identity_counting.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                       C.c_int, C.c_void_p, C.c_void_p]
+    L.vo_identity_counting.restype = C.c_int
+    rc = L.vo_identity_counting(_p(recs), len(recs), _p(_u8(pool) if len(pool) else np.zeros(1, np.uint8)), _p(_i32(len1)),
+                                _p(_i32(len2)), _p(genome if G else np.zeros(1, np.uint8)), G, window_size, thread_num,
+                                _p(ident), _p(cov))
+    if rc != 0:
+        raise ValueError("identity counting: the Java would throw ArrayIndexOutOfBounds")
+    return ident[:G], cov[:G]
+
+
 def consensus(counts, genome, save_uncovered=False, coverage_threshold=0):
     genome = _u8(genome)
     counts = np.ascontiguousarray(counts, np.int32)

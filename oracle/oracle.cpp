@@ -1462,6 +1462,97 @@ int vo_pileup(const PairRec* recs, int64_t N, const uint8_t* seq1pool, int G, in
   return 0;
 }
 
+// ProblemIntervalBuilder.IdentityCounting.run (ProblemIntervalBuilder.java:35-133) + countIdentity (:135-160): sliding-window
+// identity of every mapped read summed per window start, in binary32 and in the reference's order: thread t sums its
+// reads [t*size, (t+1)*size) (the last one up to the end) in list order into its own array, the arrays are then added in
+// thread order. mappedReads = r1, r2 of every pair in order (Mapper.java:240-377). len1/len2 = read.seq.length per record.
+// Returns 0, or -1 where the Java would have thrown ArrayIndexOutOfBounds.
+int vo_identity_counting(const PairRec* recs, int64_t N, const uint8_t* seq1pool, const int32_t* len1, const int32_t* len2,
+                         const uint8_t* genome, int G, int windowSize, int threadNum, float* identityOut, int32_t* coverageOut) {
+  struct Item { const MateRec* m; int seqLen; };
+  std::vector<Item> list;
+  for (int64_t i = 0; i < N; i++)
+    for (int k = 0; k < 2; k++)
+      if (recs[i].m[k].present) list.push_back({&recs[i].m[k], k == 0 ? len1[i] : len2[i]});
+  for (int i = 0; i < G; i++) identityOut[i] = 0.0f, coverageOut[i] = 0;
+  if (threadNum < 1) return -1;
+  const int64_t size = (int64_t)list.size() / threadNum;
+  std::vector<float> sumIdentity((size_t)std::max(G, 1));
+  std::vector<int32_t> coverage((size_t)std::max(G, 1));
+  for (int t = 0; t < threadNum; t++) {
+    const int64_t from = t * size, to = (t == threadNum - 1) ? (int64_t)list.size() : from + size;
+    std::fill(sumIdentity.begin(), sumIdentity.end(), 0.0f);
+    std::fill(coverage.begin(), coverage.end(), 0);
+    for (int64_t n = from; n < to; n++) {
+      const MateRec& a = *list[n].m;
+      const int seqLen = list[n].seqLen;
+      if (seqLen < windowSize) continue;
+      const uint8_t* seq1 = seq1pool + a.seq1_offset;
+      const int alnLen = a.length;
+      int identity = 0;
+      const int startNoClip = a.start + a.start2;
+      const int start = std::max(0, startNoClip - a.start1);
+      const int endNoClip = a.start + a.end2;
+      const int end = std::min(G, endNoClip + seqLen - a.end1);
+      int alnEndPos = 0, len, alnStartPos = 0;
+#define IDC_SEQ(p) ((p) < 0 || (p) >= alnLen ? (oob = true, (uint8_t)0) : seq1[p])
+#define IDC_GEN(p) ((p) < 0 || (p) >= G ? (oob = true, (uint8_t)0) : genome[p])
+      bool oob = false;
+      if (a.start1 >= windowSize) {
+        len = windowSize;
+      } else {
+        len = a.start1;
+        if (alnLen > windowSize - a.start1) {
+          for (int i = startNoClip; i < startNoClip + windowSize - a.start1 && alnEndPos < alnLen;) {
+            const uint8_t c = seq1[alnEndPos];
+            if (c != GAP && c == IDC_GEN(i)) {
+              identity++, alnEndPos++, len++, i++;
+            } else if (c < 'a') {
+              alnEndPos++, len++, i++;
+            } else {
+              do {
+                alnEndPos++, len++;
+              } while (IDC_SEQ(alnEndPos) >= 'a');
+            }
+            if (oob) return -1;
+          }
+          while (alnEndPos < alnLen && seq1[alnEndPos] >= 'a') alnEndPos++, len++;
+        } else {
+          identity += a.identity;
+          len += windowSize - a.start1;
+          alnEndPos = alnLen;
+        }
+      }
+      if (start < 0 || start >= G) return -1;
+      sumIdentity[start] += (float)identity / (float)len;
+      coverage[start]++;
+      for (int i = start + 1; i <= end - windowSize; i++) {
+        if (i > startNoClip && i <= endNoClip) {
+          const uint8_t c = IDC_SEQ(alnStartPos);
+          if (c != GAP && c == IDC_GEN(i - 1)) identity--;
+          alnStartPos++;
+          if (alnStartPos < alnLen)
+            while (IDC_SEQ(alnStartPos) >= 'a') alnStartPos++, len--;
+        }
+        if (i > startNoClip - windowSize && i <= endNoClip - windowSize) {
+          const uint8_t c = IDC_SEQ(alnEndPos);
+          if (c != GAP && c == IDC_GEN(i + windowSize - 1)) identity++;
+          alnEndPos++;
+          if (alnEndPos < alnLen)
+            while (IDC_SEQ(alnEndPos) >= 'a') alnEndPos++, len++;
+        }
+        if (oob) return -1;
+        sumIdentity[i] += (float)identity / (float)len;
+        coverage[i]++;
+      }
+#undef IDC_SEQ
+#undef IDC_GEN
+    }
+    for (int i = 0; i < G; i++) identityOut[i] += sumIdentity[i], coverageOut[i] += coverage[i];
+  }
+  return 0;
+}
+
 // ConsensusBuildingSimple.run (:98-120)
 void vo_consensus(const int32_t* counts, int G, int saveUncovered, int coverageThreshold, const uint8_t* genome,
                   uint8_t* consensus) {

@@ -288,6 +288,37 @@ def test_graph_sw_score_and_reference_finder(built):
     mapper.ctx.close()
 
 
+@pytest.mark.parametrize("window,threads", [(50, 1), (50, 8), (100, 3), (30, 16)])
+def test_identity_counting(hiv, window, threads):
+    """vg_identity_counting vs the oracle's restatement of ProblemIntervalBuilder.countIdentity, bit-exact
+    float32 sums in the reference's per-thread order (ragged reads, indels, soft clips, reads shorter than the window)."""
+    import oracle
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    ref, cut = hiv
+    cut = np.concatenate([cut, np.full(300, cut[-1], np.int32)])
+    m1, m2 = synth.config_pairs(3, 1500)
+    rng = np.random.default_rng(window * 100 + threads)
+    r1 = [m1[i].tobytes()[:int(rng.integers(20, 251))] for i in range(len(m1))]
+    r2 = [m2[i].tobytes()[int(rng.integers(0, 30)):] for i in range(len(m2))]
+    r1[7], r2[11] = b"*", b"*"
+    bases, off1, len1, off2, len2 = synth.pack_ragged(r1, r2)
+    o = oracle.Oracle(K=5, cutoffs=cut)
+    o.set_reference(ref, index_thread_num=8)
+    orec, opool, _ = o.map_pairs(bases, off1, len1, off2, len2, n_threads=8)
+    want_i, want_c = oracle.identity_counting(orec, opool, len1, len2, ref, window, threads)
+    mapper = vg.Mapper(K=5, cutoffs=cut)
+    mapper.mapReads(vg.PairedReads(bases, off1, len1, off2, len2), vg.Reference(ref, K=5, thread_num=8))
+    got_i, got_c = vg.ProblemIntervalBuilder(mapper, window, threads).countIdentity()
+    assert (got_c == want_c).all()
+    assert got_i.view(np.uint32).tolist() == want_i.view(np.uint32).tolist()
+    assert want_c.sum() > 100000 // window
+    if threads == 8:  # the order of the float sums matters: one thread gives other bits
+        one_i, _ = oracle.identity_counting(orec, opool, len1, len2, ref, window, 1)
+        assert (one_i.view(np.uint32) != want_i.view(np.uint32)).any()
+    mapper.ctx.close()
+
+
 _FUZZ_SEEDS = list(range(16))
 if os.environ.get("VG_FUZZ_SEEDS"):  # e.g. VG_FUZZ_SEEDS=16:100 for a longer one-off run
     _a, _b = os.environ["VG_FUZZ_SEEDS"].split(":")
@@ -513,6 +544,10 @@ def test_map_fuzz_pipeline(built, seed):
     _compare_bam(mapper, orec, opool, len1, len2, ends)
     mapper.ctx.pileup()
     assert (mapper.ctx.counts() == oracle.pileup(orec, opool, len(ref))).all()
+    window, threads = int(rng.choice([20, 50, 120])), int(rng.choice([1, 2, 7]))
+    want_i, want_c = oracle.identity_counting(orec, opool, len1, len2, ref, window, threads)
+    got_i, got_c = vg.ProblemIntervalBuilder(mapper, window, threads).countIdentity()
+    assert (got_c == want_c).all() and got_i.view(np.uint32).tolist() == want_i.view(np.uint32).tolist()
     mapper.ctx.close()
 
 

@@ -370,3 +370,30 @@ def test_map_read_classes():
     assert m["score"] == 500 and m["identity"] == 250 and m["start"] + m["start2"] == 1000
     # stats 1)-7): pairs, bothExist, readsTotal, totalMapped, fwd, rev, bothMapped, totalScore, concordant
     assert st[0] == 7 and st[1] == 6 and st[2] == 13 and st[3] == 9 and st[6] == 3 and st[8] == 2
+
+
+def test_identity_counting_hand_derived():
+    """ProblemIntervalBuilder.IdentityCounting.run (ProblemIntervalBuilder.java:35-133), three walks derived by hand:
+    a mismatch leaving and entering the window; a soft-clipped read head (the clipped bases count in len, not in identity);
+    an insertion (lower case: len grows / shrinks as it enters / leaves) and a deletion ('-' never matches)."""
+    import oracle
+
+    def one(genome, seq1, mate, read_len, window, **f):
+        rec = np.zeros(1, oracle.PAIR_DTYPE)
+        m = rec["m"][0][mate]
+        m["present"], m["start"], m["seq1_offset"], m["length"] = 1, 0, 0, len(seq1)
+        for k, v in f.items():
+            m[k] = v
+        lens = [[read_len], [0]] if mate == 0 else [[0], [read_len]]
+        return oracle.identity_counting(rec, np.frombuffer(seq1, np.uint8), lens[0], lens[1], np.frombuffer(genome, np.uint8), window, 1)
+
+    ident, cov = one(b"ACGTACGTAC", b"GAACGT", 0, 6, 4, start1=0, end1=6, start2=2, end2=8, identity=5)
+    assert ident.tolist() == [0, 0, 0.75, 0.75, 1.0, 0, 0, 0, 0, 0] and cov.tolist() == [0, 0, 1, 1, 1, 0, 0, 0, 0, 0]
+    ident, cov = one(b"ACGTACGTAC", b"GTACGT", 1, 8, 4, start1=2, end1=8, start2=2, end2=8, identity=6)
+    assert ident.tolist() == [0.5, 0.75, 1.0, 1.0, 1.0, 0, 0, 0, 0, 0] and cov.tolist() == [1, 1, 1, 1, 1, 0, 0, 0, 0, 0]
+    ident, cov = one(b"ACGTACGTACGT", b"GTaA-GT", 0, 6, 3, start1=0, end1=6, start2=2, end2=8, identity=5)
+    third = np.float32(2) / np.float32(3)
+    assert ident.tolist() == [0, 0, 0.75, 0.5, third, third, 0, 0, 0, 0, 0, 0] and cov.tolist() == [0, 0, 1, 1, 1, 1] + [0] * 6
+    # reads shorter than the window are skipped but still count when the list is cut into per-thread chunks
+    ident, cov = one(b"ACGTACGTAC", b"GAACGT", 0, 6, 7, start1=0, end1=6, start2=2, end2=8, identity=5)
+    assert not ident.any() and not cov.any()

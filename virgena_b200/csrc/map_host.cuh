@@ -4,6 +4,7 @@
 #include "ctx.cuh"
 #include "pileup.cuh"
 #include "bam.cuh"
+#include "identity.cuh"
 #include "seed_host.cuh"
 #include "sw_host.cuh"
 
@@ -69,9 +70,9 @@ __global__ void mh_scan2_kernel(int64_t* blockSums, int64_t nb, int64_t* total) 
   if (lane == 0) *total = carry;
 }
 __global__ void mh_scan3_kernel(int64_t* __restrict__ out, const int64_t* __restrict__ blockSums, const int32_t* __restrict__ in,
-                                int64_t n) {
+                                int64_t n, int plain) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = in[i] > 0 ? out[i] + blockSums[blockIdx.x] : -1;  // -1: nothing to emit
+  if (i < n) out[i] = (plain || in[i] > 0) ? out[i] + blockSums[blockIdx.x] : -1;  // -1: nothing to emit (unless plain)
 }
 
 __global__ void mh_lengths_kernel(const vg_pair_result* __restrict__ res, const SwAln* __restrict__ alns, int64_t n2,
@@ -133,7 +134,7 @@ __global__ void mh_stats_kernel(const vg_pair_result* __restrict__ res, int64_t 
   if (threadIdx.x < 9 && acc[threadIdx.x]) atomicAdd(&st[threadIdx.x], acc[threadIdx.x]);
 }
 
-static int mh_exclusive_scan(vg_ctx* c, const int32_t* d_in, int64_t* d_out, int64_t n, int64_t* totalOut) {
+static int mh_exclusive_scan(vg_ctx* c, const int32_t* d_in, int64_t* d_out, int64_t n, int64_t* totalOut, bool plain = false) {
   const int threads = 1024;
   const int64_t nb = (n + threads - 1) / threads;
   VG_CUDA(c, c->d_misc.reserve((size_t)(nb + 2) * 8 + 64));
@@ -143,7 +144,7 @@ static int mh_exclusive_scan(vg_ctx* c, const int32_t* d_in, int64_t* d_out, int
   VG_LAUNCH_CHECK(c);
   mh_scan2_kernel<<<1, 32, 0, c->stream>>>(bs, nb, tot);
   VG_LAUNCH_CHECK(c);
-  mh_scan3_kernel<<<(unsigned)nb, threads, 0, c->stream>>>(d_out, bs, d_in, n);
+  mh_scan3_kernel<<<(unsigned)nb, threads, 0, c->stream>>>(d_out, bs, d_in, n, plain ? 1 : 0);
   VG_LAUNCH_CHECK(c);
   VG_CUDA(c, cudaMemcpyAsync(totalOut, tot, 8, cudaMemcpyDeviceToHost, c->stream));
   VG_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -489,6 +490,78 @@ int vg_bam_fields(vg_ctx* c, vg_bam_record* out, int64_t n_records, uint32_t* ci
   VG_CUDA(c, cudaMemcpyAsync(out, A.out, (size_t)n * 2 * sizeof(vg_bam_record), cudaMemcpyDeviceToHost, c->stream));
   if (total > 0) VG_CUDA(c, cudaMemcpyAsync(cigar_pool, A.ops, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream));
   VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VG_OK;
+}
+
+// ProblemIntervalBuilder.countIdentity (ProblemIntervalBuilder.java:35-160) over the alignments of the last
+// vg_map_pairs call and the reference they were mapped to; thread_num = the reference's ThreadNumber (it fixes the order
+// of the binary32 sums). identity / coverage: G entries each.
+int vg_identity_counting(vg_ctx* c, int32_t window_size, int32_t thread_num, float* identity, int32_t* coverage) {
+  if (!c) return VG_ERR_INVALID;
+  VG_CUDA(c, cudaSetDevice(c->device));
+  if (!c->haveRef) return vg_fail(c, VG_ERR_STATE, "vg_set_reference has not been called");
+  if (c->resultsMsa) return vg_fail(c, VG_ERR_STATE, "the last mapping was MSA mode (no alignments)");
+  if (window_size < 1 || thread_num < 1 || thread_num > 65535) return vg_fail(c, VG_ERR_INVALID, "bad window size / thread number");
+  const int G = c->G;
+  const int64_t n = c->nResults;
+  if (G == 0) return VG_OK;
+  if (!identity || !coverage) return vg_fail(c, VG_ERR_INVALID, "null output");
+  if (n == 0) {
+    memset(identity, 0, (size_t)G * 4);
+    memset(coverage, 0, (size_t)G * 4);
+    return VG_OK;
+  }
+  const int64_t n2 = n * 2;
+  IdcArgs A;
+  memset(&A, 0, sizeof A);
+  A.res = c->d_results.as<vg_pair_result>();
+  A.nPairs = n;
+  A.seq1pool = c->d_seq1pool.as<uint8_t>();
+  A.pairIdx = c->d_pairIdx.as<int64_t>();
+  A.len1 = c->d_len1.as<int32_t>();
+  A.len2 = c->d_len2.as<int32_t>();
+  A.genome = c->d_ref.as<uint8_t>();
+  A.G = G;
+  A.windowSize = window_size;
+  VG_CUDA(c, c->d_bamN.reserve((size_t)n2 * 2 * 4 + 64));
+  VG_CUDA(c, c->d_bamOff.reserve((size_t)n2 * 2 * 8 + 64));
+  VG_CUDA(c, c->d_bamRec.reserve((size_t)n2 * sizeof(IdcRead)));
+  VG_CUDA(c, c->d_counter.reserve(16));
+  VG_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, 16, c->stream));
+  A.isMapped = c->d_bamN.as<int32_t>();
+  A.npos = A.isMapped + n2;
+  A.reads = c->d_bamRec.as<IdcRead>();
+  A.err = c->d_counter.as<int>();
+  const unsigned blocks = (unsigned)((n2 + 127) / 128);
+  idc_plan_kernel<<<blocks, 128, 0, c->stream>>>(A);
+  VG_LAUNCH_CHECK(c);
+  int64_t nMapped = 0, nVals = 0;
+  int64_t* d_listIdx = c->d_bamOff.as<int64_t>();
+  int64_t* d_valOff = d_listIdx + n2;
+  VG_TRY(mh_exclusive_scan(c, A.isMapped, d_listIdx, n2, &nMapped, true));
+  VG_TRY(mh_exclusive_scan(c, A.npos, d_valOff, n2, &nVals, true));
+  A.listIdx = d_listIdx;
+  A.valOff = d_valOff;
+  VG_CUDA(c, c->d_bamOps.reserve((size_t)std::max<int64_t>(nVals, 1) * 4));
+  A.vals = c->d_bamOps.as<float>();
+  idc_walk_kernel<<<blocks, 128, 0, c->stream>>>(A);
+  VG_LAUNCH_CHECK(c);
+  const int nTiles = (G + IDC_TILE - 1) / IDC_TILE, T = thread_num;
+  VG_CUDA(c, c->d_scratch.reserve((size_t)T * G * 8 + (size_t)G * 8 + 64));
+  float* d_partial = c->d_scratch.as<float>();
+  int32_t* d_partialCov = (int32_t*)(d_partial + (size_t)T * G);
+  float* d_identity = (float*)(d_partialCov + (size_t)T * G);
+  int32_t* d_coverage = (int32_t*)(d_identity + G);
+  idc_sum_kernel<<<dim3(nTiles, T), IDC_TILE, 0, c->stream>>>(A.reads, d_listIdx, n2, nMapped, T, A.vals, G, d_partial, d_partialCov);
+  VG_LAUNCH_CHECK(c);
+  idc_final_kernel<<<(G + 255) / 256, 256, 0, c->stream>>>(d_partial, d_partialCov, G, T, d_identity, d_coverage);
+  VG_LAUNCH_CHECK(c);
+  int flag = 0;
+  VG_CUDA(c, cudaMemcpyAsync(&flag, c->d_counter.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaMemcpyAsync(identity, d_identity, (size_t)G * 4, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaMemcpyAsync(coverage, d_coverage, (size_t)G * 4, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (flag) return vg_fail(c, VG_ERR_INVALID, "an alignment walks outside its sequence or the reference (the Java would throw)");
   return VG_OK;
 }
 

@@ -45,6 +45,9 @@ final class VirgenaGpu implements AutoCloseable {
   native void pileupAlignments(long ctx, ByteBuffer seq1, long[] seq1Off, int[] length, long[] pos, long totalPositions,
                                int[] counts);
 
+  // vg_identity_counting: ProblemIntervalBuilder.countIdentity (ProblemIntervalBuilder.java:135-160)
+  native void identityCounting(long ctx, int windowSize, int threadNum, float[] identity, int[] coverage);
+
   long handle() { return ctx; }
 
   @Override public void close() { if (ctx != 0) { destroy(ctx); ctx = 0; } }

@@ -335,6 +335,13 @@ class Context:
                                               int(total_positions), ptr(counts)))
         return counts[:int(total_positions)]
 
+    def identity_counting(self, window_size, thread_num=1):
+        """vg_identity_counting: (identity float32[G], coverage int32[G]) of the last mapping."""
+        ident = np.zeros(max(self.G, 1), np.float32)
+        cov = np.zeros(max(self.G, 1), np.int32)
+        self._chk(self.L.vg_identity_counting(self.h, int(window_size), int(thread_num), ptr(ident), ptr(cov)))
+        return ident[:self.G], cov[:self.G]
+
     def debug_seed_hits(self, read, msa=False):
         """Test hook: LongHits (genomePos, readPos, len) of one read after mergeHits + splitLongHits."""
         read = _u8(read)
@@ -553,6 +560,17 @@ class ReferenceFinder:
             for (v, j), r in zip(where, rec):
                 scores[v, j] = r[0]
         return scores
+
+
+class ProblemIntervalBuilder:
+    """The identity / coverage profile of ProblemIntervalBuilder (ProblemIntervalBuilder.java:35-160) over the last mapping
+    of `mapper`: sliding windows of `window_size` read bases, binary32 sums in the order fixed by `thread_num`."""
+
+    def __init__(self, mapper, window_size, thread_num=1):
+        self.mapper, self.windowSize, self.threadNum = mapper, window_size, thread_num
+
+    def countIdentity(self):
+        return self.mapper.ctx.identity_counting(self.windowSize, self.threadNum)
 
 
 class BamPrinter:
