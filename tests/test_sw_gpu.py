@@ -97,11 +97,12 @@ def test_short_and_long_reads(env):
     ctx, o = env
     rng = np.random.default_rng(12)
     al = np.frombuffer(b"ACGT", np.uint8)
-    for L, W in ((30, 45), (100, 150), (150, 225), (180, 200), (300, 450), (400, 520), (500, 600)):
-        s2 = [al[rng.integers(0, 4, W)] for _ in range(101)]
+    # 513 .. 1024 rows: contigs as queries (Graph.SWScore, ReferenceFinder.SWScoreCounter), 24 / 32 rows per lane
+    for L, W in ((30, 45), (100, 150), (150, 225), (180, 200), (300, 450), (400, 520), (500, 600), (700, 760), (1024, 1100), (900, 400)):
+        s2 = [al[rng.integers(0, 4, W)] for _ in range(101 if L <= 512 else 41)]
         s1 = []
         for w in s2:
-            r = w[5:5 + L].copy()
+            r = w[5:5 + L].copy() if L + 5 <= W else np.concatenate([al[rng.integers(0, 4, (L - W) // 2)], w, al[rng.integers(0, 4, L - W - (L - W) // 2)]])
             mut = rng.random(len(r)) < 0.08
             r[mut] = al[rng.integers(0, 4, int(mut.sum()))]
             s1.append(r.tobytes())

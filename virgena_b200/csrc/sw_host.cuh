@@ -6,7 +6,7 @@
 #include "sw.cuh"
 
 static inline int sw_pick_R(int mmax) {
-  static const int Rs[] = {2, 3, 4, 5, 6, 8, 10, 12, 16};
+  static const int Rs[] = {2, 3, 4, 5, 6, 8, 10, 12, 16, 24, 32};
   for (int r : Rs)
     if (32 * r >= mmax) return r;
   return -1;
@@ -19,7 +19,7 @@ static inline int sw_validate(vg_ctx* c, int mmax, int nmax) {
                    p.mismatch, p.gop, p.gep);
   if (p.match - p.mismatch > 250 || p.gep > 8000 || p.gop > 8000)
     return vg_fail(c, VG_ERR_INVALID, "aligner parameters out of the int16 kernel's range");
-  if (sw_pick_R(mmax) < 0) return vg_fail(c, VG_ERR_INVALID, "read length %d exceeds the supported 512", mmax);
+  if (sw_pick_R(mmax) < 0) return vg_fail(c, VG_ERR_INVALID, "sequence length %d exceeds the supported 1024", mmax);
   if ((int64_t)p.match * std::min(mmax, nmax) + p.match + 1 > 32000)
     return vg_fail(c, VG_ERR_INVALID, "alignment scores would exceed int16 (%d x %d)", mmax, nmax);
   return VG_OK;
@@ -121,6 +121,8 @@ static int sw_run(vg_ctx* c, const SwTask* d_tasks, int64_t ntasks, const uint8_
     SW_CASE(10)
     SW_CASE(12)
     SW_CASE(16)
+    SW_CASE(24)
+    SW_CASE(32)
   }
 #undef SW_CASE
   return vg_fail(c, VG_ERR_INVALID, "no kernel for read length %d", mmax);
