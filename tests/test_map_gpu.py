@@ -551,6 +551,56 @@ def test_map_fuzz_pipeline(built, seed):
     mapper.ctx.close()
 
 
+@pytest.mark.parametrize("seed", _MSA_FUZZ_SEEDS)
+def test_regions_fuzz(built, seed):
+    """Differential fuzz of vg_map_to_regions (mapReadToRegion against many small references, each with its own
+    single-threaded index): random regions of 5 .. 3000 bases with N / gap bytes and repeats, K = 3 .. 7, reads shorter
+    than K, longer than their region, junk and homopolymers."""
+    import oracle
+    import virgena_b200 as vg
+    rng = np.random.default_rng(7000 + seed)
+    K = int(rng.choice([3, 4, 5, 6, 7]))
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    regions, reads, rr = [], [], []
+    for g in range(int(rng.integers(1, 14))):
+        ln = int(rng.choice([5, 40, 200, 800, 3000]))
+        reg = acgt[rng.choice(4, ln, p=[0.4, 0.2, 0.2, 0.2])].copy()
+        if ln > 60 and rng.random() < 0.5:
+            a, b, l2 = int(rng.integers(0, ln - 30)), int(rng.integers(0, ln - 30)), int(rng.integers(8, 30))
+            reg[b:b + l2] = reg[a:a + l2]
+        if ln > 20 and rng.random() < 0.3:
+            p = int(rng.integers(0, ln - 6))
+            reg[p:p + int(rng.integers(1, 6))] = ord("N") if rng.random() < 0.5 else ord("-")
+        regions.append(reg.tobytes())
+        for _ in range(int(rng.integers(1, 25))):
+            L = int(rng.integers(1, 400))
+            if L <= ln and rng.random() < 0.8:
+                p = int(rng.integers(0, ln - L + 1))
+                r = reg[p:p + L].copy()
+                mut = rng.random(L) < rng.choice([0.0, 0.05, 0.2])
+                r[mut] = acgt[rng.integers(0, 4, int(mut.sum()))]
+            elif rng.random() < 0.5:
+                r = np.concatenate([acgt[rng.integers(0, 4, 10)], reg, acgt[rng.integers(0, 4, 10)]])[:400]
+            else:
+                r = acgt[rng.integers(0, 4, L)] if rng.random() < 0.7 else np.full(L, acgt[rng.integers(0, 4)], np.uint8)
+            reads.append(r.tobytes())
+            rr.append(g)
+    ctx = vg.Context(K=K, cutoffs=np.zeros(600, np.int32))
+    goff, roff = _offs(regions), _offs(reads)
+    win, found = ctx.map_to_regions(np.frombuffer(b"".join(regions), np.uint8), goff, np.frombuffer(b"".join(reads), np.uint8), roff,
+                                    np.asarray(rr, np.int32))
+    oracles = {}
+    for i, r in enumerate(reads):
+        if rr[i] not in oracles:
+            o = oracle.Oracle(K=K, cutoffs=np.zeros(600, np.int32))
+            o.set_reference(regions[rr[i]], index_thread_num=1)
+            oracles[rr[i]] = o
+        w = oracles[rr[i]].map_read_to_region(r)
+        assert (found[i] != 0) == (w is not None), (seed, K, i, rr[i], len(r), len(regions[rr[i]]))
+        assert w is None or tuple(win[i]) == w, (seed, K, i, tuple(win[i]), w)
+    ctx.close()
+
+
 def test_seed_host_csr_index(hiv):
     """The host-built CSR index (with its duplicated boundary positions, Q1) gives the same result as
     letting the library rebuild it from the thread count."""

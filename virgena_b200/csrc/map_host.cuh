@@ -739,7 +739,7 @@ int vg_map_to_regions(vg_ctx* c, const uint8_t* region_pool, const int64_t* regi
     return vg_fail(c, VG_ERR_INVALID, "bad arguments");
   if (n_reads == 0) return VG_OK;
   const int K = c->seed.K;
-  if (K < 1 || K > 6) return vg_fail(c, VG_ERR_INVALID, "region seeding supports K = 1..6 (got %d)", K);
+  if (K < 1 || K > 7) return vg_fail(c, VG_ERR_INVALID, "region seeding supports K = 1..7 (got %d)", K);
   // layout: region bytes padded by 16, codes padded to a multiple of 128 entries
   std::vector<int64_t> refOff(n_regions + 1, 0), codeOff(n_regions + 1, 0);
   std::vector<int32_t> rlen(std::max<int64_t>(n_regions, 1), 0);

@@ -84,6 +84,13 @@ struct SeedArgs {
   int singleReads;             // 1: items are single forward reads (vg_seed_batch)
   int bestOnly;                // 1: mapReadToRegion / computeKMerCount over [0, G): first window of maximal count, no cutoff,
                                //    no splitLongHits, no pruning (see seed2.cuh)
+  // region mode (vg_map_to_regions): item w is seeded against its own small reference, tables in global memory
+  const uint8_t* regRef;
+  const uint16_t* regCode;
+  const int64_t* regRefOff;
+  const int64_t* regCodeOff;
+  const int32_t* regLen;
+  const int32_t* itemRegion;
   // scratch + outputs
   uint64_t* scratchS;          // [warpSlots][capS]
   uint16_t* scratchR;          // [warpSlots][4][capR]: hitG, hitR, hitL, P
@@ -261,6 +268,7 @@ __device__ __forceinline__ void sd_tma_stage(uint8_t* smemDst, const uint8_t* gs
 //   aux        : pending u64[SD_PENDING] | bins int[256] | bucket u16[nBuckets] | win u64[SD_WIN]
 //   rd         : u8[SD_MAXL + 16], ids u16[SD_MAXL] (MSA)
 // ------------------------------------------------------------------------------------------------
+template <bool REGIONS>
 __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
   extern __shared__ __align__(16) uint8_t sd_smem[];
   __shared__ uint64_t sd_mbar;
@@ -268,11 +276,12 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
   const int warp = threadIdx.x >> 5;
   const int warpsPerBlock = blockDim.x >> 5;
   const int warpSlot = blockIdx.x * warpsPerBlock + warp;
-  const int K = A.K, G = A.G;
+  const int K = A.K;
+  int G = A.G;
 
   const uint8_t* ref = A.ref;
   const uint16_t* poscode = A.poscode;
-  if (A.geom.refBytes > 0) {
+  if (!REGIONS && A.geom.refBytes > 0) {
     sd_tma_stage(sd_smem, A.blob, A.blobBytes, &sd_mbar);
     ref = sd_smem;
     poscode = (const uint16_t*)(sd_smem + A.blobRefBytes);
@@ -324,6 +333,12 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
       if (wi >= A.nItems) break;
     }
     if (A.itemList) wi = A.itemList[wi];
+    if (REGIONS) {
+      const int rg = A.itemRegion[wi];
+      ref = A.regRef + A.regRefOff[rg];
+      poscode = A.regCode + A.regCodeOff[rg];
+      G = A.regLen[rg];
+    }
     hitG = A.scratchR + (size_t)warpSlot * 4 * capR;  // (phase E may have redirected it to shared memory)
     // ---- which read, which orientation ---------------------------------------------------------
     int64_t off;

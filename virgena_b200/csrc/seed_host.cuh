@@ -173,13 +173,26 @@ static int seed_build_msa(vg_ctx* c, const uint8_t* keys, const int64_t* offsets
 
 // Launches seed_kernel over nItems work items. Windows land in c->d_cand ([nItems][maxWin][3]) and
 // c->d_ncand ([nItems]).
+// Region mode (vg_map_to_regions): per-item references prepared by the caller on the device.
+struct SeedRegions {
+  const uint8_t* d_ref;
+  const uint16_t* d_code;
+  const int64_t* d_refOff;
+  const int64_t* d_codeOff;
+  const int32_t* d_len;
+  const int32_t* d_itemRegion;
+  const uint64_t* d_exo;
+  int nExo;
+  int maxLen;
+};
+
 static int seed_launch_v1(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_t* d_off1, const int32_t* d_len1,
                           const int64_t* d_off2, const int32_t* d_len2, const int64_t* d_pairIdx, int64_t nItems,
                           bool singleReads, int maxReadLen, int maxWin, int32_t* dbgHits, int32_t* dbgNHits,
-                          const int32_t* d_itemList = nullptr, bool bestOnly = false) {
+                          const int32_t* d_itemList = nullptr, bool bestOnly = false, const SeedRegions* regs = nullptr) {
   const SeedConfig& sc = msa ? c->seedMsa : c->seed;
   const int K = sc.K;
-  const int range = msa ? c->msaLength : c->G;
+  const int range = regs ? regs->maxLen : msa ? c->msaLength : c->G;
   if (K < 1 || K > 7) return vg_fail(c, VG_ERR_INVALID, "K=%d outside the supported range 1..7", K);
   if (range >= 65535) return vg_fail(c, VG_ERR_INVALID, "reference longer than 65534 is not supported by the 16-bit seeding tables");
   if (maxReadLen > SD_MAXL) return vg_fail(c, VG_ERR_INVALID, "read length %d exceeds the supported %d", maxReadLen, SD_MAXL);
@@ -197,7 +210,7 @@ static int seed_launch_v1(vg_ctx* c, bool msa, const uint8_t* d_bases, const int
   A.nCutoffs = (int)sc.cutoffs.size();
   A.msa = msa ? 1 : 0;
   SeedGeom g;
-  const int nContigs = msa ? 1 : (int)c->contigEnds.size();
+  const int nContigs = (msa || regs) ? 1 : (int)c->contigEnds.size();
   g.capR = std::max(256, std::min(16384, range / K + nContigs + 16));
   g.nBuckets = (range >> 5) + 2;
   const int regAB = 2 * SD_HS * 4 + SD_MAXL * 2;  // table/hash + nxt
@@ -205,7 +218,15 @@ static int seed_launch_v1(vg_ctx* c, bool msa, const uint8_t* d_bases, const int
   g.regA = (std::max(regAB, regCG) + 15) & ~15;
   g.warpBytes = (g.regA + (SD_WIN + 32) * 8 + SD_MAXL + 16 + 15) & ~15;
   g.refBytes = 0;
-  if (!msa) {
+  if (regs) {
+    A.regRef = regs->d_ref, A.regCode = regs->d_code, A.regRefOff = regs->d_refOff, A.regCodeOff = regs->d_codeOff;
+    A.regLen = regs->d_len, A.itemRegion = regs->d_itemRegion;
+    A.exoKeys = regs->d_exo;
+    A.nExo = regs->nExo;
+    A.contigEnds = nullptr;  // one contig = the whole region: never looked up
+    A.nContigs = 1;
+    A.direct = ((1 << (2 * K)) + regs->nExo <= 2 * SD_HS && !getenv("VG_SEED_HASH")) ? 1 : 0;
+  } else if (!msa) {
     const int refPad = sdh_ref_pad(c->G), codePad = sdh_code_pad(c->G);
     A.blob = c->d_poscode.as<uint8_t>();
     A.blobRefBytes = refPad;
@@ -237,9 +258,10 @@ static int seed_launch_v1(vg_ctx* c, bool msa, const uint8_t* d_bases, const int
   if (const char* e = getenv("VG_SEED_WARPS")) warps = std::max(1, std::min(warps, atoi(e)));
   if (warps < 1) return vg_fail(c, VG_ERR_INVALID, "reference too large for the seeding kernel's shared memory");
   const size_t smem = (size_t)g.refBytes + (size_t)warps * g.warpBytes;
-  VG_CUDA(c, cudaFuncSetAttribute(seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = regs ? seed_kernel<true> : seed_kernel<false>;
+  VG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int perSm = 1;
-  VG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, seed_kernel, warps * 32, smem));
+  VG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, warps * 32, smem));
   if (perSm < 1) return vg_fail(c, VG_ERR_INVALID, "seeding kernel does not fit on the device");
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((nItems + warps - 1) / warps, (int64_t)c->smCount * perSm));
   const int warpSlots = blocks * warps;
@@ -288,7 +310,7 @@ static int seed_launch_v1(vg_ctx* c, bool msa, const uint8_t* d_bases, const int
     VG_CUDA(c, cudaMemsetAsync(A.prof, 0, 128, c->stream));
   }
   if (nItems > 0) {
-    seed_kernel<<<blocks, warps * 32, smem, c->stream>>>(A);
+    kern<<<blocks, warps * 32, smem, c->stream>>>(A);
     VG_LAUNCH_CHECK(c);
   }
   int flags[2] = {0, 0};
@@ -311,19 +333,6 @@ static int seed_launch_v1(vg_ctx* c, bool msa, const uint8_t* d_bases, const int
   }
   return VG_OK;
 }
-
-// Region mode (vg_map_to_regions): per-item references prepared by the caller on the device.
-struct SeedRegions {
-  const uint8_t* d_ref;
-  const uint16_t* d_code;
-  const int64_t* d_refOff;
-  const int64_t* d_codeOff;
-  const int32_t* d_len;
-  const int32_t* d_itemRegion;
-  const uint64_t* d_exo;
-  int nExo;
-  int maxLen;
-};
 
 // Seeding entry point. Single-reference mode with a direct-addressed k-mer table (K <= 5, few exotic k-mers) and a
 // reference that fits in shared memory runs the two-kernel fast path (seed2.cuh) in sub-chunks of items; the items
@@ -373,11 +382,9 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     winWarps = std::min(32, winMax / A.winWarpBytes);
     if (genWarps < 8 || winWarps < 8 || nContigs > 64) fast = false;
   }
-  if (!fast && regs)
-    return vg_fail(c, VG_ERR_INVALID, "region seeding needs the fast path (K <= 6, region + read length < 65535)");
   if (!fast)
     return seed_launch_v1(c, msa, d_bases, d_off1, d_len1, d_off2, d_len2, d_pairIdx, nItems, singleReads, maxReadLen, maxWin,
-                          dbgHits, dbgNHits, nullptr, bestOnly);
+                          dbgHits, dbgNHits, nullptr, bestOnly, regs);
   if (const char* e = getenv("VG_SEED_WARPS")) {
     genWarps = std::max(1, std::min(genWarps, atoi(e)));
     winWarps = std::max(1, std::min(winWarps, atoi(e)));
@@ -538,13 +545,10 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
                    (f & 8) ? " window list" : "", (f & 16) ? " read too long" : "");
   }
   c->seedFallbacks = flags[3];
-  if (flags[3] > 0 && regs)
-    return vg_fail(c, VG_ERR_OVERFLOW, "%d reads need the general seeding kernel (low-complexity reads), which has no region mode",
-                   flags[3]);
   if (flags[3] > 0) {
     VG_CUDA(c, cudaEventRecord(c->seedEv[0], c->stream));
     VG_TRY(seed_launch_v1(c, msa, d_bases, d_off1, d_len1, d_off2, d_len2, d_pairIdx, flags[3], singleReads, maxReadLen, maxWin,
-                          dbgHits, dbgNHits, c->d_seedFb.as<int32_t>(), bestOnly));
+                          dbgHits, dbgNHits, c->d_seedFb.as<int32_t>(), bestOnly, regs));
     VG_CUDA(c, cudaEventRecord(c->seedEv[1], c->stream));
     VG_CUDA(c, cudaEventSynchronize(c->seedEv[1]));
     float f = 0;
