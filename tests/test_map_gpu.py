@@ -460,6 +460,20 @@ def test_seed_fuzz_msa(built, seed):
         h, oh = ctx.debug_seed_hits(r, msa=True), o.get_hits(r, msa=True)
         assert h.shape == oh.shape and (h == oh).all(), (seed, W, R, K, len(r))
     ctx.close()
+    # MapperMSA.mapAllReads over pairs made of consecutive reads (some mates absent)
+    from virgena_b200 import synth
+    r1 = [reads[i] if i % 11 else b"*" for i in range(0, len(reads) - 1, 2)]
+    r2 = [synth.revcomp(np.frombuffer(reads[i], np.uint8)).tobytes() if i % 3 else reads[i] for i in range(1, len(reads), 2)]
+    bases, off1, len1, off2, len2 = synth.pack_ragged(r1, r2)
+    orec, _, ostats = o.map_pairs(bases, off1, len1, off2, len2, msa=True, n_threads=4)
+    mapper = vg.MapperMSA(K=K, indel_tolerance=high, cutoffs=cut, insert_len=1000)
+    md = mapper.mapAllReads(vg.PairedReads(bases, off1, len1, off2, len2), vg.ReferenceAlignment(rows, K=K))
+    rec = md.records
+    assert (rec["cls"] == orec["cls"]).all(), (seed, W, R, K)
+    for f in ["present", "start", "end", "count", "reverse"]:
+        assert (rec["m"][f] == orec["m"][f]).all(), (seed, W, R, K, f)
+    assert (md.stats == ostats).all(), (md.stats, ostats)
+    mapper.ctx.close()
 
 
 _PIPE_FUZZ_SEEDS = list(range(8))
