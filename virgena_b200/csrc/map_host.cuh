@@ -740,7 +740,7 @@ int vg_map_to_regions(vg_ctx* c, const uint8_t* region_pool, const int64_t* regi
   if (n_reads == 0) return VG_OK;
   const int K = c->seed.K;
   if (K < 1 || K > 7) return vg_fail(c, VG_ERR_INVALID, "region seeding supports K = 1..7 (got %d)", K);
-  // layout: region bytes padded by 16, codes padded to a multiple of 128 entries
+  // layout: region bytes padded by 16, codes padded to a multiple of SD2_SCAN entries
   std::vector<int64_t> refOff(n_regions + 1, 0), codeOff(n_regions + 1, 0);
   std::vector<int32_t> rlen(std::max<int64_t>(n_regions, 1), 0);
   int maxLen = 0;
@@ -750,7 +750,7 @@ int vg_map_to_regions(vg_ctx* c, const uint8_t* region_pool, const int64_t* regi
     rlen[r] = (int32_t)l;
     maxLen = std::max(maxLen, (int)l);
     refOff[r + 1] = refOff[r] + ((l + 15) & ~(int64_t)15) + 16;
-    codeOff[r + 1] = codeOff[r] + std::max<int64_t>(128, (l + 127) & ~(int64_t)127);
+    codeOff[r + 1] = codeOff[r] + std::max<int64_t>(SD2_SCAN, (l + SD2_SCAN - 1) & ~(int64_t)(SD2_SCAN - 1));
   }
   for (int64_t i = 0; i < region_off[n_regions]; i++)
     if (region_pool[i] >= 127) return vg_fail(c, VG_ERR_ALPHABET, "region byte >= 127");
@@ -778,7 +778,7 @@ int vg_map_to_regions(vg_ctx* c, const uint8_t* region_pool, const int64_t* regi
   std::sort(exo.begin(), exo.end());
   exo.erase(std::unique(exo.begin(), exo.end()), exo.end());
   std::vector<uint8_t> hRef((size_t)refOff[n_regions] + 16, 0);
-  std::vector<uint16_t> hCode((size_t)codeOff[n_regions] + 128, (uint16_t)SD_NONE16);
+  std::vector<uint16_t> hCode((size_t)codeOff[n_regions] + SD2_SCAN, (uint16_t)SD_NONE16);
   for (int64_t r = 0; r < n_regions; r++) {
     const uint8_t* p = region_pool + region_off[r];
     memcpy(hRef.data() + refOff[r], p, rlen[r]);

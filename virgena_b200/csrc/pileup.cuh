@@ -111,7 +111,6 @@ __global__ void pu_scatter_kernel(const PuRead* __restrict__ reads, const int32_
                                   int nTiles, unsigned long long* __restrict__ cursor, PuRead* __restrict__ sorted) {
   extern __shared__ __align__(16) int pu_sm[];
   int* hist = pu_sm;                // per-block count per tile
-  int* base = pu_sm + nTiles;       // reserved global base per tile (low 32 bits of a 64-bit offset pair)
   unsigned long long* base64 = (unsigned long long*)(pu_sm + 2 * nTiles + 2);  // 8-byte aligned whatever nTiles is
   for (int t = threadIdx.x; t < nTiles; t += blockDim.x) hist[t] = 0;
   __syncthreads();
@@ -126,7 +125,6 @@ __global__ void pu_scatter_kernel(const PuRead* __restrict__ reads, const int32_
     if (hist[t]) base64[t] = atomicAdd(&cursor[t], (unsigned long long)hist[t]);
   __syncthreads();
   if (tile >= 0) sorted[base64[tile] + rank] = reads[q];
-  (void)base;
 }
 
 // The count kernel: grid (nTiles, nSlices), PU_TILE threads. Atomic-free.

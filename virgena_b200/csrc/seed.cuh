@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(512) seed_kernel(SeedArgs A) {
   uint32_t* hval = hkey + SD_HS;
   uint16_t* nxt = (uint16_t*)(hval + SD_HS);
   uint8_t* aux = wbase;  // aliases regA after phase B
-  uint64_t* pending = (uint64_t*)aux;                                  // SD_PENDING x 8
+  // (the first SD_PENDING x 8 bytes of aux were the serial sweep's re-insertion queue; it now lives in ckey)
   int* bins = (int*)(aux + SD_PENDING * 8);                            // 256 x 4
   uint16_t* bucket = (uint16_t*)(aux + SD_PENDING * 8 + 1024);         // nBuckets x 2
   uint64_t* pendL = (uint64_t*)(aux + SD_PENDING * 8 + 1024 + ((A.geom.nBuckets * 2 + 15) & ~15));  // 32 x SD_LPEND x 8

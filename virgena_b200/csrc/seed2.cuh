@@ -18,6 +18,11 @@
 
 #include "seed.cuh"
 
+#ifndef SD2_PN
+#define SD2_PN 8               // genome positions per lane and trip of the scan (4 or 8)
+#endif
+#define SD2_SCAN (32 * SD2_PN)   // positions per trip; the position-code tables are padded to a multiple of it
+
 struct Seed2Args {
   // reference
   const uint8_t* blob;         // [ref padded to 16][poscode u16 padded to a multiple of 128 entries]
@@ -195,26 +200,38 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
     for (int gb = 0; gb <= G - K && !bad;) {
       int nq = 0;
       bool qfull = false;
-      // B1: 128 genome positions per trip, 4 consecutive positions per lane; every raw hit (g, i) is queued in
+      // B1: SD2_SCAN genome positions per trip, SD2_PN consecutive positions per lane; every raw hit (g, i) is queued in
       // (g, i) order. Offsets come from ballots over the bits of the per-lane hit count.
 #pragma unroll 1
-      for (; gb <= G - K && !qfull; gb += 128) {
-        const int g0 = gb + 4 * lane;
-        const uint2 pc = *(const uint2*)(poscode + g0);  // beyond G-K the table holds SD_NONE16
-        uint32_t hv[4];
-        hv[0] = tab[min((int)(pc.x & 0x7FFFu), emptyId)];
-        hv[1] = tab[min((int)((pc.x >> 16) & 0x7FFFu), emptyId)];
-        hv[2] = tab[min((int)(pc.y & 0x7FFFu), emptyId)];
-        hv[3] = tab[min((int)((pc.y >> 16) & 0x7FFFu), emptyId)];
-        const int c0 = hv[0] >> 9, c1 = hv[1] >> 9, c2 = hv[2] >> 9, c3 = hv[3] >> 9;
-        const int tot = c0 + c1 + c2 + c3;
+      for (; gb <= G - K && !qfull; gb += SD2_SCAN) {
+        const int g0 = gb + SD2_PN * lane;
+        uint32_t hv[SD2_PN];
+#if SD2_PN == 8
+        const uint4 pc = *(const uint4*)(poscode + g0);  // beyond G-K the table holds SD_NONE16
+        const uint32_t pw[4] = {pc.x, pc.y, pc.z, pc.w};
+#else
+        const uint2 pc = *(const uint2*)(poscode + g0);
+        const uint32_t pw[2] = {pc.x, pc.y};
+#endif
+        int tot = 0;
+#pragma unroll
+        for (int u = 0; u < SD2_PN; u++) {
+          const uint32_t code = (u & 1) ? (pw[u >> 1] >> 16) : pw[u >> 1];
+          hv[u] = tab[min((int)(code & 0x7FFFu), emptyId)];
+          tot += hv[u] >> 9;
+        }
         const unsigned b0 = __ballot_sync(VG_FULL, tot & 1), b1 = __ballot_sync(VG_FULL, tot & 2),
-                       b2 = __ballot_sync(VG_FULL, tot & 4), bh = __ballot_sync(VG_FULL, tot >> 3);
+                       b2 = __ballot_sync(VG_FULL, tot & 4);
+#if SD2_PN == 8
+        const unsigned b3 = __ballot_sync(VG_FULL, tot & 8), bh = __ballot_sync(VG_FULL, tot >> 4);
+#else
+        const unsigned b3 = 0, bh = __ballot_sync(VG_FULL, tot >> 3);
+#endif
         int excl, total;
         if (bh == 0) {
-          total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+          total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
           if (total == 0) continue;
-          excl = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+          excl = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt) + 8 * __popc(b3 & lt);
         } else {
           const int incl = sd_warp_incl_scan(tot, lane);
           total = __shfl_sync(VG_FULL, incl, 31);
@@ -226,13 +243,13 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
         }
         if (nq + total > QCAP) {  // does not fit any more: flush first, then redo this block
           qfull = true;
-          gb -= 128;
+          gb -= SD2_SCAN;
           continue;
         }
         int o = nq + excl;
 #pragma unroll
-        for (int u = 0; u < 4; u++) {  // chains of 1 or 2 read positions are the rule: branch-free, misses go to a
-          const int cu = hv[u] >> 9;   // spare slot behind the queue
+        for (int u = 0; u < SD2_PN; u++) {  // chains of 1 or 2 read positions are the rule: branch-free, misses go to a
+          const int cu = hv[u] >> 9;        // spare slot behind the queue
           const uint32_t i0 = hv[u] & 511u;
           const uint32_t gk = (uint32_t)(g0 + u) << 16;
           queue[cu ? o : QCAP] = gk | i0;

@@ -9,9 +9,9 @@
 struct SeedHostState {  // lives in vg_ctx via the DevBufs; plain helpers here
 };
 
-// blob = [ref padded to 16][poscode u16, padded with SD_NONE16 to a multiple of 128 entries]
+// blob = [ref padded to 16][poscode u16, padded with SD_NONE16 to a multiple of 256 entries (the scan's stride, SD2_SCAN)]
 static inline int sdh_ref_pad(int G) { return (G + 15) & ~15; }
-static inline int sdh_code_pad(int G) { return std::max(128, (G + 127) & ~127) * 2; }
+static inline int sdh_code_pad(int G) { return std::max(256, (G + 255) & ~255) * 2; }
 
 static inline int sdh_code2(uint8_t b) { return b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : b == 'T' ? 3 : -1; }
 
@@ -359,10 +359,12 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
       A.emptyId = (1 << (2 * K)) + nExoRef;
       A.tabBytes = ((A.emptyId + 1) * 2 + 15) & ~15;
       A.nxtBytes = (maxReadLen * 2 + 15) & ~15;
-      A.qcap = 512;
-      A.genWarpBytes = A.tabBytes + A.nxtBytes + (A.qcap + 4) * 4 + A.rdBytes;
       A.blobRefBytes = regs ? 0 : sdh_ref_pad(G);
       A.blobBytes = regs ? 0 : A.blobRefBytes + sdh_code_pad(G);
+      // raw-hit queue: 512 entries, up to 1024 when 32 warps per SM still fit (a trip of the scan must fit in it)
+      const int perWarp = ((smemMax - 64 - A.blobBytes) / 32) & ~15;
+      A.qcap = std::max(512, std::min(1024, ((perWarp - A.tabBytes - A.nxtBytes - A.rdBytes) / 4 - 4) & ~63));
+      A.genWarpBytes = A.tabBytes + A.nxtBytes + (A.qcap + 4) * 4 + A.rdBytes;
       genWarps = std::min(32, (smemMax - 64 - A.blobBytes) / A.genWarpBytes);
       if (A.emptyId >= SD_NONE16 || A.emptyId > 8191) fast = false;
     } else {
