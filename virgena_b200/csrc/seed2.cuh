@@ -270,33 +270,43 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
       // B2: one lane per raw hit (two per trip): chain-start test, extension, ballot-compacted ordered writes
 #pragma unroll 1
       for (int q0 = 0; q0 < nq && !bad; q0 += 64) {
-        bool em[2] = {false, false};
-        int gg[2], ii[2], ll[2] = {0, 0};
-        uint32_t e[2];
-        uint8_t ca[2], cb[2];
+        // straight-line for both hits of the lane: chain-start test, first 4 bytes of the extension (they decide almost
+        // every chain), Q1 flag; only chains that go on take the loop below
+        bool em[2], more[2];
+        int gg[2], ii[2], ll[2], mx[2];
 #pragma unroll
         for (int u = 0; u < 2; u++) {
           const int q = q0 + 32 * u + lane;
-          e[u] = (q < nq) ? queue[q] : 0xFFFFFFFFu;
+          const bool ok = q < nq;
+          const uint32_t e = ok ? queue[q] : 0u;
+          const int g = (int)(e >> 16), i = (int)(e & 0xFFFFu);
+          gg[u] = g, ii[u] = i;
+          const uint8_t ca = rd[max(i - 1, 0)], cb = ref[max(g - 1, 0)];
+          const bool start = (i == 0) | (g == 0) | (ca != cb);
+          const int maxLen = min(L - i - K, G - g - K);
+          const uint32_t x0 = sd_load4(rd, i + K) ^ sd_load4(ref, g + K);
+          const int len = x0 ? (__ffs(x0) - 1) >> 3 : 4;
+          // Q1: a chain passing through a twice-indexed position adds a zero-length hit
+          em[u] = ok & (start | ((poscode[g] & 0x8000u) != 0));
+          ll[u] = start ? min(len, maxLen) : 0;
+          mx[u] = maxLen;
+          more[u] = ok & start & (x0 == 0) & (maxLen > 4);
         }
+        if (more[0] | more[1]) {
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
-          gg[u] = (int)(e[u] >> 16);
-          ii[u] = (int)(e[u] & 0xFFFFu);
-          const bool ok = e[u] != 0xFFFFFFFFu;
-          ca[u] = (ok && ii[u] > 0) ? rd[ii[u] - 1] : 0;
-          cb[u] = (ok && gg[u] > 0) ? ref[gg[u] - 1] : 1;
-        }
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-          if (e[u] == 0xFFFFFFFFu) continue;
-          const int g = gg[u], i = ii[u];
-          const bool start = (i == 0) || (g == 0) || (ca[u] != cb[u]);
-          if (start) {
-            em[u] = true;
-            ll[u] = sd_extend(rd, ref, i, g, K, L, G);
-          } else if (poscode[g] & 0x8000u) {
-            em[u] = true;  // Q1: a chain passing through a twice-indexed position adds a zero-length hit
+          for (int u = 0; u < 2; u++) {
+            if (!more[u]) continue;
+            int len = 4;
+#pragma unroll 1
+            while (len < mx[u]) {
+              const uint32_t x = sd_load4(rd, ii[u] + K + len) ^ sd_load4(ref, gg[u] + K + len);
+              if (x) {
+                len += (__ffs(x) - 1) >> 3;
+                break;
+              }
+              len += 4;
+            }
+            ll[u] = min(len, mx[u]);
           }
         }
         const unsigned m0 = __ballot_sync(VG_FULL, em[0]);
