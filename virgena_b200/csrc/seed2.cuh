@@ -73,6 +73,7 @@ struct Seed2Args {
   const int32_t* msaOff;
   const int32_t* msaCols;
   uint32_t* rawBuf;            // [warpSlots][4][capRaw]
+  int msaPacked;               // MSA stream kernel: LongHits packed into one word for the second sort
   int capRaw;
   int msaWarpBytes, idsBytes;
   // region mode (vg_map_to_regions): every work item has its own small reference (cluster centroid / reference
@@ -356,7 +357,8 @@ __device__ __forceinline__ void sd2_scan_bins(int* bins, int lane) {
 }
 
 __device__ __noinline__ int sd2_radix_sort_counted(uint32_t* k0, uint32_t* k1, uint32_t* v0, uint32_t* v1, int n, int* binsAll,
-                                                   int passes, int lane) {
+                                                   int passes, int lane, int bits = 8) {
+  const uint32_t dmask = (1u << bits) - 1u;  // digit width (the bins of a pass stay 256 apart)
 #pragma unroll 1
   for (int pass = 0; pass < passes; pass++) {
     const uint32_t* ks = (pass & 1) ? k1 : k0;
@@ -364,7 +366,7 @@ __device__ __noinline__ int sd2_radix_sort_counted(uint32_t* k0, uint32_t* k1, u
     uint32_t* kd = (pass & 1) ? k0 : k1;
     uint32_t* vd = (pass & 1) ? v0 : v1;
     int* bins = binsAll + 256 * pass;
-    const int shift = pass * 8;
+    const int shift = pass * bits;
     __syncwarp();
     sd2_scan_bins(bins, lane);
     __syncwarp();
@@ -390,7 +392,7 @@ __device__ __noinline__ int sd2_radix_sort_counted(uint32_t* k0, uint32_t* k1, u
         if (e0 + 32 * u >= n) break;
         const int e = e0 + 32 * u + lane;
         const bool ok = e < n;
-        const uint32_t d = ok ? ((kk[u] >> shift) & 255u) : (256u + lane);
+        const uint32_t d = ok ? ((kk[u] >> shift) & dmask) : (256u + lane);
         const unsigned grp = __match_any_sync(VG_FULL, d);
         const int rank = __popc(grp & ((1u << lane) - 1));
         const int leader = __ffs(grp) - 1;
@@ -530,13 +532,22 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
       //    in one pass: a start is closed by the next start (len = distance - 1); the last start of a chunk of 32 stays
       //    open (warp-uniform) until a later chunk, or the end of the list, closes it. (The digits of the second sort's
       //    keys are counted on the way.)
+      // packed (alignment shorter than 16384 columns, reads up to 512): column | readPos << 14 | len << 23 in one word,
+      // sorted by two 7-bit digits of the column, so that only K0 / K1 are touched (they stay in L2)
+      const bool pk = A.msaPacked != 0;
       auto emit = [&](int idx, uint32_t k, int len) {
         const int i = (int)(k >> 16);
         const int c = (int)dBias - (int)(k & 0xFFFFu) + i;
-        V0[idx] = ((uint32_t)i << 16) | (uint32_t)c;
-        V1[idx] = (uint32_t)len;
-        atomicAdd(&binsLo[c & 255], 1);
-        atomicAdd(&binsHi[(c >> 8) & 255], 1);
+        if (pk) {
+          K1[idx] = (uint32_t)c | ((uint32_t)i << 14) | ((uint32_t)len << 23);
+          atomicAdd(&binsLo[c & 127], 1);
+          atomicAdd(&binsHi[(c >> 7) & 127], 1);
+        } else {
+          V0[idx] = ((uint32_t)i << 16) | (uint32_t)c;
+          V1[idx] = (uint32_t)len;
+          atomicAdd(&binsLo[c & 255], 1);
+          atomicAdd(&binsHi[(c >> 8) & 255], 1);
+        }
       };
       bool haveOpen = false;
       uint32_t openKey = 0;
@@ -581,13 +592,22 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
       } else {
         SD2_PH(11)
         // 4. stable sort by column; K0 / K1 are free again and serve as the other halves
-        sd2_radix_sort_counted(V0, K0, V1, K1, nSt, binsLo, 2, lane);
-        const uint32_t* k2 = V0;
-        const uint32_t* v2 = V1;
+        if (pk) {
+          sd2_radix_sort_counted(K1, K0, nullptr, nullptr, nSt, binsLo, 2, lane, 7);
 #pragma unroll 4
-        for (int e = lane; e < nSt; e += 32) {
-          const uint32_t k = k2[e];
-          S[e] = ((uint64_t)(k & 0xFFFFu) << 32) | ((uint64_t)(k >> 16) << 16) | (uint64_t)v2[e];
+          for (int e = lane; e < nSt; e += 32) {
+            const uint32_t k = K1[e];
+            S[e] = ((uint64_t)(k & 0x3FFFu) << 32) | ((uint64_t)((k >> 14) & 0x1FFu) << 16) | (uint64_t)(k >> 23);
+          }
+        } else {
+          sd2_radix_sort_counted(V0, K0, V1, K1, nSt, binsLo, 2, lane);
+          const uint32_t* k2 = V0;
+          const uint32_t* v2 = V1;
+#pragma unroll 4
+          for (int e = lane; e < nSt; e += 32) {
+            const uint32_t k = k2[e];
+            S[e] = ((uint64_t)(k & 0xFFFFu) << 32) | ((uint64_t)(k >> 16) << 16) | (uint64_t)v2[e];
+          }
         }
       }
     }

@@ -371,6 +371,7 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
       A.idsBytes = (maxReadLen * 2 + 15) & ~15;
       A.msaWarpBytes = A.idsBytes + 2048 + A.rdBytes;
       genWarps = std::min(32, smemMax / A.msaWarpBytes);
+      if (const char* e = getenv("VG_SEED_MSAWARPS")) genWarps = std::max(8, std::min(std::min(32, smemMax / A.msaWarpBytes), atoi(e)));
     }
     const int nContigs = (msa || regs) ? 1 : (int)c->contigEnds.size();
     A.capR = std::max(256, std::min(16384, G / K + nContigs + 16));
@@ -473,6 +474,7 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     if (const char* e = getenv("VG_SEED_CAPRAW")) A.capRaw = std::max(256, atoi(e)) & ~255;
     VG_CUDA(c, c->d_scratch.reserve((size_t)genSlots * 4 * A.capRaw * 4));
     A.rawBuf = c->d_scratch.as<uint32_t>();
+    A.msaPacked = (G < 16384 && maxReadLen <= 512 && !getenv("VG_SEED_WIDE")) ? 1 : 0;
   }
   A.S = c->d_seedS.as<uint64_t>();
   A.nS = c->d_seedNS.as<int32_t>();
