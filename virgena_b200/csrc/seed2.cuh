@@ -495,21 +495,31 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
       const int excl = incl - cnt;
       const int src0 = lo - excl;  // msaCols index of round entry t when this lane owns it: src0 + t
 #pragma unroll 1
-      for (int t0 = 0; t0 < total; t0 += 32) {
-        const int t = t0 + lane;
-        int owner = 0;
+      for (int t0 = 0; t0 < total; t0 += 64) {  // two trips at a time: both column loads are in flight together
+        int own[2], col[2];
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-          const int ex = __shfl_sync(VG_FULL, excl, owner + d);  // owner + d <= 31
-          if (ex <= t) owner += d;
+        for (int u = 0; u < 2; u++) {
+          const int t = t0 + 32 * u + lane;
+          int owner = 0;
+#pragma unroll
+          for (int d = 16; d >= 1; d >>= 1) {
+            const int ex = __shfl_sync(VG_FULL, excl, owner + d);  // owner + d <= 31
+            if (ex <= t) owner += d;
+          }
+          const int oSrc = __shfl_sync(VG_FULL, src0, owner);
+          own[u] = owner;
+          col[u] = (t < total) ? A.msaCols[oSrc + t] : 0;
         }
-        const int oSrc = __shfl_sync(VG_FULL, src0, owner);
-        if (t < total) {
-          const uint32_t io = (uint32_t)(base + owner);
-          const uint32_t key = (io << 16) + dBias + io - (uint32_t)A.msaCols[oSrc + t];  // low half: dBias - (c - i)
-          K0[nRaw + t] = key;
-          atomicAdd(&binsLo[key & 255u], 1);
-          atomicAdd(&binsHi[(key >> 8) & 255u], 1);
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const int t = t0 + 32 * u + lane;
+          if (t < total) {
+            const uint32_t io = (uint32_t)(base + own[u]);
+            const uint32_t key = (io << 16) + dBias + io - (uint32_t)col[u];  // low half: dBias - (c - i)
+            K0[nRaw + t] = key;
+            atomicAdd(&binsLo[key & 255u], 1);
+            atomicAdd(&binsHi[(key >> 8) & 255u], 1);
+          }
         }
       }
       nRaw += total;
