@@ -138,6 +138,54 @@ def test_other_scoring(env, built):
         ctx.close()
 
 
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_sw_fuzz(built, seed):
+    """Differential fuzz of the aligner: random penalties (both checkpoint formats, gop < gep included), lengths 1 .. 1024
+    on either side, related / unrelated / low-complexity sequences with N, '-', lower case and IUPAC bytes."""
+    import oracle
+    import virgena_b200 as vg
+    rng = np.random.default_rng(3000 + seed)
+    ma, mi = int(rng.integers(1, 6)), -int(rng.integers(1, 7))
+    go, ge = int(rng.integers(1, 14)), int(rng.integers(0, 5))
+    if seed % 4 == 3:
+        go = ge + int(rng.integers(16, 40))  # wide checkpoints
+    al = np.frombuffer(b"ACGT", np.uint8)
+    odd = np.frombuffer(b"N-acgtRYKM", np.uint8)
+    s1, s2 = [], []
+    for _ in range(160):
+        n = int(rng.choice([1, 5, 40, 150, 300, 700, 1024])) if rng.random() < 0.3 else int(rng.integers(1, 420))
+        m = int(rng.choice([1, 7, 64, 250, 512, 800, 1024])) if rng.random() < 0.3 else int(rng.integers(1, 300))
+        if ma * min(m, n) + ma + 1 > 32000:
+            m = min(m, 300)
+        w = al[rng.integers(0, 4, n)].copy()
+        kind = rng.random()
+        if kind < 0.6:      # the query is a mutated piece of the window (tiled when it is longer)
+            r = np.resize(w[int(rng.integers(0, max(1, n - 1))):], m).copy()
+            mut = rng.random(m) < rng.choice([0.0, 0.05, 0.25])
+            r[mut] = al[rng.integers(0, 4, int(mut.sum()))]
+            for _ in range(int(rng.integers(0, 3))):
+                if len(r) > 12:
+                    q = int(rng.integers(3, len(r) - 6))
+                    r = np.delete(r, slice(q, q + int(rng.integers(1, 5)))) if rng.random() < 0.5 else \
+                        np.insert(r, q, al[rng.integers(0, 4, int(rng.integers(1, 5)))])
+            r = r[:1024]
+        elif kind < 0.8:
+            r = al[rng.integers(0, 4, m)]
+        else:               # low complexity: many equal-score cells (tie-breaking)
+            r = np.resize(al[rng.integers(0, 4, int(rng.integers(1, 4)))], m)
+            w = np.resize(r[:int(rng.integers(1, 4))], n)
+        r, w = r.copy(), w.copy()
+        if rng.random() < 0.15:
+            r[rng.integers(0, len(r), 2)] = odd[rng.integers(0, len(odd), 2)]
+            w[rng.integers(0, len(w), 2)] = odd[rng.integers(0, len(odd), 2)]
+        s1.append(r.tobytes())
+        s2.append(w.tobytes())
+    ctx = vg.Context(match=ma, mismatch=mi, gop=go, gep=ge)
+    o = oracle.Oracle(match=ma, mismatch=mi, gop=go, gep=ge)
+    _check(ctx, o, s1, s2)
+    ctx.close()
+
+
 def test_sw_throughput_and_dpx(env):
     ctx, o = env
     rng = np.random.default_rng(14)
