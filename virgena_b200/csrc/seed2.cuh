@@ -653,6 +653,7 @@ struct SdWin<false> {
   static __device__ __forceinline__ int g(E v) { return (int)(v >> 32); }
   static __device__ __forceinline__ int r(E v) { return (int)((v >> 16) & 0xFFFFu); }
   static __device__ __forceinline__ int l(E v) { return (int)(v & 0xFFFFu); }
+  static __device__ __forceinline__ E withLen(E v, int l) { return (v & ~(uint64_t)0xFFFFu) | (uint64_t)l; }
   static __device__ __forceinline__ uint64_t key(E v) { return v >> 16; }  // (genomePos, readPos): the TreeSet order
   static __device__ __forceinline__ uint64_t mkkey(int g, int r) { return ((uint64_t)g << 16) | (uint64_t)r; }
 };
@@ -670,6 +671,7 @@ struct SdWin<true> {
   static __device__ __forceinline__ int g(E v) { return (int)(v >> 18); }
   static __device__ __forceinline__ int r(E v) { return (int)((v >> 9) & 0x1FFu); }
   static __device__ __forceinline__ int l(E v) { return (int)(v & 0x1FFu); }
+  static __device__ __forceinline__ E withLen(E v, int l) { return (v & ~0x1FFu) | (uint32_t)l; }
   static __device__ __forceinline__ uint32_t key(E v) { return v >> 9; }
   static __device__ __forceinline__ uint32_t mkkey(int g, int r) { return ((uint32_t)g << 9) | (uint32_t)r; }
 };
@@ -824,34 +826,39 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
         //   overlap, prev at least as long  -> curr clipped on the left and re-inserted if it keeps >= K (:435-441)
         int si = s0, w = s0;
         bool have = false;
-        int pg = 0, pr = 0, pl = 0;
-#pragma unroll 1
-        for (;;) {
+        typename W::E pv = 0;  // prev, as it sits in the window
+        // one polled element per lane; branch-free except for the (rare) re-insertion. A lane only touches its own
+        // range of the window, so the trips need no barrier.
+        auto step = [&]() {
           const bool act = si < s1;
-          if (!__any_sync(VG_FULL, act)) break;
-          if (act) {
-            const typename W::E v = win[sd2_wi<P32>(si)];  // TreeSet.pollFirst
-            si++;
-            const int cg = W::g(v), cr = W::r(v), cl = W::l(v);
-            const int pe = pg + pl + K;
-            const bool ov = have && pe - 1 >= cg;
-            const bool keepPrev = ov && pl >= cl;
-            const int tl = cg - pg - K;
-            if (have && !keepPrev && (!ov || tl >= 0)) {
-              win[sd2_wi<P32>(w)] = W::pack(pg, pr, ov ? tl : pl);
-              w++;
-            }
-            have = true;
-            if (!keepPrev) {
-              pg = cg, pr = cr, pl = cl;
-            } else if (cl - (pe - cg) >= 0) {
-              si = sd2_reinsert<P32>(win, si, s1, pe, cr + (pe - cg), cl - (pe - cg));
-            }
+          const typename W::E v = win[sd2_wi<P32>(act ? si : s0)];  // TreeSet.pollFirst
+          const int cg = W::g(v), cl = W::l(v);
+          const int pg = W::g(pv), pl = W::l(pv);
+          const int pe = pg + pl + K;
+          const bool ov = have & (pe > cg);  // prev.genomePos + prev.len + K - 1 >= curr.genomePos
+          const bool keepPrev = ov & (pl >= cl);
+          const int tl = cg - pg - K;
+          if (act & have & !keepPrev & (!ov | (tl >= 0))) {
+            win[sd2_wi<P32>(w)] = ov ? W::withLen(pv, tl) : pv;
+            w++;
           }
-          __syncwarp();
+          const int rest = cl - (pe - cg);
+          if (act) {
+            si++;
+            have = true;
+            if (!keepPrev) pv = v;
+            else if (rest >= 0) si = sd2_reinsert<P32>(win, si, s1, pe, W::r(v) + (pe - cg), rest);
+          }
+        };
+        {
+          const int n0 = __reduce_max_sync(VG_FULL, s1 - s0);  // without re-insertions the longest range decides
+#pragma unroll 1
+          for (int t = 0; t < n0; t++) step();
+#pragma unroll 1
+          while (__any_sync(VG_FULL, si < s1)) step();
         }
         if (have) {
-          win[sd2_wi<P32>(w)] = W::pack(pg, pr, pl);
+          win[sd2_wi<P32>(w)] = pv;
           w++;
         }
         __syncwarp();
