@@ -246,10 +246,14 @@ def main():
         host_batches.append(hb)
         del t
     torch.cuda.synchronize()
-    off1 = np.arange(n, dtype=np.int64) * L
-    off2 = n * L + off1
-    len1 = np.full(n, L, np.int32)
-    len2 = np.full(n, L, np.int32)
+    def pinned(a):  # host arrays of the e2e arm live in pinned memory (no staging copies inside cudaMemcpyAsync)
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True)
+        t.copy_(torch.from_numpy(a))
+        return t.numpy()
+    off1 = pinned(np.arange(n, dtype=np.int64) * L)
+    off2 = pinned(n * L + off1)
+    len1 = pinned(np.full(n, L, np.int32))
+    len2 = pinned(np.full(n, L, np.int32))
     n_bases = 2 * n * L
 
     counts_tensor = [None]
@@ -286,7 +290,7 @@ def main():
         c2 = vg.Context(K=5, low_coef=0.0, high_coef=1.25, cutoffs=cut, insert_len=1000, device=local)
         c2.set_reference(genome)
         e2e_ctx.append(c2)
-    rec_hosts = [np.zeros(n, vg.PAIR_DTYPE) for _ in range(n_e2e)]
+    rec_hosts = [torch.zeros(n * vg.PAIR_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True).numpy().view(vg.PAIR_DTYPE) for _ in range(n_e2e)]
     pool_hosts = [torch.empty(n * 2 * (L + L * 3 // 2 + 8), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(n_e2e)]
     d2h = [0]
     turn = [0]
