@@ -321,3 +321,32 @@ def cutoffs(seq, K=5, coef=1.25, order=4, read_num=10000, min_len=250, max_len=2
         lib().vo_cutoffs(_p(seq), len(seq), _p(ce), len(ce), int(is_fragmented), K, coef, order, read_num, min_len,
                          max_len, step, p_value, index_thread_num, seed, 0, None, 0, 0, _p(out))
     return out
+
+
+def walk_crafted(hits, K, read_len, from_=0, to=1 << 30, low_coef=0.0, high_coef=1.25):
+    """KAT hook: getInitState + computeCount (the literal updateCount state machine) over a crafted LongHit list.
+    Returns int32[n, 5] = (start, end, count, startIndex, endIndex) after every step."""
+    h = _i32(hits).reshape(-1, 3)
+    out = np.zeros((len(h), 5), np.int32)
+    L = lib()
+    L.vo_walk_crafted.argtypes = [C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    L.vo_walk_crafted.restype = None
+    L.vo_walk_crafted(K, low_coef, high_coef, from_, to, read_len, _p(h), len(h), _p(out))
+    return out
+
+
+def pair_select(forward1, reverse1, forward2, reverse2, fragment_ends=(1 << 30,), is_fragmented=False, insert_len=1000):
+    """KAT hook: the decision of Mapper.mapRead (Mapper.java:100-389) on crafted candidate lists of (start, end, count).
+    Returns dict(cls, r1=(side, index) or None, r2=..., frag1, frag2)."""
+    fe = _i32(fragment_ends)
+    lists = [_i32(x).reshape(-1, 3) for x in (forward1, reverse1, forward2, reverse2)]
+    out = np.zeros(7, np.int32)
+    L = lib()
+    L.vo_pair_select.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p, C.c_int] * 4 + [C.c_void_p]
+    L.vo_pair_select.restype = None
+    args = []
+    for a in lists:
+        args += [_p(a if len(a) else np.zeros((1, 3), np.int32)), len(a)]
+    L.vo_pair_select(_p(fe), len(fe), int(is_fragmented), insert_len, *args, _p(out))
+    o = [int(x) for x in out]
+    return dict(cls=o[0], r1=(o[1], o[2]) if o[2] >= 0 else None, r2=(o[3], o[4]) if o[4] >= 0 else None, frag1=o[5], frag2=o[6])

@@ -839,12 +839,14 @@ struct Mapper {
     r.hasAln = true;
   }
 
-  PairResult mapRead(const std::string& seq1, const std::string& seq2, const Reference& genome) const {
-    std::string rc1 = getComplement(seq1), rc2 = getComplement(seq2);
-    std::vector<MappedRead> forward1 = mapReadFast(seq1, genome);
-    std::vector<MappedRead> reverse1 = mapReadFast(rc1, genome);
-    std::vector<MappedRead> forward2 = mapReadFast(seq2, genome);
-    std::vector<MappedRead> reverse2 = mapReadFast(rc2, genome);
+  // The decision of mapRead (Mapper.java:100-389) on the four candidate lists, without the alignments: which class, and
+  // which candidate (side 0 = forward list, 1 = reverse list; index) becomes r1 / r2 (-1 = null). chooseFragment
+  // (MappedRead.java:39-50) is applied to the lists in place, as in the Java.
+  struct Decision {
+    int cls = CLS_UNMAPPED, sd1 = -1, i1 = -1, sd2 = -1, i2 = -1;
+  };
+  Decision decide(std::vector<MappedRead>& forward1, std::vector<MappedRead>& reverse1, std::vector<MappedRead>& forward2,
+                  std::vector<MappedRead>& reverse2, const Reference& genome) const {
     int maxCount = 0, max1 = -1, max2 = -1, side = -1;
     int maxInd1 = -1, count1 = 0, side1 = -1;
     int maxInd2 = -1, count2 = 0, side2 = -1;
@@ -928,42 +930,26 @@ struct Mapper {
         }
       }
     }
-    PairResult res;
-    auto take1 = [&](int sd, int ind) {
-      res.r1 = (sd == 0) ? forward1[ind] : reverse1[ind];
-      res.r1.reverse = sd;
-      res.has1 = true;
-      alignTo(res.r1, sd == 0 ? seq1 : rc1, genome);
-    };
-    auto take2 = [&](int sd, int ind) {
-      res.r2 = (sd == 0) ? forward2[ind] : reverse2[ind];
-      res.r2.reverse = sd;
-      res.has2 = true;
-      alignTo(res.r2, sd == 0 ? seq2 : rc2, genome);
-    };
+    Decision d;
     switch (side) {
       case 0:  // :226-244
-        take1(0, max1);
-        take2(1, max2);
-        res.cls = CLS_CONC0;
+        d.cls = CLS_CONC0, d.sd1 = 0, d.i1 = max1, d.sd2 = 1, d.i2 = max2;
         break;
       case 1:  // :245-263
-        take1(1, max1);
-        take2(0, max2);
-        res.cls = CLS_CONC1;
+        d.cls = CLS_CONC1, d.sd1 = 1, d.i1 = max1, d.sd2 = 0, d.i2 = max2;
         break;
       default:
         if (side1 == -1) {
           if (side2 == -1) {
-            res.cls = CLS_UNMAPPED;  // :267
+            d.cls = CLS_UNMAPPED;  // :267
           } else {
-            res.cls = CLS_RIGHT;  // :271-287
-            take2(side2, maxInd2);
+            d.cls = CLS_RIGHT;  // :271-287
+            d.sd2 = side2, d.i2 = maxInd2;
           }
         } else {
           if (side2 == -1) {
-            res.cls = CLS_LEFT;  // :291-307
-            take1(side1, maxInd1);
+            d.cls = CLS_LEFT;  // :291-307
+            d.sd1 = side1, d.i1 = maxInd1;
           } else if (genome.isFragmented) {  // :309-353
             int maxSum = 0, maxIndex = -1;
             for (size_t i = 0; i < nf; i++) {
@@ -973,18 +959,42 @@ struct Mapper {
               }
             }
             if (maxIndex != -1) {
-              res.cls = CLS_DISCORDANT;
-              take1(sideFrag1[maxIndex], maxIndFrag1[maxIndex]);
-              take2(sideFrag2[maxIndex], maxIndFrag2[maxIndex]);
+              d.cls = CLS_DISCORDANT;
+              d.sd1 = sideFrag1[maxIndex], d.i1 = maxIndFrag1[maxIndex];
+              d.sd2 = sideFrag2[maxIndex], d.i2 = maxIndFrag2[maxIndex];
             } else {
-              res.cls = CLS_UNMAPPED;
+              d.cls = CLS_UNMAPPED;
             }
           } else {  // :355-385
-            res.cls = CLS_DISCORDANT;
-            take1(side1, maxInd1);
-            take2(side2, maxInd2);
+            d.cls = CLS_DISCORDANT;
+            d.sd1 = side1, d.i1 = maxInd1;
+            d.sd2 = side2, d.i2 = maxInd2;
           }
         }
+    }
+    return d;
+  }
+
+  PairResult mapRead(const std::string& seq1, const std::string& seq2, const Reference& genome) const {
+    std::string rc1 = getComplement(seq1), rc2 = getComplement(seq2);
+    std::vector<MappedRead> forward1 = mapReadFast(seq1, genome);
+    std::vector<MappedRead> reverse1 = mapReadFast(rc1, genome);
+    std::vector<MappedRead> forward2 = mapReadFast(seq2, genome);
+    std::vector<MappedRead> reverse2 = mapReadFast(rc2, genome);
+    const Decision d = decide(forward1, reverse1, forward2, reverse2, genome);
+    PairResult res;
+    res.cls = d.cls;
+    if (d.i1 >= 0) {
+      res.r1 = (d.sd1 == 0) ? forward1[d.i1] : reverse1[d.i1];
+      res.r1.reverse = d.sd1;
+      res.has1 = true;
+      alignTo(res.r1, d.sd1 == 0 ? seq1 : rc1, genome);
+    }
+    if (d.i2 >= 0) {
+      res.r2 = (d.sd2 == 0) ? forward2[d.i2] : reverse2[d.i2];
+      res.r2.reverse = d.sd2;
+      res.has2 = true;
+      alignTo(res.r2, d.sd2 == 0 ? seq2 : rc2, genome);
     }
     return res;
   }
@@ -1328,6 +1338,48 @@ int vo_window_walk(OracleCtx* c, int msa, const uint8_t* read, int L, int32_t* o
     }
   }
   return (int)h.size();
+}
+
+// KAT hook: concordanceArray + getInitState(from, to) + computeCount(from, to) (KMerCounterBase.java:13-36, 38-166, 266-279)
+// over a CRAFTED LongHit list (hits = n x {genomePos, readPos, len}; it need not satisfy the invariants of mergeHits'
+// output), so that the literal state machine can be pinned by hand-derived cases (Q4, Q5). Per hit i writes
+// {start, end, count, startIndex, endIndex} after the i-th step.
+void vo_walk_crafted(int K, float lowCoef, float highCoef, int from, int to, int readLen, const int32_t* hits, int n,
+                     int32_t* out) {
+  KMerCounter kc;
+  kc.K = K, kc.lowCoef = lowCoef, kc.highCoef = highCoef;
+  std::vector<LongHit> h(n);
+  for (int i = 0; i < n; i++) h[i] = LongHit{hits[3 * i], hits[3 * i + 1], hits[3 * i + 2]};
+  if (n == 0) return;
+  std::vector<uint8_t> adj = kc.concordanceArray(h);
+  Location loc = kc.getInitState(from, to, readLen, h, adj);
+  for (int i = 0; i < n; i++) {
+    if (i > 0) kc.computeCount(from, to, readLen, h, i, loc, adj);
+    out[5 * i] = loc.start, out[5 * i + 1] = loc.end, out[5 * i + 2] = loc.count;
+    out[5 * i + 3] = loc.startIndex, out[5 * i + 4] = loc.endIndex;
+  }
+}
+
+// KAT hook: the decision part of Mapper.mapRead (Mapper.java:100-389) on CRAFTED candidate lists (each n x {start, end,
+// count}): out = {class, side of r1 (0 forward1, 1 reverse1, -1 null), index, side of r2, index, fragmentID of r1,
+// fragmentID of r2}.
+void vo_pair_select(const int32_t* fragmentEnds, int nF, int isFragmented, int insertLen, const int32_t* f1, int nf1,
+                    const int32_t* r1, int nr1, const int32_t* f2, int nf2, const int32_t* r2, int nr2, int32_t* out) {
+  Reference g;
+  g.fragmentEnds.assign(fragmentEnds, fragmentEnds + nF);
+  g.isFragmented = isFragmented != 0;
+  Mapper m;
+  m.insertLen = insertLen;
+  auto mk = [](const int32_t* p, int n) {
+    std::vector<MappedRead> v(n);
+    for (int i = 0; i < n; i++) v[i].start = p[3 * i], v[i].end = p[3 * i + 1], v[i].count = p[3 * i + 2];
+    return v;
+  };
+  std::vector<MappedRead> F1 = mk(f1, nf1), R1 = mk(r1, nr1), F2 = mk(f2, nf2), R2 = mk(r2, nr2);
+  const Mapper::Decision d = m.decide(F1, R1, F2, R2, g);
+  out[0] = d.cls, out[1] = d.sd1, out[2] = d.i1, out[3] = d.sd2, out[4] = d.i2;
+  out[5] = d.i1 >= 0 ? (d.sd1 == 0 ? F1 : R1)[d.i1].fragmentID : -1;
+  out[6] = d.i2 >= 0 ? (d.sd2 == 0 ? F2 : R2)[d.i2].fragmentID : -1;
 }
 
 // SmithWatermanGotoh.align. seq1 receives `length` bytes; returns length. rec = 7 ints.

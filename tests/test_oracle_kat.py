@@ -107,6 +107,34 @@ def test_merge_hits_q1_duplicate_adds_zero_length_hit():
     assert o1.get_hits(b"TACGT").tolist() == [[0, 1, 0], [3, 0, 2]]
 
 
+def test_merge_hits_q2_treeset_key_collision_on_reinsert():
+    # Q2 (KMerCounterBase.java:435-441 + Hit.compareTo, Hit.java:13-19): a clipped LongHit is put back with
+    # sortedSet.add(curr); when an element with the same (genomePos, readPos) is already in the TreeSet the add is a
+    # no-op and the clipped hit is lost, whatever its len.
+    # ref (16 bases, all 3-mers distinct) = AACAGATCCGCTGGTA; 2 index threads: size = 8, task 0 indexes [0, 8]
+    # inclusive and task 1 starts at 8, so "CGC" -> [8, 8] (Q1).
+    # read = ref[2:8] + ref[6:12] = CAGATC TCCGCT. Read k-mers (K = 3): i=0 CAG [2]; 1 AGA [3]; 2 GAT [4]; 3 ATC [5];
+    # 4 TCT []; 5 CTC []; 6 TCC [6]; 7 CCG [7]; 8 CGC [8, 8]; 9 GCT [9].
+    # Phase 1: P = (2,0) extended at i = 1, 2, 3 -> len 3. i = 4, 5: empty -> the sets are reset. i = 6: X = (6,6).
+    # i = 7: 6+0+1 == 7 -> X.len = 1. i = 8: rHit 8 == 6+1+1 -> X.len = 2, the iterator is exhausted -> break; the
+    # remainder loop (:412-418) makes the second copy a new hit Z = (8,8,0). i = 9: X: 6+2+1 == 9 -> X.len = 3.
+    # TreeSet: P(2,0,3) X(6,6,3) Z(8,8,0).
+    # Phase 2: prev = P: 2+3+3-1 = 7 >= 6 and P.len 3 is not < X.len 3 -> lenDiff = 2+3+3-6 = 2, X.len = 1 >= 0,
+    # X = (8,8,1), sortedSet.add(X): key (8,8) is Z's -> dropped. Z: 7 >= 8 is false -> emit P, prev = Z; end: emit Z.
+    ref = b"AACAGATCCGCTGGTA"
+    read = ref[2:8] + ref[6:12]
+    o = _o(K=3)
+    o.set_reference(ref, index_thread_num=2)
+    keys, offs, pos = o.index_csr()
+    got = {keys[i].tobytes(): pos[offs[i]:offs[i + 1]].tolist() for i in range(len(keys))}
+    assert got[b"CGC"] == [8, 8] and all(len(v) == 1 for k, v in got.items() if k != b"CGC")
+    assert o.get_hits(read).tolist() == [[2, 0, 3], [8, 8, 0]]
+    # with a single index thread there is no Z: the clipped X = (8,8,1) goes back into the set and survives
+    o1 = _o(K=3)
+    o1.set_reference(ref, index_thread_num=1)
+    assert o1.get_hits(read).tolist() == [[2, 0, 3], [8, 8, 1]]
+
+
 def test_read_shorter_than_k_and_null_seq():
     o = _o(K=5)
     o.set_reference(b"ACGTACGTACGT", index_thread_num=1)
@@ -188,6 +216,40 @@ def test_incremental_window_count_equals_direct_recount():
     assert n > 10000
 
 
+def test_init_state_q4_breaks_at_first_non_fitting_hit():
+    # Q4 (KMerCounterBase.java:23-27): the loop of getInitState stops at the FIRST hit that does not fit the window,
+    # even if a later one would. Crafted list (not something mergeHits can produce: the hits overlap), K = 3, read of 60:
+    #   h0 = (10, 0, 2): start = max(0, 10 - 0*3/2) = 10; end = min(10+2+3 + (60-0-2-3)*3/2, 100) = 15 + 165/2 = 97.
+    #   h1 = (12, 5, 90): 12+3+90 = 105 > 97 -> break: endIndex = 0, count = len(h0) = 2.
+    #   h2 = (20, 10, 1): 20+3+1 = 24 <= 97 would fit, and (20-12)/(10-5) = 1.6 is not adjacent anyway — never looked at.
+    w = oracle.walk_crafted([[10, 0, 2], [12, 5, 90], [20, 10, 1]], K=3, read_len=60, from_=0, to=100)
+    assert w[0].tolist() == [10, 97, 2, 0, 0]
+    # without the long hit in between both fit: count = 2 + 1 (+1: (20-10)/(10-0) = 1.0 lies in [0, 1.25])
+    w = oracle.walk_crafted([[10, 0, 2], [20, 10, 1]], K=3, read_len=60, from_=0, to=100)
+    assert w[0].tolist() == [10, 97, 4, 0, 1]
+
+
+def test_update_count_q5_literal_state_machine_on_crafted_list():
+    # Q5 (KMerCounterBase.java:38-158): updateCount is an incremental state machine, not a recount. Crafted list
+    # (overlapping hits, outside mergeHits' invariant), K = 3, read of 30, window [0, 200), lowCoef 0, highCoef 1.25:
+    #   h0 = (50,20,2)  h1 = (52,0,40)  h2 = (58,25,1)
+    # isAdjacent[0]: (52-50)/(0-20) = -0.1 -> false; isAdjacent[1]: (58-52)/(25-0) = 0.24 -> true.
+    # i=0 getInitState: start = 50 - 20*3/2 = 20; end = 50+2+3 + (30-20-2-3)*3/2 = 55 + 7 = 62; count = 2;
+    #     j=1: 52+3+40 = 95 > 62 -> break. (startIndex, endIndex) = (0, 0).
+    # i=1 h1: start = 52 - 0 = 52; end = 52+40+3 + (30-0-40-3)*3/2 = 95 + (-39/2 = -19, truncation) = 76.
+    #     start moved right (:68-96): h0.genomePos 50 >= 52 is false -> count -= 2 -> 0; the loop over
+    #     (startIndex, endIndex] = (0, 0] is empty; j = 1 > endIndex -> scan from 1: h1.genomePos 52 >= 52 -> sIndex = 1.
+    #     end moved right (:104-124): prevInWindow = (h[endIndex=0].genomePos 50 >= 52) = false; j = 1: 95 > 76 ->
+    #     eIndex = 0. State (52, 76, count 0, startIndex 1, endIndex 0). A recount would see h2 (58 >= 52, 62 <= 76): 1.
+    # i=2 h2: start = 58 - 25*3/2 = 58 - 37 = 21; end = 58+1+3 + (30-25-1-3)*3/2 = 62 + 1 = 63.
+    #     start moved left (:48-67): startHit = h[1]: prevInWindow = (95 <= 63) = false; j = 0: 50 < 21 no; 55 > 63 no;
+    #     no bonus (prevInWindow false); count += 2 -> 2; loop ends, sIndex = 0.
+    #     end moved left (:125-152): h[endIndex=0]: 55 > 63 is false -> eIndex stays 0.
+    #     State (21, 63, count 2, 0, 0). A recount would give 2 + 1 = 3 (h2 itself lies in its window).
+    w = oracle.walk_crafted([[50, 20, 2], [52, 0, 40], [58, 25, 1]], K=3, read_len=30, from_=0, to=200)
+    assert w.tolist() == [[20, 62, 2, 0, 0], [52, 76, 0, 1, 0], [21, 63, 2, 0, 0]]
+
+
 def test_prune_windows_ties_first_wins():
     # pruneWindows (KMerCounterBase.java:317-335): among overlapping windows the larger count wins, ties keep the
     # first in (start asc, end desc) order. Crafted through equal k-mer content at two overlapping loci is hard to
@@ -243,6 +305,33 @@ def test_sw_first_maximum_in_row_major_order():
     # s1 = ACGTNNACGT, s2 = ACGT: 8 is reached in row 4 (col 4) before row 10
     rec, seq = _o().sw_align(b"ACGTTTACGT", b"ACGT")
     assert rec.tolist() == [8, 0, 4, 0, 4, 4, 4]
+
+
+def test_sw_pointer_priority_on_ties():
+    # SmithWatermanGotoh.java:135-143: STOP (v == 0) > DIAGONAL (v == f) > UP (v == g) > LEFT. Three cases where the
+    # tie decides the alignment; V matrices worked out by hand (rows = s1, columns = s2).
+    # (a) v == f == g with 2/-1/3/1, s1 = AAGCA, s2 = AACAGGA:
+    #        A  A  C  A  G  G  A
+    #     A  2  2  0  2  0  0  2
+    #     A  2  4  1  2  1  0  2
+    #     G  0  1  3  0  4  3  0
+    #     C  0  0  3  2  1  3  2
+    #     A  2  2  0  5  2  1  5      first maximum 5 at (5,4)
+    #     path (5,4) D (4,3) D (3,2): f = V(2,1) + mismatch = 2 - 1 = 1 and g = V(2,2) - gop = 4 - 3 = 1: DIAGONAL wins
+    #     -> (2,1) D -> (1,0) STOP: sequence1 = AGCA, start1 = 1, start2 = 0, identity 3 (G/A mismatches).
+    #     UP first would give AAgCA.
+    rec, seq = _o(match=2, mismatch=-1, gop=3, gep=1).sw_align(b"AAGCA", b"AACAGGA")
+    assert rec.tolist() == [5, 1, 5, 0, 4, 3, 4] and seq == b"AGCA"
+    # (b) v == f == h with the default 2/-3/5/2, s1 = CCCAGCAA, s2 = CCCGAGCA: maximum 9 at (7,8); the path runs
+    #     diagonally to (4,5) = 3, then (3,4): f = V(2,3) + mismatch(C/G) = 4 - 3 = 1 and h = V(3,3) - gop = 6 - 5 = 1:
+    #     DIAGONAL wins -> (2,3)=4, (1,2)=2, (0,1) STOP: CCCAGCA, start1 0, start2 1; LEFT first would give CCC-AGCA.
+    rec, seq = _o().sw_align(b"CCCAGCAA", b"CCCGAGCA")
+    assert rec.tolist() == [9, 0, 7, 1, 8, 6, 7] and seq == b"CCCAGCA"
+    # (c) v == g == h with 1/-1/1/1, s1 = CACAGA, s2 = ACAAGAA: maximum 4 at (6,6), diagonal down to (3,3) = 1 where
+    #     f = V(2,2) + mismatch = 0 - 1, g = V(2,3) - gop = 2 - 1 = 1, h = V(3,2) - gop = 2 - 1 = 1: UP wins over LEFT
+    #     -> one lower-case read base, then (2,3) D (1,2) D (0,1): CAcAGA; LEFT first would give AC-AGA.
+    rec, seq = _o(match=1, mismatch=-1, gop=1, gep=1).sw_align(b"CACAGA", b"ACAAGAA")
+    assert rec.tolist() == [4, 0, 6, 1, 6, 5, 6] and seq == b"CAcAGA"
 
 
 def test_sw_q9_unknown_base_in_insertion_becomes_zero_byte():
@@ -370,6 +459,46 @@ def test_map_read_classes():
     assert m["score"] == 500 and m["identity"] == 250 and m["start"] + m["start2"] == 1000
     # stats 1)-7): pairs, bothExist, readsTotal, totalMapped, fwd, rev, bothMapped, totalScore, concordant
     assert st[0] == 7 and st[1] == 6 and st[2] == 13 and st[3] == 9 and st[6] == 3 and st[8] == 2
+
+
+def test_pair_select_q7_fragment_id_stays_zero():
+    # Q7 (MappedRead.chooseFragment, MappedRead.java:39-50): a window that fits no fragment keeps fragmentID = 0 (the
+    # field's default), so it pairs with mates in fragment 0. Fragments [0,100) [100,200) [200,300), insert 1000.
+    # reverse1 = [(190, 210, 30)] straddles fragments 1 / 2 -> fragmentID 0; forward2 = [(10, 60, 20)] lies in fragment 0.
+    # Side 1 (Mapper.java:209-224): read2.start 10 < read1.end 210, 210 - 10 = 200 <= 1000, fragment 0 == 0 ->
+    # concordant RF across two fragments.
+    fe = [100, 200, 300]
+    d = oracle.pair_select([], [[190, 210, 30]], [[10, 60, 20]], [], fe, True)
+    assert d == dict(cls=1, r1=(1, 0), r2=(0, 0), frag1=0, frag2=0)
+    # the same mate properly inside fragment 1: fragment 1 != 0 -> no concordant pair; best singles exist on both sides, and
+    # the fragment-aware rule (:309-353) finds no fragment holding both mates -> the pair is UNMAPPED (:347-351)
+    d = oracle.pair_select([], [[150, 190, 30]], [[10, 60, 20]], [], fe, True)
+    assert d == dict(cls=5, r1=None, r2=None, frag1=-1, frag2=-1)
+    # not fragmented: plain discordant with the best singles (:355-385)
+    d = oracle.pair_select([], [[150, 190, 30]], [[10, 60, 20]], [], fe, False)
+    assert d["cls"] == 1  # 10 < 190 and 190 - 10 <= 1000 with fragmentID 0 == 0 (chooseFragment is never called)
+
+
+def test_pair_select_fragment_aware_discordant_rule():
+    # Mapper.java:309-353: when no concordant pair exists in a fragmented genome, the pair goes to the fragment with the
+    # largest countFrag1 + countFrag2 among those where BOTH mates have a candidate — not to the best singles.
+    # forward1 = [(10,60,50) frag 0, (110,160,30) frag 1]; forward2 = [(120,170,25) frag 1]; reverse2 = [(210,260,45) frag 2].
+    # Side 0: forward1 x reverse2: fragments 0 != 2 and 1 != 2 -> nothing; side 1: reverse1 is empty.
+    # Best singles: mate 1 (10,60,50); mate 2 scans reverse first (:158-191): 45, forward 25 is not greater.
+    # countFrag1 = [50,30,0], countFrag2 = [0,25,45] -> only fragment 1 has both: r1 = forward1[1], r2 = forward2[0].
+    fe = [100, 200, 300]
+    f1, f2, r2 = [[10, 60, 50], [110, 160, 30]], [[120, 170, 25]], [[210, 260, 45]]
+    d = oracle.pair_select(f1, [], f2, r2, fe, True)
+    assert d == dict(cls=2, r1=(0, 1), r2=(0, 0), frag1=1, frag2=1)
+    # the unfragmented rule would take the best singles: forward1[0] and reverse2[0] — but here they even satisfy side 0
+    # (10 < 260, 250 <= 1000, fragmentID 0 == 0 without chooseFragment) and come out concordant
+    assert oracle.pair_select(f1, [], f2, r2, fe, False) == dict(cls=0, r1=(0, 0), r2=(1, 0), frag1=0, frag2=0)
+    # strict '>' everywhere: equal sums keep the first fragment, equal counts keep the first candidate, and mate 2
+    # prefers its REVERSE list on ties because that list is scanned first
+    d = oracle.pair_select([[10, 60, 20], [110, 160, 20]], [], [[20, 70, 20]], [[120, 170, 20]], fe, True, insert_len=5)
+    # side 0: (10,60) x (120,170): fragments differ; (110,160) x (120,170): 110 < 170 but 170 - 110 = 60 > 5 -> none.
+    # countFrag1 = [20,20,0], countFrag2 = [20,20,0]: fragment 0 reaches 40 first; fragment 1 is not greater.
+    assert d == dict(cls=2, r1=(0, 0), r2=(0, 0), frag1=0, frag2=0)
 
 
 def test_identity_counting_hand_derived():
