@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define VG_ABI_VERSION 1
+#define VG_ABI_VERSION 2
 
 typedef enum {
   VG_OK = 0,
@@ -155,12 +155,22 @@ int vg_result_sizes(vg_ctx* ctx, int64_t* n_results, int64_t* seq1_bytes);
  * last map call to the host. seq1_offset values index `seq1_pool`. */
 int vg_get_results(vg_ctx* ctx, vg_pair_result* out, int64_t n_out, uint8_t* seq1_pool, int64_t pool_cap);
 
+/* Installs a MappedData held by the host as the context's "last mapping": per-pair records (with seq1_offset / length
+ * addressing seq1_pool), and for each record the index of its pair in the resident read set. This is what lets the Java
+ * host edit mappedData between a mapping and its consumers the way ConsensusBuilderWithReassembling does — markRemapReads
+ * / adjustCoord rewrite the kept reads' coordinates and Mapper.mapReads(MappedData, Reference) [Mapper.java:477-523]
+ * appends the remapped pairs to the same lists — and still run getConsensusSimple (vg_pileup), BamPrinter
+ * (vg_bam_fields) and ProblemIntervalBuilder (vg_identity_counting) over mappedData.mappedReads on the device.
+ * mappedReads order = record order, r1 before r2. Requires vg_set_reference and vg_upload_reads. */
+int vg_set_results(vg_ctx* ctx, const vg_pair_result* records, int64_t n, const int64_t* pair_idx,
+                   const uint8_t* seq1_pool, int64_t pool_bytes);
+
 /* ConsensusBuilderSimple.ReadCounting [ConsensusBuilderSimple.java:56-75] +
- * the partial-matrix sum [:138-145] over the mapped reads of the last
- * vg_map_pairs call (accumulate != 0 adds to the counts of earlier calls, the
- * way remapped reads join mappedData.mappedReads). Counts are int32[G][5]
- * (A,T,G,C,gap). The device buffer is exposed so that the host plumbing can
- * all-reduce it across GPUs (the multi-GPU replacement of the serial sum). */
+ * the partial-matrix sum [:138-145] over the mapped reads of the context's last mapping (vg_map_pairs or
+ * vg_set_results). accumulate != 0 adds to the counts of the previous vg_pileup on the same reference instead of
+ * starting from zero; it fails with VG_ERR_STATE when there are none (vg_set_reference discards the counts). Counts
+ * are int32[G][5] (A,T,G,C,gap). The device buffer is exposed so that a caller that runs its own collective can
+ * all-reduce it across GPUs (the multi-GPU replacement of the serial sum); see also vg_comm_* below. */
 int vg_pileup(vg_ctx* ctx, int32_t accumulate);
 int vg_pileup_counts_device(vg_ctx* ctx, void** dev_ptr, int64_t* n_int32);
 int vg_pileup_counts_host(vg_ctx* ctx, int32_t* out, int64_t n_int32);
@@ -209,10 +219,12 @@ int vg_map_to_regions(vg_ctx* ctx, const uint8_t* region_pool, const int64_t* re
 
 /* The pileup loop of ContigBuilder.countReads (ContigBuilder.java:93-99) for a batch of alignments: alignment i (sequence1 at
  * seq1_pool + seq1_off[i], `length[i]` columns) starts at position pos[i] (= region base + MappedRead.start +
- * Alignment.start2 when the regions are laid out back to back); counts = int32[total_positions][5] (A, T, G, C, gap),
- * zeroed by the call. */
+ * Alignment.start2 when the regions are laid out back to back) and must stay below end[i] (= the end of its own region: the
+ * Java indexes that region's own counts array and throws beyond it; end == NULL means total_positions for all);
+ * counts = int32[total_positions][5] (A, T, G, C, gap), zeroed by the call. An alignment that crosses its end, or holds a
+ * byte in ('T', 'a'), fails the call with VG_ERR_ALPHABET. */
 int vg_pileup_alignments(vg_ctx* ctx, const uint8_t* seq1_pool, const int64_t* seq1_off, const int32_t* length,
-                         const int64_t* pos, int64_t n, int64_t total_positions, int32_t* counts);
+                         const int64_t* pos, const int64_t* end, int64_t n, int64_t total_positions, int32_t* counts);
 
 /* ProblemIntervalBuilder.countIdentity (ProblemIntervalBuilder.java:35-160): for every mapped read of the
  * last vg_map_pairs call (mappedData.mappedReads = r1, r2 of every pair in order) whose length is at least window_size,

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(built):
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert set(_lib.EXPORTED_SYMBOLS) == declared
-    assert L.vg_abi_version() == 1
+    assert L.vg_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_a_device(built):

@@ -672,14 +672,195 @@ def test_map_reads_single_reference(hiv, cfg, n, threads):
     orec2, opool2, ostats2 = o.map_pairs(bases, off1, len1, off2, len2, n_threads=8)
     md2 = mapper.mapReads(reads, genome2)
     _compare(md2, orec2, opool2, ostats2)
-    # Mapper.mapReads(MappedData, genome): remap a subset
-    sub = np.arange(0, n, 7, dtype=np.int64)
-    md2.needToRemap = sub
-    mapper.mapReads(md2, genome2)
-    osub = orec2[sub]
-    for f in FIELDS:
-        assert (md2.remapped.records["m"][f] == osub["m"][f]).all(), f
-    assert (md2.remapped.records["cls"] == osub["cls"]).all()
+
+
+def test_remap_reads_to_assembly(hiv):
+    """ConsensusBuilderWithReassembling.remapReadsToAssembly (:741-758): markRemapReads + adjustCoord on the host, then
+    Mapper.mapReads(MappedData, Reference) (Mapper.java:477-536) appends the remapped pairs to the kept lists; the
+    consumers (getConsensusSimple, BamPrinter, ProblemIntervalBuilder) must then see kept + remapped reads, and a batch
+    alignment in between (ProblemReadMapper uses the aligner) must not disturb them. Expectations are restated here with
+    plain Java-style lists on top of the oracle's records."""
+    import oracle
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    ref, cut = hiv
+    n = 1200
+    m1, m2 = synth.config_pairs(1, n)
+    m2 = [m2[i].tobytes() for i in range(n)]
+    m1 = [m1[i].tobytes() for i in range(n)]
+    for i in range(0, n, 11):
+        m2[i] = b"*"          # left mate only, other mate absent: may be kept
+    for i in range(5, n, 13):
+        m1[i] = b"*"
+    for i in range(3, n, 17):
+        m2[i] = bytes(np.random.default_rng(i).integers(65, 70, 250).astype(np.uint8))  # junk mate that exists: remapped
+    bases, off1, len1, off2, len2 = synth.pack_ragged(m1, m2)
+    reads = vg.PairedReads(bases, off1, len1, off2, len2)
+    o = oracle.Oracle(K=5, cutoffs=cut)
+    o.set_reference(ref, index_thread_num=8)
+    orec, opool, ostats = o.map_pairs(bases, off1, len1, off2, len2, n_threads=8)
+    mapper = vg.Mapper(K=5, cutoffs=cut)
+    genome = vg.Reference(ref, K=5, thread_num=8)
+    md = mapper.mapReads(reads, genome)
+    _compare(md, orec, opool, ostats)
+    # the assembly: the reference with 10 bases cut out at 5000 and a few substitutions; problem intervals around the cut
+    cutAt, cutLen = 5000, 10
+    asm = np.concatenate([ref[:cutAt], ref[cutAt + cutLen:]]).copy()
+    asm[1234] = ord("A") if asm[1234] != ord("A") else ord("C")
+    g2a = np.concatenate([np.arange(cutAt), np.full(cutLen, cutAt), np.arange(cutAt, len(asm))]).astype(np.int64)
+    intervals = [(4900, 5100), (8000, 8100)]
+    # ---- expectation: markRemapReads in list form (ConsensusBuilderWithReassembling.java:669-739) --------------------
+    def touches(m):
+        return any(m["start"] + m["start2"] < e and m["start"] + m["end2"] > b for b, e in intervals)
+    need, kept = [], []
+    for i in np.nonzero(np.isin(orec["cls"], (0, 1)))[0]:
+        (need if touches(orec["m"][i, 0]) or touches(orec["m"][i, 1]) else kept).append(i)
+    for i in np.nonzero(orec["cls"] == 3)[0]:
+        (need if m2[i] != b"*" or touches(orec["m"][i, 0]) else kept).append(i)
+    for i in np.nonzero(orec["cls"] == 4)[0]:
+        (need if m1[i] != b"*" or touches(orec["m"][i, 1]) else kept).append(i)
+    need += list(np.nonzero(orec["cls"] == 2)[0]) + list(np.nonzero(orec["cls"] == 5)[0])
+    assert len(need) > 50 and len(kept) > 300 and any(orec["cls"][i] == 3 for i in kept)
+    krec = orec[kept].copy()
+    kpool, at = [], 0
+    for r in range(len(krec)):
+        for k in range(2):
+            m = krec["m"][r, k]
+            if m["present"]:
+                s, s2, e2 = int(m["start"]), int(m["start2"]), int(m["end2"])
+                krec["m"]["end"][r, k] = g2a[s + e2 - 1] + 1
+                krec["m"]["start"][r, k] = g2a[s + s2]
+                krec["m"]["end2"][r, k] = e2 - s2
+                krec["m"]["start2"][r, k] = 0
+                kpool.append(opool[m["seq1_offset"]:m["seq1_offset"] + m["length"]])
+                krec["m"]["seq1_offset"][r, k] = at
+                at += int(m["length"])
+    o2 = oracle.Oracle(K=5, cutoffs=cut)
+    o2.set_reference(asm, index_thread_num=8)
+    nb = synth.pack_ragged([m1[i] for i in need], [m2[i] for i in need])
+    rrec, rpool, rstats = o2.map_pairs(*nb, n_threads=8)
+    rrec = rrec.copy()
+    pres = rrec["m"]["present"] == 1
+    rrec["m"]["seq1_offset"][pres] += at
+    want = np.concatenate([krec, rrec])
+    wpool = np.concatenate(kpool + [rpool])
+    # statistics of Mapper.java:479-523
+    kp = krec["m"]["present"] == 1
+    nconc = int(np.isin(krec["cls"], (0, 1)).sum())
+    wst = np.array([len(need) + nconc + int((krec["cls"] == 3).sum()) + int((krec["cls"] == 4).sum()),
+                    nconc + rstats[1], kp.sum() + rstats[2], kp.sum() + rstats[3],
+                    (kp & (krec["m"]["reverse"] == 0)).sum() + rstats[4], (kp & (krec["m"]["reverse"] != 0)).sum() + rstats[5],
+                    nconc + rstats[6], krec["m"]["score"][kp].sum() + rstats[7], nconc + rstats[8]], np.int64)
+    # ---- the product path ----------------------------------------------------------------------------------------------
+    vg.mark_remap_reads(md, intervals, g2a, reads)
+    assert md.pair_index[md.needToRemap].tolist() == [int(i) for i in need]
+    genome2 = vg.Reference(asm, K=5, thread_num=8)
+    mapper.mapReads(md, genome2)
+    assert md.pair_index.tolist() == [int(i) for i in kept + need]
+    _compare(md, want, wpool, wst)
+    assert len(md.needToRemap) == 0
+    # a batch alignment between the mapping and its consumers must not disturb them (it has its own output buffer)
+    mapper.ctx.sw_align_batch(b"ACGTACGTTT" * 30, [0, 300], b"ACGTACGTAA" * 40, [0, 400])
+    lens1 = np.asarray(len1)[md.pair_index]
+    lens2 = np.asarray(len2)[md.pair_index]
+    _compare_bam(mapper, want, wpool, lens1, lens2, [len(asm)])
+    cons = vg.ConsensusBuilderSimple(mapper).getConsensusSimple(False, 0, genome2.seqB)
+    wcounts = oracle.pileup(want, wpool, len(asm))
+    assert (mapper.ctx.counts() == wcounts).all()
+    assert cons.tobytes() == oracle.consensus(wcounts, asm, False, 0).tobytes()
+    ident, cov = vg.ProblemIntervalBuilder(mapper, 50, 4).countIdentity()
+    wi, wc = oracle.identity_counting(want, wpool, lens1, lens2, asm, 50, 4)
+    assert (cov == wc).all() and ident.tobytes() == wi.tobytes()
+    rec2, pool2 = mapper.ctx.get_results()
+    assert rec2.tobytes() == md.records.tobytes() and pool2.tobytes() == md.seq1_pool.tobytes()
+    # accumulate without counts is an error now (vg_set_reference discards them)
+    mapper.ctx.set_reference(genome2)
+    with pytest.raises(vg.VgError) as e:
+        mapper.ctx.pileup(True)
+    assert e.value.code == -3
+    mapper.ctx.pileup(False)
+    mapper.ctx.pileup(True)
+    assert (mapper.ctx.counts() == 2 * wcounts).all()
+
+
+def test_multi_chunk_paths(hiv, monkeypatch):
+    """The chunked paths that the default budgets (sized for an idle B200) never take on test-sized inputs: several
+    Smith-Waterman checkpoint chunks (VG_CKPT_BYTES), several seeding sub-chunks with the fallback list accumulated across
+    them (VG_SEED_SUBMB + a per-read slot that is too small for part of the reads) and several chunks of pairs in mh_map
+    (VG_MAP_CHUNK_PAIRS)."""
+    import oracle
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    ref, cut = hiv
+    n = 2600
+    m1, m2 = synth.config_pairs(3, n)
+    bases, off1, len1, off2, len2 = synth.pack_pairs(m1, m2)
+    o = oracle.Oracle(K=5, cutoffs=cut)
+    o.set_reference(ref, index_thread_num=8)
+    orec, opool, ostats = o.map_pairs(bases, off1, len1, off2, len2, n_threads=8)
+    monkeypatch.setenv("VG_CKPT_BYTES", str(40 << 20))   # ~21 KB per alignment: about 1900 per chunk, >= 3 chunks
+    monkeypatch.setenv("VG_SEED_SUBMB", "1")             # 4096 read orientations per sub-chunk: 3 sub-chunks
+    monkeypatch.setenv("VG_SEED_CAPS2", "2304")          # slot of 2304 LongHits: roughly half of the reads fall back
+    monkeypatch.setenv("VG_MAP_CHUNK_PAIRS", "1000")     # 3 chunks of pairs
+    mapper = vg.Mapper(K=5, cutoffs=cut)
+    genome = vg.Reference(ref, K=5, thread_num=8)
+    md = mapper.mapReads(vg.PairedReads(bases, off1, len1, off2, len2), genome)
+    _compare(md, orec, opool, ostats)
+    sd = mapper.ctx.seed_timings()
+    assert 0 < sd["fallback_items"] < sd["items"], sd
+    mapper.ctx.pileup()
+    assert (mapper.ctx.counts() == oracle.pileup(orec, opool, len(ref))).all()
+
+
+def test_empty_reference_resets_the_context(hiv):
+    """Mapper.java:422-426: an empty reference leaves every pair unmapped; a consensus asked for afterwards must not pile up
+    the previous mapping."""
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    ref, cut = hiv
+    m1, m2 = synth.config_pairs(1, 200)
+    reads = vg.PairedReads(*synth.pack_pairs(m1, m2))
+    mapper = vg.Mapper(K=5, cutoffs=cut)
+    genome = vg.Reference(ref, K=5, thread_num=8)
+    md = mapper.mapReads(reads, genome)
+    assert len(md.concordant) > 100
+    empty = vg.Reference(b"", K=5)
+    md0 = mapper.mapReads(reads, empty)
+    assert (md0.records["cls"] == vg.CLS_UNMAPPED).all() and not md0.records["m"]["present"].any() and not md0.stats.any()
+    cons = vg.ConsensusBuilderSimple(mapper).getConsensusSimple(True, 0, empty.seqB)
+    assert len(cons) == 0
+    rec, pool = mapper.ctx.get_results()
+    assert len(rec) == 200 and len(pool) == 0 and (rec["cls"] == vg.CLS_UNMAPPED).all()
+
+
+def test_alphabet_guards(hiv):
+    """Bytes the packed Smith-Waterman lanes cannot hold (>= 127; they throw in the Java tables) are rejected, not
+    silently mis-scored."""
+    import virgena_b200 as vg
+    ref, cut = hiv
+    ctx = vg.Context(K=5, cutoffs=cut)
+    for s1, s2 in ((b"ACG\x7fT", b"ACGT"), (b"ACGT", b"AC\x80T"), (b"\xff", b"A")):
+        with pytest.raises(vg.VgError) as e:
+            ctx.sw_align_batch(s1, [0, len(s1)], s2, [0, len(s2)])
+        assert e.value.code == -5
+        with pytest.raises(vg.VgError) as e:
+            ctx.sw_max_score_batch(s1, [0, len(s1)], s2, [0, len(s2)])
+        assert e.value.code == -5
+    bad = ref.copy()
+    bad[100] = 127
+    with pytest.raises(vg.VgError) as e:
+        ctx.set_reference(vg.Reference(bad, K=5))
+    assert e.value.code == -5
+    # regions: reads but no region; an alignment that runs past the end of its own region
+    with pytest.raises(vg.VgError) as e:
+        ctx.map_to_regions(np.zeros(0, np.uint8), [0], b"ACGTACGT", [0, 8], [0])
+    assert e.value.code == -1
+    seq1 = b"ACGTACGT"
+    assert ctx.pileup_alignments(seq1, [0], [8], [2], 20, end=[10]).sum() == 8
+    with pytest.raises(vg.VgError) as e:
+        ctx.pileup_alignments(seq1, [0], [8], [4], 20, end=[10])   # 4 + 8 > 10: the next region's counts in the old code
+    assert e.value.code == -5
+    ctx.close()
 
 
 def _compare_bam(mapper, orec, opool, len1, len2, contig_ends):

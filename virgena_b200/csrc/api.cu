@@ -64,7 +64,7 @@ void vg_ctx_destroy(vg_ctx* c) {
                     &c->d_off1, &c->d_off2, &c->d_len1, &c->d_len2, &c->d_results, &c->d_seq1pool, &c->d_pairIdx,
                     &c->d_tasks, &c->d_fill, &c->d_alns, &c->d_rev, &c->d_rowck, &c->d_colck, &c->d_counter,
                     &c->d_scratch, &c->d_seqOff, &c->d_cand, &c->d_ncand, &c->d_misc, &c->d_s1pool, &c->d_s2pool,
-                    &c->d_s1off, &c->d_s2off, &c->d_counts, &c->d_rowpool, &c->d_rowLen, &c->d_scratchR, &c->d_seedS, &c->d_seedNS, &c->d_seedFb, &c->d_bamN,
+                    &c->d_s1off, &c->d_s2off, &c->d_counts, &c->d_swSeq1, &c->d_rowpool, &c->d_rowLen, &c->d_scratchR, &c->d_seedS, &c->d_seedNS, &c->d_seedFb, &c->d_bamN,
                     &c->d_bamOff, &c->d_bamRec, &c->d_bamOps};
   for (DevBuf* b : bufs) b->release();
   for (auto& e : c->ev)
@@ -117,6 +117,12 @@ static int sw_batch_common(vg_ctx* c, const uint8_t* s1_pool, const int64_t* s1_
   *nmaxOut = nmax;
   if (n == 0) return VG_OK;
   size_t b1 = (size_t)s1_off[n], b2 = (size_t)s2_off[n];
+  // the packed kernel keeps a symbol in the high byte of an s16 lane and pads with 0x7F / 0x00FF: bytes >= 127 would
+  // alias the padding or wrap the comparison (the Java's Constants tables have 127 entries: such bytes throw there)
+  for (size_t i = 0; i < b1; i++)
+    if (s1_pool[i] >= 127) return vg_fail(c, VG_ERR_ALPHABET, "sequence byte %d >= 127 in the first pool", (int)s1_pool[i]);
+  for (size_t i = 0; i < b2; i++)
+    if (s2_pool[i] >= 127) return vg_fail(c, VG_ERR_ALPHABET, "sequence byte %d >= 127 in the second pool", (int)s2_pool[i]);
   VG_CUDA(c, c->d_s1pool.reserve(b1 + 16));
   VG_CUDA(c, c->d_s2pool.reserve(b2 + 16));
   VG_CUDA(c, c->d_tasks.reserve(n * sizeof(SwTask)));
@@ -140,18 +146,18 @@ int vg_sw_align_batch(vg_ctx* c, const uint8_t* s1_pool, const int64_t* s1_off, 
   VG_CUDA(c, c->d_alns.reserve(n * sizeof(SwAln)));
   VG_CUDA(c, c->d_rev.reserve((size_t)n * revStride));
   VG_CUDA(c, c->d_seqOff.reserve(n * sizeof(int64_t)));
-  VG_CUDA(c, c->d_seq1pool.reserve((size_t)poolBytes + 16));
+  VG_CUDA(c, c->d_swSeq1.reserve((size_t)poolBytes + 16));  // never the sequence1 pool of the last mapping
   VG_CUDA(c, cudaMemcpyAsync(c->d_seqOff.p, seq1_off, n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
   c->timings[1] = c->timings[2] = 0;
   VG_TRY(sw_run(c, c->d_tasks.as<SwTask>(), n, c->d_s1pool.as<uint8_t>(), c->d_s2pool.as<uint8_t>(), mmax, nmax, true,
                 c->d_fill.as<SwFillOut>(), c->d_alns.as<SwAln>(), c->d_rev.as<uint8_t>(), revStride, &c->timings[1],
                 &c->timings[2]));
   sw_emit_seq1_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, c->stream>>>(
-      c->d_alns.as<SwAln>(), (int)n, c->d_rev.as<uint8_t>(), revStride, c->d_seqOff.as<int64_t>(), c->d_seq1pool.as<uint8_t>());
+      c->d_alns.as<SwAln>(), (int)n, c->d_rev.as<uint8_t>(), revStride, c->d_seqOff.as<int64_t>(), c->d_swSeq1.as<uint8_t>());
   VG_LAUNCH_CHECK(c);
   static_assert(sizeof(SwAln) == 7 * sizeof(int32_t), "SwAln layout");
   VG_CUDA(c, cudaMemcpyAsync(rec, c->d_alns.p, n * sizeof(SwAln), cudaMemcpyDeviceToHost, c->stream));
-  VG_CUDA(c, cudaMemcpyAsync(seq1_pool, c->d_seq1pool.p, (size_t)poolBytes, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaMemcpyAsync(seq1_pool, c->d_swSeq1.p, (size_t)poolBytes, cudaMemcpyDeviceToHost, c->stream));
   VG_CUDA(c, cudaStreamSynchronize(c->stream));
   double cells = 0;
   for (int64_t i = 0; i < n; i++) cells += (double)(s1_off[i + 1] - s1_off[i]) * (double)(s2_off[i + 1] - s2_off[i]);

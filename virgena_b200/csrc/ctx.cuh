@@ -92,6 +92,7 @@ struct vg_ctx {
   // scratch
   DevBuf d_tasks, d_fill, d_alns, d_rev, d_rowck, d_colck, d_counter, d_scratch, d_seqOff, d_cand, d_ncand, d_misc;
   DevBuf d_s1pool, d_s2pool, d_s1off, d_s2off, d_rowpool, d_rowLen, d_scratchR;
+  DevBuf d_swSeq1;  // sequence1 output of vg_sw_align_batch (its own buffer: d_seq1pool belongs to the last mapping)
   DevBuf d_bamN, d_bamOff, d_bamRec, d_bamOps;  // vg_bam_fields
   DevBuf d_seedS, d_seedNS, d_seedFb;  // fast seeding path: per-item LongHit slots, counts, fallback list
   int64_t seedFallbacks = 0;           // items of the last seeding call redone by the general kernel
@@ -128,6 +129,18 @@ static inline int vg_fail(vg_ctx* c, int code, const char* fmt, ...) {
     int rc__ = (expr);            \
     if (rc__ != VG_OK) return rc__; \
   } while (0)
+
+// Work-buffer budgets are sized for an idle B200 (180 GB); on a device that other contexts share they shrink to a fraction
+// of what is free right now (the work is then cut into more chunks, never refused).
+static inline size_t vg_mem_budget(size_t want, double fractionOfFree) {
+  size_t freeB = 0, totalB = 0;
+  if (cudaMemGetInfo(&freeB, &totalB) != cudaSuccess) {
+    cudaGetLastError();
+    return want;
+  }
+  const size_t cap = (size_t)((double)freeB * fractionOfFree);
+  return std::max<size_t>((size_t)64 << 20, std::min(want, cap));
+}
 
 // VG_SYNC_DEBUG=1 synchronises after every launch so that a faulting kernel is reported at its own launch site
 static inline bool vg_sync_debug() {

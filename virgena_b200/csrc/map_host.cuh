@@ -199,7 +199,8 @@ static int mh_map(vg_ctx* c, bool msa, const int64_t* pair_idx, int64_t n_idx, v
     const int nCont = msa ? 1 : (int)c->contigEnds.size();
     maxWin = std::max(8, std::min(8192, std::max(range / std::max(1, c->maxReadLen / 2), range / lmin) + 2 * nCont + 4));
   }
-  const int64_t chunkPairs = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)((size_t)(3ull << 30) / ((size_t)maxWin * 48 + 64))));
+  int64_t chunkPairs = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)((vg_mem_budget(3ull << 30, 0.2) + c->d_cand.cap) / ((size_t)maxWin * 48 + 64))));
+  if (const char* e = getenv("VG_MAP_CHUNK_PAIRS")) chunkPairs = std::max<int64_t>(1, std::min<int64_t>(n, atoll(e)));  // tests
   const int nf = (int)c->fragmentEnds.size();
   if (emptyRef) {
     VG_CUDA(c, cudaMemsetAsync(c->d_results.p, 0, (size_t)n * sizeof(vg_pair_result), c->stream));
@@ -316,7 +317,7 @@ int vg_set_reference(vg_ctx* c, const uint8_t* seq, int32_t G, const int32_t* co
   if (n_fragments < 1 || !fragment_ends) return vg_fail(c, VG_ERR_INVALID, "fragment_ends missing");
   if (keys && (!offsets || !positions || n_keys < 0)) return vg_fail(c, VG_ERR_INVALID, "incomplete CSR index");
   for (int i = 0; i < G; i++)
-    if (seq[i] >= 128) return vg_fail(c, VG_ERR_ALPHABET, "reference byte %d at %d is not ASCII", (int)seq[i], i);
+    if (seq[i] >= 127) return vg_fail(c, VG_ERR_ALPHABET, "reference byte %d at %d (bytes >= 127 are not supported: the Java tables have 127 entries)", (int)seq[i], i);
   c->haveRef = false;
   c->haveCounts = false;
   c->G = G;
@@ -440,6 +441,55 @@ int vg_get_results(vg_ctx* c, vg_pair_result* out, int64_t n_out, uint8_t* seq1_
     VG_CUDA(c, cudaMemcpyAsync(seq1_pool, c->d_seq1pool.p, (size_t)c->seq1Bytes, cudaMemcpyDeviceToHost, c->stream));
   }
   VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VG_OK;
+}
+
+int vg_set_results(vg_ctx* c, const vg_pair_result* rec, int64_t n, const int64_t* pair_idx, const uint8_t* seq1_pool,
+                   int64_t pool_bytes) {
+  if (!c) return VG_ERR_INVALID;
+  VG_CUDA(c, cudaSetDevice(c->device));
+  if (!c->haveRef) return vg_fail(c, VG_ERR_STATE, "vg_set_reference has not been called");
+  if (!c->haveReads) return vg_fail(c, VG_ERR_STATE, "vg_upload_reads has not been called");
+  if (n < 0 || pool_bytes < 0 || (n > 0 && (!rec || !pair_idx)) || (pool_bytes > 0 && !seq1_pool))
+    return vg_fail(c, VG_ERR_INVALID, "bad arguments");
+  for (int64_t i = 0; i < n; i++) {
+    if (pair_idx[i] < 0 || pair_idx[i] >= c->nPairs) return vg_fail(c, VG_ERR_INVALID, "pair index %lld out of range", (long long)pair_idx[i]);
+    if (rec[i].cls < VG_CLS_CONCORDANT_FR || rec[i].cls > VG_CLS_UNMAPPED) return vg_fail(c, VG_ERR_INVALID, "record %lld has class %d", (long long)i, rec[i].cls);
+    for (int k = 0; k < 2; k++) {
+      const vg_mate& m = rec[i].m[k];
+      if (!m.present) continue;
+      if (m.length < 0 || m.seq1_offset < 0 || m.seq1_offset + m.length > pool_bytes)
+        return vg_fail(c, VG_ERR_INVALID, "record %lld mate %d: sequence1 lies outside the pool", (long long)i, k + 1);
+      if (m.length > c->maxReadLen * 3 + 16)  // an alignment is at most |read| + |window| columns long
+        return vg_fail(c, VG_ERR_INVALID, "record %lld mate %d: alignment of %d columns is longer than any read allows", (long long)i, k + 1, m.length);
+    }
+  }
+  // the previous results are gone whatever happens below
+  c->nResults = 0;
+  c->seq1Bytes = 0;
+  c->resultsMsa = false;
+  VG_CUDA(c, c->d_results.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(vg_pair_result)));
+  VG_CUDA(c, c->d_pairIdx.reserve((size_t)std::max<int64_t>(n, 1) * 8));
+  VG_CUDA(c, c->d_seq1pool.reserve((size_t)pool_bytes + 64));
+  VG_CUDA(c, c->d_rowpool.reserve((size_t)pool_bytes + 64));
+  VG_CUDA(c, c->d_rowLen.reserve((size_t)std::max<int64_t>(n, 1) * 2 * 4 + 64));
+  VG_CUDA(c, c->d_counter.reserve(16));
+  VG_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, 16, c->stream));
+  if (n > 0) {
+    VG_CUDA(c, cudaMemcpyAsync(c->d_results.p, rec, (size_t)n * sizeof(vg_pair_result), cudaMemcpyHostToDevice, c->stream));
+    VG_CUDA(c, cudaMemcpyAsync(c->d_pairIdx.p, pair_idx, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (pool_bytes > 0) VG_CUDA(c, cudaMemcpyAsync(c->d_seq1pool.p, seq1_pool, (size_t)pool_bytes, cudaMemcpyHostToDevice, c->stream));
+    pu_rows_kernel<<<(unsigned)((n * 2 * 32 + 255) / 256), 256, 0, c->stream>>>(c->d_results.as<vg_pair_result>(), n * 2,
+                                                                                c->d_seq1pool.as<uint8_t>(), c->d_rowpool.as<uint8_t>(),
+                                                                                c->d_rowLen.as<int32_t>(), c->d_counter.as<int>());
+    VG_LAUNCH_CHECK(c);
+  }
+  int flag = 0;
+  VG_CUDA(c, cudaMemcpyAsync(&flag, c->d_counter.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (flag) return vg_fail(c, VG_ERR_ALPHABET, "a sequence1 byte lies in ('T','a'): the Java pileup throws on it");
+  c->nResults = n;
+  c->seq1Bytes = pool_bytes;
   return VG_OK;
 }
 
@@ -572,11 +622,10 @@ int vg_pileup(vg_ctx* c, int32_t accumulate) {
   if (c->resultsMsa) return vg_fail(c, VG_ERR_STATE, "the last mapping was MSA mode (no alignments to pile up)");
   const int G = c->G;
   const int64_t n = c->nResults;
+  if (accumulate && !c->haveCounts)
+    return vg_fail(c, VG_ERR_STATE, "accumulate requested but there are no counts to add to (vg_set_reference clears them)");
   VG_CUDA(c, c->d_counts.reserve((size_t)std::max(G, 1) * 5 * 4));
-  if (!accumulate || !c->haveCounts) {
-    VG_CUDA(c, cudaMemsetAsync(c->d_counts.p, 0, (size_t)std::max(G, 1) * 5 * 4, c->stream));
-    accumulate = c->haveCounts ? accumulate : 0;
-  }
+  if (!accumulate) VG_CUDA(c, cudaMemsetAsync(c->d_counts.p, 0, (size_t)std::max(G, 1) * 5 * 4, c->stream));
   c->haveCounts = true;
   if (G == 0 || n == 0) {
     VG_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -738,6 +787,7 @@ int vg_map_to_regions(vg_ctx* c, const uint8_t* region_pool, const int64_t* regi
       (n_reads > 0 && (!read_pool || !read_off || !read_region || !windows || !found)))
     return vg_fail(c, VG_ERR_INVALID, "bad arguments");
   if (n_reads == 0) return VG_OK;
+  if (n_regions == 0) return vg_fail(c, VG_ERR_INVALID, "%lld reads but no region", (long long)n_reads);
   const int K = c->seed.K;
   if (K < 1 || K > 7) return vg_fail(c, VG_ERR_INVALID, "region seeding supports K = 1..7 (got %d)", K);
   // layout: region bytes padded by 16, codes padded to a multiple of SD2_SCAN entries
@@ -826,7 +876,7 @@ int vg_map_to_regions(vg_ctx* c, const uint8_t* region_pool, const int64_t* regi
 }
 
 int vg_pileup_alignments(vg_ctx* c, const uint8_t* seq1_pool, const int64_t* seq1_off, const int32_t* length, const int64_t* pos,
-                         int64_t n, int64_t total_positions, int32_t* counts) {
+                         const int64_t* end, int64_t n, int64_t total_positions, int32_t* counts) {
   if (!c) return VG_ERR_INVALID;
   VG_CUDA(c, cudaSetDevice(c->device));
   if (n < 0 || total_positions < 0 || (n > 0 && (!seq1_pool || !seq1_off || !length || !pos)) || (total_positions > 0 && !counts))
@@ -840,9 +890,10 @@ int vg_pileup_alignments(vg_ctx* c, const uint8_t* seq1_pool, const int64_t* seq
   VG_CUDA(c, c->d_s1pool.reserve((size_t)bytes + 64));
   VG_CUDA(c, c->d_s1off.reserve((size_t)std::max<int64_t>(n, 1) * 8));
   VG_CUDA(c, c->d_s2off.reserve((size_t)std::max<int64_t>(n, 1) * 4));
-  VG_CUDA(c, c->d_s2pool.reserve((size_t)std::max<int64_t>(n, 1) * 8 + (size_t)total_positions * 20 + 256));
+  VG_CUDA(c, c->d_s2pool.reserve((size_t)std::max<int64_t>(n, 1) * 16 + (size_t)total_positions * 20 + 256));
   int64_t* d_pos = c->d_s2pool.as<int64_t>();
-  int32_t* d_counts = (int32_t*)(c->d_s2pool.as<uint8_t>() + (((size_t)std::max<int64_t>(n, 1) * 8 + 255) & ~(size_t)255));
+  int64_t* d_end = d_pos + std::max<int64_t>(n, 1);
+  int32_t* d_counts = (int32_t*)(c->d_s2pool.as<uint8_t>() + (((size_t)std::max<int64_t>(n, 1) * 16 + 255) & ~(size_t)255));
   VG_CUDA(c, c->d_counter.reserve(512));
   int* d_err = c->d_counter.as<int>();
   VG_CUDA(c, cudaMemsetAsync(d_err, 0, 4, c->stream));
@@ -852,16 +903,17 @@ int vg_pileup_alignments(vg_ctx* c, const uint8_t* seq1_pool, const int64_t* seq
     VG_CUDA(c, cudaMemcpyAsync(c->d_s1off.p, seq1_off, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
     VG_CUDA(c, cudaMemcpyAsync(c->d_s2off.p, length, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
     VG_CUDA(c, cudaMemcpyAsync(d_pos, pos, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (end) VG_CUDA(c, cudaMemcpyAsync(d_end, end, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
     pu_alignments_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->d_s1pool.as<uint8_t>(), c->d_s1off.as<int64_t>(),
-                                                                           c->d_s2off.as<int32_t>(), d_pos, n, total_positions,
-                                                                           d_counts, d_err);
+                                                                           c->d_s2off.as<int32_t>(), d_pos, end ? d_end : nullptr, n,
+                                                                           total_positions, d_counts, d_err);
     VG_LAUNCH_CHECK(c);
   }
   int err = 0;
   VG_CUDA(c, cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, c->stream));
   VG_CUDA(c, cudaMemcpyAsync(counts, d_counts, (size_t)total_positions * 20, cudaMemcpyDeviceToHost, c->stream));
   VG_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (err) return vg_fail(c, VG_ERR_ALPHABET, "an aligned byte lies in ('T', 'a') or an alignment runs past the last position (the Java would throw)");
+  if (err) return vg_fail(c, VG_ERR_ALPHABET, "an aligned byte lies in ('T', 'a') or an alignment runs past the end of its region (the Java would throw)");
   return VG_OK;
 }
 

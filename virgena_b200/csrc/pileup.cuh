@@ -57,6 +57,33 @@ __global__ void pu_emit_kernel(const SwAln* __restrict__ alns, int64_t n, const 
   if (lane == 0 && rowLen) rowLen[w] = j;
 }
 
+// Reference rows of alignments whose sequence1 is already in the pool (vg_set_results: a MappedData edited by the host,
+// e.g. after markRemapReads / adjustCoord). One warp per (pair, mate). err: a byte in ('T', 'a') (the Java pileup throws).
+__global__ void pu_rows_kernel(const vg_pair_result* __restrict__ res, int64_t n2, const uint8_t* __restrict__ pool,
+                               uint8_t* __restrict__ rowpool, int32_t* __restrict__ rowLen, int* __restrict__ err) {
+  const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= n2) return;
+  const vg_mate& m = res[q >> 1].m[q & 1];
+  if (!m.present || m.seq1_offset < 0) {
+    if (lane == 0) rowLen[q] = 0;
+    return;
+  }
+  const int len = m.length;
+  const int64_t off = m.seq1_offset;
+  int j = 0;
+  for (int t0 = 0; t0 < len; t0 += 32) {
+    const int t = t0 + lane;
+    const uint8_t ch = (t < len) ? pool[off + t] : 0xFF;
+    const bool col = (t < len) && ch < 'a';
+    if (col && ch > 'T') atomicOr(err, 1);
+    const unsigned mk = __ballot_sync(VG_FULL, col);
+    if (col) rowpool[off + j + __popc(mk & ((1u << lane) - 1))] = pu_ntoi(ch);
+    j += __popc(mk);
+  }
+  if (lane == 0) rowLen[q] = j;
+}
+
 // PuRead list of the mapped reads of the last mapping + per-tile histogram (block-aggregated).
 __global__ void pu_list_kernel(const vg_pair_result* __restrict__ res, int64_t nPairs, const int32_t* __restrict__ rowLen,
                                int G, int nTiles, PuRead* __restrict__ reads, int32_t* __restrict__ tileOf,
@@ -197,16 +224,18 @@ __global__ void pu_consensus_kernel(const int32_t* __restrict__ counts, int G, i
 // of alignments against many small regions laid out back to back: alignment i starts at position pos[i] of the
 // concatenated coordinate system. One thread per alignment; integer atomics (the result does not depend on their order).
 __global__ void pu_alignments_kernel(const uint8_t* __restrict__ seq1, const int64_t* __restrict__ off,
-                                     const int32_t* __restrict__ len, const int64_t* __restrict__ pos, int64_t n,
-                                     int64_t total, int32_t* __restrict__ counts, int* __restrict__ err) {
+                                     const int32_t* __restrict__ len, const int64_t* __restrict__ pos,
+                                     const int64_t* __restrict__ end, int64_t n, int64_t total,
+                                     int32_t* __restrict__ counts, int* __restrict__ err) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int64_t k = pos[i];
+  const int64_t kEnd = end ? min(end[i], total) : total;  // end of the alignment's own region (its counts array in the Java)
   const uint8_t* s = seq1 + off[i];
   for (int j = 0; j < len[i]; j++) {
     const uint8_t ch = s[j];
     if (ch >= 'a') continue;               // insertion in the read: no reference position
-    if (ch > 'T' || k < 0 || k >= total) {  // nToI has 'T' + 1 entries / counts[k] out of range: the Java throws
+    if (ch > 'T' || k < 0 || k >= kEnd) {  // nToI has 'T' + 1 entries / counts[k] out of range: the Java throws
       *err = 1;
       return;
     }

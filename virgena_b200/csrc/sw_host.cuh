@@ -35,8 +35,9 @@ static int sw_launch_R(vg_ctx* c, const SwTask* d_tasks, int ntasks, const uint8
   const int nTb = nT / SW_TC + 1;     // column checkpoints at t = SW_TC, 2 SW_TC, ...
   const size_t perPair = ((size_t)nT * 32 + (size_t)nTb * 32 * R) * sizeof(CkT);
   const size_t perTask = perPair / 2;
-  size_t budget = (size_t)24 << 30;
+  size_t budget = 0;
   if (const char* e = getenv("VG_CKPT_BYTES")) budget = (size_t)atoll(e);
+  else if (traceback) budget = vg_mem_budget((size_t)24 << 30, 0.6) + c->d_rowck.cap + c->d_colck.cap;  // what is held counts as free
   int64_t chunk = ntasks;
   if (traceback) {
     chunk = std::min<int64_t>(ntasks, std::max<int64_t>(2, (int64_t)(budget / perTask)));

@@ -325,15 +325,24 @@ class Context:
                                            ptr(read_off), n, ptr(read_region), ptr(win), ptr(found)))
         return win[:n], found[:n]
 
-    def pileup_alignments(self, seq1_pool, seq1_off, length, pos, total_positions):
+    def pileup_alignments(self, seq1_pool, seq1_off, length, pos, total_positions, end=None):
+        """vg_pileup_alignments; end[i] = end of alignment i's own region (None: the whole array)."""
         seq1_pool = _u8(seq1_pool)
         seq1_off = np.ascontiguousarray(seq1_off, np.int64)
         length = np.ascontiguousarray(length, np.int32)
         pos = np.ascontiguousarray(pos, np.int64)
+        end = None if end is None else np.ascontiguousarray(end, np.int64)
         counts = np.zeros((max(int(total_positions), 1), 5), np.int32)
-        self._chk(self.L.vg_pileup_alignments(self.h, ptr(seq1_pool), ptr(seq1_off), ptr(length), ptr(pos), len(length),
-                                              int(total_positions), ptr(counts)))
+        self._chk(self.L.vg_pileup_alignments(self.h, ptr(seq1_pool), ptr(seq1_off), ptr(length), ptr(pos), ptr(end),
+                                              len(length), int(total_positions), ptr(counts)))
         return counts[:int(total_positions)]
+
+    def set_results(self, md):
+        """vg_set_results: a host MappedData becomes the context's last mapping (pileup / BAM fields / identity use it)."""
+        rec = np.ascontiguousarray(md.records, PAIR_DTYPE)
+        idx = np.ascontiguousarray(md.pair_index, np.int64)
+        pool = _u8(md.seq1_pool)
+        self._chk(self.L.vg_set_results(self.h, ptr(rec), len(rec), ptr(idx), ptr(pool) if len(pool) else None, len(pool)))
 
     def identity_counting(self, window_size, thread_num=1):
         """vg_identity_counting: (identity float32[G], coverage int32[G]) of the last mapping."""
@@ -450,7 +459,7 @@ class ContigBuilder:
             for t, i in enumerate(idx):
                 seqs[i] = pool[soff[t]:soff[t] + rec[t, 6]].tobytes()
             pos = coff[read_cluster[idx]] + win[idx, 0] + rec[:, 3]  # centroid base + mRead.start + alignment.start2
-            counts = self.ctx.pileup_alignments(pool, soff[:-1], rec[:, 6], pos, total)
+            counts = self.ctx.pileup_alignments(pool, soff[:-1], rec[:, 6], pos, total, end=coff[read_cluster[idx] + 1])
         else:
             counts = np.zeros((total, 5), np.int32)
         return win, found, aln, seqs, [counts[coff[c]:coff[c + 1]] for c in range(len(centroids))]
@@ -604,27 +613,126 @@ class Mapper:
             self._genome = genome
 
     def mapReads(self, reads_or_mapped, genome):
-        """mapReads(ArrayList<PairedRead>, Reference) -> MappedData, or
-        mapReads(MappedData, Reference): remaps mappedData.needToRemap in place (Mapper.java:477-536)."""
+        """mapReads(ArrayList<PairedRead>, Reference) -> MappedData (Mapper.java:420-475), or
+        mapReads(MappedData, Reference) (Mapper.java:477-536): remaps the pairs of mappedData.needToRemap (row indices of
+        md.records) and appends their results to the lists the caller kept — md.records / pair_index / seq1_pool become
+        [kept rows in their order, remapped rows in needToRemap order], md.stats the figures of :479-523 — and installs the
+        union as the context's last mapping, so that getConsensusSimple, BamPrinter and ProblemIntervalBuilder see
+        mappedData.mappedReads = kept + remapped like the Java."""
         if isinstance(reads_or_mapped, MappedData):
             md = reads_or_mapped
-            if genome.length == 0:
-                return None
             self._bind(None, genome)
-            idx = md.pair_index[md.needToRemap] if len(md.needToRemap) else np.zeros(0, np.int64)
-            sub = self.ctx.map_pairs(idx)
-            md.remapped = sub
+            need = np.ascontiguousarray(md.needToRemap, np.int64)
+            keep = np.setdiff1d(np.arange(len(md.records), dtype=np.int64), need, assume_unique=False)
+            kept = md.records[keep]
+            # stats of Mapper.java:479-497 over what the caller kept
+            kp = kept["m"]["present"] == 1
+            conc = np.isin(kept["cls"], (_lib.CLS_CONCORDANT_FR, _lib.CLS_CONCORDANT_RF))
+            n_conc = int(conc.sum())
+            n_kept_mapped = int(kp.sum())
+            st = np.zeros(9, np.int64)
+            st[0] = len(need) + n_conc + int((kept["cls"] == _lib.CLS_LEFT).sum()) + int((kept["cls"] == _lib.CLS_RIGHT).sum())
+            st[1] = n_conc                                        # bothExist starts from concordant.size()
+            st[2] = n_kept_mapped                                 # readsTotal starts from mappedReads.size()
+            st[3] = n_kept_mapped
+            st[4] = int((kp & (kept["m"]["reverse"] == 0)).sum())
+            st[5] = int((kp & (kept["m"]["reverse"] != 0)).sum())
+            st[6] = n_conc
+            st[7] = int(kept["m"]["score"][kp].sum())
+            st[8] = n_conc
+            if genome.length == 0 or len(need) == 0:
+                # (the Java would still run an empty loop; an empty reference cannot be handed to this overload upstream:
+                # remapReadsToAssembly returns before it, ConsensusBuilderWithReassembling.java:742-754)
+                sub_rec = np.zeros(0, PAIR_DTYPE)
+                sub_pool = np.zeros(0, np.uint8)
+                sub_idx = np.zeros(0, np.int64)
+            else:
+                sub = self.ctx.map_pairs(md.pair_index[need])
+                sub_rec, sub_pool, sub_idx = sub.records, sub.seq1_pool, sub.pair_index
+                st[1:] += sub.stats[1:]                           # :508-523 (task sums; totalPairs is not touched)
+            # kept sequence1 bytes are compacted in front of the remapped ones
+            pools, recs = [], kept.copy()
+            at = 0
+            for r in range(len(recs)):
+                for k in range(2):
+                    m = recs["m"][r, k]
+                    if m["present"] and m["seq1_offset"] >= 0:
+                        o, ln = int(m["seq1_offset"]), int(m["length"])
+                        pools.append(md.seq1_pool[o:o + ln])
+                        recs["m"]["seq1_offset"][r, k] = at
+                        at += ln
+            sub_rec = sub_rec.copy()
+            pres = (sub_rec["m"]["present"] == 1) & (sub_rec["m"]["seq1_offset"] >= 0)
+            sub_rec["m"]["seq1_offset"][pres] += at
+            md.records = np.concatenate([recs, sub_rec])
+            md.pair_index = np.concatenate([md.pair_index[keep], sub_idx])
+            md.seq1_pool = np.concatenate(pools + [sub_pool]) if (pools or len(sub_pool)) else np.zeros(0, np.uint8)
+            md.stats = st
             md.needToRemap = np.zeros(0, np.int64)
+            self.ctx.set_results(md)
             return None
         reads = reads_or_mapped
-        if genome.length == 0:
-            # Mapper.java:422-426: empty reference -> every pair unmapped
-            rec = np.zeros(len(reads), PAIR_DTYPE)
-            rec["cls"] = _lib.CLS_UNMAPPED
-            rec["m"]["seq1_offset"] = -1
-            return MappedData(np.arange(len(reads), dtype=np.int64), rec, np.zeros(0, np.uint8), np.zeros(9, np.int64))
         self._bind(reads, genome)
-        return self.ctx.map_pairs()
+        md = self.ctx.map_pairs()  # an empty reference leaves every pair unmapped inside the library (Mapper.java:422-426)
+        if genome.length == 0:
+            md.stats = np.zeros(9, np.int64)  # the Java returns before any statistic is taken
+        return md
+
+
+def mark_remap_reads(md, problem_intervals, genome_to_assembly, reads):
+    """ConsensusBuilderWithReassembling.markRemapReads + adjustCoord (ConsensusBuilderWithReassembling.java:662-739) on a
+    MappedData of this module (host-side list surgery; no device work): pairs that touch a problem interval, pairs with one
+    mate mapped whose other mate exists, and all discordant / unmapped pairs go to md.needToRemap (in the Java's order:
+    concordant, left, right, discordant, unmapped); the records that stay are moved onto assembly coordinates and
+    reordered concordant, leftMateMapped, rightMateMapped — the order of the rebuilt mappedData.mappedReads.
+    problem_intervals: (start, end) pairs; genome_to_assembly: int array; reads: the resident PairedReads."""
+    rec = md.records
+    iv = np.asarray(problem_intervals, np.int64).reshape(-1, 2)
+    g2a = np.asarray(genome_to_assembly, np.int64)
+
+    def touches(m):
+        s = int(m["start"])
+        return any(s + int(m["start2"]) < e and s + int(m["end2"]) > b for b, e in iv)
+
+    def exists(pi, mate):
+        off, ln = (reads.off1, reads.len1) if mate == 0 else (reads.off2, reads.len2)
+        return not (ln[pi] == 1 and reads.bases[off[pi]] == ord("*"))
+
+    need, kc, kl, kr = [], [], [], []
+    for r in md.concordant:
+        (need if touches(rec["m"][r, 0]) or touches(rec["m"][r, 1]) else kc).append(r)
+    for r in md.leftMateMapped:
+        if exists(md.pair_index[r], 1) or touches(rec["m"][r, 0]):
+            need.append(r)
+        else:
+            kl.append(r)
+    for r in md.rightMateMapped:
+        if exists(md.pair_index[r], 0) or touches(rec["m"][r, 1]):
+            need.append(r)
+        else:
+            kr.append(r)
+    need += list(md.discordant) + list(md.unmapped)
+    keep = np.array(kc + kl + kr, np.int64)
+    out = rec[keep].copy()
+    for r in range(len(out)):
+        for k in range(2):
+            m = out["m"][r, k]
+            if m["present"]:  # adjustCoord (:662-667)
+                s, s2, e2 = int(m["start"]), int(m["start2"]), int(m["end2"])
+                out["m"]["end"][r, k] = g2a[s + e2 - 1] + 1
+                out["m"]["start"][r, k] = g2a[s + s2]
+                out["m"]["end2"][r, k] = e2 - s2
+                out["m"]["start2"][r, k] = 0
+    need_idx = md.pair_index[np.array(need, np.int64)] if need else np.zeros(0, np.int64)
+    n_keep = len(keep)
+    # the remapped pairs are parked behind the kept rows as unmapped placeholders so that needToRemap can name them
+    park = np.zeros(len(need), PAIR_DTYPE)
+    park["cls"] = _lib.CLS_UNMAPPED
+    park["m"]["seq1_offset"] = -1
+    md.records = np.concatenate([out, park])
+    md.pair_index = np.concatenate([md.pair_index[keep], need_idx])
+    md.needToRemap = np.arange(n_keep, n_keep + len(need), dtype=np.int64)
+    return md
 
 
 class MapperMSA:
