@@ -123,19 +123,56 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def cpu_baseline(ref, cut, m1, m2, n_sample, threads, index_threads):
+def cpu_baseline(ref, cut, m1, m2, n_sample, threads, index_threads, want_results=False, contig_ends=None):
     """The oracle ("port": C++ restatement of the Java mapper) on the host cores, bounded sample."""
     import oracle
     from virgena_b200 import synth
     o = oracle.Oracle(K=5, cutoffs=cut)
-    o.set_reference(ref, index_thread_num=index_threads)
+    frag = contig_ends is not None and len(contig_ends) > 1
+    o.set_reference(ref, contig_ends=contig_ends, fragment_ends=contig_ends, is_fragmented=frag, index_thread_num=index_threads)
     b = synth.pack_pairs(m1[:n_sample], m2[:n_sample])
     t0 = time.time()
     rec, pool, st = o.map_pairs(*b, batch_size=1000, n_threads=threads)
     counts = oracle.pileup(rec, pool, len(ref))
-    oracle.consensus(counts, ref, True, 0)
+    cons = oracle.consensus(counts, ref, True, 0)
     dt = time.time() - t0
+    if want_results:
+        return n_sample / dt, dt, (rec, pool, st, counts, cons)
     return n_sample / dt, dt
+
+
+PARITY_FIELDS = ("present", "start", "end", "count", "reverse", "fragment_id", "score", "start1", "end1", "start2", "end2",
+                 "identity", "length", "seq1_offset")
+
+
+def parity_check(ctx, genome_ref, reads_packed, oracle_out):
+    """Outside every timed region: the device maps the very pairs the oracle mapped for cpu_baseline and the two results
+    are compared field by field (records, sequence1 bytes, the nine statistics, pileup counts, consensus)."""
+    import virgena_b200 as vg
+    orec, opool, ostats, ocounts, ocons = oracle_out
+    ctx.upload_reads(vg.PairedReads(*reads_packed))
+    md = ctx.map_pairs()
+    ctx.pileup(False)
+    cons = ctx.consensus(genome_ref, True, 0)
+    bad = []
+    if not (md.records["cls"] == orec["cls"]).all():
+        bad.append("class")
+    for f in PARITY_FIELDS:
+        a, b = md.records["m"][f], orec["m"][f]
+        if f == "seq1_offset":
+            pres = orec["m"]["present"] == 1
+            a, b = a[pres], b[pres]
+        if not (a == b).all():
+            bad.append(f)
+    if md.seq1_pool.tobytes() != opool.tobytes():
+        bad.append("sequence1")
+    if not (md.stats == ostats).all():
+        bad.append("stats")
+    if not (ctx.counts() == ocounts).all():
+        bad.append("pileup counts")
+    if cons.tobytes() != ocons.tobytes():
+        bad.append("consensus")
+    return bad
 
 
 def msa_arm(vg, synth, device, n_pairs):
@@ -160,6 +197,56 @@ def msa_arm(vg, synth, device, n_pairs):
             "ms": best, "pairs": n_pairs, "workload": "cfg2: synthetic 2x250 reads against a %d-sequence MSA (%d columns), K=7, 1.5"
             % (rows.shape[0], rows.shape[1]), "seed_gen_msa_kernel_ms": sd["gen_ms"], "seed_win_kernel_ms": sd["win_ms"],
             "fallback_items": int(sd["fallback_items"]), "mapping_stats": [int(x) for x in md.stats]}
+
+
+def secondary_arm(vg, synth, device, cfg, n_pairs, threads_cpu, check_pairs):
+    """Secondary line for BASELINE.json configs[3] (cfg 4: 8-segment influenza-like genome, 2x150, fragmented) and configs[4]
+    (cfg 5: six-genotype HCV mixture mapped to genotype 1, 2x150): mapReads + getConsensusSimple, device-resident, timed by
+    the library's CUDA events, best of 3; the first `check_pairs` pairs are also mapped by the oracle and compared. Rank 0."""
+    cut, meta = load_cutoffs(cfg)
+    ref, ends = synth.config_reference(cfg)
+    base = min(n_pairs, 100000)  # the numpy generator makes 10^5 distinct pairs; more are distinct batches of them
+    parts1, parts2 = [], []
+    for k in range((n_pairs + base - 1) // base):
+        a, b = synth.config_pairs(cfg, base, seed_offset=k)
+        parts1.append(a)
+        parts2.append(b)
+    m1 = np.concatenate(parts1)[:n_pairs]
+    m2 = np.concatenate(parts2)[:n_pairs]
+    frag = len(ends) > 1
+    ctx = vg.Context(K=5, low_coef=0.0, high_coef=1.25, cutoffs=cut, insert_len=1000, device=device)
+    genome = vg.Reference(ref, K=5, contig_ends=ends, fragment_ends=ends, is_fragmented=frag, thread_num=meta["index_thread_num"])
+    ctx.set_reference(genome)
+    ctx.upload_reads(vg.PairedReads(*synth.pack_pairs(m1, m2)))
+    best = None
+    for _ in range(4):
+        st = ctx.map_pairs(fetch=False)
+        ctx.pileup(False)
+        ctx.consensus(ref, True, 0)
+        t = ctx.timings()
+        tot = t["total_ms"] + t["pileup_ms"]
+        if best is None or tot < best[0]:
+            best = (tot, t, ctx.seed_timings())
+    tot, t, sd = best
+    out = {"metric": METRIC, "value": n_pairs / (tot * 1e-3), "unit": UNIT, "ms": tot, "pairs": n_pairs,
+           "workload": "cfg%d: %s" % (cfg, "synthetic 8-segment influenza-A-like genome (13588 bp), 2x150, 3% divergence, fragmented"
+                                      if cfg == 4 else "synthetic HCV-like six-genotype mixture (~30% mutual divergence) mapped to genotype 1 (9600 bp), 2x150"),
+           "stage_ms": {"seed_pairselect": t["seed_ms"], "seed_gen_kernel": sd["gen_ms"], "seed_win_kernel": sd["win_ms"],
+                        "seed_fallback_kernel": sd["fallback_ms"], "sw_fill": t["sw_fill_ms"], "sw_traceback": t["traceback_ms"],
+                        "pileup": t["pileup_ms"]},
+           "gcups_fill": t["sw_cells"] / (t["sw_fill_ms"] * 1e-3) / 1e9 if t["sw_fill_ms"] else None,
+           "fallback_items": int(sd["fallback_items"]), "mapping_stats": [int(x) for x in st]}
+    if check_pairs:
+        nck = min(check_pairs, n_pairs)
+        v, dt, res = cpu_baseline(ref, cut, m1, m2, nck, threads_cpu, meta["index_thread_num"], want_results=True, contig_ends=ends)
+        bad = parity_check(ctx, ref, synth.pack_pairs(m1[:nck], m2[:nck]), res)
+        out["parity_checked_pairs"] = nck
+        out["parity_ok"] = not bad
+        if bad:
+            out["parity_mismatch"] = bad
+        out["cpu_pairs_per_s"] = v
+    ctx.close()
+    return out
 
 
 def run_reference(args):
@@ -203,6 +290,9 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs of the cpu_baseline sample (0: 3000 x host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-msa", action="store_true", help="skip the secondary MapperMSA.mapAllReads measurement (configs[1])")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary cfg4 / cfg5 lines (configs[3], configs[4])")
+    ap.add_argument("--secondary-pairs", type=int, default=200000, help="pairs of each secondary cfg4 / cfg5 line")
+    ap.add_argument("--check-pairs", type=int, default=20000, help="pairs of the sharded-vs-single check at N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -256,19 +346,23 @@ def main():
     len2 = pinned(np.full(n, L, np.int32))
     n_bases = 2 * n * L
 
-    counts_tensor = [None]
-
-    def allreduce_counts(c=None):
+    # The data path has no host-language collective: the all-reduce of the pileup counts is vg_pileup_allreduce (NCCL inside
+    # the library, on the context's own stream). torch.distributed only carries the bootstrap (the 128-byte NCCL id per
+    # communicator), the barriers and the max-over-ranks of the timings.
+    def make_comm(c):
         if world == 1:
             return
-        p, cnt = (c or ctx).counts_device()
+        ids = [vg.Context.comm_unique_id().tobytes() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        c.comm_init_rank(np.frombuffer(ids[0], np.uint8), rank, world)
 
-        class _W:
-            __cuda_array_interface__ = {"shape": (cnt,), "typestr": "<i4", "data": (p, False), "version": 3}
-        tns = torch.as_tensor(_W(), device=dev)
-        dist.all_reduce(tns)
-        torch.cuda.current_stream().synchronize()
-        counts_tensor[0] = tns
+    make_comm(ctx)
+    allreduce_ms = []
+
+    def allreduce_counts(c=None):
+        (c or ctx).pileup_allreduce()
+        if c is None and world > 1:
+            allreduce_ms.append(ctx.allreduce_ms())
 
     def upload(b):
         ctx.upload_reads_raw(host_batches[b].data_ptr(), n_bases, off1, len1, off2, len2)
@@ -289,6 +383,7 @@ def main():
     for _ in range(n_e2e - 1):
         c2 = vg.Context(K=5, low_coef=0.0, high_coef=1.25, cutoffs=cut, insert_len=1000, device=local)
         c2.set_reference(genome)
+        make_comm(c2)
         e2e_ctx.append(c2)
     rec_hosts = [torch.zeros(n * vg.PAIR_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True).numpy().view(vg.PAIR_DTYPE) for _ in range(n_e2e)]
     pool_hosts = [torch.empty(n * 2 * (L + L * 3 // 2 + 8), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(n_e2e)]
@@ -307,8 +402,6 @@ def main():
                 turn_cv.wait()
             if turn[0] != seq:
                 raise RuntimeError("another e2e worker failed")
-        if world > 1:
-            torch.cuda.set_device(local)
         allreduce_counts(c)
         with turn_cv:
             turn[0] = seq + 1
@@ -394,6 +487,52 @@ def main():
     e2e_value = n * world * args.steps / (e2e_ms * 1e-3)
     h2d = n_bases + off1.nbytes * 2 + len1.nbytes * 2
 
+    # ---- N > 1: the sharded path against the single-GPU result (not timed) --------------------------------------------
+    multi_check = None
+    if world > 1:
+        nck = max(world, args.check_pairs)
+        from virgena_b200.dist import shard_range
+        ck1, ck2 = synth.config_pairs(5, nck)   # config 5 (configs[4]: the sharded one): the same fixed set on every rank
+        cut5, meta5 = load_cutoffs(5)
+        ref5, ends5 = synth.config_reference(5)
+        cctx = vg.Context(K=5, low_coef=0.0, high_coef=1.25, cutoffs=cut5, insert_len=1000, device=local)
+        make_comm(cctx)
+        g5 = vg.Reference(ref5, K=5, thread_num=meta5["index_thread_num"])
+        cctx.set_reference(g5)
+        lo, hi = shard_range(nck, rank, world)
+        cctx.upload_reads(vg.PairedReads(*synth.pack_pairs(ck1[lo:hi], ck2[lo:hi])))
+        md = cctx.map_pairs()
+        cctx.pileup(False)
+        cctx.pileup_allreduce()
+        counts_all = cctx.counts()
+        cons_all = cctx.consensus(ref5, True, 0)
+        import hashlib
+        digest = hashlib.sha256(md.records["cls"].tobytes() + b"".join(md.records["m"][f].tobytes() for f in PARITY_FIELDS[:-1])
+                                + md.seq1_pool.tobytes()).hexdigest()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (digest, [int(x) for x in md.stats], hashlib.sha256(counts_all.tobytes() + cons_all.tobytes()).hexdigest()))
+        if rank == 0:
+            cctx.upload_reads(vg.PairedReads(*synth.pack_pairs(ck1, ck2)))
+            full = cctx.map_pairs()
+            cctx.pileup(False)   # no all-reduce: the single-GPU counts of the whole set
+            ok_counts = hashlib.sha256(cctx.counts().tobytes() + cctx.consensus(ref5, True, 0).tobytes()).hexdigest()
+            ok = all(g[2] == ok_counts for g in gathered)
+            for r in range(world):
+                a, b = shard_range(nck, r, world)
+                sub = full.records[a:b]
+                pres = (sub["m"]["present"] == 1)
+                pool_lo = int(sub["m"]["seq1_offset"][pres].min()) if pres.any() else 0
+                pool_hi = int((sub["m"]["seq1_offset"][pres] + sub["m"]["length"][pres]).max()) if pres.any() else 0
+                d = hashlib.sha256(sub["cls"].tobytes() + b"".join(sub["m"][f].tobytes() for f in PARITY_FIELDS[:-1])
+                                   + full.seq1_pool[pool_lo:pool_hi].tobytes()).hexdigest()
+                ok = ok and d == gathered[r][0]
+            ok = ok and (np.sum([g[1] for g in gathered], axis=0) == full.stats).all()
+            multi_check = {"pairs": nck, "ranks": world, "ok": bool(ok),
+                           "what": "a fixed config-5 set sharded over the ranks: every rank's records + sequence1 bytes == its block of "
+                                   "the single-GPU result, summed statistics equal, NCCL-all-reduced counts and consensus on every rank "
+                                   "== single-GPU counts and consensus"}
+        cctx.close()
+
     if rank == 0:
         peaks = {}
         pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -408,20 +547,34 @@ def main():
         #   gen: read bases in (every read is seeded in both orientations: 2 x (L1 + L2) per pair) + stream out
         #   win: stream in + window records out (12 B per window + 4 B count per orientation)
         gen_ms, win_ms, fb_ms, lh_in, lh_kept, fb_items, win_out, items = seed_acc / args.steps
-        gen_bytes = 4 * L * n + 8 * lh_in
-        win_bytes = 8 * lh_in + 12 * win_out + 4 * items
-        kern = {"seed_gen_kernel": (gen_ms, gen_bytes), "seed_win_kernel": (win_ms, win_bytes)}
-        traffic_all = {}
-        tp = os.path.join(ROOT, "profiles", "traffic_r1.json")
-        if os.path.exists(tp):
-            traffic_all = json.load(open(tp)).get("dram_bytes_per_pair", {})
+        # the ALGORITHMIC HBM bytes of the seeding stage are the read bases in (L1 + L2 per pair at 1 B/base)
+        # and the candidate records out (12 B per window + 4 B per orientation); the LongHit stream between the two
+        # kernels is an intermediate of this implementation, not algorithmic traffic. Both kernels are bound by
+        # instruction issue on shared-memory data (issue_slot_frac below), so the HBM fraction is ~1e-3 by construction.
+        algo_bytes = 2 * L * n + 12 * win_out + 4 * items
+        stream_gen = 4 * L * n + 8 * lh_in                    # bytes the implementation actually moves: reads in both
+        stream_win = 8 * lh_in + 12 * win_out + 4 * items     # orientations + the LongHit stream (8 B each)
+        kern = {"seed_gen_kernel": (gen_ms, stream_gen), "seed_win_kernel": (win_ms, stream_win)}
+        prof = {}
+        pp = os.path.join(ROOT, "profiles", "kernel_metrics_r2.json")
+        if os.path.exists(pp):
+            prof = json.load(open(pp))
         rl = {}
         for k, (kms, kb) in kern.items():
-            gbs = kb / (kms * 1e-3) / 1e9 if kms else None
+            gbs = algo_bytes / (kms * 1e-3) / 1e9 if kms else None
+            pk_ = prof.get("kernels", {}).get(k, {})
             rl[k] = {"bound": "hbm", "kernel": k, "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": gbs / hbm_peak if gbs else None,
-                     "traffic": traffic_all[k] * n if k in traffic_all else None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": kb, "ms_per_step": kms}
+                     "traffic": pk_["dram_bytes_per_pair"] * n if "dram_bytes_per_pair" in pk_ else None,
+                     "traffic_source": ("static: ncu --set full capture of this kernel (%s), scaled to this launch" % prof.get("source", "profiles/"))
+                     if "dram_bytes_per_pair" in pk_ else None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "ms_per_step": kms,
+                     "issue_slot_frac": pk_.get("issue_active_frac"), "warp_instr_per_orientation": pk_.get("warp_instr_per_orientation"),
+                     "issue_source": "static: same ncu capture" if pk_ else None,
+                     "stream_inclusive": {"bytes_per_launch": kb, "achieved": kb / (kms * 1e-3) / 1e9 if kms else None,
+                                          "frac": kb / (kms * 1e-3) / 1e9 / hbm_peak if kms else None,
+                                          "what": "with the LongHit stream between the two kernels counted (an intermediate, 8 B per LongHit)"},
+                     "longhits_per_s": lh_in / (kms * 1e-3) if kms else None}
         dominant = max(kern, key=lambda k: kern[k][0])
         # pileup: algorithmic bytes = aligned columns read once (1 B each) + 16 B per mapped read + G*5*4 B out
         n_res, seq1_bytes = ctx.result_sizes()
@@ -445,10 +598,10 @@ def main():
             "stage_ms_per_step": {"seed_pairselect": seed_ms, "seed_gen_kernel": gen_ms, "seed_win_kernel": win_ms,
                                   "seed_fallback_kernel": fb_ms, "sw_fill": fill_ms, "sw_traceback": tb_ms, "pileup": pu_ms,
                                   "map_total": tot_ms},
-            "roofline": dict(rl[dominant], note="dominant kernel of the step; the seeding kernels are issue / shared-memory bound by "
-                             "construction (SURVEY 8d): LongHits generated per second = %.3e, swept per second = %.3e; "
-                             "%d of %d read orientations took the general (fallback) kernel"
-                             % (lh_in / (gen_ms * 1e-3) if gen_ms else 0, lh_in / (win_ms * 1e-3) if win_ms else 0, int(fb_items), int(items))),
+            "roofline": dict(rl[dominant], note="dominant kernel of the step. achieved = SURVEY 8(d) algorithmic bytes of the seeding "
+                             "stage (read bases in + window records out) / this kernel's time: ~1e-3 of the HBM peak by construction — "
+                             "the kernel is bound by instruction issue on shared-memory data (issue_slot_frac), not by HBM; "
+                             "%d of %d read orientations took the general (fallback) kernel" % (int(fb_items), int(items))),
             "seed_gen_roofline": rl["seed_gen_kernel"],
             "seed_win_roofline": rl["seed_win_kernel"],
             "sw_roofline": {"bound": "dpx", "gcups_fill": cells / (fill_ms * 1e-3) / 1e9 if fill_ms else None,
@@ -462,17 +615,30 @@ def main():
             "pileup_roofline": pile,
             "mapping_stats": [int(x) for x in stats],
         }
+        if world > 1:
+            out["multi_gpu_check"] = multi_check
+            out["allreduce_us"] = float(np.median(allreduce_ms)) * 1e3 if allreduce_ms else None
+            out["collective"] = "ncclAllReduce(int32, sum) of the pileup counts inside libvirgena_gpu.so (vg_pileup_allreduce); no host-language collective in the data path"
+        threads = os.cpu_count() or 1
         if not args.no_msa:
             out["msa_mode"] = msa_arm(vg, synth, local, min(n, 200000))
+        if not args.no_secondary:
+            out["cfg4_fragmented"] = secondary_arm(vg, synth, local, 4, min(n, args.secondary_pairs), threads, 0 if args.no_cpu_baseline else 4000)
+            out["cfg5_hcv_mixture"] = secondary_arm(vg, synth, local, 5, min(n, args.secondary_pairs), threads, 0 if args.no_cpu_baseline else 4000)
         if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
             ncpu = min(n, args.cpu_pairs or 3000 * threads)
             m1 = host_batches[0][0][:ncpu].numpy()
             m2 = host_batches[0][1][:ncpu].numpy()
-            v, dt = cpu_baseline(ref, cut, m1, m2, ncpu, threads, meta["index_thread_num"])
+            v, dt, res = cpu_baseline(ref, cut, m1, m2, ncpu, threads, meta["index_thread_num"], want_results=True)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                    "sample": "first %d pairs of batch 0 (%.1f s wall on %d threads, BatchSize=1000 tasks)" % (ncpu, dt, threads),
                                    "note": "C++ restatement of the reference (oracle/), not the JVM"}
+            # the sample the oracle just mapped is the head of the batch the timed steps mapped: compare, outside the timed region
+            bad = parity_check(ctx, ref, synth.pack_pairs(m1, m2), res)
+            out["parity_checked_pairs"] = ncpu
+            out["parity_ok"] = not bad
+            if bad:
+                out["parity_mismatch"] = bad
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -252,6 +252,55 @@ typedef struct {
 } vg_bam_record;
 int vg_bam_fields(vg_ctx* ctx, vg_bam_record* out, int64_t n_records, uint32_t* cigar_pool, int64_t pool_cap, int64_t* n_ops);
 
+/* ---- Multi-GPU ------------------------------------------------------------------------------------------
+ * Read pairs shard over the GPUs in contiguous blocks, reference / index / cutoffs are replicated; the only exchange is
+ * the integer sum of the pileup counts, which replaces the serial sum of the per-thread matrices at
+ * ConsensusBuilderSimple.java:138-145. NCCL (libnccl.so.2) is loaded at first use.
+ *
+ * (a) one process per GPU: rank 0 calls vg_comm_unique_id, the host ships the VG_COMM_ID_BYTES bytes to the other ranks by
+ *     any channel it has, every rank calls vg_comm_init_rank on its context; from then on vg_pileup_allreduce after vg_pileup
+ *     leaves the global counts on every rank (in place, on the context's stream). */
+#define VG_COMM_ID_BYTES 128
+int vg_comm_unique_id(uint8_t* id128);
+int vg_comm_init_rank(vg_ctx* ctx, const uint8_t* id128, int rank, int n_ranks);
+/* (b) one process, n contexts on n distinct devices (ncclCommInitAll): then vg_pileup_allreduce must be called for all n
+ *     contexts concurrently (one host thread each) — or use vg_multi_*, which does exactly that. */
+int vg_comm_init_all(vg_ctx** ctxs, int n);
+void vg_comm_destroy(vg_ctx* ctx);
+int vg_comm_size(const vg_ctx* ctx);             /* 0 when the context has no communicator */
+int vg_pileup_allreduce(vg_ctx* ctx);            /* no-op without a communicator */
+int vg_last_allreduce_ms(vg_ctx* ctx, double* ms);
+
+/* (c) vg_multi: `new Mapper(document)` bound to n_dev GPUs of this process — the `vg_ctx_create(params, device_ids[], n_dev)`
+ *     of SURVEY 8b, for a host that is one process (one JVM). Same call sequence and semantics as the single-context entry
+ *     points of the same name; results come back in input order (the order of pair_idx for a subset), the sequence1 pools of
+ *     the devices laid out one after the other. vg_multi_pileup = vg_pileup on every device + the all-reduce, so that
+ *     vg_multi_consensus / vg_multi_pileup_counts_host see the counts of all reads. vg_multi_ctx(m, i) exposes the i-th
+ *     device's context for the per-context queries (timings, kernel launches, BAM fields of its shard, ...). */
+typedef struct vg_multi vg_multi;
+int vg_multi_create(const vg_params* params, const int32_t* device_ids, int32_t n_dev, vg_multi** out);
+void vg_multi_destroy(vg_multi* m);
+const char* vg_multi_last_error(const vg_multi* m);
+int64_t vg_multi_last_required(const vg_multi* m);
+int32_t vg_multi_size(const vg_multi* m);
+vg_ctx* vg_multi_ctx(vg_multi* m, int32_t i);
+int vg_multi_set_reference(vg_multi* m, const uint8_t* seq, int32_t G, const int32_t* contig_ends, int32_t n_contigs,
+                           const int32_t* fragment_ends, int32_t n_fragments, int32_t is_fragmented, const uint8_t* keys,
+                           const int64_t* offsets, const int32_t* positions, int32_t n_keys, int32_t index_thread_num);
+int vg_multi_set_msa_index(vg_multi* m, int32_t K, float low_coef, float high_coef, const int32_t* cutoffs,
+                           int32_t n_cutoffs, const uint8_t* keys, const int64_t* offsets, const int32_t* columns,
+                           int32_t n_keys, int32_t msa_length);
+int vg_multi_upload_reads(vg_multi* m, const uint8_t* bases, int64_t n_bases, const int64_t* off1, const int32_t* len1,
+                          const int64_t* off2, const int32_t* len2, int64_t n_pairs);
+int vg_multi_map_pairs(vg_multi* m, const int64_t* pair_idx, int64_t n_idx, vg_map_stats* stats);
+int vg_multi_map_pairs_msa(vg_multi* m, vg_map_stats* stats);
+int vg_multi_result_sizes(vg_multi* m, int64_t* n_results, int64_t* seq1_bytes);
+int vg_multi_get_results(vg_multi* m, vg_pair_result* out, int64_t n_out, uint8_t* seq1_pool, int64_t pool_cap);
+int vg_multi_pileup(vg_multi* m, int32_t accumulate);
+int vg_multi_pileup_counts_host(vg_multi* m, int32_t* out, int64_t n_int32);
+int vg_multi_consensus(vg_multi* m, int32_t save_uncovered, int32_t coverage_threshold, const uint8_t* genome, int32_t G,
+                       uint8_t* out);
+
 /* Timing of the device stages of the last map / pileup call, in milliseconds
  * (CUDA events on the context's stream): [0]=seeding+pair select, [1]=SW fill,
  * [2]=traceback, [3]=pileup, [4]=total, [5]=SW cells (as a double count). */

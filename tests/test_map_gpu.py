@@ -912,6 +912,41 @@ def test_map_reads_fragmented_reference(built, cutv):
     assert (mapper.ctx.counts() == oracle.pileup(orec, opool, len(ref))).all()
 
 
+@pytest.mark.parametrize("cfg", [4, 5])
+def test_map_reads_cfg4_cfg5_at_scale(built, cfg):
+    """BASELINE.json configs[3] (8-segment influenza-like genome, 2x150, fragmented) and configs[4] (six-genotype HCV
+    mixture at ~30 % mutual divergence mapped to genotype 1: most pairs are distant or unmappable — a class mix unlike
+    config 3) at 20 000 pairs with the committed cutoffs: records, sequence1, statistics, pileup and consensus against the
+    oracle."""
+    import json
+    import oracle
+    import virgena_b200 as vg
+    from virgena_b200 import synth
+    n = 20000
+    ref, ends = synth.config_reference(cfg)
+    meta = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "cutoffs.json")))["cfg%d" % cfg]
+    cut = np.array(meta["cutoffs"], np.int32)
+    frag = len(ends) > 1
+    m1, m2 = synth.config_pairs(cfg, n)
+    bases, off1, len1, off2, len2 = synth.pack_pairs(m1, m2)
+    o = oracle.Oracle(K=5, cutoffs=cut)
+    o.set_reference(ref, contig_ends=ends, fragment_ends=ends, is_fragmented=frag, index_thread_num=meta["index_thread_num"])
+    orec, opool, ostats = o.map_pairs(bases, off1, len1, off2, len2, n_threads=os.cpu_count() or 1)
+    mapper = vg.Mapper(K=5, cutoffs=cut)
+    genome = vg.Reference(ref, K=5, contig_ends=ends, fragment_ends=ends, is_fragmented=frag, thread_num=meta["index_thread_num"])
+    md = mapper.mapReads(vg.PairedReads(bases, off1, len1, off2, len2), genome)
+    _compare(md, orec, opool, ostats)
+    cons = vg.ConsensusBuilderSimple(mapper).getConsensusSimple(True, 0, genome.seqB)
+    ocounts = oracle.pileup(orec, opool, len(ref))
+    assert (mapper.ctx.counts() == ocounts).all()
+    assert cons.tobytes() == oracle.consensus(ocounts, ref, True, 0).tobytes()
+    classes = np.bincount(md.records["cls"], minlength=6)
+    if cfg == 5:
+        assert classes[0] + classes[1] < n and classes[2:].sum() > 0, classes  # not everything is concordant
+    sd = mapper.ctx.seed_timings()
+    print("cfg%d class mix %s, fallback items %d of %d" % (cfg, classes.tolist(), sd["fallback_items"], sd["items"]))
+
+
 def test_map_reads_ragged_and_edge_cases(hiv):
     import oracle
     import virgena_b200 as vg

@@ -84,6 +84,32 @@ _SIGS = {
     "vg_set_results": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]),
     "vg_identity_counting": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "vg_bam_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "vg_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "vg_comm_init_rank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "vg_comm_init_all": (C.c_int, [C.c_void_p, C.c_int]),
+    "vg_comm_destroy": (None, [C.c_void_p]),
+    "vg_comm_size": (C.c_int, [C.c_void_p]),
+    "vg_pileup_allreduce": (C.c_int, [C.c_void_p]),
+    "vg_last_allreduce_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "vg_multi_create": (C.c_int, [C.POINTER(VgParams), C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "vg_multi_destroy": (None, [C.c_void_p]),
+    "vg_multi_last_error": (C.c_char_p, [C.c_void_p]),
+    "vg_multi_last_required": (C.c_int64, [C.c_void_p]),
+    "vg_multi_size": (C.c_int32, [C.c_void_p]),
+    "vg_multi_ctx": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "vg_multi_set_reference": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "vg_multi_set_msa_index": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_int32, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "vg_multi_upload_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int64]),
+    "vg_multi_map_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(VgMapStats)]),
+    "vg_multi_map_pairs_msa": (C.c_int, [C.c_void_p, C.POINTER(VgMapStats)]),
+    "vg_multi_result_sizes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "vg_multi_get_results": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+    "vg_multi_pileup": (C.c_int, [C.c_void_p, C.c_int32]),
+    "vg_multi_pileup_counts_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "vg_multi_consensus": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "vg_dpx_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "vg_kernel_launches": (C.c_int64, [C.c_void_p]),
     "vg_ctx_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -2,6 +2,7 @@
 #include "ctx.cuh"
 #include "sw_host.cuh"
 #include "map_host.cuh"
+#include "multi.cuh"
 
 extern "C" {
 
@@ -59,6 +60,7 @@ void vg_ctx_destroy(vg_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
   }
+  vg_comm_release(c);
   DevBuf* bufs[] = {&c->seed.d_cutoffs, &c->seedMsa.d_cutoffs, &c->d_ref, &c->d_contigEnds, &c->d_fragmentEnds,
                     &c->d_poscode, &c->d_exoKeys, &c->d_msaOff, &c->d_msaCols, &c->d_msaExoKeys, &c->d_bases,
                     &c->d_off1, &c->d_off2, &c->d_len1, &c->d_len2, &c->d_results, &c->d_seq1pool, &c->d_pairIdx,

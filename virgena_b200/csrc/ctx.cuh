@@ -104,6 +104,10 @@ struct vg_ctx {
   DevBuf d_counts;
   bool haveCounts = false;
   double timings[6] = {0, 0, 0, 0, 0, 0};
+  // multi-GPU (multi.cuh): NCCL communicator of this context's rank, if any
+  void* comm = nullptr;
+  int commRank = -1, commSize = 0;
+  double allreduceMs = 0;
 };
 
 static inline int vg_fail(vg_ctx* c, int code, const char* fmt, ...) {

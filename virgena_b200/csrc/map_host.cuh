@@ -75,6 +75,17 @@ __global__ void mh_scan3_kernel(int64_t* __restrict__ out, const int64_t* __rest
   if (i < n) out[i] = (plain || in[i] > 0) ? out[i] + blockSums[blockIdx.x] : -1;  // -1: nothing to emit (unless plain)
 }
 
+// Mapper.java:422-426 (empty reference): every pair goes to `unmapped`, r1 = r2 = null
+__global__ void mh_unmapped_kernel(vg_pair_result* __restrict__ res, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  vg_pair_result r;
+  memset(&r, 0, sizeof r);
+  r.cls = VG_CLS_UNMAPPED;
+  r.m[0].seq1_offset = r.m[1].seq1_offset = -1;
+  res[i] = r;
+}
+
 __global__ void mh_lengths_kernel(const vg_pair_result* __restrict__ res, const SwAln* __restrict__ alns, int64_t n2,
                                   int32_t* __restrict__ lens) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,7 +214,8 @@ static int mh_map(vg_ctx* c, bool msa, const int64_t* pair_idx, int64_t n_idx, v
   if (const char* e = getenv("VG_MAP_CHUNK_PAIRS")) chunkPairs = std::max<int64_t>(1, std::min<int64_t>(n, atoll(e)));  // tests
   const int nf = (int)c->fragmentEnds.size();
   if (emptyRef) {
-    VG_CUDA(c, cudaMemsetAsync(c->d_results.p, 0, (size_t)n * sizeof(vg_pair_result), c->stream));
+    mh_unmapped_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_results.as<vg_pair_result>(), n);
+    VG_LAUNCH_CHECK(c);
   }
   for (int64_t s = 0; s < n && !emptyRef; s += chunkPairs) {
     const int64_t np = std::min(chunkPairs, n - s);

@@ -400,6 +400,30 @@ class Context:
     def kernel_launches(self):
         return int(self.L.vg_kernel_launches(self.h))
 
+    # --- multi-GPU, one process per GPU (include/virgena_gpu.h, "Multi-GPU" (a)) ----------------------------
+    @staticmethod
+    def comm_unique_id():
+        """vg_comm_unique_id: 128 bytes that rank 0 hands to the other ranks by any channel the host has."""
+        buf = np.zeros(128, np.uint8)
+        rc = _lib.lib().vg_comm_unique_id(ptr(buf))
+        if rc != 0:
+            raise VgError(rc, "NCCL is not available (libnccl.so.2 could not be loaded)")
+        return buf
+
+    def comm_init_rank(self, uid, rank, n_ranks):
+        uid = np.ascontiguousarray(uid, np.uint8)
+        assert len(uid) == 128
+        self._chk(self.L.vg_comm_init_rank(self.h, ptr(uid), int(rank), int(n_ranks)))
+
+    def pileup_allreduce(self):
+        """vg_pileup_allreduce: the counts of all ranks summed in place (no-op without a communicator)."""
+        self._chk(self.L.vg_pileup_allreduce(self.h))
+
+    def allreduce_ms(self):
+        v = C.c_double()
+        self._chk(self.L.vg_last_allreduce_ms(self.h, C.byref(v)))
+        return v.value
+
     def bam_fields(self):
         """vg_bam_fields: (records BAM_DTYPE[2 * n_results], CIGAR pool uint32) of the last single-reference mapping."""
         n = C.c_int64()
@@ -413,6 +437,146 @@ class Context:
             rc = self.L.vg_bam_fields(self.h, ptr(rec), len(rec), ptr(pool), len(pool), C.byref(nops))
         self._chk(rc)
         return rec, pool[:nops.value]
+
+
+class _BorrowedContext(Context):
+    """A Context whose vg_ctx belongs to somebody else (vg_multi_ctx): never destroyed from here."""
+
+    def __init__(self, owner, handle):
+        self.L, self.h, self._owner = owner.L, handle, owner
+        self.K, self.G, self.n_pairs, self.sw_params, self.cutoffs = owner.K, owner.G, 0, owner.sw_params, owner.cutoffs
+
+    def close(self):
+        self.h = None
+
+
+class MultiContext:
+    """One vg_multi: the same Mapper bound to several GPUs of this process (include/virgena_gpu.h, "Multi-GPU" (c)). Pairs
+    are sharded in contiguous blocks, the index is replicated, pileup() all-reduces the counts with NCCL inside the
+    library. The call surface is the subset of Context that Mapper / ConsensusBuilderSimple use."""
+
+    def __init__(self, devices, K=5, low_coef=0.0, high_coef=1.25, cutoffs=None, insert_len=1000, match=2, mismatch=-3,
+                 gop=5, gep=2):
+        self.L = _lib.lib()
+        self.cutoffs = np.ascontiguousarray(cutoffs if cutoffs is not None else np.zeros(1024, np.int32), np.int32)
+        self.K = K
+        self.devices = np.ascontiguousarray(devices, np.int32)
+        p = VgParams(K, low_coef, high_coef, self.cutoffs.ctypes.data, len(self.cutoffs), insert_len, match, mismatch,
+                     gop, gep)
+        h = C.c_void_p()
+        rc = self.L.vg_multi_create(C.byref(p), ptr(self.devices), len(self.devices), C.byref(h))
+        self.h = h
+        if rc != 0:
+            msg = self.L.vg_multi_last_error(h).decode() if h else "allocation failed"
+            if h:
+                self.L.vg_multi_destroy(h)
+                self.h = None
+            raise VgError(rc, msg)
+        self.n_pairs = 0
+        self.G = 0
+        self.sw_params = (match, mismatch, gop, gep)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vg_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise VgError(rc, self.L.vg_multi_last_error(self.h).decode())
+
+    def device_ctx(self, i):
+        """Borrowed Context view of the i-th device's vg_ctx (timings, launches, BAM fields of its shard, ...); it stays
+        owned by the multi-context."""
+        return _BorrowedContext(self, C.c_void_p(self.L.vg_multi_ctx(self.h, i)))
+
+    def set_reference(self, ref: Reference):
+        keys = offs = pos = None
+        nk = 0
+        if ref.index_csr is not None:
+            keys, offs, pos = ref.index_csr
+            keys = np.ascontiguousarray(keys, np.uint8)
+            offs = np.ascontiguousarray(offs, np.int64)
+            pos = np.ascontiguousarray(pos, np.int32)
+            nk = len(offs) - 1
+        self._chk(self.L.vg_multi_set_reference(self.h, ptr(ref.seqB), ref.length, ptr(ref.contigEnds), len(ref.contigEnds),
+                                                ptr(ref.fragmentEnds), len(ref.fragmentEnds), int(ref.isFragmented),
+                                                ptr(keys), ptr(offs), ptr(pos), nk, ref.threadNum))
+        self.G = ref.length
+
+    def set_msa(self, aln: ReferenceAlignment, low_coef, high_coef, cutoffs):
+        cut = np.ascontiguousarray(cutoffs, np.int32)
+        self._chk(self.L.vg_multi_set_msa_index(self.h, aln.K, low_coef, high_coef, ptr(cut), len(cut), ptr(aln.keys),
+                                                ptr(aln.offsets), ptr(aln.columns), len(aln.offsets) - 1, aln.length))
+
+    def upload_reads(self, reads: PairedReads):
+        self._chk(self.L.vg_multi_upload_reads(self.h, ptr(reads.bases), len(reads.bases), ptr(reads.off1), ptr(reads.len1),
+                                               ptr(reads.off2), ptr(reads.len2), len(reads)))
+        self.n_pairs = len(reads)
+
+    def upload_reads_raw(self, bases_ptr, n_bases, off1, len1, off2, len2):
+        self._chk(self.L.vg_multi_upload_reads(self.h, C.c_void_p(bases_ptr), n_bases, ptr(off1), ptr(len1), ptr(off2),
+                                               ptr(len2), len(off1)))
+        self.n_pairs = len(off1)
+
+    def get_results(self):
+        n = C.c_int64()
+        nb = C.c_int64()
+        self._chk(self.L.vg_multi_result_sizes(self.h, C.byref(n), C.byref(nb)))
+        rec = np.zeros(n.value, PAIR_DTYPE)
+        pool = np.zeros(max(nb.value, 1), np.uint8)
+        self._chk(self.L.vg_multi_get_results(self.h, ptr(rec), n.value, ptr(pool), len(pool)))
+        return rec, pool[:nb.value]
+
+    def get_results_into(self, rec, pool):
+        n = C.c_int64()
+        nb = C.c_int64()
+        self._chk(self.L.vg_multi_result_sizes(self.h, C.byref(n), C.byref(nb)))
+        self._chk(self.L.vg_multi_get_results(self.h, ptr(rec), len(rec), ptr(pool), len(pool)))
+        return n.value, nb.value
+
+    def map_pairs(self, pair_idx=None, fetch=True):
+        st = VgMapStats()
+        if pair_idx is None:
+            self._chk(self.L.vg_multi_map_pairs(self.h, None, 0, C.byref(st)))
+            idx = np.arange(self.n_pairs, dtype=np.int64)
+        else:
+            idx = np.ascontiguousarray(pair_idx, np.int64)
+            self._chk(self.L.vg_multi_map_pairs(self.h, ptr(idx), len(idx), C.byref(st)))
+        if not fetch:
+            return st.as_array()
+        rec, pool = self.get_results()
+        return MappedData(idx, rec, pool, st.as_array())
+
+    def map_pairs_msa(self, fetch=True):
+        st = VgMapStats()
+        self._chk(self.L.vg_multi_map_pairs_msa(self.h, C.byref(st)))
+        if not fetch:
+            return st.as_array()
+        rec, pool = self.get_results()
+        return MappedData(np.arange(self.n_pairs, dtype=np.int64), rec, pool, st.as_array(), msa=True)
+
+    def pileup(self, accumulate=False):
+        """vg_pileup on every device + the NCCL all-reduce of the counts (ConsensusBuilderSimple.java:138-145)."""
+        self._chk(self.L.vg_multi_pileup(self.h, int(accumulate)))
+
+    def counts(self):
+        out = np.zeros((self.G, 5), np.int32)
+        self._chk(self.L.vg_multi_pileup_counts_host(self.h, ptr(out), out.size))
+        return out
+
+    def consensus(self, genome, save_uncovered=False, coverage_threshold=0):
+        genome = _u8(genome)
+        out = np.zeros(len(genome), np.uint8)
+        self._chk(self.L.vg_multi_consensus(self.h, int(save_uncovered), coverage_threshold, ptr(genome), len(genome),
+                                            ptr(out)))
+        return out
 
 
 CIGAR_OPS = "MID?S"
@@ -599,8 +763,11 @@ class Mapper:
     and stay resident across mapping passes (iterations of ConsensusBuilderWithReassembling)."""
 
     def __init__(self, K=5, pValue=0.01, indel_tolerance=1.25, low_coef=0.0, cutoffs=None, insert_len=1000,
-                 match=2, mismatch=-3, gop=5, gep=2, device=0):
-        self.ctx = Context(K, low_coef, indel_tolerance, cutoffs, insert_len, match, mismatch, gop, gep, device)
+                 match=2, mismatch=-3, gop=5, gep=2, device=0, devices=None):
+        if devices is not None:  # several GPUs of this process: sharded pairs + NCCL all-reduce inside the library
+            self.ctx = MultiContext(devices, K, low_coef, indel_tolerance, cutoffs, insert_len, match, mismatch, gop, gep)
+        else:
+            self.ctx = Context(K, low_coef, indel_tolerance, cutoffs, insert_len, match, mismatch, gop, gep, device)
         self._reads = None
         self._genome = None
 
@@ -772,8 +939,10 @@ class ConsensusBuilderSimple:
 
     def getConsensusSimple(self, saveUncovered, coverageThreshold, genome):
         ctx = self.mapper.ctx
-        ctx.pileup(False)
+        ctx.pileup(False)  # a MultiContext all-reduces inside
         if self._allreduce is not None:
             p, n = ctx.counts_device()
             self._allreduce(p, n)
+        elif isinstance(ctx, Context):
+            ctx.pileup_allreduce()  # one process per GPU: no-op unless comm_init_rank was called
         return ctx.consensus(genome, saveUncovered, coverageThreshold)
