@@ -350,8 +350,8 @@ int vg_multi_result_sizes(vg_multi* m, int64_t* n_results, int64_t* seq1_bytes) 
   return VG_OK;
 }
 
-// Results in the caller's order (input order, or the order of pair_idx); the sequence1 pools of the devices are laid
-// out one after the other and seq1_offset is rebased accordingly.
+// Results in the caller's order (input order, or the order of pair_idx), with the sequence1 pool laid out in that same
+// order: the output is byte-identical to what one device would have returned for the same call.
 int vg_multi_get_results(vg_multi* m, vg_pair_result* out, int64_t n_out, uint8_t* seq1_pool, int64_t pool_cap) {
   if (!m) return VG_ERR_INVALID;
   if (n_out < m->nResults || pool_cap < m->seq1Bytes) {
@@ -360,34 +360,52 @@ int vg_multi_get_results(vg_multi* m, vg_pair_result* out, int64_t n_out, uint8_
                     (long long)m->seq1Bytes);
   }
   if (m->nResults > 0 && !out) return vgm_fail(m, VG_ERR_INVALID, "null output");
+  if (m->seq1Bytes > 0 && !seq1_pool) return vgm_fail(m, VG_ERR_INVALID, "null sequence1 pool");
   const int n = (int)m->ctx.size();
   std::vector<int64_t> resBase(n + 1, 0), poolBase(n + 1, 0);
   for (int d = 0; d < n; d++) resBase[d + 1] = resBase[d] + m->nRes[d], poolBase[d + 1] = poolBase[d] + m->poolBytes[d];
-  return vgm_each(m, [&](int d) {
-    vg_ctx* c = m->ctx[d];
-    const int64_t nr = m->nRes[d];
-    if (nr == 0) return (int)VG_OK;
-    auto rebase = [&](vg_pair_result& r) {
-      for (int k = 0; k < 2; k++)
-        if (r.m[k].present && r.m[k].seq1_offset >= 0) r.m[k].seq1_offset += poolBase[d];
-    };
-    if (m->contiguous) {  // device d's results are the block [lo[d], lo[d + 1]) of the output
+  if (m->contiguous) {
+    // device d's results are the block [lo[d], lo[d + 1]) of the output and its pool the next block of the pool: the
+    // offsets (prefix sums in (pair, mate) order on every device) only need the base of the block added
+    return vgm_each(m, [&](int d) {
+      vg_ctx* c = m->ctx[d];
+      const int64_t nr = m->nRes[d];
+      if (nr == 0) return (int)VG_OK;
       vg_pair_result* dst = out + resBase[d];
-      const int rc = vg_get_results(c, dst, nr, seq1_pool ? seq1_pool + poolBase[d] : nullptr, m->poolBytes[d]);
+      const int rc = vg_get_results(c, dst, nr, seq1_pool + poolBase[d], m->poolBytes[d]);
       if (rc != VG_OK) return rc;
       if (poolBase[d])
-        for (int64_t i = 0; i < nr; i++) rebase(dst[i]);
+        for (int64_t i = 0; i < nr; i++)
+          for (int k = 0; k < 2; k++)
+            if (dst[i].m[k].present && dst[i].m[k].seq1_offset >= 0) dst[i].m[k].seq1_offset += poolBase[d];
       return (int)VG_OK;
-    }
-    std::vector<vg_pair_result> tmp(nr);
-    const int rc = vg_get_results(c, tmp.data(), nr, seq1_pool ? seq1_pool + poolBase[d] : nullptr, m->poolBytes[d]);
-    if (rc != VG_OK) return rc;
-    for (int64_t i = 0; i < nr; i++) {
-      rebase(tmp[i]);
-      out[m->outPos[d][i]] = tmp[i];
-    }
-    return (int)VG_OK;
+    });
+  }
+  // a subset in the caller's own order: fetch per device, then lay records and sequence1 bytes out in that order
+  std::vector<std::vector<vg_pair_result>> tmp(n);
+  std::vector<std::vector<uint8_t>> tpool(n);
+  const int rc = vgm_each(m, [&](int d) {
+    tmp[d].resize(m->nRes[d]);
+    tpool[d].resize(m->poolBytes[d]);
+    if (m->nRes[d] == 0) return (int)VG_OK;
+    return vg_get_results(m->ctx[d], tmp[d].data(), m->nRes[d], tpool[d].data(), m->poolBytes[d]);
   });
+  if (rc != VG_OK) return rc;
+  for (int d = 0; d < n; d++)
+    for (int64_t i = 0; i < m->nRes[d]; i++) out[m->outPos[d][i]] = tmp[d][i];
+  std::vector<int> owner(m->nResults);
+  for (int d = 0; d < n; d++)
+    for (int64_t i = 0; i < m->nRes[d]; i++) owner[m->outPos[d][i]] = d;
+  int64_t at = 0;
+  for (int64_t i = 0; i < m->nResults; i++)
+    for (int k = 0; k < 2; k++) {
+      vg_mate& mt = out[i].m[k];
+      if (!mt.present || mt.seq1_offset < 0) continue;
+      if (mt.length > 0) memcpy(seq1_pool + at, tpool[owner[i]].data() + mt.seq1_offset, (size_t)mt.length);
+      mt.seq1_offset = at;
+      at += mt.length;
+    }
+  return VG_OK;
 }
 
 // getConsensusSimple's counting step on every device + the all-reduce: afterwards every device holds the global counts.
