@@ -105,6 +105,7 @@ struct vg_ctx {
   bool haveCounts = false;
   double timings[6] = {0, 0, 0, 0, 0, 0};
   // multi-GPU (multi.cuh): NCCL communicator of this context's rank, if any
+  size_t budgetCkpt = 0, budgetSeed = 0, budgetWin = 0;  // work-buffer budgets, fixed at first use
   void* comm = nullptr;
   int commRank = -1, commSize = 0;
   double allreduceMs = 0;
@@ -135,14 +136,15 @@ static inline int vg_fail(vg_ctx* c, int code, const char* fmt, ...) {
   } while (0)
 
 // Work-buffer budgets are sized for an idle B200 (180 GB); on a device that other contexts share they shrink to a fraction
-// of what is free right now (the work is then cut into more chunks, never refused).
-static inline size_t vg_mem_budget(size_t want, double fractionOfFree) {
+// of what is free right now plus what this buffer already holds (the work is then cut into more chunks, never refused).
+// The device is asked once per context and buffer kind (cudaMemGetInfo costs a driver round trip).
+static inline size_t vg_mem_budget(size_t want, double fraction, size_t held) {
   size_t freeB = 0, totalB = 0;
   if (cudaMemGetInfo(&freeB, &totalB) != cudaSuccess) {
     cudaGetLastError();
     return want;
   }
-  const size_t cap = (size_t)((double)freeB * fractionOfFree);
+  const size_t cap = (size_t)((double)(freeB + held) * fraction);
   return std::max<size_t>((size_t)64 << 20, std::min(want, cap));
 }
 

@@ -210,7 +210,8 @@ static int mh_map(vg_ctx* c, bool msa, const int64_t* pair_idx, int64_t n_idx, v
     const int nCont = msa ? 1 : (int)c->contigEnds.size();
     maxWin = std::max(8, std::min(8192, std::max(range / std::max(1, c->maxReadLen / 2), range / lmin) + 2 * nCont + 4));
   }
-  int64_t chunkPairs = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)((vg_mem_budget(3ull << 30, 0.2) + c->d_cand.cap) / ((size_t)maxWin * 48 + 64))));
+  if (!c->budgetWin) c->budgetWin = vg_mem_budget(3ull << 30, 0.2, c->d_cand.cap);
+  int64_t chunkPairs = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)(c->budgetWin / ((size_t)maxWin * 48 + 64))));
   if (const char* e = getenv("VG_MAP_CHUNK_PAIRS")) chunkPairs = std::max<int64_t>(1, std::min<int64_t>(n, atoll(e)));  // tests
   const int nf = (int)c->fragmentEnds.size();
   if (emptyRef) {

@@ -442,7 +442,10 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   }
   size_t sBudget = 0;
   if (const char* e = getenv("VG_SEED_SUBMB")) sBudget = (size_t)std::max(1, atoi(e)) << 20;
-  else sBudget = vg_mem_budget(8ull << 30, 0.3) + c->d_seedS.cap;  // the slot buffer already held counts as free
+  else {
+    if (!c->budgetSeed) c->budgetSeed = vg_mem_budget(8ull << 30, 0.3, c->d_seedS.cap);
+    sBudget = c->budgetSeed;
+  }
   A.capC = A.capR;
   A.key24 = (G < 16384 && !getenv("VG_SEED_KEY32")) ? 1 : 0;
   const int64_t subItems = std::max<int64_t>(4096, std::min<int64_t>(nItems, (int64_t)(sBudget / ((size_t)A.capS * 8))));

@@ -37,7 +37,10 @@ static int sw_launch_R(vg_ctx* c, const SwTask* d_tasks, int ntasks, const uint8
   const size_t perTask = perPair / 2;
   size_t budget = 0;
   if (const char* e = getenv("VG_CKPT_BYTES")) budget = (size_t)atoll(e);
-  else if (traceback) budget = vg_mem_budget((size_t)24 << 30, 0.6) + c->d_rowck.cap + c->d_colck.cap;  // what is held counts as free
+  else if (traceback) {
+    if (!c->budgetCkpt) c->budgetCkpt = vg_mem_budget((size_t)24 << 30, 0.6, c->d_rowck.cap + c->d_colck.cap);
+    budget = c->budgetCkpt;
+  }
   int64_t chunk = ntasks;
   if (traceback) {
     chunk = std::min<int64_t>(ntasks, std::max<int64_t>(2, (int64_t)(budget / perTask)));
