@@ -134,3 +134,29 @@ def test_cutoffs_fixture_has_all_configs():
     d = json.load(open(os.path.join(ROOT, "tests", "golden", "cutoffs.json")))
     for k in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5"):
         assert len(d[k]["cutoffs"]) == d[k]["L"] + 1
+
+
+def test_jni_layer_type_checks_against_the_header_and_matches_the_java_natives():
+    """The Java shim cannot be compiled here (no JDK). What can be checked is checked: the JNI C file compiles against
+    include/virgena_gpu.h with a stub jni.h (every call into the library has the declared argument types), every `native`
+    method of VirgenaGpu.java has its Java_VirgenaGpu_* function and vice versa, and every vg_* symbol it calls is declared."""
+    jdir = os.path.join(ROOT, "virgena_b200", "java")
+    csrc = os.path.join(jdir, "virgena_gpu_jni.c")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-I", os.path.join(ROOT, "tests", "jni_stub"), csrc], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    java = open(os.path.join(jdir, "VirgenaGpu.java")).read()
+    natives = set(re.findall(r"\bnative\s+[\w\[\]]+\s+(\w+)\s*\(", java))
+    ctxt = open(csrc).read()
+    cfuncs = set(re.findall(r"Java_VirgenaGpu_(\w+)\s*\(", ctxt))
+    assert natives and natives == cfuncs, (sorted(natives - cfuncs), sorted(cfuncs - natives))
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "virgena_gpu.h")).read(), flags=re.S)
+    declared = set(re.findall(r"\b(vg_[a-z0-9_]+)\s*\(", hdr))
+    called = set(re.findall(r"\b(vg_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", ctxt, flags=re.S)))
+    assert called <= declared, sorted(called - declared)
+    # the drop-in classes exist and keep the reference's signatures
+    for f, sig in (("MapperGpu.java", "MappedData mapReads(ArrayList<PairedRead> reads, Reference genome)"),
+                   ("MapperGpu.java", "void mapReads(MappedData mappedData, Reference genome)"),
+                   ("MapperMSAGpu.java", "MappedData mapAllReads(ArrayList<PairedRead> reads, ReferenceAlignment refAlignment)"),
+                   ("ConsensusBuilderSimpleGpu.java", "byte[] getConsensusSimple(boolean saveUncovered, int coverageThreshold, byte[] genome)")):
+        assert sig in open(os.path.join(jdir, f)).read(), (f, sig)
