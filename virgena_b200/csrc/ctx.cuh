@@ -92,6 +92,7 @@ struct vg_ctx {
   // scratch
   DevBuf d_tasks, d_fill, d_alns, d_rev, d_rowck, d_colck, d_counter, d_scratch, d_seqOff, d_cand, d_ncand, d_misc;
   DevBuf d_s1pool, d_s2pool, d_s1off, d_s2off, d_rowpool, d_rowLen, d_scratchR;
+  DevBuf d_swSorted, d_swBins;  // alignment tasks sorted by (R bin, window length), the counting sort's tables
   DevBuf d_swSeq1;  // sequence1 output of vg_sw_align_batch (its own buffer: d_seq1pool belongs to the last mapping)
   DevBuf d_bamN, d_bamOff, d_bamRec, d_bamOps;  // vg_bam_fields
   DevBuf d_seedS, d_seedNS, d_seedFb;  // fast seeding path: per-item LongHit slots, counts, fallback list

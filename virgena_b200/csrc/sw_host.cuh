@@ -97,13 +97,80 @@ static int sw_launch_R(vg_ctx* c, const SwTask* d_tasks, int ntasks, const uint8
   return VG_OK;
 }
 
-// Runs fill (+ traceback) over device-resident tasks. d_alns/d_rev are indexed by SwTask.out.
-static int sw_run(vg_ctx* c, const SwTask* d_tasks, int64_t ntasks, const uint8_t* d_s1, const uint8_t* d_s2, int mmax,
-                  int nmax, bool traceback, SwFillOut* d_fill, SwAln* d_alns, uint8_t* d_rev, int64_t revStride,
-                  double* msFill, double* msTb) {
-  if (ntasks == 0) return VG_OK;
-  if (ntasks > 0x7fffffff) return vg_fail(c, VG_ERR_INVALID, "too many alignment tasks in one call");
-  VG_TRY(sw_validate(c, mmax, nmax));
+// ---- length binning -----------------------------------------------------------------------------------------------------
+// The fill kernel gives every lane R consecutive rows, R from the longest read of the launch, and packs two alignments
+// into one warp whose wavefront runs max(n_a, n_b) + lanes steps: a ragged batch (trimmed Illumina reads, windows cut
+// by contig ends) wastes lanes and steps. The tasks are therefore counting-sorted on the device by (R bin of |s1|, |s2|):
+// every bin is launched with its own R and checkpoint geometry, partners inside a bin have (nearly) equal |s2|, and the
+// 32 alignments of a traceback warp walk paths of similar length. Results are addressed by SwTask.out, so the order in
+// which tasks run is invisible to the caller.
+#define SW_NBINS 11
+#define SW_NKEYS 1024  // |s2| buckets per bin
+__constant__ int sw_binR[SW_NBINS] = {2, 3, 4, 5, 6, 8, 10, 12, 16, 24, 32};
+static const int sw_binR_host[SW_NBINS] = {2, 3, 4, 5, 6, 8, 10, 12, 16, 24, 32};
+
+__device__ __forceinline__ int sw_task_key(const SwTask& t, int nShift, int minBin) {
+  int b = 0;
+#pragma unroll
+  for (int k = 0; k < SW_NBINS - 1; k++) b += (32 * sw_binR[k] < t.m) ? 1 : 0;
+  b = max(b, minBin);
+  // inside a bin: eight groups of |s1| (partners use the same lanes), then 128 buckets of |s2|
+  const int mg = min(7, max(t.m - 1, 0) * 8 / (32 * sw_binR[b]));
+  return b * SW_NKEYS + mg * 128 + min(t.n >> nShift, 127);
+}
+// hist[key]++, binMaxN[bin] = max |s2|, binMaxM[bin] = max |s1|
+__global__ void sw_bin_hist_kernel(const SwTask* __restrict__ tasks, int n, int nShift, int minBin, int* __restrict__ hist,
+                                   int* __restrict__ binMaxN, int* __restrict__ binMaxM) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const SwTask t = tasks[i];
+  const int key = sw_task_key(t, nShift, minBin);
+  atomicAdd(hist + key, 1);
+  atomicMax(binMaxN + key / SW_NKEYS, t.n);
+  atomicMax(binMaxM + key / SW_NKEYS, t.m);
+}
+// exclusive scan of hist[SW_NBINS * SW_NKEYS] by one block of 1024 threads (11 keys per thread); binStart[b] = first task
+// of bin b, binStart[SW_NBINS] = n
+__global__ void sw_bin_scan_kernel(int* __restrict__ hist, int* __restrict__ binStart) {
+  __shared__ int part[1024];
+  const int t = threadIdx.x;
+  int loc[SW_NBINS], sum = 0;
+#pragma unroll
+  for (int k = 0; k < SW_NBINS; k++) {
+    loc[k] = hist[t * SW_NBINS + k];
+    sum += loc[k];
+  }
+  part[t] = sum;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    const int v = (t >= d) ? part[t - d] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int run = part[t] - sum;
+#pragma unroll
+  for (int k = 0; k < SW_NBINS; k++) {
+    const int key = t * SW_NBINS + k;
+    if (key % SW_NKEYS == 0) binStart[key / SW_NKEYS] = run;
+    hist[key] = run;
+    run += loc[k];
+  }
+  if (t == 1023) binStart[SW_NBINS] = run;
+}
+__global__ void sw_bin_scatter_kernel(const SwTask* __restrict__ tasks, int n, int nShift, int minBin, int* __restrict__ cursor,
+                                      SwTask* __restrict__ sorted) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const SwTask t = tasks[i];
+  sorted[atomicAdd(cursor + sw_task_key(t, nShift, minBin), 1)] = t;
+}
+
+// Runs fill (+ traceback) over device-resident tasks. d_alns/d_rev are indexed by SwTask.out. With traceback the tasks
+// run in length bins (see above); d_fill is scratch then. Score-only keeps the caller's order (d_fill[i] = task i).
+static int sw_run_bin(vg_ctx* c, const SwTask* d_tasks, int64_t ntasks, const uint8_t* d_s1, const uint8_t* d_s2, int mmax,
+                      int nmax, bool traceback, SwFillOut* d_fill, SwAln* d_alns, uint8_t* d_rev, int64_t revStride,
+                      double* msFill, double* msTb) {
   const int R = sw_pick_R(mmax);
   // 4-byte checkpoints (V in 12 bits + the 4 bits of the gap state that matter, see SwCk) when the scores and the
   // penalties allow it, else 8-byte ones
@@ -130,4 +197,54 @@ static int sw_run(vg_ctx* c, const SwTask* d_tasks, int64_t ntasks, const uint8_
   }
 #undef SW_CASE
   return vg_fail(c, VG_ERR_INVALID, "no kernel for read length %d", mmax);
+}
+
+static int sw_run(vg_ctx* c, const SwTask* d_tasks, int64_t ntasks, const uint8_t* d_s1, const uint8_t* d_s2, int mmax,
+                  int nmax, bool traceback, SwFillOut* d_fill, SwAln* d_alns, uint8_t* d_rev, int64_t revStride,
+                  double* msFill, double* msTb) {
+  if (ntasks == 0) return VG_OK;
+  if (ntasks > 0x7fffffff) return vg_fail(c, VG_ERR_INVALID, "too many alignment tasks in one call");
+  VG_TRY(sw_validate(c, mmax, nmax));
+  if (!traceback || getenv("VG_SW_NOBIN"))
+    return sw_run_bin(c, d_tasks, ntasks, d_s1, d_s2, mmax, nmax, traceback, d_fill, d_alns, d_rev, revStride, msFill, msTb);
+  // counting sort by (R bin, |s2|)
+  const int n = (int)ntasks;
+  int nShift = 0;
+  while ((nmax >> nShift) >= 128) nShift++;
+  // the smallest R in use: thin strips make the fill of short reads efficient but the traceback crosses more of them
+  int minBin = 5;  // R = 8 (measured on a 50..250 batch, profiles/sw_r2.md)
+  if (const char* e = getenv("VG_SW_MINR")) {
+    minBin = 0;
+    while (minBin < SW_NBINS - 1 && sw_binR_host[minBin] < atoi(e)) minBin++;
+  }
+  const size_t histBytes = (size_t)SW_NBINS * SW_NKEYS * 4;
+  VG_CUDA(c, c->d_swBins.reserve(histBytes + 256));
+  VG_CUDA(c, c->d_swSorted.reserve((size_t)n * sizeof(SwTask)));
+  int* d_hist = c->d_swBins.as<int>();
+  int* d_binStart = d_hist + SW_NBINS * SW_NKEYS;  // [SW_NBINS + 1], then binMaxN[SW_NBINS], binMaxM[SW_NBINS]
+  int* d_binMaxN = d_binStart + SW_NBINS + 1;
+  int* d_binMaxM = d_binMaxN + SW_NBINS;
+  VG_CUDA(c, cudaMemsetAsync(d_hist, 0, histBytes + 256, c->stream));
+  sw_bin_hist_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_tasks, n, nShift, minBin, d_hist, d_binMaxN, d_binMaxM);
+  VG_LAUNCH_CHECK(c);
+  sw_bin_scan_kernel<<<1, 1024, 0, c->stream>>>(d_hist, d_binStart);
+  VG_LAUNCH_CHECK(c);
+  sw_bin_scatter_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_tasks, n, nShift, minBin, d_hist, c->d_swSorted.as<SwTask>());
+  VG_LAUNCH_CHECK(c);
+  int host[3 * SW_NBINS + 1];
+  VG_CUDA(c, cudaMemcpyAsync(host, d_binStart, sizeof host, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int* binStart = host;
+  const int* binMaxN = host + SW_NBINS + 1;
+  const int* binMaxM = binMaxN + SW_NBINS;
+  if (binStart[SW_NBINS] != n) return vg_fail(c, VG_ERR_CUDA, "alignment task binning lost tasks (%d of %d)", binStart[SW_NBINS], n);
+  for (int b = 0; b < SW_NBINS; b++) {
+    const int cnt = binStart[b + 1] - binStart[b];
+    if (cnt <= 0) continue;
+    // a bin's tasks all have |s1| <= 32 R of the bin; empty reads (m == 0) sit in the first bin
+    const int mBin = std::max(32 * (b ? sw_binR_host[b - 1] : 0) + 1, std::min(binMaxM[b], 32 * sw_binR_host[b]));
+    VG_TRY(sw_run_bin(c, c->d_swSorted.as<SwTask>() + binStart[b], cnt, d_s1, d_s2, mBin, std::max(1, binMaxN[b]), true,
+                      d_fill + binStart[b], d_alns, d_rev, revStride, msFill, msTb));
+  }
+  return VG_OK;
 }
