@@ -387,15 +387,40 @@ def main():
         e2e_ctx.append(c2)
     rec_hosts = [torch.zeros(n * vg.PAIR_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True).numpy().view(vg.PAIR_DTYPE) for _ in range(n_e2e)]
     pool_hosts = [torch.empty(n * 2 * (L + L * 3 // 2 + 8), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(n_e2e)]
+    ops_hosts = [torch.empty(n * 2 * 24, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32) for _ in range(n_e2e)]
+    # the packed transfer form of the same batches (2 bits per ACGT base + exceptions), made once by the library's host-side
+    # packer, in pinned memory: the form a read loader hands to vg_upload_reads_packed
+    import ctypes as C
+    packed_batches = []
+    for b in range(n_batches):
+        hb = host_batches[b].numpy().reshape(-1)
+        pk = torch.zeros((n_bases + 3) // 4 + 64, dtype=torch.uint8, pin_memory=True)
+        cap = max(1 << 16, n_bases // 50)
+        epos = torch.zeros(cap, dtype=torch.int64, pin_memory=True)
+        ebyt = torch.zeros(cap, dtype=torch.uint8, pin_memory=True)
+        ne = C.c_int64()
+        rc = vg._lib.lib().vg_pack_reads(C.c_void_p(hb.ctypes.data), n_bases, C.c_void_p(pk.data_ptr()), C.c_void_p(epos.data_ptr()),
+                                         C.c_void_p(ebyt.data_ptr()), cap, C.byref(ne))
+        if rc != 0:
+            raise RuntimeError("vg_pack_reads: %d (%d exceptions)" % (rc, ne.value))
+        packed_batches.append((pk, epos.numpy()[:ne.value], ebyt.numpy()[:ne.value]))
     d2h = [0]
     turn = [0]
     turn_cv = threading.Condition()
+    e2e_mode = ["packed"]
 
     def step_e2e(tid, b, seq):
         c = e2e_ctx[tid]
-        c.upload_reads_raw(host_batches[b].data_ptr(), n_bases, off1, len1, off2, len2)
-        st = c.map_pairs(fetch=False)
-        nres, nbytes = c.get_results_into(rec_hosts[tid], pool_hosts[tid])
+        if e2e_mode[0] == "packed":
+            pk, epos, ebyt = packed_batches[b]
+            c.upload_reads_packed_raw(pk.data_ptr(), n_bases, epos, ebyt, off1, len1, off2, len2)
+            st = c.map_pairs(fetch=False)
+            nres = n
+            nbytes = 4 * c.get_results_compact_into(rec_hosts[tid], ops_hosts[tid])
+        else:
+            c.upload_reads_raw(host_batches[b].data_ptr(), n_bases, off1, len1, off2, len2)
+            st = c.map_pairs(fetch=False)
+            nres, nbytes = c.get_results_into(rec_hosts[tid], pool_hosts[tid])
         c.pileup(False)
         with turn_cv:  # collectives in the same order on every rank
             while turn[0] < seq:
@@ -473,19 +498,29 @@ def main():
     ms = float(tt.item())
     value = n * world * args.steps / (ms * 1e-3)
 
-    # ---- end-to-end arm ----------------------------------------------------------------------------------
-    run_e2e(2 * n_e2e)
-    barrier()
-    t0 = time.time()
-    run_e2e(args.steps)
-    barrier()
-    e2e_ms = (time.time() - t0) * 1e3
-    tt = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    e2e_ms = float(tt.item())
+    # ---- end-to-end arms -----------------------------------------------------------------------------------
+    # headline: packed upload (vg_upload_reads_packed) + compact results (vg_get_results_compact); beside it the byte API
+    # of round 1 (vg_upload_reads + vg_get_results with the full sequence1 pool)
+    def time_e2e(mode):
+        e2e_mode[0] = mode
+        run_e2e(2 * n_e2e)
+        barrier()
+        t0 = time.time()
+        run_e2e(args.steps)
+        barrier()
+        ms_ = (time.time() - t0) * 1e3
+        tt_ = torch.tensor([ms_], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+        return float(tt_.item()), int(d2h[0])
+
+    bytes_ms, bytes_d2h = time_e2e("bytes")
+    bytes_value = n * world * args.steps / (bytes_ms * 1e-3)
+    bytes_h2d = n_bases + off1.nbytes * 2 + len1.nbytes * 2
+    e2e_ms, e2e_d2h = time_e2e("packed")
     e2e_value = n * world * args.steps / (e2e_ms * 1e-3)
-    h2d = n_bases + off1.nbytes * 2 + len1.nbytes * 2
+    h2d = (n_bases + 3) // 4 + 9 * int(np.mean([len(p[1]) for p in packed_batches])) + off1.nbytes * 2 + len1.nbytes * 2
+    d2h[0] = e2e_d2h
 
     # ---- N > 1: the sharded path against the single-GPU result (not timed) --------------------------------------------
     multi_check = None
@@ -590,9 +625,14 @@ def main():
                        "cache": "inputs larger than L2 (0.5 GB of reads per step, two alternating batches)",
                        "step": "mapReads + getConsensusSimple (seed, pair-select, SW fill, traceback, pileup, allreduce, argmax)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h[0]),
-                    "ms_per_step": e2e_ms / args.steps,
+                    "ms_per_step": e2e_ms / args.steps, "over_device_resident": e2e_value / value,
                     "how": "%d host threads with one context each alternate over the steps (copies of one overlap kernels of the "
-                           "other); each step = vg_upload_reads + vg_map_pairs + vg_get_results + vg_pileup + vg_consensus" % n_e2e},
+                           "other); each step = vg_upload_reads_packed (2 bits per base + exceptions, pinned) + vg_map_pairs + "
+                           "vg_get_results_compact (records + run-length edit operations, from which sequence1 is a function of "
+                           "the read) + vg_pileup + vg_consensus" % n_e2e},
+            "e2e_byte_api": {"value": bytes_value, "unit": UNIT, "h2d_bytes_per_step": int(bytes_h2d), "d2h_bytes_per_step": int(bytes_d2h),
+                             "ms_per_step": bytes_ms / args.steps,
+                             "how": "the same with 1 byte per base up (vg_upload_reads) and the full sequence1 pool down (vg_get_results)"},
             "gpu_launches": int(launches2 - launches1),
             "clocks": clocks,
             "stage_ms_per_step": {"seed_pairselect": seed_ms, "seed_gen_kernel": gen_ms, "seed_win_kernel": win_ms,

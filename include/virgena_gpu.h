@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define VG_ABI_VERSION 2
+#define VG_ABI_VERSION 3
 
 typedef enum {
   VG_OK = 0,
@@ -138,6 +138,19 @@ int vg_set_msa_index(vg_ctx* ctx, int32_t K, float low_coef, float high_coef, co
 int vg_upload_reads(vg_ctx* ctx, const uint8_t* bases, int64_t n_bases, const int64_t* off1, const int32_t* len1,
                     const int64_t* off2, const int32_t* len2, int64_t n_pairs);
 
+/* The same with the bases packed for the transfer (north star: 2-bit reads): 2 bits per base (A=0, C=1, G=2, T=3), base i
+ * in bits 2*(i&3) of byte i>>2, plus n_exc exceptions (exc_pos[k], exc_byte[k]) for every byte that is not ACGT ('N',
+ * '-', the '*' of an absent mate, ...). off/len address bases exactly as in vg_upload_reads. The device unpacks into
+ * the same resident byte pool (the path's alphabet is bytes: any byte takes part in byte equality), so everything
+ * downstream is identical; the host-to-device copy is 4x smaller. vg_pack_reads is the host-side packer (plain C loop,
+ * no device): packed holds (n_bases+3)/4 bytes; exceptions come out in ascending position order; VG_ERR_CAPACITY with
+ * *n_exc = the number needed when exc_cap is too small. */
+int vg_upload_reads_packed(vg_ctx* ctx, const uint8_t* packed, int64_t n_bases, const int64_t* exc_pos,
+                           const uint8_t* exc_byte, int64_t n_exc, const int64_t* off1, const int32_t* len1,
+                           const int64_t* off2, const int32_t* len2, int64_t n_pairs);
+int vg_pack_reads(const uint8_t* bases, int64_t n_bases, uint8_t* packed, int64_t* exc_pos, uint8_t* exc_byte,
+                  int64_t exc_cap, int64_t* n_exc);
+
 /* Mapper.mapReads(reads, genome) [Mapper.java:420] when pair_idx == NULL
  * (all resident pairs, in order), or Mapper.mapReads(mappedData, genome)
  * [Mapper.java:477] over the subset pair_idx[0..n_idx) (needToRemap).
@@ -154,6 +167,15 @@ int vg_result_sizes(vg_ctx* ctx, int64_t* n_results, int64_t* seq1_bytes);
 /* Copies the per-pair results (input order) and the sequence1 byte pool of the
  * last map call to the host. seq1_offset values index `seq1_pool`. */
 int vg_get_results(vg_ctx* ctx, vg_pair_result* out, int64_t n_out, uint8_t* seq1_pool, int64_t pool_cap);
+
+/* vg_get_results without the sequence1 bytes ("an edit string from which sequence1 is reconstructible"): in
+ * the records written to `out`, seq1_offset is the index of the mate's first element in `ops` and pad_ their number; an
+ * element is len << 4 | op with op 0 = alignment columns holding a read base (DIAGONAL), 1 = lower-cased read bases (UP:
+ * insertion), 2 = '-' (LEFT: deletion) [SmithWatermanGotoh.java:157-222]. sequence1 = the read in the mate's orientation
+ * (reverse: Constants.getComplement) from start1 on, copied / lower-cased (Constants.lower) / skipped per element. The
+ * device keeps sequence1, so vg_pileup / vg_bam_fields / vg_identity_counting are unaffected. VG_ERR_CAPACITY with
+ * vg_last_required = the number of elements when ops_cap is too small (*n_ops is set either way). */
+int vg_get_results_compact(vg_ctx* ctx, vg_pair_result* out, int64_t n_out, uint32_t* ops, int64_t ops_cap, int64_t* n_ops);
 
 /* Installs a MappedData held by the host as the context's "last mapping": per-pair records (with seq1_offset / length
  * addressing seq1_pool), and for each record the index of its pair in the resident read set. This is what lets the Java

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(built):
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert set(_lib.EXPORTED_SYMBOLS) == declared
-    assert L.vg_abi_version() == 2
+    assert L.vg_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_a_device(built):
@@ -160,3 +160,28 @@ def test_jni_layer_type_checks_against_the_header_and_matches_the_java_natives()
                    ("MapperMSAGpu.java", "MappedData mapAllReads(ArrayList<PairedRead> reads, ReferenceAlignment refAlignment)"),
                    ("ConsensusBuilderSimpleGpu.java", "byte[] getConsensusSimple(boolean saveUncovered, int coverageThreshold, byte[] genome)")):
         assert sig in open(os.path.join(jdir, f)).read(), (f, sig)
+
+
+def test_pack_reads_host_helper(built):
+    """vg_pack_reads is a host-side formatter (no device): 2 bits per ACGT base, everything else an exception."""
+    import ctypes as C
+    from virgena_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    b = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 1003)].copy()
+    exc = {0: ord("*"), 7: ord("N"), 500: ord("-"), 1002: ord("R"), 1001: ord("a")}
+    for p, v in exc.items():
+        b[p] = v
+    pk = np.zeros((len(b) + 3) // 4, np.uint8)
+    pos = np.zeros(16, np.int64)
+    byt = np.zeros(16, np.uint8)
+    ne = C.c_int64()
+    assert L.vg_pack_reads(_lib.ptr(b), len(b), _lib.ptr(pk), _lib.ptr(pos), _lib.ptr(byt), 16, C.byref(ne)) == 0
+    assert ne.value == 5 and pos[:5].tolist() == sorted(exc) and byt[:5].tolist() == [exc[k] for k in sorted(exc)]
+    codes = (pk[np.arange(len(b)) >> 2] >> (2 * (np.arange(len(b)) & 3))) & 3
+    back = np.frombuffer(b"ACGT", np.uint8)[codes]
+    keep = np.ones(len(b), bool)
+    keep[sorted(exc)] = False
+    assert (back[keep] == b[keep]).all()
+    # capacity: the count needed comes back with VG_ERR_CAPACITY
+    assert L.vg_pack_reads(_lib.ptr(b), len(b), _lib.ptr(pk), _lib.ptr(pos), _lib.ptr(byt), 2, C.byref(ne)) == -4 and ne.value == 5

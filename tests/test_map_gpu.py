@@ -983,6 +983,30 @@ def test_map_reads_ragged_and_edge_cases(hiv):
     _compare(md, orec, opool, ostats)
     mapper.ctx.pileup()
     assert (mapper.ctx.counts() == oracle.pileup(orec, opool, len(ref))).all()
+    # the same reads through the packed upload (2 bits per ACGT base + exceptions for '*', N, IUPAC, junk bytes) and the
+    # compact result form (edit operations instead of sequence1): identical records, sequence1 reconstructed byte for byte
+    reads = vg.PairedReads(bases, off1, len1, off2, len2)
+    pk, epos, ebyte = reads.packed()
+    assert len(epos) > 0 and (bases[epos] == ebyte).all() and (np.diff(epos) > 0).all()
+    ctx2 = vg.Context(K=5, cutoffs=cut)
+    ctx2.set_reference(vg.Reference(ref, K=5, thread_num=8))
+    ctx2.upload_reads_packed(reads)
+    md2 = ctx2.map_pairs()
+    _compare(md2, orec, opool, ostats)
+    crec, ops = ctx2.get_results_compact()
+    assert (crec["cls"] == orec["cls"]).all()
+    for f in FIELDS:
+        assert (crec["m"][f] == orec["m"][f]).all(), f
+    cmd = vg.MappedData(md2.pair_index, crec, None, md2.stats, ops=ops, reads=reads)
+    n_checked = 0
+    for r, k in zip(*cmd.mappedReads):
+        m = orec["m"][r, k]
+        want = opool[m["seq1_offset"]:m["seq1_offset"] + m["length"]].tobytes()
+        assert cmd.sequence1(r, k) == want, (r, k)
+        n_checked += 1
+    assert n_checked > 200 and int(crec["m"]["pad_"].sum()) == len(ops)
+    ctx2.pileup()  # the device still holds sequence1: consumers are unaffected
+    assert (ctx2.counts() == oracle.pileup(orec, opool, len(ref))).all()
 
 
 def test_reference_with_gaps_and_n(hiv):

@@ -62,6 +62,10 @@ _SIGS = {
                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "vg_upload_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int64]),
+    "vg_upload_reads_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_int64]),
+    "vg_pack_reads": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "vg_get_results_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "vg_map_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(VgMapStats)]),
     "vg_map_pairs_msa": (C.c_int, [C.c_void_p, C.POINTER(VgMapStats)]),
     "vg_result_sizes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -83,6 +83,7 @@ struct vg_ctx {
   int maxReadLen = 0;
   int minReadLenGe[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // shortest read of at least k bases (sizes the window lists)
   DevBuf d_bases, d_off1, d_off2, d_len1, d_len2;
+  DevBuf d_packed;  // staging of vg_upload_reads_packed (2-bit words + exceptions)
   std::vector<uint8_t> h_exist;  // per pair: bit0 mate1 exists, bit1 mate2 exists
 
   // results of the last map call

@@ -27,6 +27,105 @@ __global__ void mh_validate_kernel(const uint8_t* __restrict__ b, int64_t n, int
   if (__any_sync(VG_FULL, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
+// ---- packed reads (north star: 2-bit reads; SURVEY 8b "vg_upload_reads ... or /4 packed + mask") -------------------------
+// Host format: 2 bits per base (A=0, C=1, G=2, T=3), base i in bits 2 (i & 3) of byte i >> 2, plus a list of exceptions
+// (position, byte) for everything that is not ACGT ('N', '-', the '*' of an absent mate, IUPAC codes). The device
+// unpacks into the 1 B/base pool the kernels read: the alphabet of the path is bytes, not 2-bit codes (any byte takes part
+// in byte equality), so the packing is a transfer format — 4x fewer PCIe bytes — not a change of the kernels' input.
+__global__ void mh_unpack_kernel(const uint32_t* __restrict__ packed, int64_t nWords, uint4* __restrict__ bases) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nWords) return;
+  const uint32_t w = packed[i];
+  uint32_t o[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const uint32_t code = (w >> (8 * q + 2 * b)) & 3u;
+      const uint32_t ch = (0x54474341u >> (8 * code)) & 0xFFu;  // "ACGT"
+      v |= ch << (8 * b);
+    }
+    o[q] = v;
+  }
+  bases[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+__global__ void mh_exceptions_kernel(const int64_t* __restrict__ pos, const uint8_t* __restrict__ byte, int64_t n,
+                                     int64_t nBases, uint8_t* __restrict__ bases, int* __restrict__ flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t p = pos[i];
+  if (p < 0 || p >= nBases) atomicOr(flag, 2);
+  else bases[p] = byte[i];
+}
+
+// ---- compact results: sequence1 as run-length edit operations -----------------------------------------------------------
+// Alignment.sequence1 (SmithWatermanGotoh.java:157-222) holds, per alignment column, the read base (DIAGONAL), the lower-
+// cased read base (UP: insertion in the read) or '-' (LEFT: deletion). Given the read, its strand and start1, the string is
+// therefore a function of the run lengths of these three column classes: len << 4 | op with op 0 = aligned base, 1 =
+// insertion, 2 = deletion (the BAM op codes). One warp per alignment; EMIT = false counts the runs.
+template <bool EMIT>
+__global__ void mh_ops_kernel(const vg_pair_result* __restrict__ res, int64_t n2, const uint8_t* __restrict__ pool,
+                              int32_t* __restrict__ nOps, const int64_t* __restrict__ opOff, uint32_t* __restrict__ ops) {
+  const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= n2) return;
+  const vg_mate& m = res[q >> 1].m[q & 1];
+  if (!m.present || m.seq1_offset < 0) {
+    if (!EMIT && lane == 0) nOps[q] = 0;
+    return;
+  }
+  const int len = m.length;
+  const uint8_t* s = pool + m.seq1_offset;
+  uint32_t* out = EMIT ? ops + opOff[q] : nullptr;
+  const unsigned lt = (1u << lane) - 1u;
+  int n = 0, openPos = 0, openCls = 0, prevCls = -1;
+  for (int t0 = 0; t0 < len; t0 += 32) {
+    const int t = t0 + lane;
+    const uint8_t ch = (t < len) ? s[t] : 0;
+    const int cls = (ch == '-') ? 2 : (ch < 'a') ? 0 : 1;
+    int p = __shfl_up_sync(VG_FULL, cls, 1);
+    if (lane == 0) p = prevCls;
+    const bool st = (t < len) && cls != p;
+    const unsigned mk = __ballot_sync(VG_FULL, st);
+    prevCls = __shfl_sync(VG_FULL, cls, 31);
+    if (mk) {
+      if (EMIT) {
+        if (n > 0 && lane == 0) out[n - 1] = ((uint32_t)(t0 + __ffs(mk) - 1 - openPos) << 4) | (uint32_t)openCls;
+        const unsigned higher = mk & ~((2u << lane) - 1u);
+        if (st && higher) out[n + __popc(mk & lt)] = ((uint32_t)(__ffs(higher) - 1 - lane) << 4) | (uint32_t)cls;
+      }
+      const int last = 31 - __clz(mk);
+      openPos = t0 + last;
+      openCls = __shfl_sync(VG_FULL, cls, last);
+      n += __popc(mk);
+    }
+  }
+  if (EMIT) {
+    if (n > 0 && lane == 0) out[n - 1] = ((uint32_t)(len - openPos) << 4) | (uint32_t)openCls;
+  } else if (lane == 0) {
+    nOps[q] = n;
+  }
+}
+// the caller's copy of the records: seq1_offset -> first operation, pad_ -> number of operations
+__global__ void mh_compact_records_kernel(const vg_pair_result* __restrict__ res, int64_t n2, const int32_t* __restrict__ nOps,
+                                          const int64_t* __restrict__ opOff, vg_pair_result* __restrict__ out) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n2) return;
+  if ((q & 1) == 0) {
+    out[q >> 1].cls = res[q >> 1].cls;
+    out[q >> 1].pad_ = 0;
+  }
+  vg_mate m = res[q >> 1].m[q & 1];
+  if (m.present && m.seq1_offset >= 0) {
+    m.seq1_offset = opOff[q];
+    m.pad_ = nOps[q];
+  } else {
+    m.pad_ = 0;
+  }
+  out[q >> 1].m[q & 1] = m;
+}
+
 // exclusive scan int32 -> int64, three kernels
 __global__ void mh_scan1_kernel(const int32_t* __restrict__ in, int64_t* __restrict__ out, int64_t* __restrict__ blockSums, int64_t n) {
   __shared__ int64_t wsum[32];
@@ -376,11 +475,13 @@ int vg_set_msa_index(vg_ctx* c, int32_t K, float low_coef, float high_coef, cons
   return VG_OK;
 }
 
-int vg_upload_reads(vg_ctx* c, const uint8_t* bases, int64_t n_bases, const int64_t* off1, const int32_t* len1,
-                    const int64_t* off2, const int32_t* len2, int64_t n_pairs) {
+static int mh_upload(vg_ctx* c, const uint8_t* bases, const uint8_t* packed, const int64_t* exc_pos, const uint8_t* exc_byte,
+                     int64_t n_exc, int64_t n_bases, const int64_t* off1, const int32_t* len1, const int64_t* off2,
+                     const int32_t* len2, int64_t n_pairs) {
   if (!c) return VG_ERR_INVALID;
   VG_CUDA(c, cudaSetDevice(c->device));
-  if (n_pairs < 0 || n_bases < 0 || (n_pairs > 0 && (!bases || !off1 || !len1 || !off2 || !len2)))
+  if (n_pairs < 0 || n_bases < 0 || n_exc < 0 || (n_pairs > 0 && ((!bases && !packed) || !off1 || !len1 || !off2 || !len2)) ||
+      (n_exc > 0 && (!exc_pos || !exc_byte)))
     return vg_fail(c, VG_ERR_INVALID, "bad read arrays");
   c->haveReads = false;
   int maxLen = 0;
@@ -394,19 +495,42 @@ int vg_upload_reads(vg_ctx* c, const uint8_t* bases, int64_t n_bases, const int6
       for (int k = std::min(l, 8); k >= 0 && minGe[k] > l; k--) minGe[k] = l;
   }
   for (int k = 0; k < 9; k++) c->minReadLenGe[k] = minGe[k];
-  VG_CUDA(c, c->d_bases.reserve((size_t)n_bases + 64));
+  const int64_t nWords = (n_bases + 15) / 16;  // 16 bases per packed 32-bit word
+  VG_CUDA(c, c->d_bases.reserve((size_t)nWords * 16 + 64));
   VG_CUDA(c, c->d_off1.reserve((size_t)n_pairs * 8 + 8));
   VG_CUDA(c, c->d_off2.reserve((size_t)n_pairs * 8 + 8));
   VG_CUDA(c, c->d_len1.reserve((size_t)n_pairs * 4 + 8));
   VG_CUDA(c, c->d_len2.reserve((size_t)n_pairs * 4 + 8));
   if (n_pairs > 0) {
-    VG_CUDA(c, cudaMemcpyAsync(c->d_bases.p, bases, (size_t)n_bases, cudaMemcpyHostToDevice, c->stream));
+    VG_CUDA(c, c->d_counter.reserve(16));
+    VG_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, 16, c->stream));
+    if (packed) {
+      VG_CUDA(c, c->d_packed.reserve((size_t)nWords * 4 + (size_t)n_exc * 9 + 64));
+      uint8_t* d_pk = c->d_packed.as<uint8_t>();
+      int64_t* d_ep = (int64_t*)(d_pk + (((size_t)nWords * 4 + 15) & ~(size_t)15));
+      uint8_t* d_eb = (uint8_t*)(d_ep + n_exc);
+      // the last word may be partly outside the caller's buffer: copy the bytes that exist
+      VG_CUDA(c, cudaMemcpyAsync(d_pk, packed, (size_t)((n_bases + 3) / 4), cudaMemcpyHostToDevice, c->stream));
+      if (n_exc > 0) {
+        VG_CUDA(c, cudaMemcpyAsync(d_ep, exc_pos, (size_t)n_exc * 8, cudaMemcpyHostToDevice, c->stream));
+        VG_CUDA(c, cudaMemcpyAsync(d_eb, exc_byte, (size_t)n_exc, cudaMemcpyHostToDevice, c->stream));
+      }
+      if (nWords > 0) {
+        mh_unpack_kernel<<<(unsigned)((nWords + 255) / 256), 256, 0, c->stream>>>((const uint32_t*)d_pk, nWords, c->d_bases.as<uint4>());
+        VG_LAUNCH_CHECK(c);
+      }
+      if (n_exc > 0) {
+        mh_exceptions_kernel<<<(unsigned)((n_exc + 255) / 256), 256, 0, c->stream>>>(d_ep, d_eb, n_exc, n_bases, c->d_bases.as<uint8_t>(),
+                                                                                     c->d_counter.as<int>());
+        VG_LAUNCH_CHECK(c);
+      }
+    } else {
+      VG_CUDA(c, cudaMemcpyAsync(c->d_bases.p, bases, (size_t)n_bases, cudaMemcpyHostToDevice, c->stream));
+    }
     VG_CUDA(c, cudaMemcpyAsync(c->d_off1.p, off1, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, c->stream));
     VG_CUDA(c, cudaMemcpyAsync(c->d_off2.p, off2, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, c->stream));
     VG_CUDA(c, cudaMemcpyAsync(c->d_len1.p, len1, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
     VG_CUDA(c, cudaMemcpyAsync(c->d_len2.p, len2, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
-    VG_CUDA(c, c->d_counter.reserve(16));
-    VG_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, 16, c->stream));
     if (n_bases > 0) {
       mh_validate_kernel<<<c->smCount * 8, 256, 0, c->stream>>>(c->d_bases.as<uint8_t>(), n_bases, c->d_counter.as<int>());
       VG_LAUNCH_CHECK(c);
@@ -414,6 +538,7 @@ int vg_upload_reads(vg_ctx* c, const uint8_t* bases, int64_t n_bases, const int6
     int flag = 0;
     VG_CUDA(c, cudaMemcpyAsync(&flag, c->d_counter.p, 4, cudaMemcpyDeviceToHost, c->stream));
     VG_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (flag & 2) return vg_fail(c, VG_ERR_INVALID, "an exception position lies outside the read pool");
     if (flag)
       return vg_fail(c, VG_ERR_ALPHABET, "a read contains a byte >= 127 or in ('T','a'): the Java reference throws on it");
   }
@@ -422,6 +547,43 @@ int vg_upload_reads(vg_ctx* c, const uint8_t* bases, int64_t n_bases, const int6
   c->maxReadLen = maxLen;
   c->haveReads = true;
   return VG_OK;
+}
+
+int vg_upload_reads(vg_ctx* c, const uint8_t* bases, int64_t n_bases, const int64_t* off1, const int32_t* len1,
+                    const int64_t* off2, const int32_t* len2, int64_t n_pairs) {
+  if (c && n_pairs > 0 && !bases) return vg_fail(c, VG_ERR_INVALID, "bad read arrays");
+  return mh_upload(c, bases, nullptr, nullptr, nullptr, 0, n_bases, off1, len1, off2, len2, n_pairs);
+}
+
+int vg_upload_reads_packed(vg_ctx* c, const uint8_t* packed, int64_t n_bases, const int64_t* exc_pos, const uint8_t* exc_byte,
+                           int64_t n_exc, const int64_t* off1, const int32_t* len1, const int64_t* off2, const int32_t* len2,
+                           int64_t n_pairs) {
+  if (c && n_pairs > 0 && !packed) return vg_fail(c, VG_ERR_INVALID, "bad read arrays");
+  return mh_upload(c, nullptr, packed, exc_pos, exc_byte, n_exc, n_bases, off1, len1, off2, len2, n_pairs);
+}
+
+// Host-side helper (no device involved): bytes -> the packed format of vg_upload_reads_packed. packed: (n_bases + 3) / 4
+// bytes; exceptions are written in ascending position order; VG_ERR_CAPACITY (and *n_exc = the number needed) when there are
+// more than exc_cap of them.
+int vg_pack_reads(const uint8_t* bases, int64_t n_bases, uint8_t* packed, int64_t* exc_pos, uint8_t* exc_byte, int64_t exc_cap,
+                  int64_t* n_exc) {
+  if (n_bases < 0 || (n_bases > 0 && (!bases || !packed)) || !n_exc) return VG_ERR_INVALID;
+  int64_t ne = 0;
+  for (int64_t i = 0; i < n_bases; i += 4) {
+    uint8_t b = 0;
+    for (int k = 0; k < 4 && i + k < n_bases; k++) {
+      const uint8_t ch = bases[i + k];
+      const int cd = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : -1;
+      if (cd >= 0) b |= (uint8_t)(cd << (2 * k));
+      else {
+        if (ne < exc_cap && exc_pos && exc_byte) exc_pos[ne] = i + k, exc_byte[ne] = bases[i + k];
+        ne++;
+      }
+    }
+    packed[i >> 2] = b;
+  }
+  *n_exc = ne;
+  return ne > exc_cap ? VG_ERR_CAPACITY : VG_OK;
 }
 
 int vg_map_pairs(vg_ctx* c, const int64_t* pair_idx, int64_t n_idx, vg_map_stats* stats) {
@@ -453,6 +615,56 @@ int vg_get_results(vg_ctx* c, vg_pair_result* out, int64_t n_out, uint8_t* seq1_
     if (!seq1_pool) return vg_fail(c, VG_ERR_INVALID, "null sequence1 pool");
     VG_CUDA(c, cudaMemcpyAsync(seq1_pool, c->d_seq1pool.p, (size_t)c->seq1Bytes, cudaMemcpyDeviceToHost, c->stream));
   }
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VG_OK;
+}
+
+// vg_get_results without the sequence1 bytes: records whose seq1_offset / pad_ address run-length edit operations
+// (mh_ops_kernel) from which Alignment.sequence1 is a function of the read (SURVEY 8b "an edit string from which sequence1
+// is reconstructible"). 4-5x fewer device-to-host bytes.
+int vg_get_results_compact(vg_ctx* c, vg_pair_result* out, int64_t n_out, uint32_t* ops, int64_t ops_cap, int64_t* n_ops) {
+  if (!c) return VG_ERR_INVALID;
+  VG_CUDA(c, cudaSetDevice(c->device));
+  if (n_ops) *n_ops = 0;
+  const int64_t n = c->nResults;
+  if (n_out < n) {
+    c->required = n;
+    return vg_fail(c, VG_ERR_CAPACITY, "record buffer too small (%lld results)", (long long)n);
+  }
+  if (n == 0) return VG_OK;
+  if (!out) return vg_fail(c, VG_ERR_INVALID, "null output");
+  const int64_t n2 = 2 * n;
+  VG_CUDA(c, c->d_bamN.reserve((size_t)n2 * 4 + 64));
+  VG_CUDA(c, c->d_bamOff.reserve((size_t)n2 * 8 + 64));
+  VG_CUDA(c, c->d_bamRec.reserve((size_t)n * sizeof(vg_pair_result)));
+  const vg_pair_result* d_res = c->d_results.as<vg_pair_result>();
+  int64_t total = 0;
+  const unsigned wblocks = (unsigned)((n2 * 32 + 255) / 256);
+  if (c->resultsMsa) {  // no alignments in MSA mode: the records as they are (seq1_offset = -1)
+    VG_CUDA(c, cudaMemsetAsync(c->d_bamN.p, 0, (size_t)n2 * 4, c->stream));
+    VG_CUDA(c, cudaMemsetAsync(c->d_bamOff.p, 0, (size_t)n2 * 8, c->stream));
+  } else {
+    mh_ops_kernel<false><<<wblocks, 256, 0, c->stream>>>(d_res, n2, c->d_seq1pool.as<uint8_t>(), c->d_bamN.as<int32_t>(), nullptr, nullptr);
+    VG_LAUNCH_CHECK(c);
+    VG_TRY(mh_exclusive_scan(c, c->d_bamN.as<int32_t>(), c->d_bamOff.as<int64_t>(), n2, &total, true));
+  }
+  if (n_ops) *n_ops = total;
+  if (ops_cap < total) {
+    c->required = total;
+    return vg_fail(c, VG_ERR_CAPACITY, "operation pool too small (%lld elements)", (long long)total);
+  }
+  if (total > 0 && !ops) return vg_fail(c, VG_ERR_INVALID, "null operation pool");
+  VG_CUDA(c, c->d_bamOps.reserve((size_t)std::max<int64_t>(total, 1) * 4));
+  if (total > 0) {
+    mh_ops_kernel<true><<<wblocks, 256, 0, c->stream>>>(d_res, n2, c->d_seq1pool.as<uint8_t>(), nullptr, c->d_bamOff.as<int64_t>(),
+                                                        c->d_bamOps.as<uint32_t>());
+    VG_LAUNCH_CHECK(c);
+  }
+  mh_compact_records_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, c->stream>>>(d_res, n2, c->d_bamN.as<int32_t>(),
+                                                                                c->d_bamOff.as<int64_t>(), c->d_bamRec.as<vg_pair_result>());
+  VG_LAUNCH_CHECK(c);
+  VG_CUDA(c, cudaMemcpyAsync(out, c->d_bamRec.p, (size_t)n * sizeof(vg_pair_result), cudaMemcpyDeviceToHost, c->stream));
+  if (total > 0) VG_CUDA(c, cudaMemcpyAsync(ops, c->d_bamOps.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream));
   VG_CUDA(c, cudaStreamSynchronize(c->stream));
   return VG_OK;
 }

@@ -118,16 +118,23 @@ __device__ __forceinline__ int sw_task_key(const SwTask& t, int nShift, int minB
   const int mg = min(7, max(t.m - 1, 0) * 8 / (32 * sw_binR[b]));
   return b * SW_NKEYS + mg * 128 + min(t.n >> nShift, 127);
 }
-// hist[key]++, binMaxN[bin] = max |s2|, binMaxM[bin] = max |s1|
+// hist[key]++, binMaxN[bin] = max |s2|, binMaxM[bin] = max |s1|. The batches of the mapping pipeline have nearly uniform
+// lengths (a handful of hot keys), so the atomics are aggregated per warp: one per distinct key of the warp.
 __global__ void sw_bin_hist_kernel(const SwTask* __restrict__ tasks, int n, int nShift, int minBin, int* __restrict__ hist,
                                    int* __restrict__ binMaxN, int* __restrict__ binMaxM) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const SwTask t = tasks[i];
-  const int key = sw_task_key(t, nShift, minBin);
-  atomicAdd(hist + key, 1);
-  atomicMax(binMaxN + key / SW_NKEYS, t.n);
-  atomicMax(binMaxM + key / SW_NKEYS, t.m);
+  const bool ok = i < n;
+  SwTask t;
+  t.m = t.n = 0;
+  if (ok) t = tasks[i];
+  const int key = ok ? sw_task_key(t, nShift, minBin) : -1 - (int)(threadIdx.x & 31);
+  const unsigned grp = __match_any_sync(VG_FULL, key);
+  const int gn = __reduce_max_sync(grp, t.n), gm = __reduce_max_sync(grp, t.m);
+  if (ok && (int)(threadIdx.x & 31) == __ffs(grp) - 1) {
+    atomicAdd(hist + key, __popc(grp));
+    atomicMax(binMaxN + key / SW_NKEYS, gn);
+    atomicMax(binMaxM + key / SW_NKEYS, gm);
+  }
 }
 // exclusive scan of hist[SW_NBINS * SW_NKEYS] by one block of 1024 threads (11 keys per thread); binStart[b] = first task
 // of bin b, binStart[SW_NBINS] = n
@@ -161,9 +168,18 @@ __global__ void sw_bin_scan_kernel(int* __restrict__ hist, int* __restrict__ bin
 __global__ void sw_bin_scatter_kernel(const SwTask* __restrict__ tasks, int n, int nShift, int minBin, int* __restrict__ cursor,
                                       SwTask* __restrict__ sorted) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const SwTask t = tasks[i];
-  sorted[atomicAdd(cursor + sw_task_key(t, nShift, minBin), 1)] = t;
+  const int lane = threadIdx.x & 31;
+  const bool ok = i < n;
+  SwTask t;
+  t.m = t.n = 0;
+  if (ok) t = tasks[i];
+  const int key = ok ? sw_task_key(t, nShift, minBin) : -1 - lane;
+  const unsigned grp = __match_any_sync(VG_FULL, key);
+  const int leader = __ffs(grp) - 1;
+  int base = 0;
+  if (ok && lane == leader) base = atomicAdd(cursor + key, __popc(grp));
+  base = __shfl_sync(VG_FULL, base, leader);
+  if (ok) sorted[base + __popc(grp & ((1u << lane) - 1u))] = t;
 }
 
 // Runs fill (+ traceback) over device-resident tasks. d_alns/d_rev are indexed by SwTask.out. With traceback the tasks

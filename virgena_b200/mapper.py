@@ -96,18 +96,41 @@ class PairedReads:
     def seq2(self, i):
         return self.bases[self.off2[i]:self.off2[i] + self.len2[i]].tobytes()
 
+    def packed(self):
+        """(packed, exc_pos, exc_byte): the transfer format of vg_upload_reads_packed (2 bits per ACGT base + exceptions),
+        made by the library's host-side packer vg_pack_reads."""
+        if getattr(self, "_packed", None) is None:
+            L = _lib.lib()
+            n = len(self.bases)
+            pk = np.zeros((n + 3) // 4 + 16, np.uint8)
+            ne = C.c_int64()
+            cap = max(1024, n // 64)
+            while True:
+                pos = np.zeros(cap, np.int64)
+                byt = np.zeros(cap, np.uint8)
+                rc = L.vg_pack_reads(ptr(self.bases), n, ptr(pk), ptr(pos), ptr(byt), cap, C.byref(ne))
+                if rc == 0:
+                    break
+                if rc != -4:
+                    raise VgError(rc, "vg_pack_reads failed")
+                cap = ne.value
+            self._packed = (pk, pos[:ne.value].copy(), byt[:ne.value].copy())
+        return self._packed
+
 
 class MappedData:
     """MappedData (MappedData.java): per-pair records in input order + the sequence1 byte pool.
     The six Java lists are views by class (task order == input order, Mapper.java:446-461)."""
 
-    def __init__(self, pair_index, records, pool, stats, msa=False):
+    def __init__(self, pair_index, records, pool, stats, msa=False, ops=None, reads=None):
         self.pair_index = pair_index      # index of each record's pair in the resident read set
         self.records = records            # PAIR_DTYPE
         self.seq1_pool = pool
         self.stats = stats
         self.msa = msa
         self.needToRemap = np.zeros(0, np.int64)
+        self.ops = ops                    # compact results (vg_get_results_compact): edit operations instead of sequence1
+        self.reads = reads                # the PairedReads the compact records refer to
 
     def _cls(self, *classes):
         return np.nonzero(np.isin(self.records["cls"], classes))[0]
@@ -141,7 +164,42 @@ class MappedData:
 
     def sequence1(self, rec, mate):
         m = self.records["m"][rec, mate]
+        if self.ops is not None:
+            p = int(self.pair_index[rec])
+            read = self.reads.seq1(p) if mate == 0 else self.reads.seq2(p)
+            return sequence1_from_ops(read, bool(m["reverse"]), int(m["start1"]),
+                                      self.ops[m["seq1_offset"]:m["seq1_offset"] + m["pad_"]])
         return self.seq1_pool[m["seq1_offset"]:m["seq1_offset"] + m["length"]].tobytes()
+
+
+_COMPLEMENT = np.zeros(256, np.uint8)   # Constants.complement (Constants.java:11-20): anything unlisted -> 0
+for _a, _b in (("A", "T"), ("T", "A"), ("G", "C"), ("C", "G"), ("-", "-"), ("N", "N")):
+    _COMPLEMENT[ord(_a)] = ord(_b)
+_LOWER = np.zeros(256, np.uint8)        # Constants.lower (Constants.java:22-30)
+for _a in "ATGCN":
+    _LOWER[ord(_a)] = ord(_a.lower())
+
+
+def sequence1_from_ops(read, reverse, start1, ops):
+    """Alignment.sequence1 from the compact result form: the read in the mate's orientation (reverse =
+    Constants.getComplement, i.e. the reverse complement) from start1 on; op 0 copies read bases, op 1 lower-cases them
+    (insertion), op 2 writes '-' (deletion)."""
+    r = np.frombuffer(read, np.uint8)
+    if reverse:
+        r = _COMPLEMENT[r[::-1]]
+    out = []
+    i = start1
+    for e in ops:
+        ln, op = int(e) >> 4, int(e) & 15
+        if op == 0:
+            out.append(r[i:i + ln])
+            i += ln
+        elif op == 1:
+            out.append(_LOWER[r[i:i + ln]])
+            i += ln
+        else:
+            out.append(np.full(ln, ord("-"), np.uint8))
+    return np.concatenate(out).tobytes() if out else b""
 
 
 class Context:
@@ -207,6 +265,39 @@ class Context:
         self._chk(self.L.vg_upload_reads(self.h, ptr(reads.bases), len(reads.bases), ptr(reads.off1), ptr(reads.len1),
                                          ptr(reads.off2), ptr(reads.len2), len(reads)))
         self.n_pairs = len(reads)
+
+    def upload_reads_packed(self, reads: PairedReads):
+        """vg_upload_reads_packed: the same resident reads, 4x fewer host-to-device bytes."""
+        pk, pos, byt = reads.packed()
+        self._chk(self.L.vg_upload_reads_packed(self.h, ptr(pk), len(reads.bases), ptr(pos), ptr(byt), len(pos), ptr(reads.off1),
+                                                ptr(reads.len1), ptr(reads.off2), ptr(reads.len2), len(reads)))
+        self.n_pairs = len(reads)
+
+    def get_results_compact(self):
+        """vg_get_results_compact: (records, ops) — seq1_offset / pad_ of a mate address its run-length edit operations."""
+        n, _ = self.result_sizes()
+        rec = np.zeros(n, PAIR_DTYPE)
+        no = C.c_int64()
+        cap = max(1024, n * 16)
+        while True:
+            ops = np.zeros(cap, np.uint32)
+            rc = self.L.vg_get_results_compact(self.h, ptr(rec), n, ptr(ops), cap, C.byref(no))
+            if rc != -4:
+                break
+            cap = no.value
+        self._chk(rc)
+        return rec, ops[:no.value]
+
+    def get_results_compact_into(self, rec, ops):
+        """vg_get_results_compact into caller-owned (e.g. pinned) arrays; returns the number of operations."""
+        no = C.c_int64()
+        self._chk(self.L.vg_get_results_compact(self.h, ptr(rec), len(rec), ptr(ops), len(ops), C.byref(no)))
+        return no.value
+
+    def upload_reads_packed_raw(self, packed_ptr, n_bases, exc_pos, exc_byte, off1, len1, off2, len2):
+        self._chk(self.L.vg_upload_reads_packed(self.h, C.c_void_p(packed_ptr), n_bases, ptr(exc_pos), ptr(exc_byte), len(exc_pos),
+                                                ptr(off1), ptr(len1), ptr(off2), ptr(len2), len(off1)))
+        self.n_pairs = len(off1)
 
     # --- mapping -----------------------------------------------------------------------------
     def map_pairs(self, pair_idx=None, fetch=True):
