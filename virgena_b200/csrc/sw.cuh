@@ -62,8 +62,9 @@ template <>
 struct SwCk<true> {
   using T = uint32_t;
   static __device__ __forceinline__ T make(uint32_t v, uint32_t xs, uint32_t ngepP) {
-    const uint32_t d = __vsub2(__viaddmax_s16x2(xs, ngepP, v), v);  // max(Xs - gep, V) - V per lane, 0 .. 15
-    return v | (d << 12);
+    // max(Xs - gep, V) - V per lane, 0 .. 15: no half is negative, so the 32-bit subtraction is exact per half (FMA pipe)
+    const uint32_t d = __viaddmax_s16x2(xs, ngepP, v) - v;
+    return d * 4096u + v;  // = v | d << 12 (the fields do not overlap); a multiply-add issues on the FMA pipe
   }
   static __device__ __forceinline__ void get(T w, int hi, int gep, int& v, int& xs) {
     const uint32_t h = hi ? (w >> 16) : (w & 0xFFFFu);
@@ -87,7 +88,11 @@ struct SwCk<true> {
     cm4 = 0;                                                                  \
   }
 
-template <int R, bool STORE, bool COMPACT>
+// FASTF (gop + mismatch >= 0): the diagonal term is kept shifted by +gop like E and F, g_s = V_diag + (equal ? match + gop :
+// mismatch + gop). Both summands are non-negative in both 16-bit halves and the sum stays below 2^15, so a plain 32-bit
+// add is exact per half and issues on the FMA pipe (IMAD.IADD) instead of the ALU / DPX pipe that bounds the kernel;
+// V = relu(max(Es, Fs, g_s) - gop) is VIMNMX3 + VIADDMNMX.RELU. 6.5 instead of 7.5 ALU-pipe instructions per cell-pair.
+template <int R, bool STORE, bool COMPACT, bool FASTF>
 __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__ tasks, int ntasks,
                                                       const uint8_t* __restrict__ s1pool,
                                                       const uint8_t* __restrict__ s2pool, SwParams prm,
@@ -104,6 +109,8 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
   const uint32_t NGOPp = vg_pk2(-prm.gop);
   const uint32_t MATCH1p = vg_pk2(prm.match + 1);
   const uint32_t MISp = vg_pk2(prm.mismatch);
+  const uint32_t MATCHG1p = vg_pk2(prm.match + prm.gop + 1);  // FASTF: equal -> nx + this = match + gop
+  const uint32_t MISGp = vg_pk2(prm.mismatch + prm.gop);      //        else mismatch + gop (>= 0)
   const int npairs = (ntasks + 1) >> 1;
 
   for (;;) {
@@ -180,13 +187,24 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
 #pragma unroll
           for (int r = 0; r < R; r++) {
             uint32_t nx = a[r] ^ b;  // 0xFFFF in a lane whose symbols are equal, negative and < -256 otherwise
-            uint32_t sim = __viaddmax_s16x2(nx, MATCH1p, MISp);  // equal: match, else mismatch
-            uint32_t f = __vadd2(vd, sim);
-            e = __viaddmax_s16x2(e, NGEPp, vu);
-            F[r] = __viaddmax_s16x2(F[r], NGEPp, V[r]);
-            uint32_t tm = __vmaxs2(e, F[r]);
-            vd = V[r];
-            uint32_t v = __viaddmax_s16x2_relu(tm, NGOPp, f);
+            uint32_t v;
+            if constexpr (FASTF) {
+              const uint32_t simg = __viaddmax_s16x2(nx, MATCHG1p, MISGp);  // equal: match + gop, else mismatch + gop
+              const uint32_t gs = vd + simg;                               // exact per half (see above): FMA pipe
+              e = __viaddmax_s16x2(e, NGEPp, vu);
+              F[r] = __viaddmax_s16x2(F[r], NGEPp, V[r]);
+              const uint32_t t2 = __vimax3_s16x2(e, F[r], gs);
+              vd = V[r];
+              v = __viaddmax_s16x2_relu(t2, NGOPp, NGOPp);  // relu(t2 - gop): the third operand (negative) never wins
+            } else {
+              uint32_t sim = __viaddmax_s16x2(nx, MATCH1p, MISp);  // equal: match, else mismatch
+              uint32_t f = __vadd2(vd, sim);
+              e = __viaddmax_s16x2(e, NGEPp, vu);
+              F[r] = __viaddmax_s16x2(F[r], NGEPp, V[r]);
+              uint32_t tm = __vmaxs2(e, F[r]);
+              vd = V[r];
+              v = __viaddmax_s16x2_relu(tm, NGOPp, f);
+            }
             V[r] = v;
             vu = v;
             if (r & 1)
@@ -217,8 +235,15 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
         }
         if (((tg + 4) & (SW_TC - 1)) == 0 && lane <= lastLane && j4 >= 1 && j4 <= nmax) {  // column checkpoint of the rows
           typename CK::T* dst = colp + (int64_t)((tg + 4) / SW_TC) * (32 * R);
+          if constexpr (COMPACT && (R % 4 == 0)) {  // a lane's R words are contiguous and 16-byte aligned: whole-sector stores
 #pragma unroll
-          for (int r = 0; r < R; r++) dst[r] = CK::make(V[r], F[r], NGEPp);
+            for (int r = 0; r < R; r += 4)
+              *(uint4*)(dst + r) = make_uint4(CK::make(V[r], F[r], NGEPp), CK::make(V[r + 1], F[r + 1], NGEPp),
+                                              CK::make(V[r + 2], F[r + 2], NGEPp), CK::make(V[r + 3], F[r + 3], NGEPp));
+          } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) dst[r] = CK::make(V[r], F[r], NGEPp);
+          }
         }
       }
     }

@@ -54,13 +54,18 @@ static int sw_launch_R(vg_ctx* c, const SwTask* d_tasks, int ntasks, const uint8
   const size_t smem = (size_t)warps * nW * sizeof(uint32_t);
   int perSm = 1;
   if (traceback) {
-    VG_CUDA(c, cudaFuncSetAttribute(sw_fill_kernel<R, true, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, sw_fill_kernel<R, true, COMPACT>, threads, smem));
+    VG_CUDA(c, cudaFuncSetAttribute(sw_fill_kernel<R, true, COMPACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VG_CUDA(c, cudaFuncSetAttribute(sw_fill_kernel<R, true, COMPACT, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, sw_fill_kernel<R, true, COMPACT, false>, threads, smem));
   } else {
-    VG_CUDA(c, cudaFuncSetAttribute(sw_fill_kernel<R, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, sw_fill_kernel<R, false, false>, threads, smem));
+    VG_CUDA(c, cudaFuncSetAttribute(sw_fill_kernel<R, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VG_CUDA(c, cudaFuncSetAttribute(sw_fill_kernel<R, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, sw_fill_kernel<R, false, false, false>, threads, smem));
   }
   if (perSm < 1) return vg_fail(c, VG_ERR_INVALID, "window length %d needs too much shared memory", nmax);
+  // the diagonal term on the FMA pipe (sw.cuh, FASTF) needs mismatch + gop >= 0; instantiated for the compact-checkpoint
+  // and the score-only kernels (the defaults)
+  const bool fastf = c->sw.mismatch + c->sw.gop >= 0 && (COMPACT || !traceback) && !getenv("VG_SW_SLOWF");
   float fms = 0, tms = 0;
   for (int64_t s = 0; s < ntasks; s += chunk) {
     const int nt = (int)std::min<int64_t>(chunk, ntasks - s);
@@ -68,14 +73,22 @@ static int sw_launch_R(vg_ctx* c, const SwTask* d_tasks, int ntasks, const uint8
     const int blocks = std::max(1, std::min((npairs + warps - 1) / warps, c->smCount * perSm));
     VG_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(int), c->stream));
     VG_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
-    if (traceback)
-      sw_fill_kernel<R, true, COMPACT><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw,
-                                                                             c->d_rowck.as<CkT>(), c->d_colck.as<CkT>(), nT,
-                                                                             nTb, d_fill + s, c->d_counter.as<int>(), nW);
+    if (traceback && fastf)  // FASTF is only instantiated with COMPACT (the last argument is false for wide checkpoints)
+      sw_fill_kernel<R, true, COMPACT, COMPACT><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw,
+                                                                                      c->d_rowck.as<CkT>(), c->d_colck.as<CkT>(), nT,
+                                                                                      nTb, d_fill + s, c->d_counter.as<int>(), nW);
+    else if (traceback)
+      sw_fill_kernel<R, true, COMPACT, false><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw,
+                                                                                    c->d_rowck.as<CkT>(), c->d_colck.as<CkT>(), nT,
+                                                                                    nTb, d_fill + s, c->d_counter.as<int>(), nW);
+    else if (fastf)
+      sw_fill_kernel<R, false, false, true><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw, nullptr,
+                                                                                  nullptr, nT, nTb, d_fill + s,
+                                                                                  c->d_counter.as<int>(), nW);
     else
-      sw_fill_kernel<R, false, false><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw, nullptr,
-                                                                            nullptr, nT, nTb, d_fill + s,
-                                                                            c->d_counter.as<int>(), nW);
+      sw_fill_kernel<R, false, false, false><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw, nullptr,
+                                                                                   nullptr, nT, nTb, d_fill + s,
+                                                                                   c->d_counter.as<int>(), nW);
     VG_LAUNCH_CHECK(c);
     VG_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
     if (traceback) {
