@@ -283,7 +283,10 @@ struct SwTb {
   static constexpr int WPC = (R + 7) / 8;  // flag words per column
 };
 
-template <int R, bool COMPACT>
+// Flag word of 8 rows of one column: bits 2r..2r+1 pointer of row r (STOP=0, LEFT=1, DIAGONAL=2, UP=3), bit 16+r vertical
+// gap extended at row r, bit 24+r horizontal gap extended.
+// PROBE: also look for the end cell (smallest (row, column) with V == probeS); only the first tile(s) of an alignment need it.
+template <int R, bool COMPACT, bool PROBE>
 __device__ __forceinline__ void sw_tile_recompute(const SwTask& tk, const uint8_t* __restrict__ s1,
                                                   const uint8_t* __restrict__ s2, const SwParams& prm,
                                                   const typename SwCk<COMPACT>::T* __restrict__ rowckP,
@@ -325,12 +328,13 @@ __device__ __forceinline__ void sw_tile_recompute(const SwTask& tk, const uint8_
     asm volatile("prefetch.global.L2 [%0];" ::"l"(topRow + min(jmax, cl + SW_TC)));
     wNext = topRow[cl + 1];
   }
+  const int gep = prm.gep, gop = prm.gop, match = prm.match, mismatch = prm.mismatch;
   for (int j = cl + 1; j <= jmax; j++) {
     int vtop = 0, es = SW_NEG;
     if (k > 0) {
       const typename CK::T w = wNext;
       if (j + 1 <= jmax) wNext = topRow[j + 1];
-      CK::get(w, hi, prm.gep, vtop, es);
+      CK::get(w, hi, gep, vtop, es);
     }
     const uint8_t bsym = s2[j - 1];
     int vd = vtopPrev, vu = vtop;
@@ -340,27 +344,30 @@ __device__ __forceinline__ void sw_tile_recompute(const SwTask& tk, const uint8_
     for (int w = 0; w < WPC; w++) word[w] = 0;
 #pragma unroll
     for (int r = 0; r < R; r++) {
-      const int i = r0 + r + 1;
-      int sim = (asym[r] == bsym) ? prm.match : prm.mismatch;
-      int f = vd + sim;
-      int g1 = es - prm.gep;
-      bool vext = g1 > vu;
-      es = vext ? g1 : vu;
-      int h1 = hs[r] - prm.gep;
-      bool hext = h1 > v[r];
-      hs[r] = hext ? h1 : v[r];
+      const int f = vd + ((asym[r] == bsym) ? match : mismatch);
+      // "extend only if strictly greater" (:115, :124): the predicate of the maximum is (kept >= extended)
+      bool keepV, keepH, fGeE, mGeF;
+      es = __vibmax_s32(vu, es - gep, &keepV);         // Es' = max(V_up, Es_up - gep)
+      hs[r] = __vibmax_s32(v[r], hs[r] - gep, &keepH);  // Fs' = max(V_left, Fs_left - gep)
       vd = v[r];
-      int E = es - prm.gop, Fv = hs[r] - prm.gop;
-      int V = max(max(f, E), max(Fv, 0));
-      uint32_t dir = (V == 0) ? 0u : (V == f) ? 2u : (V == E) ? 3u : 1u;
-      uint32_t nib = dir | (vext ? 4u : 0u) | (hext ? 8u : 0u);
-      word[r >> 3] |= nib << ((r & 7) * 4);
+      const int m1 = __vibmax_s32(f, es - gop, &fGeE);
+      const int m2 = __vibmax_s32(m1, hs[r] - gop, &mGeF);
+      const int V = max(m2, 0);
+      // STOP (V == 0) > DIAGONAL (V == f) > UP (V == E) > LEFT (:135-143)
+      const uint32_t dir = (m2 > 0) ? (mGeF ? (fGeE ? 2u : 3u) : 1u) : 0u;
+      uint32_t wv = word[r >> 3] + (dir << (2 * (r & 7)));
+      if (!keepV) wv |= 1u << (16 + (r & 7));
+      if (!keepH) wv |= 1u << (24 + (r & 7));
+      word[r >> 3] = wv;
       v[r] = V;
       vu = V;
-      if (V == probeS && i <= tk.m && (probeCol < 0 || (j <= probeCol && j + 3 >= probeCol))) {
-        if (i < bestI || (i == bestI && j < bestJ)) {
-          bestI = i;
-          bestJ = j;
+      if constexpr (PROBE) {
+        const int i = r0 + r + 1;
+        if (V == probeS && i <= tk.m && (probeCol < 0 || (j <= probeCol && j + 3 >= probeCol))) {
+          if (i < bestI || (i == bestI && j < bestJ)) {
+            bestI = i;
+            bestJ = j;
+          }
         }
       }
     }
@@ -377,7 +384,7 @@ __device__ __forceinline__ int sw_tile_left(int k, int j) {
 }
 
 template <int R, bool COMPACT>
-__global__ void __launch_bounds__(128, 6) sw_traceback_kernel(const SwTask* __restrict__ tasks, int ntasks,
+__global__ void __launch_bounds__(128, 7) sw_traceback_kernel(const SwTask* __restrict__ tasks, int ntasks,
                                                            const uint8_t* __restrict__ s1pool,
                                                            const uint8_t* __restrict__ s2pool, SwParams prm,
                                                            const typename SwCk<COMPACT>::T* __restrict__ rowck,
@@ -419,12 +426,12 @@ __global__ void __launch_bounds__(128, 6) sw_traceback_kernel(const SwTask* __re
     if (!fo.tie) {
       const int jEnd = min(fo.col, tk.n);  // fo.col = last column of the group of 4 that reached the maximum
       int cl = sw_tile_left(fo.strip, jEnd);
-      sw_tile_recompute<R, COMPACT>(tk, s1, s2, prm, rowckP, colckP, nT, hi, fo.strip, cl, jEnd, flags, 128, fo.score, fo.col, bi, bj);
+      sw_tile_recompute<R, COMPACT, true>(tk, s1, s2, prm, rowckP, colckP, nT, hi, fo.strip, cl, jEnd, flags, 128, fo.score, fo.col, bi, bj);
       haveK = fo.strip, haveCl = cl;
     } else {
       for (int jj = tk.n; jj >= 1;) {  // rare: the strip reached S at several columns
         int cl = sw_tile_left(fo.strip, jj);
-        sw_tile_recompute<R, COMPACT>(tk, s1, s2, prm, rowckP, colckP, nT, hi, fo.strip, cl, jj, flags, 128, fo.score, -1, bi, bj);
+        sw_tile_recompute<R, COMPACT, true>(tk, s1, s2, prm, rowckP, colckP, nT, hi, fo.strip, cl, jj, flags, 128, fo.score, -1, bi, bj);
         jj = cl;
       }
     }
@@ -439,7 +446,7 @@ __global__ void __launch_bounds__(128, 6) sw_traceback_kernel(const SwTask* __re
       k = (i - 1) / R;
       cl = sw_tile_left(k, j);
       if (k != haveK || cl != haveCl)
-        sw_tile_recompute<R, COMPACT>(tk, s1, s2, prm, rowckP, colckP, nT, hi, k, cl, j, flags, 128, -1, -1, no1, no2);
+        sw_tile_recompute<R, COMPACT, false>(tk, s1, s2, prm, rowckP, colckP, nT, hi, k, cl, j, flags, 128, -1, -1, no1, no2);
       haveK = -1;
     }
     while (!done) {
@@ -449,9 +456,9 @@ __global__ void __launch_bounds__(128, 6) sw_traceback_kernel(const SwTask* __re
       }
       if ((i - 1) / R != k || j <= cl) break;  // left the tile
       const int rr = (i - 1) - k * R;
-      const uint32_t nib = (flags[((j - cl - 1) * WPC + (rr >> 3)) * 128] >> ((rr & 7) * 4)) & 15u;
+      const uint32_t fw = flags[((j - cl - 1) * WPC + (rr >> 3)) * 128];
       if (mode == 0) {
-        const uint32_t dir = nib & 3u;
+        const uint32_t dir = (fw >> (2 * (rr & 7))) & 3u;
         if (dir == 0u) {
           done = true;
           break;
@@ -467,12 +474,12 @@ __global__ void __launch_bounds__(128, 6) sw_traceback_kernel(const SwTask* __re
       }
       if (mode == 1) {  // UP: sizesOfVerticalGaps[k+j] lower-case read bases
         out[len++] = vg_lower(sw_s1_byte(s1, tk.m, tk.rc, i - 1));
-        const bool ext = (nib & 4u) != 0;
+        const bool ext = ((fw >> (16 + (rr & 7))) & 1u) != 0;
         i--;
         if (!ext) mode = 0;
       } else {  // LEFT: sizesOfHorizontalGaps[k+j] gap characters
         out[len++] = '-';
-        const bool ext = (nib & 8u) != 0;
+        const bool ext = ((fw >> (24 + (rr & 7))) & 1u) != 0;
         j--;
         if (!ext) mode = 0;
       }
