@@ -881,12 +881,10 @@ int vg_pileup(vg_ctx* c, int32_t accumulate) {
   pu_scatter_kernel<<<(unsigned)((n2 + 255) / 256), 256, (size_t)(2 * nTiles + 2) * 4 + (size_t)nTiles * 8, c->stream>>>(
       d_reads, d_tileOf, n2, nTiles, (unsigned long long*)d_cursor, d_sorted);
   VG_LAUNCH_CHECK(c);
-  const int maxRow = c->maxReadLen * 3 + 16;  // rows are at most |read| + |window| long
-  const int backTiles = maxRow / PU_TILE + 1;
-  const int nSlices = std::max(1, std::min(64, (c->smCount * 4) / nTiles));
+  const int nSlices = std::max(1, std::min(64, (c->smCount * 8) / nTiles));  // 8 CTAs of 256 threads per SM
   VG_CUDA(c, c->d_scratch.reserve((size_t)nSlices * G * 5 * 4 + 64));
   dim3 grid(nTiles, nSlices);
-  pu_count_kernel<<<grid, PU_TILE, 0, c->stream>>>(d_sorted, d_tileStart, nTiles, backTiles, c->d_rowpool.as<uint8_t>(), G,
+  pu_count_kernel<<<grid, PU_TILE, 0, c->stream>>>(d_sorted, d_tileStart, nTiles, c->d_counter.as<int>() + 1, c->d_rowpool.as<uint8_t>(), G,
                                                    nSlices, c->d_scratch.as<int32_t>());
   VG_LAUNCH_CHECK(c);
   pu_reduce_kernel<<<(unsigned)(((int64_t)G * 5 + 255) / 256), 256, 0, c->stream>>>(c->d_scratch.as<int32_t>(), G, nSlices,

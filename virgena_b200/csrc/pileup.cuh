@@ -108,6 +108,7 @@ __global__ void pu_list_kernel(const vg_pair_result* __restrict__ res, int64_t n
         } else {
           tile = r.s / PU_TILE;
           atomicAdd(&pu_hist[tile], 1);
+          if (r.len > err[1]) atomicMax(err + 1, r.len);  // longest row: how many tiles back a read can start (pu_count_kernel)
         }
       }
     }
@@ -157,11 +158,12 @@ __global__ void pu_scatter_kernel(const PuRead* __restrict__ reads, const int32_
 // The count kernel: grid (nTiles, nSlices), PU_TILE threads. Atomic-free.
 __global__ void __launch_bounds__(PU_TILE) pu_count_kernel(const PuRead* __restrict__ sorted,
                                                           const int64_t* __restrict__ tileStart, int nTiles,
-                                                          int backTiles, const uint8_t* __restrict__ rowpool, int G,
+                                                          const int* __restrict__ maxRowLen, const uint8_t* __restrict__ rowpool, int G,
                                                           int nSlices, int32_t* __restrict__ partial) {
   const int T = blockIdx.x, sl = blockIdx.y;
   const int x = T * PU_TILE + threadIdx.x;
-  const int t0 = max(0, T - backTiles);
+  // a row of at most *maxRowLen positions that covers this tile starts at most ceil(maxRowLen / tile) tiles before it
+  const int t0 = max(0, T - (*maxRowLen + PU_TILE - 1) / PU_TILE);
   const int64_t lo = tileStart[t0], hi = tileStart[T + 1];
   const int64_t per = (hi - lo + nSlices - 1) / nSlices;
   const int64_t a = lo + per * sl, b = (a + per < hi) ? (a + per) : hi;
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(PU_TILE) pu_count_kernel(const PuRead* __restr
     __syncthreads();
     if (threadIdx.x < nb) buf[threadIdx.x] = sorted[q0 + threadIdx.x];
     __syncthreads();
-#pragma unroll 4
+#pragma unroll 8
     for (int i = 0; i < nb; i++) {
       const PuRead r = buf[i];
       const unsigned d = (unsigned)(x - r.s);
