@@ -314,10 +314,14 @@ int vg_multi_set_msa_index(vg_multi* m, int32_t K, float low_coef, float high_co
                            int32_t n_keys, int32_t msa_length);
 int vg_multi_upload_reads(vg_multi* m, const uint8_t* bases, int64_t n_bases, const int64_t* off1, const int32_t* len1,
                           const int64_t* off2, const int32_t* len2, int64_t n_pairs);
+int vg_multi_upload_reads_packed(vg_multi* m, const uint8_t* packed, int64_t n_bases, const int64_t* exc_pos,
+                                 const uint8_t* exc_byte, int64_t n_exc, const int64_t* off1, const int32_t* len1,
+                                 const int64_t* off2, const int32_t* len2, int64_t n_pairs);
 int vg_multi_map_pairs(vg_multi* m, const int64_t* pair_idx, int64_t n_idx, vg_map_stats* stats);
 int vg_multi_map_pairs_msa(vg_multi* m, vg_map_stats* stats);
 int vg_multi_result_sizes(vg_multi* m, int64_t* n_results, int64_t* seq1_bytes);
 int vg_multi_get_results(vg_multi* m, vg_pair_result* out, int64_t n_out, uint8_t* seq1_pool, int64_t pool_cap);
+int vg_multi_get_results_compact(vg_multi* m, vg_pair_result* out, int64_t n_out, uint32_t* ops, int64_t ops_cap, int64_t* n_ops);
 int vg_multi_pileup(vg_multi* m, int32_t accumulate);
 int vg_multi_pileup_counts_host(vg_multi* m, int32_t* out, int64_t n_int32);
 int vg_multi_consensus(vg_multi* m, int32_t save_uncovered, int32_t coverage_threshold, const uint8_t* genome, int32_t G,

@@ -65,6 +65,17 @@ def test_vg_multi_equals_single_gpu(built, n_dev):
     multi.ctx.pileup()
     single.ctx.pileup()
     assert (multi.ctx.counts() == single.ctx.counts()).all()
+    # packed upload + compact download through the multi layer == the single device's (records and operations byte for byte)
+    reads = vg.PairedReads(*packed)
+    multi.ctx.upload_reads_packed(reads)
+    single.ctx.upload_reads_packed(reads)
+    for sub_idx in (None, sub):
+        a1 = single.ctx.map_pairs(sub_idx, fetch=False)
+        aN = multi.ctx.map_pairs(sub_idx, fetch=False)
+        assert (np.asarray(a1) == np.asarray(aN)).all()
+        r1, o1 = single.ctx.get_results_compact()
+        rN, oN = multi.ctx.get_results_compact()
+        assert rN.tobytes() == r1.tobytes() and oN.tobytes() == o1.tobytes()
     multi.ctx.close()
     single.ctx.close()
 

@@ -107,6 +107,9 @@ _SIGS = {
                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "vg_multi_upload_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int64]),
+    "vg_multi_upload_reads_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_int64]),
+    "vg_multi_get_results_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "vg_multi_map_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(VgMapStats)]),
     "vg_multi_map_pairs_msa": (C.c_int, [C.c_void_p, C.POINTER(VgMapStats)]),
     "vg_multi_result_sizes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

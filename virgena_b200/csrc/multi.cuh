@@ -297,6 +297,42 @@ int vg_multi_upload_reads(vg_multi* m, const uint8_t* bases, int64_t n_bases, co
   });
 }
 
+// The same with the packed transfer form (vg_upload_reads_packed): every device receives the bytes of the packed pool
+// that hold its span (from the 4-base boundary below its first base) and the exceptions that fall into it.
+int vg_multi_upload_reads_packed(vg_multi* m, const uint8_t* packed, int64_t n_bases, const int64_t* exc_pos,
+                                 const uint8_t* exc_byte, int64_t n_exc, const int64_t* off1, const int32_t* len1,
+                                 const int64_t* off2, const int32_t* len2, int64_t n_pairs) {
+  if (!m) return VG_ERR_INVALID;
+  if (n_pairs < 0 || n_bases < 0 || n_exc < 0 || (n_pairs > 0 && (!packed || !off1 || !len1 || !off2 || !len2)) ||
+      (n_exc > 0 && (!exc_pos || !exc_byte)))
+    return vgm_fail(m, VG_ERR_INVALID, "bad read arrays");
+  const int n = (int)m->ctx.size();
+  const int64_t base = n_pairs / n, rem = n_pairs % n;
+  for (int d = 0; d <= n; d++) m->lo[d] = d * base + std::min<int64_t>(d, rem);
+  m->nPairs = n_pairs;
+  m->nResults = 0;
+  return vgm_each(m, [&](int d) {
+    const int64_t a = m->lo[d], b = m->lo[d + 1], np = b - a;
+    vg_ctx* c = m->ctx[d];
+    int64_t lo = n_bases, hi = 0;
+    for (int64_t i = a; i < b; i++) {
+      if (len1[i] < 0 || len2[i] < 0 || off1[i] < 0 || off2[i] < 0 || off1[i] + len1[i] > n_bases || off2[i] + len2[i] > n_bases)
+        return vg_fail(c, VG_ERR_INVALID, "read %lld lies outside the byte pool", (long long)i);
+      lo = std::min(lo, std::min(off1[i], off2[i]));
+      hi = std::max(hi, std::max(off1[i] + len1[i], off2[i] + len2[i]));
+    }
+    if (np == 0) lo = hi = 0;
+    lo &= ~(int64_t)3;  // a whole packed byte
+    std::vector<int64_t> o1(np), o2(np), ep;
+    std::vector<uint8_t> eb;
+    for (int64_t i = 0; i < np; i++) o1[i] = off1[a + i] - lo, o2[i] = off2[a + i] - lo;
+    for (int64_t k = 0; k < n_exc; k++)
+      if (exc_pos[k] >= lo && exc_pos[k] < hi) ep.push_back(exc_pos[k] - lo), eb.push_back(exc_byte[k]);
+    return vg_upload_reads_packed(c, packed + lo / 4, hi - lo, ep.data(), eb.data(), (int64_t)ep.size(), o1.data(), len1 + a,
+                                  o2.data(), len2 + a, np);
+  });
+}
+
 static void vgm_add_stats(vg_map_stats* acc, const vg_map_stats& s) {
   acc->total_pairs += s.total_pairs, acc->both_exist += s.both_exist, acc->reads_total += s.reads_total;
   acc->total_mapped += s.total_mapped, acc->mapped_forward += s.mapped_forward, acc->mapped_reverse += s.mapped_reverse;
@@ -404,6 +440,61 @@ int vg_multi_get_results(vg_multi* m, vg_pair_result* out, int64_t n_out, uint8_
       if (mt.length > 0) memcpy(seq1_pool + at, tpool[owner[i]].data() + mt.seq1_offset, (size_t)mt.length);
       mt.seq1_offset = at;
       at += mt.length;
+    }
+  return VG_OK;
+}
+
+// vg_get_results_compact over all devices, in the caller's order: the records of device d with their operation indices moved
+// behind those of the devices before it (input order), or re-laid in the order of pair_idx (a subset).
+int vg_multi_get_results_compact(vg_multi* m, vg_pair_result* out, int64_t n_out, uint32_t* ops, int64_t ops_cap, int64_t* n_ops) {
+  if (!m) return VG_ERR_INVALID;
+  if (n_ops) *n_ops = 0;
+  if (n_out < m->nResults) {
+    m->required = m->nResults;
+    return vgm_fail(m, VG_ERR_CAPACITY, "record buffer too small (%lld results)", (long long)m->nResults);
+  }
+  if (m->nResults > 0 && !out) return vgm_fail(m, VG_ERR_INVALID, "null output");
+  const int n = (int)m->ctx.size();
+  std::vector<std::vector<vg_pair_result>> tmp(n);
+  std::vector<std::vector<uint32_t>> tops(n);
+  const int rc = vgm_each(m, [&](int d) {
+    vg_ctx* c = m->ctx[d];
+    tmp[d].resize(m->nRes[d]);
+    if (m->nRes[d] == 0) return (int)VG_OK;
+    int64_t cnt = 0;
+    int r = vg_get_results_compact(c, tmp[d].data(), m->nRes[d], nullptr, 0, &cnt);  // sizes first
+    if (r == VG_ERR_CAPACITY) {
+      tops[d].resize(cnt);
+      r = vg_get_results_compact(c, tmp[d].data(), m->nRes[d], tops[d].data(), cnt, &cnt);
+    }
+    return r;
+  });
+  if (rc != VG_OK) return rc;
+  int64_t total = 0;
+  for (int d = 0; d < n; d++) total += (int64_t)tops[d].size();
+  if (n_ops) *n_ops = total;
+  if (ops_cap < total) {
+    m->required = total;
+    return vgm_fail(m, VG_ERR_CAPACITY, "operation pool too small (%lld elements)", (long long)total);
+  }
+  if (total > 0 && !ops) return vgm_fail(m, VG_ERR_INVALID, "null operation pool");
+  std::vector<int64_t> resBase(n + 1, 0);
+  for (int d = 0; d < n; d++) resBase[d + 1] = resBase[d] + m->nRes[d];
+  std::vector<int> owner(m->nResults);
+  for (int d = 0; d < n; d++)
+    for (int64_t i = 0; i < m->nRes[d]; i++) {
+      const int64_t at = m->contiguous ? resBase[d] + i : m->outPos[d][i];
+      out[at] = tmp[d][i];
+      owner[at] = d;
+    }
+  int64_t at = 0;
+  for (int64_t i = 0; i < m->nResults; i++)
+    for (int k = 0; k < 2; k++) {
+      vg_mate& mt = out[i].m[k];
+      if (!mt.present || mt.seq1_offset < 0) continue;
+      if (mt.pad_ > 0) memcpy(ops + at, tops[owner[i]].data() + mt.seq1_offset, (size_t)mt.pad_ * 4);
+      mt.seq1_offset = at;
+      at += mt.pad_;
     }
   return VG_OK;
 }

@@ -616,6 +616,27 @@ class MultiContext:
                                                ptr(len2), len(off1)))
         self.n_pairs = len(off1)
 
+    def upload_reads_packed(self, reads: PairedReads):
+        pk, pos, byt = reads.packed()
+        self._chk(self.L.vg_multi_upload_reads_packed(self.h, ptr(pk), len(reads.bases), ptr(pos), ptr(byt), len(pos),
+                                                      ptr(reads.off1), ptr(reads.len1), ptr(reads.off2), ptr(reads.len2), len(reads)))
+        self.n_pairs = len(reads)
+
+    def get_results_compact(self):
+        n = C.c_int64()
+        self._chk(self.L.vg_multi_result_sizes(self.h, C.byref(n), None))
+        rec = np.zeros(n.value, PAIR_DTYPE)
+        no = C.c_int64()
+        cap = max(1024, n.value * 16)
+        while True:
+            ops = np.zeros(cap, np.uint32)
+            rc = self.L.vg_multi_get_results_compact(self.h, ptr(rec), n.value, ptr(ops), cap, C.byref(no))
+            if rc != -4:
+                break
+            cap = no.value
+        self._chk(rc)
+        return rec, ops[:no.value]
+
     def get_results(self):
         n = C.c_int64()
         nb = C.c_int64()
