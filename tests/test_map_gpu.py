@@ -562,6 +562,16 @@ def test_map_fuzz_pipeline(built, seed):
     want_i, want_c = oracle.identity_counting(orec, opool, len1, len2, ref, window, threads)
     got_i, got_c = vg.ProblemIntervalBuilder(mapper, window, threads).countIdentity()
     assert (got_c == want_c).all() and got_i.view(np.uint32).tolist() == want_i.view(np.uint32).tolist()
+    # transfer forms: the packed upload gives the same mapping, the compact download the same sequence1 for every mate
+    reads = vg.PairedReads(bases, off1, len1, off2, len2)
+    mapper.ctx.upload_reads_packed(reads)
+    md2 = mapper.ctx.map_pairs()
+    _compare(md2, orec, opool, ostats)
+    crec, ops = mapper.ctx.get_results_compact()
+    cmd = vg.MappedData(md2.pair_index, crec, None, md2.stats, ops=ops, reads=reads)
+    for r, k in zip(*cmd.mappedReads):
+        m = orec["m"][r, k]
+        assert cmd.sequence1(r, k) == opool[m["seq1_offset"]:m["seq1_offset"] + m["length"]].tobytes(), (r, k)
     mapper.ctx.close()
 
 
