@@ -379,7 +379,9 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     const int bucketBytes = (A.nBuckets * 2 + 15) & ~15;
     const int cBytes = (SD_WIN + 32) * 8;
     const int winMax = smemMax - 512;  // the window kernel keeps the contig ends in 256 bytes of static shared memory
-    const int budget = (winMax / 32) & ~15;  // per-warp bytes at 32 warps per SM
+    int budgetWarps = 32;
+    if (const char* e = getenv("VG_SEED_WINWARPS")) budgetWarps = std::max(8, std::min(32, atoi(e)));
+    const int budget = (winMax / budgetWarps) & ~15;  // per-warp bytes at 32 warps per SM
     A.capRs = std::max(0, std::min(A.capR, (budget - bucketBytes - 16) / 5)) & ~7;
     A.winWarpBytes = (std::max(std::max(cBytes, 1024), A.capRs * 5 + 16 + bucketBytes) + 15) & ~15;
     winWarps = std::min(32, winMax / A.winWarpBytes);

@@ -241,7 +241,9 @@ static int sw_run(vg_ctx* c, const SwTask* d_tasks, int64_t ntasks, const uint8_
   int nShift = 0;
   while ((nmax >> nShift) >= 128) nShift++;
   // the smallest R in use: thin strips make the fill of short reads efficient but the traceback crosses more of them
-  int minBin = 5;  // R = 8 (measured on a 50..250 batch, profiles/sw_r2.md)
+  // R = 6: on a 50..250 batch within 1 % of R = 8, on 150-base reads (cfg4 / cfg5) fill + traceback 12-16 % faster than R = 8
+  // (25 instead of 19 lanes hold rows; profiles/sw_r2.md)
+  int minBin = 4;
   if (const char* e = getenv("VG_SW_MINR")) {
     minBin = 0;
     while (minBin < SW_NBINS - 1 && sw_binR_host[minBin] < atoi(e)) minBin++;
