@@ -229,6 +229,21 @@ int vg_seed_batch(vg_ctx* ctx, int32_t msa, const uint8_t* pool, const int64_t* 
 int vg_best_window_batch(vg_ctx* ctx, int32_t msa, const uint8_t* pool, const int64_t* off, int64_t n, int32_t* windows,
                          int32_t* found);
 
+/* RandomModel.RandomCountsComputing.run (RandomModel.java:113-128): n_reads random reads of read_len bases drawn from the
+ * order-`order` Markov model of `genomes` (MarkovModel.java:18-119; genomes = byte pool + n_genomes + 1 offsets: the
+ * contigs of a fragmented reference, else the whole sequence, RandomModel.java:88-98; for the MSA model the ungapped
+ * references), each scored with KMerCounterBase.computeKMerCount (:468-487) against the context's reference (msa = 0)
+ * or MSA index (msa = 1): counts[r] = the score (unsorted). Generation and scoring run on the device; reads_out
+ * (optional, n_reads x read_len bytes) receives the reads. RNG policy (Q10): the reference creates an unseeded
+ * java.util.Random per read (MarkovModel.java:95), so there is no reference stream to reproduce; read r draws from
+ * SplitMix64 started at state seed + (first_draw + r * (2 + read_len - order)) * 0x9E3779B97F4A7C15, i.e. the reads are
+ * the ones a single sequential SplitMix64(seed) stream yields when read r starts at draw first_draw + r * (2 + read_len -
+ * order). The context's lowCoef / highCoef are used as they are: RandomModel's own counter has lowCoef = 1 / highCoef
+ * (KMerCounter.java:51-55, Q3), so the host creates the context it scores with accordingly. SURVEY 8f N3. */
+int vg_random_model_counts(vg_ctx* ctx, int32_t msa, const uint8_t* genomes, const int64_t* genome_off, int32_t n_genomes,
+                           int32_t order, uint64_t seed, int64_t first_draw, int32_t read_len, int64_t n_reads,
+                           int32_t* counts, uint8_t* reads_out);
+
 /* KMerCounter.mapReadToRegion (KMerCounter.java:119-140) for (read, region) pairs where every region is its own small
  * reference with its own StringIndexer.buildIndex index: ContigBuilder.countReads against cluster centroids
  * (ContigBuilder.java:72-104, 219-227), Graph.SWScore against reference sub-sequences (Graph.java:493-550). Regions and

@@ -323,6 +323,31 @@ def cutoffs(seq, K=5, coef=1.25, order=4, read_num=10000, min_len=250, max_len=2
     return out
 
 
+def random_model(seq, K=5, coef=1.25, order=4, read_num=10000, min_len=250, max_len=250, step=10, p_value=0.01,
+                 contig_ends=None, is_fragmented=False, index_thread_num=1, seed=1, msa_rows=None):
+    """RandomModel.genModel + computeCuttofs with the seeded stand-in RNG: (cutoffs, sorted counts [size][read_num],
+    the read_num reads of length max_len)."""
+    seq = _u8(seq)
+    ce = _i32(contig_ends if contig_ends is not None else [len(seq)])
+    out = np.zeros(max_len + 1, np.int32)
+    size = (max_len - min_len) // step + 1
+    counts = np.zeros((size, read_num), np.int32)
+    reads = np.zeros((read_num, max_len), np.uint8)
+    f = lib().vo_random_model
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+                  C.c_int, C.c_float, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                  C.c_void_p]
+    if msa_rows is not None:
+        rows = np.ascontiguousarray(msa_rows, np.uint8)
+        f(_p(seq), len(seq), _p(ce), len(ce), int(is_fragmented), K, coef, order, read_num, min_len, max_len, step, p_value,
+          index_thread_num, seed, 1, _p(rows), rows.shape[0], rows.shape[1], _p(out), _p(counts), _p(reads))
+    else:
+        f(_p(seq), len(seq), _p(ce), len(ce), int(is_fragmented), K, coef, order, read_num, min_len, max_len, step, p_value,
+          index_thread_num, seed, 0, None, 0, 0, _p(out), _p(counts), _p(reads))
+    return out, counts, reads
+
+
 def walk_crafted(hits, K, read_len, from_=0, to=1 << 30, low_coef=0.0, high_coef=1.25):
     """KAT hook: getInitState + computeCount (the literal updateCount state machine) over a crafted LongHit list.
     Returns int32[n, 5] = (start, end, count, startIndex, endIndex) after every step."""

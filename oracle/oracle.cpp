@@ -1658,9 +1658,12 @@ void vo_revcomp(const uint8_t* seq, int L, uint8_t* out) {
 // RandomModel.genModel + computeCuttofs with a seeded RNG. genomes = contigs of the reference when
 // fragmented, else the whole sequence (RandomModel.java:88-98). cutoffs has maxReadLen+1 entries.
 // The random model's own counter uses lowCoef = 1/highCoef (KMerCounter.java:51-55, Q3).
-void vo_cutoffs(const uint8_t* seq, int G, const int32_t* contigEnds, int nC, int isFragmented, int K, float coef,
-                int order, int readNum, int minReadLen, int maxReadLen, int step, float pValue, int indexThreadNum,
-                uint64_t seed, int msa, const uint8_t* msaRows, int nRefs, int alnLength, int32_t* cutoffs) {
+// countsOut (optional): the sorted scores, [size][readNum]; readsOut (optional): the readNum reads of the first length
+// generated (maxReadLen), readNum x maxReadLen bytes.
+void vo_random_model(const uint8_t* seq, int G, const int32_t* contigEnds, int nC, int isFragmented, int K, float coef,
+                     int order, int readNum, int minReadLen, int maxReadLen, int step, float pValue, int indexThreadNum,
+                     uint64_t seed, int msa, const uint8_t* msaRows, int nRefs, int alnLength, int32_t* cutoffs,
+                     int32_t* countsOut, uint8_t* readsOut) {
   std::string s((const char*)seq, G);
   KMerCounter kc;
   kc.K = K;
@@ -1697,8 +1700,13 @@ void vo_cutoffs(const uint8_t* seq, int G, const int32_t* contigEnds, int nC, in
   std::vector<std::vector<int>> counts(size, std::vector<int>(readNum));
   Rng rnd(seed);
   for (int len = maxReadLen, i = size - 1; i >= 0; len -= step, i--) {
-    for (int r = 0; r < readNum; r++) counts[i][r] = kc.computeKMerCount(model.generate(len, rnd), index, from, to);
+    for (int r = 0; r < readNum; r++) {
+      const std::string read = model.generate(len, rnd);
+      if (readsOut && len == maxReadLen) memcpy(readsOut + (size_t)r * maxReadLen, read.data(), maxReadLen);
+      counts[i][r] = kc.computeKMerCount(read, index, from, to);
+    }
     std::sort(counts[i].begin(), counts[i].end());
+    if (countsOut) memcpy(countsOut + (size_t)i * readNum, counts[i].data(), (size_t)readNum * 4);
   }
   // computeCuttofs (KMerCounterBase.java:229-251); note counts here is [size][readNum] so num = size (sic: the
   // Java passes model.counts = int[size][readNum] and uses counts.length as `num`).
@@ -1719,6 +1727,13 @@ void vo_cutoffs(const uint8_t* seq, int G, const int32_t* contigEnds, int nC, in
       cutoffs[i] = (distToRight * interp[right - 1] + distToLeft * interp[right]) / step;
     }
   }
+}
+
+void vo_cutoffs(const uint8_t* seq, int G, const int32_t* contigEnds, int nC, int isFragmented, int K, float coef,
+                int order, int readNum, int minReadLen, int maxReadLen, int step, float pValue, int indexThreadNum,
+                uint64_t seed, int msa, const uint8_t* msaRows, int nRefs, int alnLength, int32_t* cutoffs) {
+  vo_random_model(seq, G, contigEnds, nC, isFragmented, K, coef, order, readNum, minReadLen, maxReadLen, step, pValue,
+                  indexThreadNum, seed, msa, msaRows, nRefs, alnLength, cutoffs, nullptr, nullptr);
 }
 
 }  // extern "C"

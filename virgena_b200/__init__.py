@@ -8,7 +8,7 @@ from ._lib import (CLS_CONCORDANT_FR, CLS_CONCORDANT_RF, CLS_DISCORDANT, CLS_LEF
                    BAM_DTYPE, EXPORTED_SYMBOLS, LIB_PATH, MATE_DTYPE, PAIR_DTYPE, VgError)
 from .mapper import (BamPrinter, ConsensusBuilderSimple, ContigBuilder, Context, Graph, MappedData, Mapper, MapperMSA, MultiContext,
                      PairedReads,
-                     ProblemIntervalBuilder, Reference, ReferenceAlignment, ReferenceFinder, cigar_string, mark_remap_reads)
+                     ProblemIntervalBuilder, RandomModel, Reference, ReferenceAlignment, ReferenceFinder, cigar_string, mark_remap_reads)
 
 __all__ = ["Context", "MultiContext", "Mapper", "MapperMSA", "ConsensusBuilderSimple", "Reference", "ReferenceAlignment",
-           "BamPrinter", "ContigBuilder", "Graph", "ReferenceFinder", "ProblemIntervalBuilder", "BAM_DTYPE", "PairedReads", "MappedData", "VgError", "PAIR_DTYPE", "MATE_DTYPE", "EXPORTED_SYMBOLS", "LIB_PATH", "mark_remap_reads"]
+           "BamPrinter", "ContigBuilder", "Graph", "ReferenceFinder", "ProblemIntervalBuilder", "RandomModel", "BAM_DTYPE", "PairedReads", "MappedData", "VgError", "PAIR_DTYPE", "MATE_DTYPE", "EXPORTED_SYMBOLS", "LIB_PATH", "mark_remap_reads"]

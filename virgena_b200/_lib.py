@@ -76,6 +76,8 @@ _SIGS = {
     "vg_consensus": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "vg_sw_align_batch": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vg_sw_max_score_batch": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]),
+    "vg_random_model_counts": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_int64,
+                                         C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "vg_seed_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                 C.c_void_p]),
     "vg_last_timings": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -67,7 +67,7 @@ void vg_ctx_destroy(vg_ctx* c) {
                     &c->d_tasks, &c->d_fill, &c->d_alns, &c->d_rev, &c->d_rowck, &c->d_colck, &c->d_counter,
                     &c->d_scratch, &c->d_seqOff, &c->d_cand, &c->d_ncand, &c->d_misc, &c->d_s1pool, &c->d_s2pool,
                     &c->d_s1off, &c->d_s2off, &c->d_counts, &c->d_swSeq1, &c->d_packed, &c->d_swSorted, &c->d_swBins, &c->d_rowpool, &c->d_rowLen, &c->d_scratchR, &c->d_seedS, &c->d_seedNS, &c->d_seedFb, &c->d_bamN,
-                    &c->d_bamOff, &c->d_bamRec, &c->d_bamOps};
+                    &c->d_bamOff, &c->d_bamRec, &c->d_bamOps, &c->d_rand};
   for (DevBuf* b : bufs) b->release();
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);

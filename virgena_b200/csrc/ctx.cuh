@@ -96,6 +96,7 @@ struct vg_ctx {
   DevBuf d_swSorted, d_swBins;  // alignment tasks sorted by (R bin, window length), the counting sort's tables
   DevBuf d_swSeq1;  // sequence1 output of vg_sw_align_batch (its own buffer: d_seq1pool belongs to the last mapping)
   DevBuf d_bamN, d_bamOff, d_bamRec, d_bamOps;  // vg_bam_fields
+  DevBuf d_rand;  // vg_random_model_counts: genomes, Markov table, offsets
   DevBuf d_seedS, d_seedNS, d_seedFb;  // fast seeding path: per-item LongHit slots, counts, fallback list
   int64_t seedFallbacks = 0;           // items of the last seeding call redone by the general kernel
   std::vector<cudaEvent_t> seedEv;     // 3 events per sub-chunk of the fast seeding path

@@ -988,6 +988,149 @@ static int mh_seed_batch(vg_ctx* c, int32_t msa, const uint8_t* pool, const int6
   return VG_OK;
 }
 
+// ---- random model ------------------------------------------------------------------------------------
+// MarkovModel.generate (MarkovModel.java:94-119): one thread per random read. The reference draws from an unseeded
+// java.util.Random created per read (:95, Q10), so no stream is "the reference's"; the policy here is SplitMix64 with the state
+// seed + (first_draw + r * draws_per_read) * golden for read r, draws_per_read = 2 + read_len - order (genome, position, one
+// draw per further base) — the stream the oracle's seeded restatement consumes sequentially.
+struct RmRng {
+  uint64_t s;
+  __device__ __forceinline__ uint64_t next() {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+  }
+  __device__ __forceinline__ int nextInt(int n) { return (int)(next() % (uint64_t)n); }
+  __device__ __forceinline__ float nextFloat() { return (float)(next() >> 40) / 16777216.0f; }
+};
+// freqs: [4^order][4] cumulative frequencies in the order A, T, G, C (fr[3] < 0: the k-mer is not in the model);
+// k-mer code: 2 bits per base in that order, first base most significant
+__global__ void rm_generate_kernel(const uint8_t* __restrict__ genomes, const int64_t* __restrict__ genomeOff, int nGenomes,
+                                   int order, const float4* __restrict__ freqs, uint64_t seed, int64_t firstDraw, int readLen,
+                                   int64_t nReads, uint8_t* __restrict__ out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nReads) return;
+  RmRng rnd;
+  rnd.s = seed + (uint64_t)(firstDraw + r * (int64_t)(2 + readLen - order)) * 0x9E3779B97F4A7C15ULL;
+  const int gid = rnd.nextInt(nGenomes);
+  const uint8_t* genome = genomes + genomeOff[gid];
+  const int glen = (int)(genomeOff[gid + 1] - genomeOff[gid]);
+  const int gpos = rnd.nextInt(glen - order + 1);
+  uint8_t* dst = out + r * (int64_t)readLen;
+  const uint32_t cmask = (order >= 16) ? 0xFFFFFFFFu : ((1u << (2 * order)) - 1u);
+  uint32_t code = 0;
+  int good = 0;  // trailing bases that are A/T/G/C
+  auto push = [&](uint8_t b) {
+    const int v = b == 'A' ? 0 : b == 'T' ? 1 : b == 'G' ? 2 : b == 'C' ? 3 : -1;
+    code = ((code << 2) | (uint32_t)(v & 3)) & cmask;
+    good = v >= 0 ? good + 1 : 0;
+  };
+  for (int j = 0; j < order && j < readLen; j++) {
+    dst[j] = genome[gpos + j];
+    push(genome[gpos + j]);
+  }
+  for (int j = order; j < readLen; j++) {
+    float4 fr = make_float4(0.f, 0.f, 0.f, -1.f);
+    if (good >= order) fr = freqs[code];
+    uint8_t b;
+    if (fr.w < 0.f) {  // freqs.get(...) == null
+      const int n = rnd.nextInt(4);
+      b = n == 0 ? 'A' : n == 1 ? 'T' : n == 2 ? 'G' : 'C';  // Constants.iToN
+    } else {
+      const float pr = rnd.nextFloat();
+      b = pr <= fr.x ? 'A' : pr <= fr.y ? 'T' : pr <= fr.z ? 'G' : 'C';
+    }
+    dst[j] = b;
+    push(b);
+  }
+}
+__global__ void rm_offsets_kernel(int64_t n, int readLen, int64_t* __restrict__ off, int32_t* __restrict__ len) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r <= n) off[r] = r * readLen;
+  if (r < n) len[r] = readLen;
+}
+
+// RandomModel.RandomCountsComputing.run (RandomModel.java:113-128): counts[r] = computeKMerCount(model.generate(len), index, 0, length)
+int vg_random_model_counts(vg_ctx* c, int32_t msa, const uint8_t* genomes, const int64_t* genome_off, int32_t n_genomes,
+                           int32_t order, uint64_t seed, int64_t first_draw, int32_t read_len, int64_t n_reads,
+                           int32_t* counts, uint8_t* reads_out) {
+  if (!c) return VG_ERR_INVALID;
+  VG_CUDA(c, cudaSetDevice(c->device));
+  if (msa ? !c->haveMsa : !c->haveRef) return vg_fail(c, VG_ERR_STATE, "reference / MSA index not set");
+  if (!genomes || !genome_off || n_genomes < 1 || order < 1 || order > 8 || read_len < order || read_len > SD_MAXL || n_reads < 0 ||
+      first_draw < 0 || (n_reads > 0 && !counts))
+    return vg_fail(c, VG_ERR_INVALID, "bad arguments (order 1..8, order <= read_len <= %d)", SD_MAXL);
+  if (n_reads == 0) return VG_OK;
+  // MarkovModel(String[] genomes, int order) (MarkovModel.java:18-71): float32 arithmetic in the reference's order
+  const int nCodes = 1 << (2 * order);
+  std::vector<int32_t> cnt((size_t)nCodes * 4, 0);
+  std::vector<uint8_t> seen(nCodes, 0);
+  auto v4 = [](uint8_t b) { return b == 'A' ? 0 : b == 'T' ? 1 : b == 'G' ? 2 : b == 'C' ? 3 : -1; };
+  for (int g = 0; g < n_genomes; g++) {
+    const uint8_t* s = genomes + genome_off[g];
+    const int64_t gl = genome_off[g + 1] - genome_off[g];
+    if (gl < order) return vg_fail(c, VG_ERR_INVALID, "genome %d is shorter than the model order (Random.nextInt would throw)", g);
+    for (int64_t j = 0; j < gl - order; j++) {
+      uint32_t code = 0;
+      bool ok = true;
+      for (int t = 0; t < order; t++) {
+        const int v = v4(s[j + t]);
+        ok &= v >= 0;
+        code = (code << 2) | (uint32_t)(v & 3);
+      }
+      if (!ok) continue;
+      seen[code] = 1;
+      const int v = v4(s[j + order]);
+      if (v >= 0) cnt[(size_t)code * 4 + v]++;
+    }
+  }
+  std::vector<float> fr((size_t)nCodes * 4);
+  for (int k = 0; k < nCodes; k++) {
+    float* f = &fr[(size_t)k * 4];
+    if (!seen[k]) {
+      f[0] = f[1] = f[2] = 0.f, f[3] = -1.f;
+      continue;
+    }
+    const int* q = &cnt[(size_t)k * 4];
+    const int total = q[0] + q[1] + q[2] + q[3];
+    volatile float cf = 1.0f / (float)total;  // total == 0: +Inf, the products are NaN and every comparison fails -> 'C'
+    volatile float a = (float)q[0] * cf;
+    volatile float t1 = (float)q[1] * cf;
+    volatile float b = a + t1;
+    volatile float t2 = (float)q[2] * cf;
+    volatile float d = b + t2;
+    f[0] = a, f[1] = b, f[2] = d, f[3] = 1.0f;
+  }
+  const size_t gbytes = (size_t)genome_off[n_genomes];
+  VG_CUDA(c, c->d_rand.reserve(gbytes + 64 + (size_t)(n_genomes + 1) * 8 + fr.size() * 4 + 64));
+  uint8_t* d_gen = c->d_rand.as<uint8_t>();
+  float4* d_fr = (float4*)(d_gen + ((gbytes + 63) & ~(size_t)63));
+  int64_t* d_goff = (int64_t*)((uint8_t*)d_fr + fr.size() * 4);
+  VG_CUDA(c, cudaMemcpyAsync(d_gen, genomes, gbytes, cudaMemcpyHostToDevice, c->stream));
+  VG_CUDA(c, cudaMemcpyAsync(d_fr, fr.data(), fr.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  VG_CUDA(c, cudaMemcpyAsync(d_goff, genome_off, (size_t)(n_genomes + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  VG_CUDA(c, c->d_s1pool.reserve((size_t)n_reads * read_len + 64));
+  VG_CUDA(c, c->d_s1off.reserve((size_t)(n_reads + 1) * 8));
+  VG_CUDA(c, c->d_s2off.reserve((size_t)n_reads * 4 + 64));
+  const int blocks = (int)((n_reads + 1 + 127) / 128);
+  rm_generate_kernel<<<blocks, 128, 0, c->stream>>>(d_gen, d_goff, n_genomes, order, d_fr, seed, first_draw, read_len, n_reads,
+                                                    c->d_s1pool.as<uint8_t>());
+  VG_LAUNCH_CHECK(c);
+  rm_offsets_kernel<<<blocks, 128, 0, c->stream>>>(n_reads, read_len, c->d_s1off.as<int64_t>(), c->d_s2off.as<int32_t>());
+  VG_LAUNCH_CHECK(c);
+  if (reads_out)
+    VG_CUDA(c, cudaMemcpyAsync(reads_out, c->d_s1pool.p, (size_t)n_reads * read_len, cudaMemcpyDeviceToHost, c->stream));
+  VG_TRY(seed_launch(c, msa != 0, c->d_s1pool.as<uint8_t>(), c->d_s1off.as<int64_t>(), c->d_s2off.as<int32_t>(), nullptr,
+                     nullptr, nullptr, n_reads, true, read_len, 1, nullptr, nullptr, true));
+  std::vector<int32_t> win((size_t)n_reads * 3), found(n_reads);
+  VG_CUDA(c, cudaMemcpyAsync(win.data(), c->d_cand.p, (size_t)n_reads * 3 * 4, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaMemcpyAsync(found.data(), c->d_ncand.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, c->stream));
+  VG_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int64_t r = 0; r < n_reads; r++) counts[r] = found[r] ? win[(size_t)r * 3 + 2] : 0;  // no hit: computeKMerCount returns 0
+  return VG_OK;
+}
+
 int vg_seed_batch(vg_ctx* c, int32_t msa, const uint8_t* pool, const int64_t* off, int64_t n, int32_t max_windows,
                   int32_t* windows, int32_t* n_windows) {
   return mh_seed_batch(c, msa, pool, off, n, max_windows, windows, n_windows, nullptr, 0, nullptr);

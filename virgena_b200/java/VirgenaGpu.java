@@ -61,6 +61,9 @@ final class VirgenaGpu implements AutoCloseable {
   static native void pileupAlignments(long h, ByteBuffer seq1, long[] seq1Off, int[] length, long[] pos, long[] endOrNull,
                                       long totalPositions, int[] counts);
   static native void identityCounting(long h, int windowSize, int threadNum, float[] identity, int[] coverage);
+  // vg_random_model_counts: RandomModel.RandomCountsComputing.run (RandomModel.java:113-128) for readNum reads of one length
+  static native void randomModelCounts(long h, boolean msa, ByteBuffer genomes, long[] genomeOff, int order, long seed,
+                                       long firstDraw, int readLen, int[] counts);
 
   long handle() { return handle; }
   boolean isMulti() { return multi; }

@@ -240,6 +240,21 @@ JNIEXPORT void JNICALL Java_VirgenaGpu_bestWindows(JNIEnv* e, jclass cls, jlong 
   CHECK(rc, h, JNI_FALSE, )
 }
 
+/* vg_random_model_counts  <-  RandomModel.RandomCountsComputing.run (RandomModel.java:113-128), MarkovModel.generate (:94-119) */
+JNIEXPORT void JNICALL Java_VirgenaGpu_randomModelCounts(JNIEnv* e, jclass cls, jlong h, jboolean msa, jobject genomes,
+                                                         jlongArray genomeOff, jint order, jlong seed, jlong firstDraw,
+                                                         jint readLen, jintArray counts) {
+  (void)cls;
+  jlong* go = GET_L(genomeOff);
+  jint* c = GET_I(counts);
+  int rc = vg_random_model_counts(CTX(h), msa ? 1 : 0, (const uint8_t*)DIRECT(genomes), (const int64_t*)go,
+                                  (int32_t)(LEN(genomeOff) - 1), order, (uint64_t)seed, firstDraw, readLen, LEN(counts),
+                                  (int32_t*)c, NULL);
+  REL_L(genomeOff, go, JNI_ABORT);
+  REL_I(counts, c, 0);
+  CHECK(rc, h, JNI_FALSE, )
+}
+
 /* vg_map_to_regions  <-  ContigBuilder.countReads (ContigBuilder.java:72-104), Graph.SWScore (Graph.java:493-550) */
 JNIEXPORT void JNICALL Java_VirgenaGpu_mapToRegions(JNIEnv* e, jclass cls, jlong h, jobject regions, jlongArray regionOff,
                                                     jobject reads, jlongArray readOff, jintArray readRegion,

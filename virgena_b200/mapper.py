@@ -402,6 +402,21 @@ class Context:
         self._chk(self.L.vg_best_window_batch(self.h, int(msa), ptr(pool), ptr(off), n, ptr(win), ptr(found)))
         return win[:n], found[:n]
 
+    def random_model_counts(self, genomes, order, seed, first_draw, read_len, n_reads, msa=False, want_reads=False):
+        """vg_random_model_counts: n_reads random reads of read_len bases from the order-`order` Markov model of `genomes`
+        (list of byte strings), generated and scored (computeKMerCount) on the device. Returns counts int32[n] (unsorted)
+        or (counts, reads uint8[n, read_len])."""
+        gs = [_u8(g) for g in genomes]
+        pool = np.concatenate(gs) if gs else np.zeros(0, np.uint8)
+        off = np.zeros(len(gs) + 1, np.int64)
+        off[1:] = np.cumsum([len(g) for g in gs])
+        counts = np.zeros(max(n_reads, 1), np.int32)
+        reads = np.zeros((max(n_reads, 1), read_len), np.uint8) if want_reads else None
+        self._chk(self.L.vg_random_model_counts(self.h, int(msa), ptr(pool), ptr(off), len(gs), int(order), C.c_uint64(int(seed)),
+                                                int(first_draw), int(read_len), int(n_reads), ptr(counts),
+                                                ptr(reads) if want_reads else None))
+        return (counts[:n_reads], reads[:n_reads]) if want_reads else counts[:n_reads]
+
     def map_to_regions(self, region_pool, region_off, read_pool, read_off, read_region):
         """vg_map_to_regions: mapReadToRegion of read i against region read_region[i] (each region its own index).
         Returns (windows int32[n, 3], found int32[n])."""
@@ -845,6 +860,70 @@ class ReferenceFinder:
             for (v, j), r in zip(where, rec):
                 scores[v, j] = r[0]
         return scores
+
+
+class RandomModel:
+    """RandomModel / RandomModelMSA (RandomModel.java:25-145, RandomModelMSA.java:56-135) + KMerCounterBase.computeCuttofs
+    (:229-251): the null distribution of the k-mer score of random reads and the cutoffs derived from it. Reads are generated
+    (MarkovModel.generate) and scored (computeKMerCount) on the device; sorting and the quantile stay on the host.
+
+    The model's counter is its own KMerCounter instance with lowCoef = 1 / coef (KMerCounter.java:51-55, Q3), hence its own
+    context. The reference's RNG is unseeded (Q10); here the reads are those of one SplitMix64(seed) stream consumed length by
+    length from maxReadLen down, read by read, which is also what the oracle's seeded restatement draws."""
+
+    def __init__(self, genome, K=5, order=4, coef=1.25, seed=1, device=0):
+        self.K, self.modelK, self.coef, self.seed = K, order, float(coef), int(seed)
+        self.msa = isinstance(genome, ReferenceAlignment)
+        self.ctx = Context(K, float(np.float32(1.0) / np.float32(coef)), float(coef), np.zeros(1, np.int32), device=device)
+        if self.msa:
+            self.ctx.set_msa(genome, float(np.float32(1.0) / np.float32(coef)), float(coef), np.zeros(1, np.int32))
+            self.genomes = [row[row != ord("-")] for row in genome.rows]          # RandomModelMSA.java:63-66
+        else:
+            self.ctx.set_reference(genome)
+            if genome.isFragmented:                                                 # RandomModel.java:88-94
+                ends = [0] + [int(e) for e in genome.contigEnds]
+                self.genomes = [genome.seqB[a:b] for a, b in zip(ends[:-1], ends[1:])]
+            else:
+                self.genomes = [genome.seqB]
+        self.counts = None
+
+    def genModel(self, readNum, minReadLen, maxReadLen, step):
+        """counts[size][readNum], every row sorted (genRandomScores ends with Arrays.sort)."""
+        size = (maxReadLen - minReadLen) // step + 1
+        self.counts = np.zeros((size, readNum), np.int32)
+        draw = 0
+        ln = maxReadLen
+        for i in range(size - 1, -1, -1):
+            c = self.ctx.random_model_counts(self.genomes, self.modelK, self.seed, draw, ln, readNum, msa=self.msa)
+            self.counts[i] = np.sort(c)
+            draw += readNum * (2 + ln - self.modelK)
+            ln -= step
+        return self.counts
+
+    @staticmethod
+    def computeCuttofs(minReadLen, maxReadLen, step, counts, pValue):
+        """KMerCounterBase.computeCuttofs (:229-251) verbatim, including `num = counts.length` (the number of read-length
+        bins, not readNum) as the base of the quantile index."""
+        num = len(counts)
+        size = (maxReadLen - minReadLen) // step + 1
+        index = int(np.floor(np.float32(num) * (np.float32(1.0) - np.float32(pValue)) + np.float32(0.5)))  # Math.round
+        interp = [int(counts[i][index]) for i in range(size)]
+        cutoffs = np.zeros(maxReadLen + 1, np.int32)
+        cutoffs[:minReadLen + 1] = interp[0]
+        for i in range(maxReadLen, minReadLen, -1):
+            right = size - (maxReadLen - i) // step - 1
+            if right == 0:
+                cutoffs[i] = interp[0]
+            else:
+                d_right = (maxReadLen - i) % step
+                d_left = step - d_right
+                v = d_right * interp[right - 1] + d_left * interp[right]
+                cutoffs[i] = int(v / step) if v >= 0 else -int(-v / step)  # Java int division truncates
+        return cutoffs
+
+    def cutoffs(self, readNum=10000, minReadLen=250, maxReadLen=250, step=10, pValue=0.01):
+        self.genModel(readNum, minReadLen, maxReadLen, step)
+        return self.computeCuttofs(minReadLen, maxReadLen, step, self.counts, pValue)
 
 
 class ProblemIntervalBuilder:
