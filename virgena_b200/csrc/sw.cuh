@@ -92,7 +92,10 @@ struct SwCk<true> {
 // mismatch + gop). Both summands are non-negative in both 16-bit halves and the sum stays below 2^15, so a plain 32-bit
 // add is exact per half and issues on the FMA pipe (IMAD.IADD) instead of the ALU / DPX pipe that bounds the kernel;
 // V = relu(max(Es, Fs, g_s) - gop) is VIMNMX3 + VIADDMNMX.RELU. 6.5 instead of 7.5 ALU-pipe instructions per cell-pair.
-template <int R, bool STORE, bool COMPACT, bool FASTF>
+// W (32, 16 or 8) = lanes per pair of alignments: reads of at most W * R bases run 32 / W pairs per warp, every group of W
+// lanes its own wavefront (shuffles of width W, a skew of W - 1 steps instead of 31, no idle lanes for short reads). The
+// checkpoint layouts are the same with W in the place of 32.
+template <int R, bool STORE, bool COMPACT, bool FASTF, int W = 32>
 __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__ tasks, int ntasks,
                                                       const uint8_t* __restrict__ s1pool,
                                                       const uint8_t* __restrict__ s2pool, SwParams prm,
@@ -101,9 +104,12 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
                                                       int nT, int nTb, SwFillOut* __restrict__ out,
                                                       int* __restrict__ counter, int smemWordsPerWarp) {
   extern __shared__ uint32_t sw_smem[];
+  constexpr int NG = 32 / W;  // pairs per warp
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  uint32_t* wsym = sw_smem + (size_t)warp * smemWordsPerWarp;
+  const int grp = lane / W, gl = lane % W;  // group of the lane, lane inside the group (= strip)
+  const unsigned gmask = (W == 32) ? VG_FULL : (((1u << (W & 31)) - 1u) << (grp * W));
+  uint32_t* wsym = sw_smem + ((size_t)warp * NG + grp) * smemWordsPerWarp;
   const uint32_t NEGp = vg_pk2(SW_NEG);
   const uint32_t NGEPp = vg_pk2(-prm.gep);
   const uint32_t NGOPp = vg_pk2(-prm.gop);
@@ -115,13 +121,23 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
 
   for (;;) {
     int pi = 0;
-    if (lane == 0) pi = atomicAdd(counter, 1);
+    if (lane == 0) pi = atomicAdd(counter, NG);
     pi = __shfl_sync(VG_FULL, pi, 0);
     if (pi >= npairs) break;
+    pi += grp;
+    const bool have = pi < npairs;  // a group beyond the last pair runs along with empty sequences
     const int ia = 2 * pi, ib = 2 * pi + 1;
-    const SwTask ta = tasks[ia];
+    SwTask ta;
+    if (have) {
+      ta = tasks[ia];
+    } else {
+      ta.s1_off = ta.s2_off = 0;
+      ta.m = ta.n = 0;
+      ta.rc = 0;
+      ta.out = -1;
+    }
     SwTask tb;
-    if (ib < ntasks) {
+    if (have && ib < ntasks) {
       tb = tasks[ib];
     } else {
       tb.s1_off = tb.s2_off = 0;
@@ -137,7 +153,7 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
     const int mmax = max(ta.m, tb.m);
 
     __syncwarp();
-    for (int j = lane; j < nmax; j += 32) {
+    for (int j = gl; j < nmax; j += W) {
       uint32_t ca = (j < ta.n) ? ((uint32_t)a2[j] << 8) : SW_PAD_S2;
       uint32_t cb = (j < tb.n) ? ((uint32_t)b2[j] << 8) : SW_PAD_S2;
       wsym[j + 1] = ca | (cb << 16);
@@ -145,7 +161,7 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
     uint32_t a[R], V[R], F[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
-      int idx = lane * R + r;
+      int idx = gl * R + r;
       uint32_t ca = (idx < ta.m) ? ((uint32_t)sw_s1_byte(a1, ta.m, ta.rc, idx) << 8) : SW_PAD_S1;
       uint32_t cb = (idx < tb.m) ? ((uint32_t)sw_s1_byte(b1, tb.m, tb.rc, idx) << 8) : SW_PAD_S1;
       a[r] = ~(ca | (cb << 16));  // complemented: a[r] ^ b is the XNOR of the codes in one LOP3
@@ -158,13 +174,13 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
     int colA = 0, colB = 0;
     bool tieA = false, tieB = false;
     // lanes whose strip starts beyond both reads never influence a result
-    const int lastLane = min(31, (mmax - 1) / R);
-    const int tEnd = nmax + lastLane;
+    const int lastLane = mmax > 0 ? min(W - 1, (mmax - 1) / R) : 0;
+    const int tEnd = (W == 32) ? nmax + lastLane : __reduce_max_sync(VG_FULL, nmax > 0 ? nmax + lastLane : 0);
     // checkpoints of the lane's bottom row: nT entries per lane, entry t - 1 = wavefront step t, written 4 steps
     // (one 32-byte sector) at a time so that the traceback reads the boundary of a tile as one contiguous run
     using CK = SwCk<COMPACT>;
-    typename CK::T* rowp = rowck + ((int64_t)pi * 32 + lane) * nT;
-    typename CK::T* colp = colck + ((int64_t)pi * nTb) * (32 * R) + lane * R;
+    typename CK::T* rowp = rowck + ((int64_t)pi * W + gl) * nT;
+    typename CK::T* colp = colck + ((int64_t)pi * nTb) * (W * R) + gl * R;
     const int tEnd4 = (tEnd + 3) & ~3;  // steps beyond tEnd find every lane inactive
 
 #pragma unroll 1
@@ -173,14 +189,14 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
 #pragma unroll
       for (int s4 = 1; s4 <= 4; s4++) {
         const int t = tg + s4;
-        uint32_t vin = __shfl_up_sync(VG_FULL, vbot, 1);
-        uint32_t ein = __shfl_up_sync(VG_FULL, ebot, 1);
-        if (lane == 0) {
+        uint32_t vin = __shfl_up_sync(VG_FULL, vbot, 1, W);
+        uint32_t ein = __shfl_up_sync(VG_FULL, ebot, 1, W);
+        if (gl == 0) {
           vin = 0;
           ein = NEGp;
         }
-        const int j = t - lane;
-        const bool active = (j >= 1 && j <= nmax && lane <= lastLane);
+        const int j = t - gl;
+        const bool active = (j >= 1 && j <= nmax && gl <= lastLane);
         if (active) {
           const uint32_t b = wsym[j];
           uint32_t vd = vup_prev, vu = vin, e = ein, cm = cm4;  // running maximum of the current group of 4 steps
@@ -221,10 +237,10 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
       }
       // once per group of 4 steps (warp-uniform): exact maximum of the strip, the group of 4 columns that reached it
       // first, and whether a later group reached it again
-      SW_MAX_BOOKKEEPING(tg + 4 - lane)
+      SW_MAX_BOOKKEEPING(tg + 4 - gl)
       if (STORE) {
-        const int j1 = tg + 1 - lane, j4 = tg + 4 - lane;
-        if (lane <= lastLane && j4 >= 1 && j1 <= nmax) {
+        const int j1 = tg + 1 - gl, j4 = tg + 4 - gl;
+        if (gl <= lastLane && j4 >= 1 && j1 <= nmax) {
           uint4* dst = (uint4*)(rowp + tg);
           if constexpr (COMPACT) {
             dst[0] = make_uint4(rb[0], rb[1], rb[2], rb[3]);
@@ -233,8 +249,8 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
             dst[1] = make_uint4(rb[2].x, rb[2].y, rb[3].x, rb[3].y);
           }
         }
-        if (((tg + 4) & (SW_TC - 1)) == 0 && lane <= lastLane && j4 >= 1 && j4 <= nmax) {  // column checkpoint of the rows
-          typename CK::T* dst = colp + (int64_t)((tg + 4) / SW_TC) * (32 * R);
+        if (((tg + 4) & (SW_TC - 1)) == 0 && gl <= lastLane && j4 >= 1 && j4 <= nmax) {  // column checkpoint of the rows
+          typename CK::T* dst = colp + (int64_t)((tg + 4) / SW_TC) * (W * R);
           if constexpr (COMPACT && (R % 4 == 0)) {  // a lane's R words are contiguous and 16-byte aligned: whole-sector stores
 #pragma unroll
             for (int r = 0; r < R; r += 4)
@@ -248,19 +264,19 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
       }
     }
     // warp reduction: S, the smallest strip holding it, its first column group and tie flag
-    int sA = __reduce_max_sync(VG_FULL, vg_lo(lanemax));
-    int sB = __reduce_max_sync(VG_FULL, vg_hi(lanemax));
-    unsigned candA = __ballot_sync(VG_FULL, vg_lo(lanemax) == sA);
-    unsigned candB = __ballot_sync(VG_FULL, vg_hi(lanemax) == sB);
-    int kA = __ffs(candA) - 1, kB = __ffs(candB) - 1;
+    int sA = __reduce_max_sync(gmask, vg_lo(lanemax));
+    int sB = __reduce_max_sync(gmask, vg_hi(lanemax));
+    unsigned candA = __ballot_sync(VG_FULL, vg_lo(lanemax) == sA) & gmask;
+    unsigned candB = __ballot_sync(VG_FULL, vg_hi(lanemax) == sB) & gmask;
+    int kA = __ffs(candA) - 1, kB = __ffs(candB) - 1;  // lanes of the warp; the strip is the lane inside the group
     int cA = __shfl_sync(VG_FULL, colA, kA), cB = __shfl_sync(VG_FULL, colB, kB);
     int tA = __shfl_sync(VG_FULL, (int)tieA, kA), tB = __shfl_sync(VG_FULL, (int)tieB, kB);
-    if (lane == 0) {
+    if (gl == 0 && have) {
       SwFillOut o;
-      o.score = sA, o.strip = kA, o.col = cA, o.tie = tA;
+      o.score = sA, o.strip = kA - grp * W, o.col = cA, o.tie = tA;
       out[ia] = o;
       if (ib < ntasks) {
-        o.score = sB, o.strip = kB, o.col = cB, o.tie = tB;
+        o.score = sB, o.strip = kB - grp * W, o.col = cB, o.tie = tB;
         out[ib] = o;
       }
     }
@@ -286,7 +302,7 @@ struct SwTb {
 // Flag word of 8 rows of one column: bits 2r..2r+1 pointer of row r (STOP=0, LEFT=1, DIAGONAL=2, UP=3), bit 16+r vertical
 // gap extended at row r, bit 24+r horizontal gap extended.
 // PROBE: also look for the end cell (smallest (row, column) with V == probeS); only the first tile(s) of an alignment need it.
-template <int R, bool COMPACT, bool PROBE>
+template <int R, bool COMPACT, bool PROBE, int W = 32>
 __device__ __forceinline__ void sw_tile_recompute(const SwTask& tk, const uint8_t* __restrict__ s1,
                                                   const uint8_t* __restrict__ s2, const SwParams& prm,
                                                   const typename SwCk<COMPACT>::T* __restrict__ rowckP,
@@ -308,7 +324,7 @@ __device__ __forceinline__ void sw_tile_recompute(const SwTask& tk, const uint8_
     if (i <= tk.m) {
       asym[r] = sw_s1_byte(s1, tk.m, tk.rc, i - 1);
       if (cl > 0) {
-        SwCk<COMPACT>::get(colckP[(int64_t)tb * (32 * R) + (i - 1)], hi, prm.gep, v[r], hs[r]);
+        SwCk<COMPACT>::get(colckP[(int64_t)tb * (W * R) + (i - 1)], hi, prm.gep, v[r], hs[r]);
       }
     }
   }
@@ -383,7 +399,7 @@ __device__ __forceinline__ int sw_tile_left(int k, int j) {
   return cl < 1 ? 0 : cl;
 }
 
-template <int R, bool COMPACT>
+template <int R, bool COMPACT, int W = 32>
 __global__ void __launch_bounds__(128, 7) sw_traceback_kernel(const SwTask* __restrict__ tasks, int ntasks,
                                                            const uint8_t* __restrict__ s1pool,
                                                            const uint8_t* __restrict__ s2pool, SwParams prm,
@@ -411,8 +427,8 @@ __global__ void __launch_bounds__(128, 7) sw_traceback_kernel(const SwTask* __re
   const uint8_t* s1 = s1pool + tk.s1_off;
   const uint8_t* s2 = s2pool + tk.s2_off;
   const int hi = ti & 1;
-  const typename SwCk<COMPACT>::T* rowckP = rowck + ((int64_t)(ti >> 1) * 32) * nT;
-  const typename SwCk<COMPACT>::T* colckP = colck + ((int64_t)(ti >> 1) * nTb) * (32 * R);
+  const typename SwCk<COMPACT>::T* rowckP = rowck + ((int64_t)(ti >> 1) * W) * nT;
+  const typename SwCk<COMPACT>::T* colckP = colck + ((int64_t)(ti >> 1) * nTb) * (W * R);
   uint32_t* flags = flagS + tid;
   uint8_t* out = rev + (int64_t)tk.out * revStride;
   int no1 = 1 << 30, no2 = 1 << 30;
@@ -426,12 +442,12 @@ __global__ void __launch_bounds__(128, 7) sw_traceback_kernel(const SwTask* __re
     if (!fo.tie) {
       const int jEnd = min(fo.col, tk.n);  // fo.col = last column of the group of 4 that reached the maximum
       int cl = sw_tile_left(fo.strip, jEnd);
-      sw_tile_recompute<R, COMPACT, true>(tk, s1, s2, prm, rowckP, colckP, nT, hi, fo.strip, cl, jEnd, flags, 128, fo.score, fo.col, bi, bj);
+      sw_tile_recompute<R, COMPACT, true, W>(tk, s1, s2, prm, rowckP, colckP, nT, hi, fo.strip, cl, jEnd, flags, 128, fo.score, fo.col, bi, bj);
       haveK = fo.strip, haveCl = cl;
     } else {
       for (int jj = tk.n; jj >= 1;) {  // rare: the strip reached S at several columns
         int cl = sw_tile_left(fo.strip, jj);
-        sw_tile_recompute<R, COMPACT, true>(tk, s1, s2, prm, rowckP, colckP, nT, hi, fo.strip, cl, jj, flags, 128, fo.score, -1, bi, bj);
+        sw_tile_recompute<R, COMPACT, true, W>(tk, s1, s2, prm, rowckP, colckP, nT, hi, fo.strip, cl, jj, flags, 128, fo.score, -1, bi, bj);
         jj = cl;
       }
     }
@@ -446,7 +462,7 @@ __global__ void __launch_bounds__(128, 7) sw_traceback_kernel(const SwTask* __re
       k = (i - 1) / R;
       cl = sw_tile_left(k, j);
       if (k != haveK || cl != haveCl)
-        sw_tile_recompute<R, COMPACT, false>(tk, s1, s2, prm, rowckP, colckP, nT, hi, k, cl, j, flags, 128, -1, -1, no1, no2);
+        sw_tile_recompute<R, COMPACT, false, W>(tk, s1, s2, prm, rowckP, colckP, nT, hi, k, cl, j, flags, 128, -1, -1, no1, no2);
       haveK = -1;
     }
     while (!done) {

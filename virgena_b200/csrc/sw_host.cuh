@@ -5,10 +5,19 @@
 #include "ctx.cuh"
 #include "sw.cuh"
 
-static inline int sw_pick_R(int mmax) {
-  static const int Rs[] = {2, 3, 4, 5, 6, 8, 10, 12, 16, 24, 32};
-  for (int r : Rs)
-    if (32 * r >= mmax) return r;
+// Alignment geometry by read length: W lanes per pair of alignments (32 / W pairs per warp), R rows per lane; a bin holds the
+// reads of at most W * R bases. Short reads get narrow groups (full lanes, a skew of W - 1 steps), never thin strips: the
+// traceback crosses |s1| / R strips whatever the read length.
+// Measured per read length (tools/sw_len_probe.py, profiles/sw_r2.md): (8, 8) 3.0x, (16, 6) 1.9x, (16, 8) 1.6x the fill rate of
+// (32, 6) for their lengths; (32, 5) and (32, 7) were no better than (32, 6) and (32, 8): a step costs about the same for 5 rows
+// as for 6.
+#define SW_NBINS 10
+static const int sw_binW_host[SW_NBINS] = {8, 16, 16, 32, 32, 32, 32, 32, 32, 32};
+static const int sw_binR_host[SW_NBINS] = {8, 6, 8, 6, 8, 10, 12, 16, 24, 32};
+static inline int sw_bin_maxm(int b) { return sw_binW_host[b] * sw_binR_host[b]; }
+static inline int sw_pick_bin(int mmax, int minBin = 0) {
+  for (int b = minBin; b < SW_NBINS; b++)
+    if (sw_bin_maxm(b) >= mmax) return b;
   return -1;
 }
 
@@ -19,21 +28,21 @@ static inline int sw_validate(vg_ctx* c, int mmax, int nmax) {
                    p.mismatch, p.gop, p.gep);
   if (p.match - p.mismatch > 250 || p.gep > 8000 || p.gop > 8000)
     return vg_fail(c, VG_ERR_INVALID, "aligner parameters out of the int16 kernel's range");
-  if (sw_pick_R(mmax) < 0) return vg_fail(c, VG_ERR_INVALID, "sequence length %d exceeds the supported 1024", mmax);
+  if (sw_pick_bin(mmax) < 0) return vg_fail(c, VG_ERR_INVALID, "sequence length %d exceeds the supported 1024", mmax);
   if ((int64_t)p.match * std::min(mmax, nmax) + p.match + 1 > 32000)
     return vg_fail(c, VG_ERR_INVALID, "alignment scores would exceed int16 (%d x %d)", mmax, nmax);
   return VG_OK;
 }
 
-template <int R, bool COMPACT>
+template <int R, bool COMPACT, int W>
 static int sw_launch_R(vg_ctx* c, const SwTask* d_tasks, int ntasks, const uint8_t* d_s1, const uint8_t* d_s2,
                        int nmax, bool traceback, SwFillOut* d_fill, SwAln* d_alns, uint8_t* d_rev, int64_t revStride,
                        double* msFill, double* msTb) {
   using CkT = typename SwCk<COMPACT>::T;
   const int nW = nmax + 1;
-  const int nT = (nmax + 32 + 3) & ~3;  // wavefront steps 1 .. nmax + 31, rounded to whole groups of 4
+  const int nT = (nmax + W + 3) & ~3;  // wavefront steps 1 .. nmax + W - 1, rounded to whole groups of 4
   const int nTb = nT / SW_TC + 1;     // column checkpoints at t = SW_TC, 2 SW_TC, ...
-  const size_t perPair = ((size_t)nT * 32 + (size_t)nTb * 32 * R) * sizeof(CkT);
+  const size_t perPair = ((size_t)nT * W + (size_t)nTb * W * R) * sizeof(CkT);
   const size_t perTask = perPair / 2;
   size_t budget = 0;
   if (const char* e = getenv("VG_CKPT_BYTES")) budget = (size_t)atoll(e);
@@ -46,21 +55,22 @@ static int sw_launch_R(vg_ctx* c, const SwTask* d_tasks, int ntasks, const uint8
     chunk = std::min<int64_t>(ntasks, std::max<int64_t>(2, (int64_t)(budget / perTask)));
     chunk &= ~(int64_t)1;
     if (chunk < 2) chunk = 2;
-    VG_CUDA(c, c->d_rowck.reserve((size_t)(chunk / 2) * nT * 32 * sizeof(CkT)));
-    VG_CUDA(c, c->d_colck.reserve((size_t)(chunk / 2) * nTb * 32 * R * sizeof(CkT)));
+    VG_CUDA(c, c->d_rowck.reserve((size_t)(chunk / 2) * nT * W * sizeof(CkT)));
+    VG_CUDA(c, c->d_colck.reserve((size_t)(chunk / 2) * nTb * W * R * sizeof(CkT)));
   }
   VG_CUDA(c, c->d_counter.reserve(sizeof(int)));
+  constexpr int NG = 32 / W;  // pairs of alignments per warp
   const int threads = 256, warps = threads / 32;
-  const size_t smem = (size_t)warps * nW * sizeof(uint32_t);
+  const size_t smem = (size_t)warps * NG * nW * sizeof(uint32_t);
   int perSm = 1;
   if (traceback) {
-    VG_CUDA(c, cudaFuncSetAttribute(sw_fill_kernel<R, true, COMPACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VG_CUDA(c, cudaFuncSetAttribute(sw_fill_kernel<R, true, COMPACT, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, sw_fill_kernel<R, true, COMPACT, false>, threads, smem));
+    VG_CUDA(c, cudaFuncSetAttribute(sw_fill_kernel<R, true, COMPACT, false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VG_CUDA(c, cudaFuncSetAttribute(sw_fill_kernel<R, true, COMPACT, COMPACT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, sw_fill_kernel<R, true, COMPACT, false, W>, threads, smem));
   } else {
-    VG_CUDA(c, cudaFuncSetAttribute(sw_fill_kernel<R, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VG_CUDA(c, cudaFuncSetAttribute(sw_fill_kernel<R, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, sw_fill_kernel<R, false, false, false>, threads, smem));
+    VG_CUDA(c, cudaFuncSetAttribute(sw_fill_kernel<R, false, false, false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VG_CUDA(c, cudaFuncSetAttribute(sw_fill_kernel<R, false, false, true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, sw_fill_kernel<R, false, false, false, W>, threads, smem));
   }
   if (perSm < 1) return vg_fail(c, VG_ERR_INVALID, "window length %d needs too much shared memory", nmax);
   // the diagonal term on the FMA pipe (sw.cuh, FASTF) needs mismatch + gop >= 0; instantiated for the compact-checkpoint
@@ -70,29 +80,29 @@ static int sw_launch_R(vg_ctx* c, const SwTask* d_tasks, int ntasks, const uint8
   for (int64_t s = 0; s < ntasks; s += chunk) {
     const int nt = (int)std::min<int64_t>(chunk, ntasks - s);
     const int npairs = (nt + 1) / 2;
-    const int blocks = std::max(1, std::min((npairs + warps - 1) / warps, c->smCount * perSm));
+    const int blocks = std::max(1, std::min((npairs + warps * NG - 1) / (warps * NG), c->smCount * perSm));
     VG_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(int), c->stream));
     VG_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
     if (traceback && fastf)  // FASTF is only instantiated with COMPACT (the last argument is false for wide checkpoints)
-      sw_fill_kernel<R, true, COMPACT, COMPACT><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw,
+      sw_fill_kernel<R, true, COMPACT, COMPACT, W><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw,
                                                                                       c->d_rowck.as<CkT>(), c->d_colck.as<CkT>(), nT,
                                                                                       nTb, d_fill + s, c->d_counter.as<int>(), nW);
     else if (traceback)
-      sw_fill_kernel<R, true, COMPACT, false><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw,
+      sw_fill_kernel<R, true, COMPACT, false, W><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw,
                                                                                     c->d_rowck.as<CkT>(), c->d_colck.as<CkT>(), nT,
                                                                                     nTb, d_fill + s, c->d_counter.as<int>(), nW);
     else if (fastf)
-      sw_fill_kernel<R, false, false, true><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw, nullptr,
+      sw_fill_kernel<R, false, false, true, W><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw, nullptr,
                                                                                   nullptr, nT, nTb, d_fill + s,
                                                                                   c->d_counter.as<int>(), nW);
     else
-      sw_fill_kernel<R, false, false, false><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw, nullptr,
+      sw_fill_kernel<R, false, false, false, W><<<blocks, threads, smem, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw, nullptr,
                                                                                    nullptr, nT, nTb, d_fill + s,
                                                                                    c->d_counter.as<int>(), nW);
     VG_LAUNCH_CHECK(c);
     VG_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
     if (traceback) {
-      sw_traceback_kernel<R, COMPACT><<<(nt + 127) / 128, 128, 0, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw,
+      sw_traceback_kernel<R, COMPACT, W><<<(nt + 127) / 128, 128, 0, c->stream>>>(d_tasks + s, nt, d_s1, d_s2, c->sw,
                                                                                c->d_rowck.as<CkT>(), c->d_colck.as<CkT>(), nT,
                                                                                nTb, d_fill + s, d_alns, d_rev, revStride);
       VG_LAUNCH_CHECK(c);
@@ -117,18 +127,16 @@ static int sw_launch_R(vg_ctx* c, const SwTask* d_tasks, int ntasks, const uint8
 // every bin is launched with its own R and checkpoint geometry, partners inside a bin have (nearly) equal |s2|, and the
 // 32 alignments of a traceback warp walk paths of similar length. Results are addressed by SwTask.out, so the order in
 // which tasks run is invisible to the caller.
-#define SW_NBINS 11
 #define SW_NKEYS 1024  // |s2| buckets per bin
-__constant__ int sw_binR[SW_NBINS] = {2, 3, 4, 5, 6, 8, 10, 12, 16, 24, 32};
-static const int sw_binR_host[SW_NBINS] = {2, 3, 4, 5, 6, 8, 10, 12, 16, 24, 32};
+__constant__ int sw_binMaxM[SW_NBINS] = {64, 96, 128, 192, 256, 320, 384, 512, 768, 1024};
 
 __device__ __forceinline__ int sw_task_key(const SwTask& t, int nShift, int minBin) {
   int b = 0;
 #pragma unroll
-  for (int k = 0; k < SW_NBINS - 1; k++) b += (32 * sw_binR[k] < t.m) ? 1 : 0;
+  for (int k = 0; k < SW_NBINS - 1; k++) b += (sw_binMaxM[k] < t.m) ? 1 : 0;
   b = max(b, minBin);
   // inside a bin: eight groups of |s1| (partners use the same lanes), then 128 buckets of |s2|
-  const int mg = min(7, max(t.m - 1, 0) * 8 / (32 * sw_binR[b]));
+  const int mg = min(7, max(t.m - 1, 0) * 8 / sw_binMaxM[b]);
   return b * SW_NKEYS + mg * 128 + min(t.n >> nShift, 127);
 }
 // hist[key]++, binMaxN[bin] = max |s2|, binMaxM[bin] = max |s1|. The batches of the mapping pipeline have nearly uniform
@@ -149,7 +157,7 @@ __global__ void sw_bin_hist_kernel(const SwTask* __restrict__ tasks, int n, int 
     atomicMax(binMaxM + key / SW_NKEYS, gm);
   }
 }
-// exclusive scan of hist[SW_NBINS * SW_NKEYS] by one block of 1024 threads (11 keys per thread); binStart[b] = first task
+// exclusive scan of hist[SW_NBINS * SW_NKEYS] by one block of 1024 threads (SW_NBINS keys per thread); binStart[b] = first task
 // of bin b, binStart[SW_NBINS] = n
 __global__ void sw_bin_scan_kernel(int* __restrict__ hist, int* __restrict__ binStart) {
   __shared__ int part[1024];
@@ -199,30 +207,29 @@ __global__ void sw_bin_scatter_kernel(const SwTask* __restrict__ tasks, int n, i
 // run in length bins (see above); d_fill is scratch then. Score-only keeps the caller's order (d_fill[i] = task i).
 static int sw_run_bin(vg_ctx* c, const SwTask* d_tasks, int64_t ntasks, const uint8_t* d_s1, const uint8_t* d_s2, int mmax,
                       int nmax, bool traceback, SwFillOut* d_fill, SwAln* d_alns, uint8_t* d_rev, int64_t revStride,
-                      double* msFill, double* msTb) {
-  const int R = sw_pick_R(mmax);
+                      double* msFill, double* msTb, int minBin = 0) {
+  const int bin = sw_pick_bin(mmax, minBin);
   // 4-byte checkpoints (V in 12 bits + the 4 bits of the gap state that matter, see SwCk) when the scores and the
   // penalties allow it, else 8-byte ones
   const bool compact = traceback && (int64_t)c->sw.match * std::min(mmax, nmax) + c->sw.match + 1 < 4096 && c->sw.gop >= c->sw.gep &&
                        c->sw.gop - c->sw.gep <= 15 && !getenv("VG_SW_WIDE");
-#define SW_CASE(RR)                                                                                                   \
-  case RR:                                                                                                            \
-    return compact ? sw_launch_R<RR, true>(c, d_tasks, (int)ntasks, d_s1, d_s2, nmax, traceback, d_fill, d_alns, d_rev,  \
-                                           revStride, msFill, msTb)                                                    \
-                   : sw_launch_R<RR, false>(c, d_tasks, (int)ntasks, d_s1, d_s2, nmax, traceback, d_fill, d_alns, d_rev, \
-                                            revStride, msFill, msTb);
-  switch (R) {
-    SW_CASE(2)
-    SW_CASE(3)
-    SW_CASE(4)
-    SW_CASE(5)
-    SW_CASE(6)
-    SW_CASE(8)
-    SW_CASE(10)
-    SW_CASE(12)
-    SW_CASE(16)
-    SW_CASE(24)
-    SW_CASE(32)
+#define SW_CASE(BIN, WW, RR)                                                                                                  \
+  case BIN:                                                                                                                   \
+    return compact ? sw_launch_R<RR, true, WW>(c, d_tasks, (int)ntasks, d_s1, d_s2, nmax, traceback, d_fill, d_alns, d_rev,     \
+                                               revStride, msFill, msTb)                                                        \
+                   : sw_launch_R<RR, false, WW>(c, d_tasks, (int)ntasks, d_s1, d_s2, nmax, traceback, d_fill, d_alns, d_rev,    \
+                                                revStride, msFill, msTb);
+  switch (bin) {  // (W, R) of sw_binW_host / sw_binR_host
+    SW_CASE(0, 8, 8)
+    SW_CASE(1, 16, 6)
+    SW_CASE(2, 16, 8)
+    SW_CASE(3, 32, 6)
+    SW_CASE(4, 32, 8)
+    SW_CASE(5, 32, 10)
+    SW_CASE(6, 32, 12)
+    SW_CASE(7, 32, 16)
+    SW_CASE(8, 32, 24)
+    SW_CASE(9, 32, 32)
   }
 #undef SW_CASE
   return vg_fail(c, VG_ERR_INVALID, "no kernel for read length %d", mmax);
@@ -240,13 +247,10 @@ static int sw_run(vg_ctx* c, const SwTask* d_tasks, int64_t ntasks, const uint8_
   const int n = (int)ntasks;
   int nShift = 0;
   while ((nmax >> nShift) >= 128) nShift++;
-  // the smallest R in use: thin strips make the fill of short reads efficient but the traceback crosses more of them
-  // R = 6: on a 50..250 batch within 1 % of R = 8, on 150-base reads (cfg4 / cfg5) fill + traceback 12-16 % faster than R = 8
-  // (25 instead of 19 lanes hold rows; profiles/sw_r2.md)
-  int minBin = 4;
+  // VG_SW_MINR=r (experiments): no groups narrower than a warp and no strips thinner than r rows
+  int minBin = 0;
   if (const char* e = getenv("VG_SW_MINR")) {
-    minBin = 0;
-    while (minBin < SW_NBINS - 1 && sw_binR_host[minBin] < atoi(e)) minBin++;
+    while (minBin < SW_NBINS - 1 && (sw_binW_host[minBin] < 32 || sw_binR_host[minBin] < atoi(e))) minBin++;
   }
   const size_t histBytes = (size_t)SW_NBINS * SW_NKEYS * 4;
   VG_CUDA(c, c->d_swBins.reserve(histBytes + 256));
@@ -273,9 +277,9 @@ static int sw_run(vg_ctx* c, const SwTask* d_tasks, int64_t ntasks, const uint8_
     const int cnt = binStart[b + 1] - binStart[b];
     if (cnt <= 0) continue;
     // a bin's tasks all have |s1| <= 32 R of the bin; empty reads (m == 0) sit in the first bin
-    const int mBin = std::max(32 * (b ? sw_binR_host[b - 1] : 0) + 1, std::min(binMaxM[b], 32 * sw_binR_host[b]));
+    const int mBin = std::max((b ? sw_bin_maxm(b - 1) : 0) + 1, std::min(binMaxM[b], sw_bin_maxm(b)));
     VG_TRY(sw_run_bin(c, c->d_swSorted.as<SwTask>() + binStart[b], cnt, d_s1, d_s2, mBin, std::max(1, binMaxN[b]), true,
-                      d_fill + binStart[b], d_alns, d_rev, revStride, msFill, msTb));
+                      d_fill + binStart[b], d_alns, d_rev, revStride, msFill, msTb, b));
   }
   return VG_OK;
 }
