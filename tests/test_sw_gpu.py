@@ -109,6 +109,36 @@ def test_short_and_long_reads(env):
         _check(ctx, o, s1, [w.tobytes() for w in s2])
 
 
+def test_sub_warp_bin_borders(env):
+    """Read lengths on both sides of every border of the aligner's (lanes per pair, rows per lane) bins (8 x 8 up to 64
+    bases, 16 x 6 up to 96, 16 x 8 up to 128, 32 x 6 up to 192, 32 x 8 up to 256, ...), odd task counts per bin (a group of
+    lanes without a pair, a pair without a partner), empty reads and empty windows in between, reads planted in their windows
+    so that the traceback walks every strip."""
+    ctx, o = env
+    rng = np.random.default_rng(21)
+    al = np.frombuffer(b"ACGT", np.uint8)
+    s1, s2 = [], []
+    for L in (1, 7, 8, 9, 47, 48, 49, 63, 64, 65, 95, 96, 97, 127, 128, 129, 191, 192, 193, 255, 256, 257, 320, 321):
+        for rep in range(3 + (L % 4)):                      # 3 .. 6 tasks of this length: odd and even bin populations
+            W = int(L * rng.uniform(1.0, 1.5)) + int(rng.integers(0, 3))
+            w = al[rng.integers(0, 4, W)]
+            st = int(rng.integers(0, W - L + 1))
+            r = w[st:st + L].copy()
+            mut = rng.random(L) < 0.12
+            r[mut] = al[rng.integers(0, 4, int(mut.sum()))]
+            if L > 20 and rep % 2:
+                r = np.concatenate([r[:L // 2], r[L // 2 + 2:], al[rng.integers(0, 4, 2)]])   # a deletion in the read
+            s1.append(r.tobytes())
+            s2.append(w.tobytes())
+    s1 += [b"", b"ACGT" * 10, b"", b"A" * 64]
+    s2 += [b"ACGTACGT", b"", b"", b"A" * 70]
+    order = rng.permutation(len(s1))
+    _check(ctx, o, [s1[i] for i in order], [s2[i] for i in order])
+    for n in (1, 2, 3, 5):                                   # a handful of tasks: most groups of a warp stay empty
+        _check(ctx, o, s1[:n], s2[:n])
+        _check(ctx, o, s1[40:40 + n], s2[40:40 + n])
+
+
 def test_edge_cases(env):
     ctx, o = env
     s1 = [b"AAAAAAAAAA", b"ACGTACGTAC", b"ACGTNNACGT", b"acgtACGTRYK", b"A", b"", b"ACGT", b"T" * 200, b"AC" * 100,
