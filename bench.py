@@ -646,8 +646,11 @@ def main():
                             "dpx_s16x2_ops_per_s_measured": dpx,
                             "gcups_peak_3ops_per_cellpair": dpx * 2 / 3 / 1e9,
                             "frac_of_3op_peak_fill": (cells / (fill_ms * 1e-3)) / (dpx * 2 / 3) if fill_ms else None,
-                            "dpx_ops_per_cellpair_issued": 7.5,
-                            "frac_of_dpx_issue_peak_fill": (cells / 2 * 7.5 / (fill_ms * 1e-3)) / dpx if fill_ms else None,
+                            # SASS of the inner loop (profiles/sass_r2.md): 6.6 ALU / DPX-pipe instructions per packed
+                            # cell-pair (LOP3, 4 x VIADDMNMX, VIMNMX3, half a VIMNMX3 for the running maximum) + one IMAD.IADD
+                            # on the FMA pipe; the measured peak is the issue rate of the ALU / DPX pipe
+                            "alu_pipe_instr_per_cellpair_issued": 6.6,
+                            "frac_of_dpx_issue_peak_fill": (cells / 2 * 6.6 / (fill_ms * 1e-3)) / dpx if fill_ms else None,
                             "cells_per_step": cells},
             "pileup_roofline": pile,
             "mapping_stats": [int(x) for x in stats],
