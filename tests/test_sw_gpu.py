@@ -168,7 +168,13 @@ def test_other_scoring(env, built):
         ctx.close()
 
 
-@pytest.mark.parametrize("seed", list(range(8)))
+_SW_FUZZ_SEEDS = list(range(8))
+if __import__("os").environ.get("VG_FUZZ_SEEDS"):  # e.g. VG_FUZZ_SEEDS=8:100 for a longer one-off run
+    _a, _b = __import__("os").environ["VG_FUZZ_SEEDS"].split(":")
+    _SW_FUZZ_SEEDS = list(range(int(_a), int(_b)))
+
+
+@pytest.mark.parametrize("seed", _SW_FUZZ_SEEDS)
 def test_sw_fuzz(built, seed):
     """Differential fuzz of the aligner: random penalties (both checkpoint formats, gop < gep included), lengths 1 .. 1024
     on either side, related / unrelated / low-complexity sequences with N, '-', lower case and IUPAC bytes."""
