@@ -249,13 +249,13 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
         }
         int o = nq + excl;
 #pragma unroll
-        for (int u = 0; u < SD2_PN; u++) {  // chains of 1 or 2 read positions are the rule: branch-free, misses go to a
-          const int cu = hv[u] >> 9;        // spare slot behind the queue
+        for (int u = 0; u < SD2_PN; u++) {  // chains of 1 or 2 read positions are the rule: straight-line code with
+          const int cu = hv[u] >> 9;        // predicated stores (@P STS; a select of a spare slot cost one more instruction each)
           const uint32_t i0 = hv[u] & 511u;
           const uint32_t gk = (uint32_t)(g0 + u) << 16;
-          queue[cu ? o : QCAP] = gk | i0;
+          if (cu) queue[o] = gk | i0;
           uint32_t i = nxt[i0];
-          queue[cu > 1 ? o + 1 : QCAP] = gk | i;
+          if (cu > 1) queue[o + 1] = gk | i;
           if (cu > 2) {
 #pragma unroll 1
             for (int t = 2; t < cu; t++) {
