@@ -46,7 +46,8 @@ struct Seed2Args {
   int nItems;                  // items of this launch
   int singleReads;
   // per-item scratch
-  uint64_t* S;                 // [nItems][capS]  g << 32 | r << 16 | len
+  uint64_t* S;                 // [nItems][capS] stream elements: g << 32 | r << 16 | len, or (reference shorter than 16384, reads up
+                               // to 512 bases) 32 bits g << 18 | r << 9 | len — the element of the sweep window, SdWin<P32>::E
   int capS;
   int32_t* nS;                 // [nItems]; -1 = handed to the fallback
   // per-warp-slot scratch of the window kernel
@@ -122,7 +123,10 @@ __device__ __forceinline__ void sd2_fallback(const Seed2Args& A, int local, int 
 // ------------------------------------------------------------------------------------------------
 // REGIONS: every work item has its own reference in global memory (vg_map_to_regions); otherwise the one reference is
 // staged in shared memory and addressed as such.
-template <bool REGIONS>
+template <bool P32>
+struct SdWin;  // element of the LongHit stream and of the sweep window (below)
+
+template <bool REGIONS, bool P32>
 __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
   extern __shared__ __align__(16) uint8_t sd_smem[];
   __shared__ uint64_t sd_mbar;
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
     }
     bad = __any_sync(VG_FULL, bad);
     // ---- B: scan the reference in genome order -> LongHits sorted by (g, i) -------------------------
-    uint64_t* S = A.S + (size_t)it * A.capS;
+    typename SdWin<P32>::E* S = (typename SdWin<P32>::E*)A.S + (size_t)it * A.capS;
     int nS = 0;
 #pragma unroll 1
     for (int gb = 0; gb <= G - K && !bad;) {
@@ -318,8 +322,8 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
           why = 1;
           break;
         }
-        if (em[0]) S[nS + __popc(m0 & lt)] = ((uint64_t)gg[0] << 32) | ((uint64_t)ii[0] << 16) | (uint64_t)ll[0];
-        if (em[1]) S[nS + t0 + __popc(m1 & lt)] = ((uint64_t)gg[1] << 32) | ((uint64_t)ii[1] << 16) | (uint64_t)ll[1];
+        if (em[0]) S[nS + __popc(m0 & lt)] = SdWin<P32>::pack(gg[0], ii[0], ll[0]);
+        if (em[1]) S[nS + t0 + __popc(m1 & lt)] = SdWin<P32>::pack(gg[1], ii[1], ll[1]);
         nS += total;
       }
       __syncwarp();
@@ -528,7 +532,8 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
     SD2_PH(8)
     if (A.prof && lane == 0) atomicAdd(A.prof + 13, (unsigned long long)nRaw);
     int nSt = 0;
-    uint64_t* S = A.S + (size_t)it * A.capS;
+    uint64_t* S = A.S + (size_t)it * A.capS;            // wide stream; packed stream (msaPacked): 32-bit elements
+    uint32_t* S32 = (uint32_t*)A.S + (size_t)it * A.capS;
     if (!bad && nRaw > 0) {
       __threadfence_block();
       // 2. stable sort by diagonal (16-bit key in the low half, read position rides in the high half)
@@ -607,7 +612,7 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_msa_kernel(Seed2Args A) {
 #pragma unroll 4
           for (int e = lane; e < nSt; e += 32) {
             const uint32_t k = K1[e];
-            S[e] = ((uint64_t)(k & 0x3FFFu) << 32) | ((uint64_t)((k >> 14) & 0x1FFu) << 16) | (uint64_t)(k >> 23);
+            S32[e] = ((k & 0x3FFFu) << 18) | (((k >> 14) & 0x1FFu) << 9) | (k >> 23);  // SdWin<true>::pack
           }
         } else {
           sd2_radix_sort_counted(V0, K0, V1, K1, nSt, binsLo, 2, lane);
@@ -647,8 +652,6 @@ template <>
 struct SdWin<false> {
   using E = uint64_t;
   static constexpr int N = SD_WIN, CH = SD_WIN / 32, SH = 4;
-  static __device__ __forceinline__ E fromS(uint64_t v) { return v; }
-  static __device__ __forceinline__ uint64_t toS(E v) { return v; }
   static __device__ __forceinline__ E pack(int g, int r, int l) { return ((uint64_t)g << 32) | ((uint64_t)r << 16) | (uint64_t)l; }
   static __device__ __forceinline__ int g(E v) { return (int)(v >> 32); }
   static __device__ __forceinline__ int r(E v) { return (int)((v >> 16) & 0xFFFFu); }
@@ -661,12 +664,6 @@ template <>
 struct SdWin<true> {
   using E = uint32_t;
   static constexpr int N = 2 * SD_WIN, CH = 2 * SD_WIN / 32, SH = 5;
-  static __device__ __forceinline__ E fromS(uint64_t v) {
-    return ((uint32_t)(v >> 32) << 18) | (((uint32_t)v >> 16) << 9) | ((uint32_t)v & 0x1FFu);
-  }
-  static __device__ __forceinline__ uint64_t toS(E v) {
-    return ((uint64_t)(v >> 18) << 32) | ((uint64_t)((v >> 9) & 0x1FFu) << 16) | (uint64_t)(v & 0x1FFu);
-  }
   static __device__ __forceinline__ E pack(int g, int r, int l) { return ((uint32_t)g << 18) | ((uint32_t)r << 9) | (uint32_t)l; }
   static __device__ __forceinline__ int g(E v) { return (int)(v >> 18); }
   static __device__ __forceinline__ int r(E v) { return (int)((v >> 9) & 0x1FFu); }
@@ -739,11 +736,13 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
     if (A.regions) G = A.regLen[A.itemRegion[gi]];
     SD2_PH(0)
     if (L > SD_MAXL && lane == 0) atomicOr(A.counters + 2, 16);
-    uint64_t* S = A.S + (size_t)it * A.capS;
+    using SE = typename SdWin<P32>::E;  // stream element = window element (32 bits packed or 64 bits)
+    SE* S = (SE*)A.S + (size_t)it * A.capS;
     // the stream was written by the other kernel and comes from HBM: pull all of it into L2 now, so that only the
     // first window pays the DRAM latency
+    constexpr int perLine = 128 / (int)sizeof(SE);
 #pragma unroll 1
-    for (int e = lane * 16; e < nS; e += 32 * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(S + e));
+    for (int e = lane * perLine; e < nS; e += 32 * perLine) asm volatile("prefetch.global.L2 [%0];" ::"l"(S + e));
     int nWin = 0, nR = 0;
     bool giveUp = false;
     int why = 4;
@@ -758,7 +757,7 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
       while (tbase < nS) {
         const int cnt = min(W::N, nS - tbase);
 #pragma unroll 4
-        for (int e = lane; e < cnt; e += 32) win[sd2_wi<P32>(e)] = W::fromS(S[tbase + e]);
+        for (int e = lane; e < cnt; e += 32) win[sd2_wi<P32>(e)] = S[tbase + e];
         __syncwarp();
         const int lo = lane * CH, nOwn = max(0, min(CH, cnt - lo));
         const typename W::E* wl = win + lane * (CH + 1);  // = win + sd2_wi(lo): the lane's chunk is contiguous
@@ -865,9 +864,9 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
         {  // ordered copy-out: every lane appends its run of survivors behind those of the lanes below
           const int c = w - s0;
           const int ic = sd_warp_incl_scan(c, lane);
-          uint64_t* dst = S + nR + ic - c;
+          SE* dst = S + nR + ic - c;
 #pragma unroll 1
-          for (int t = 0; t < c; t++) dst[t] = W::toS(win[sd2_wi<P32>(s0 + t)]);
+          for (int t = 0; t < c; t++) dst[t] = win[sd2_wi<P32>(s0 + t)];
           nR += __shfl_sync(VG_FULL, ic, 31);
         }
         __syncwarp();
@@ -881,7 +880,7 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
       __threadfence_block();
       // the pieces go to the upper half of the item's slot (a hit yields at most 3), which then replaces the lower half
       const int half = A.capS >> 1;
-      uint64_t* S2 = S + half;
+      SE* S2 = S + half;
       int nOut = 0;
       bool bad = nR > half;
 #pragma unroll 1
@@ -889,8 +888,8 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
         const int j = j0 + lane;
         int qg[3], qr[3], ql[3], np2 = 0;
         if (j < nR) {
-          const uint64_t v = S[j];
-          int g = (int)(v >> 32), r = (int)((v >> 16) & 0xFFFFu), len = (int)(v & 0xFFFFu);
+          const SE v = S[j];
+          int g = W::g(v), r = W::r(v), len = W::l(v);
           for (;;) {
             int lo2 = 0, hi2 = A.nContigs - 1;
 #pragma unroll 1
@@ -928,7 +927,7 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
         }
 #pragma unroll
         for (int t = 0; t < 3; t++)
-          if (t < np2) S2[o + t] = ((uint64_t)qg[t] << 32) | ((uint64_t)qr[t] << 16) | (uint64_t)ql[t];
+          if (t < np2) S2[o + t] = W::pack(qg[t], qr[t], ql[t]);
       }
       __syncwarp();
       __threadfence_block();
@@ -947,10 +946,10 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
     if (A.dbgHits && gi == 0) {
 #pragma unroll 1
       for (int j = lane; j < nR; j += 32) {
-        const uint64_t v = S[j];
-        A.dbgHits[3 * j] = (int)(v >> 32);
-        A.dbgHits[3 * j + 1] = (int)((v >> 16) & 0xFFFFu);
-        A.dbgHits[3 * j + 2] = (int)(v & 0xFFFFu);
+        const SE v = S[j];
+        A.dbgHits[3 * j] = W::g(v);
+        A.dbgHits[3 * j + 1] = W::r(v);
+        A.dbgHits[3 * j + 2] = W::l(v);
       }
       if (lane == 0) *A.dbgNHits = nR;
     }
@@ -966,16 +965,16 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
         (void)inShared;
         if (lane < 8) hitG[nR + lane] = 0xFFFFu;  // sentinels for the branch-free searches of phase F
         int carry = 0, pgLast = 0, prLast = 0;
-        uint64_t vNext = (lane < nR) ? S[lane] : 0;  // the slot is in L2: the next chunk is requested one trip ahead
+        SE vNext = (lane < nR) ? S[lane] : 0;  // the slot is in L2: the next chunk is requested one trip ahead
   #pragma unroll 1
         for (int j0 = 0; j0 < nR; j0 += 32) {
           const int j = j0 + lane;
           int val = 0, g = 0, r = 0;
-          const uint64_t v = vNext;
+          const SE v = vNext;
           if (j + 32 < nR) vNext = S[j + 32];
           if (j < nR) {
-            g = (int)(v >> 32), r = (int)((v >> 16) & 0xFFFFu);
-            val = (int)(v & 0xFFFFu);
+            g = W::g(v), r = W::r(v);
+            val = W::l(v);
             hitG[j] = (uint16_t)g;
             hitL[j] = (uint8_t)min(val, 255);
           }
@@ -1023,16 +1022,16 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
         SD2_PH(2)
         // ---- F: every window independently (updateCount equals a direct recount on sorted non-overlapping
         //         hits); candidates (count > cutoff, strict) compacted in hit order
-        uint64_t vNextF = (lane < nR) ? S[lane] : 0;
+        SE vNextF = (lane < nR) ? S[lane] : 0;
   #pragma unroll 1
         for (int j0 = 0; j0 < nR; j0 += 32) {
           const int j = j0 + lane;
           bool isCand = false;
           uint32_t key = 0, cnt = 0;
-          const uint64_t v = vNextF;
+          const SE v = vNextF;
           if (j + 32 < nR) vNextF = S[j + 32];
           if (j < nR) {
-            const int g = (int)(v >> 32), r = (int)((v >> 16) & 0xFFFFu), len = (int)(v & 0xFFFFu);
+            const int g = W::g(v), r = W::r(v), len = W::l(v);
             int cs = 0, ce = G;
             if (A.nContigs > 1 && !A.bestOnly) {
               int lo = 0, hi = A.nContigs - 1;
@@ -1063,8 +1062,8 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
             while (hitG[u] < end) u++;  // stops at the sentinel at the latest
             int b = u - 1;
             int lenA = hitL[a], lenB = hitL[b];
-            if (lenA == 255) lenA = (int)(S[a] & 0xFFFFu);
-            if (lenB == 255) lenB = (int)(S[b] & 0xFFFFu);
+            if (lenA == 255) lenA = W::l(S[a]);
+            if (lenB == 255) lenB = W::l(S[b]);
             if ((int)hitG[b] + K + lenB > end) b--;
             cnt = (uint32_t)((uint16_t)(Pp[b] - Pp[a])) + (uint32_t)lenA;
             isCand = (int)cnt > cutoff;

@@ -448,23 +448,26 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     if (!c->budgetSeed) c->budgetSeed = vg_mem_budget(8ull << 30, 0.3, c->d_seedS.cap);
     sBudget = c->budgetSeed;
   }
+  // packed 32-bit stream / sweep-window elements (genomePos 14 bits, readPos 9, len 9) when the coordinates fit
+  const bool p32 = G < 16384 && maxReadLen <= 512 && !getenv("VG_SEED_WIDE");
+  const size_t elemBytes = p32 ? 4 : 8;
   A.capC = A.capR;
   A.key24 = (G < 16384 && !getenv("VG_SEED_KEY32")) ? 1 : 0;
-  const int64_t subItems = std::max<int64_t>(4096, std::min<int64_t>(nItems, (int64_t)(sBudget / ((size_t)A.capS * 8))));
+  const int64_t subItems = std::max<int64_t>(4096, std::min<int64_t>(nItems, (int64_t)(sBudget / ((size_t)A.capS * elemBytes))));
   const size_t genSmem = msa ? (size_t)genWarps * A.msaWarpBytes : (size_t)A.blobBytes + (size_t)genWarps * A.genWarpBytes;
   const size_t winSmem = (size_t)winWarps * A.winWarpBytes;
   if (msa) VG_CUDA(c, cudaFuncSetAttribute(seed_gen_msa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmem));
-  else if (regs) VG_CUDA(c, cudaFuncSetAttribute(seed_gen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmem));
-  else VG_CUDA(c, cudaFuncSetAttribute(seed_gen_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmem));
-  // packed 32-bit sweep window (genomePos 14 bits, readPos 9, len 9) when the coordinates fit
-  const bool p32 = G < 16384 && maxReadLen <= 512 && !getenv("VG_SEED_WIDE");
+  else if (regs && p32) VG_CUDA(c, cudaFuncSetAttribute(seed_gen_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmem));
+  else if (regs) VG_CUDA(c, cudaFuncSetAttribute(seed_gen_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmem));
+  else if (p32) VG_CUDA(c, cudaFuncSetAttribute(seed_gen_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmem));
+  else VG_CUDA(c, cudaFuncSetAttribute(seed_gen_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmem));
   if (p32) VG_CUDA(c, cudaFuncSetAttribute(seed_win_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)winSmem));
   else VG_CUDA(c, cudaFuncSetAttribute(seed_win_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)winSmem));
   const int64_t sub0 = std::min(subItems, nItems);
   const int genBlocks = (int)std::max<int64_t>(1, std::min<int64_t>((sub0 + genWarps - 1) / genWarps, c->smCount));
   const int winBlocks = (int)std::max<int64_t>(1, std::min<int64_t>((sub0 + winWarps - 1) / winWarps, c->smCount));
   const int winSlots = winBlocks * winWarps;
-  VG_CUDA(c, c->d_seedS.reserve((size_t)sub0 * A.capS * 8));
+  VG_CUDA(c, c->d_seedS.reserve((size_t)sub0 * A.capS * elemBytes));
   VG_CUDA(c, c->d_seedNS.reserve((size_t)sub0 * 4));
   VG_CUDA(c, c->d_seedFb.reserve((size_t)nItems * 4));
   VG_CUDA(c, c->d_seqOff.reserve((size_t)winSlots * 2 * A.capC * 4 * 2));
@@ -480,7 +483,7 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     if (const char* e = getenv("VG_SEED_CAPRAW")) A.capRaw = std::max(256, atoi(e)) & ~255;
     VG_CUDA(c, c->d_scratch.reserve((size_t)genSlots * 4 * A.capRaw * 4));
     A.rawBuf = c->d_scratch.as<uint32_t>();
-    A.msaPacked = (G < 16384 && maxReadLen <= 512 && !getenv("VG_SEED_WIDE")) ? 1 : 0;
+    A.msaPacked = p32 ? 1 : 0;  // the stream's element format: must be the window kernel's
   }
   A.S = c->d_seedS.as<uint64_t>();
   A.nS = c->d_seedNS.as<int32_t>();
@@ -510,8 +513,10 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
     VG_CUDA(c, cudaMemsetAsync(A.counters, 0, 8, c->stream));
     VG_CUDA(c, cudaEventRecord(c->seedEv[3 * sub], c->stream));
     if (msa) seed_gen_msa_kernel<<<genBlocks, genWarps * 32, genSmem, c->stream>>>(A);
-    else if (regs) seed_gen_kernel<true><<<genBlocks, genWarps * 32, genSmem, c->stream>>>(A);
-    else seed_gen_kernel<false><<<genBlocks, genWarps * 32, genSmem, c->stream>>>(A);
+    else if (regs && p32) seed_gen_kernel<true, true><<<genBlocks, genWarps * 32, genSmem, c->stream>>>(A);
+    else if (regs) seed_gen_kernel<true, false><<<genBlocks, genWarps * 32, genSmem, c->stream>>>(A);
+    else if (p32) seed_gen_kernel<false, true><<<genBlocks, genWarps * 32, genSmem, c->stream>>>(A);
+    else seed_gen_kernel<false, false><<<genBlocks, genWarps * 32, genSmem, c->stream>>>(A);
     VG_LAUNCH_CHECK(c);
     VG_CUDA(c, cudaEventRecord(c->seedEv[3 * sub + 1], c->stream));
     if (p32) seed_win_kernel<true><<<winBlocks, winWarps * 32, winSmem, c->stream>>>(A);
