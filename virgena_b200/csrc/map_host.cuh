@@ -1194,7 +1194,7 @@ int vg_map_to_regions(vg_ctx* c, const uint8_t* region_pool, const int64_t* regi
   std::sort(exo.begin(), exo.end());
   exo.erase(std::unique(exo.begin(), exo.end()), exo.end());
   std::vector<uint8_t> hRef((size_t)refOff[n_regions] + 16, 0);
-  std::vector<uint16_t> hCode((size_t)codeOff[n_regions] + SD2_SCAN, (uint16_t)SD_NONE16);
+  std::vector<uint16_t> hCode((size_t)codeOff[n_regions] + SD2_SCAN, (uint16_t)((1u << (2 * K)) + exo.size()));  // padding: the id of no k-mer
   for (int64_t r = 0; r < n_regions; r++) {
     const uint8_t* p = region_pool + region_off[r];
     memcpy(hRef.data() + refOff[r], p, rlen[r]);

@@ -143,7 +143,6 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
   uint32_t* queue = (uint32_t*)(wbase + A.tabBytes + A.nxtBytes);
   uint8_t* rd = (uint8_t*)(queue + A.qcap + 4);  // queue[qcap]: spare slot for predicated-off writes
   const int QCAP = A.qcap;
-  const int emptyId = A.emptyId;
   const unsigned lt = (1u << lane) - 1u;
 
 #pragma unroll 1
@@ -212,7 +211,7 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
         const int g0 = gb + SD2_PN * lane;
         uint32_t hv[SD2_PN];
 #if SD2_PN == 8
-        const uint4 pc = *(const uint4*)(poscode + g0);  // beyond G-K the table holds SD_NONE16
+        const uint4 pc = *(const uint4*)(poscode + g0);  // beyond G-K the table holds emptyId
         const uint32_t pw[4] = {pc.x, pc.y, pc.z, pc.w};
 #else
         const uint2 pc = *(const uint2*)(poscode + g0);
@@ -222,7 +221,7 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
 #pragma unroll
         for (int u = 0; u < SD2_PN; u++) {
           const uint32_t code = (u & 1) ? (pw[u >> 1] >> 16) : pw[u >> 1];
-          hv[u] = tab[min((int)(code & 0x7FFFu), emptyId)];
+          hv[u] = tab[code & 0x7FFFu];  // beyond the last k-mer the table holds emptyId: a slot that is never filled
           tot += hv[u] >> 9;
         }
         const unsigned b0 = __ballot_sync(VG_FULL, tot & 1), b1 = __ballot_sync(VG_FULL, tot & 2),

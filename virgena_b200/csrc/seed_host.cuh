@@ -9,7 +9,7 @@
 struct SeedHostState {  // lives in vg_ctx via the DevBufs; plain helpers here
 };
 
-// blob = [ref padded to 16][poscode u16, padded with SD_NONE16 to a multiple of 256 entries (the scan's stride, SD2_SCAN)]
+// blob = [ref padded to 16][poscode u16, padded with the id of no k-mer (4^K + exotic k-mers) to a multiple of 256 entries (the scan's stride, SD2_SCAN)]
 static inline int sdh_ref_pad(int G) { return (G + 15) & ~15; }
 static inline int sdh_code_pad(int G) { return std::max(256, (G + 255) & ~255) * 2; }
 
@@ -93,7 +93,7 @@ static int seed_build_reference(vg_ctx* c, const uint8_t* keys, const int64_t* o
   memcpy(blob.data(), ref, G);
   uint16_t* pc = (uint16_t*)(blob.data() + refPad);
   for (int p = 0; p < codePad / 2; p++) {
-    uint16_t v = SD_NONE16;
+    uint16_t v = (uint16_t)((1u << (2 * K)) + exo.size());  // padding: the id of no k-mer (Seed2Args::emptyId)
     if (p < nPos) {
       uint32_t code;
       uint64_t key;
