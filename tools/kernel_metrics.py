@@ -18,9 +18,12 @@ def val(r, h, u, k):
 
 
 out = {"source": "profiles/kernels_%s.md = gpurun_out/prof_%s.ncu-rep (ncu --set full --clock-control none, kernel replay, "
-                 "tools/map_probe.py 100000 2: 149 796 read orientations per seeding launch) and prof_win_%s.ncu-rep (seed_win_kernel, "
+                 "tools/map_probe.py 70000 2: 280 000 read orientations per seeding launch) and prof_win_%s.ncu-rep (seed_win_kernel, "
                  "--replay-mode application, 20 000 pairs = 80 000 orientations)" % (tag, tag, tag), "kernels": {}}
-for rep, kern, orient in (("prof_%s.ncu-rep" % tag, "seed_gen_kernel", 149796), ("prof_win_%s.ncu-rep" % tag, "seed_win_kernel", 80000)):
+for rep, kern, orient in (("prof_%s.ncu-rep" % tag, "seed_gen_kernel", 280000), ("prof_win_%s.ncu-rep" % tag, "seed_win_kernel", 80000)):
+    alt = os.path.join(root, "gpurun_out", "prof_gen_%s.ncu-rep" % tag)
+    if kern == "seed_gen_kernel" and os.path.exists(alt):
+        rep = os.path.basename(alt)
     h, u, rows = raw(os.path.join(root, "gpurun_out", rep))
     r = next(r for r in rows if kern in r[h.index("Kernel Name")])
     out["kernels"][kern] = {

@@ -58,8 +58,10 @@ units = rows[1]
 seen = set()
 with open(os.path.join(root, "profiles", "kernels_%s.md" % tag), "w") as f:
     f.write("# Per-kernel ncu --set full summary (%s)\n\nFrom `gpurun_out/prof_%s.ncu-rep` (`ncu --set full --clock-control none --import-source on`, "
-            "tools/map_probe.py 100000 2: the mapping pipeline at 100k pairs). Times under ncu are not bench values.\n" % (tag, tag))
-    for rws, note in ((rows, ""), (rows_win, " (`--replay-mode application`, tools/map_probe.py 20000 2: the kernel rewrites its "
+            "tools/map_probe.py 70000 2: the mapping pipeline at 70k pairs). Times under ncu are not bench values.\n" % (tag, tag))
+    rep_gen = os.path.join(root, "gpurun_out", "prof_gen_%s.ncu-rep" % tag)  # optional: the stream kernel captured on its own
+    rows_gen = load(rep_gen) if os.path.exists(rep_gen) else []
+    for rws, note in ((rows_gen, " (captured on its own: `-k regex:seed_gen -s 1 -c 1`, same probe)"), (rows, ""), (rows_win, " (`--replay-mode application`, tools/map_probe.py 20000 2: the kernel rewrites its "
                                                "multi-GB input slot in place, which kernel replay does not restore)")):
         if not rws:
             continue
