@@ -246,6 +246,30 @@ def secondary_arm(vg, synth, device, cfg, n_pairs, threads_cpu, check_pairs):
     return out
 
 
+def random_model_arm(vg, synth, device, check):
+    """Secondary line: the cutoffs of config 1 from the random model (RandomModel.genModel + computeCuttofs,
+    10^4 Markov reads of 250 bases generated and scored on the device); with `check` the oracle's seeded restatement derives
+    the same cutoffs on one host core and the two are compared. Rank 0, outside every timed region."""
+    ref, ends = synth.config_reference(1)
+    genome = vg.Reference(ref, K=5, thread_num=8)
+    rm = vg.RandomModel(genome, K=5, order=4, coef=1.25, seed=20260102, device=device)
+    rm.cutoffs(readNum=2000)  # warm-up (buffers, kernels)
+    t0 = time.perf_counter()
+    cut = rm.cutoffs(readNum=10000, minReadLen=250, maxReadLen=250, step=10, pValue=0.01)
+    dt = time.perf_counter() - t0
+    out = {"what": "RandomModel.genModel(10^4 reads x 250 bases) + computeCuttofs through vg_random_model_counts, wall time of the "
+                   "call incl. the host-side sort", "ms": dt * 1e3, "reads_per_s": 10000 / dt, "cutoff_250": int(cut[250])}
+    if check:
+        import oracle
+        t0 = time.perf_counter()
+        ocut = oracle.cutoffs(ref, K=5, coef=1.25, order=4, read_num=10000, min_len=250, max_len=250, step=10, p_value=0.01,
+                              index_thread_num=8, seed=20260102)
+        out["cpu_port_ms_1_core"] = (time.perf_counter() - t0) * 1e3
+        out["parity_ok"] = bool((ocut == cut).all())
+    rm.ctx.close()
+    return out
+
+
 def run_reference(args):
     """--impl reference: the CPU path on all host cores. Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -665,6 +689,7 @@ def main():
         if not args.no_secondary:
             out["cfg4_fragmented"] = secondary_arm(vg, synth, local, 4, min(n, args.secondary_pairs), threads, 0 if args.no_cpu_baseline else 4000)
             out["cfg5_hcv_mixture"] = secondary_arm(vg, synth, local, 5, min(n, args.secondary_pairs), threads, 0 if args.no_cpu_baseline else 4000)
+            out["random_model"] = random_model_arm(vg, synth, local, not args.no_cpu_baseline)
         if not args.no_cpu_baseline:
             ncpu = min(n, args.cpu_pairs or 3000 * threads)
             m1 = host_batches[0][0][:ncpu].numpy()
