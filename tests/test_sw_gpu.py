@@ -139,6 +139,24 @@ def test_sub_warp_bin_borders(env):
         _check(ctx, o, s1[40:40 + n], s2[40:40 + n])
 
 
+def test_short_reads_against_long_windows(env):
+    """Reads of a sub-warp bin against windows too long for 32 / W of them in shared memory: the wider geometry takes over."""
+    ctx, o = env
+    rng = np.random.default_rng(22)
+    al = np.frombuffer(b"ACGT", np.uint8)
+    s1, s2 = [], []
+    for L, W in ((20, 900), (60, 3000), (60, 5000), (100, 2500), (120, 6000), (50, 40)):
+        for _ in range(3):
+            w = al[rng.integers(0, 4, W)]
+            st = int(rng.integers(0, max(1, W - L)))
+            r = w[st:st + L].copy() if W >= L else al[rng.integers(0, 4, L)]
+            mut = rng.random(len(r)) < 0.1
+            r[mut] = al[rng.integers(0, 4, int(mut.sum()))]
+            s1.append(r.tobytes())
+            s2.append(w.tobytes())
+    _check(ctx, o, s1, s2)
+
+
 def test_edge_cases(env):
     ctx, o = env
     s1 = [b"AAAAAAAAAA", b"ACGTACGTAC", b"ACGTNNACGT", b"acgtACGTRYK", b"A", b"", b"ACGT", b"T" * 200, b"AC" * 100,

@@ -208,7 +208,12 @@ __global__ void sw_bin_scatter_kernel(const SwTask* __restrict__ tasks, int n, i
 static int sw_run_bin(vg_ctx* c, const SwTask* d_tasks, int64_t ntasks, const uint8_t* d_s1, const uint8_t* d_s2, int mmax,
                       int nmax, bool traceback, SwFillOut* d_fill, SwAln* d_alns, uint8_t* d_rev, int64_t revStride,
                       double* msFill, double* msTb, int minBin = 0) {
-  const int bin = sw_pick_bin(mmax, minBin);
+  int bin = sw_pick_bin(mmax, minBin);
+  // a group of W lanes keeps its window's symbols in shared memory: 32 / W windows per warp. A short read against a very long
+  // window (vg_sw_align_batch is free to ask for it) takes the next wider geometry instead of running out of shared memory.
+  while (bin >= 0 && bin < SW_NBINS - 1 && sw_binW_host[bin] < 32 &&
+         (size_t)8 * (32 / sw_binW_host[bin]) * (size_t)(nmax + 1) * 4 > (size_t)96 * 1024)
+    bin++;
   // 4-byte checkpoints (V in 12 bits + the 4 bits of the gap state that matter, see SwCk) when the scores and the
   // penalties allow it, else 8-byte ones
   const bool compact = traceback && (int64_t)c->sw.match * std::min(mmax, nmax) + c->sw.match + 1 < 4096 && c->sw.gop >= c->sw.gep &&
