@@ -126,6 +126,27 @@ __device__ __forceinline__ void sd2_fallback(const Seed2Args& A, int local, int 
 template <bool P32>
 struct SdWin;  // element of the LongHit stream and of the sweep window (below)
 
+// sd_kmer_id for the common case of a k-mer of pure A/C/G/T: the K <= 7 bytes come from two unaligned 4-byte loads
+// (rd is 4-byte aligned and padded), the codes from (b >> 1 & 3) ^ (b >> 2 & 1): A 0, C 1, G 2, T 3. Anything else takes the
+// general function (exotic k-mers of the reference, or none).
+__device__ __forceinline__ uint32_t sd2_kmer_id(const uint8_t* rd, int i, int K, const uint64_t* exoKeys, int nExo) {
+  const uint32_t w[2] = {sd_load4(rd, i), sd_load4(rd, i + 4)};
+  uint32_t code = 0;
+  bool pure = true;
+#pragma unroll
+  for (int t = 0; t < 7; t++) {
+    if (t < K) {
+      const uint32_t b = (w[t >> 2] >> (8 * (t & 3))) & 0xFFu;
+      const uint32_t x = b - 0x41u;
+      pure &= (x < 32u) & (((0x00080045u >> (x & 31u)) & 1u) != 0u);  // A C G T
+      uint32_t c = (b >> 1) & 3u;
+      c ^= c >> 1;
+      code = (code << 2) | c;
+    }
+  }
+  return pure ? code : sd_kmer_id(rd + i, K, exoKeys, nExo);
+}
+
 template <bool REGIONS, bool P32>
 __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
   extern __shared__ __align__(16) uint8_t sd_smem[];
@@ -141,7 +162,8 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
   uint16_t* tab = (uint16_t*)wbase;
   uint16_t* nxt = (uint16_t*)(wbase + A.tabBytes);
   uint32_t* queue = (uint32_t*)(wbase + A.tabBytes + A.nxtBytes);
-  uint8_t* rd = (uint8_t*)(queue + A.qcap + 4);  // queue[qcap]: spare slot for predicated-off writes
+  uint8_t* rd = (uint8_t*)(queue + A.qcap + 4) + 4;  // rd[-1] = 0xFF: no base in front of read position 0
+  if (lane == 0) rd[-1] = 0xFFu;
   const int QCAP = A.qcap;
   const unsigned lt = (1u << lane) - 1u;
 
@@ -179,7 +201,7 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
     for (int base = ((nk - 1) >> 5) << 5; base >= 0; base -= 32) {
       const int i = base + lane;
       uint32_t id = SD_NONE16;
-      if (i < nk) id = sd_kmer_id(rd + i, K, A.exoKeys, A.nExo);
+      if (i < nk) id = sd2_kmer_id(rd, i, K, A.exoKeys, A.nExo);
       const bool valid = id != SD_NONE16;
       const unsigned grp = __match_any_sync(VG_FULL, valid ? id : (0x80000000u | lane));
       if (valid) {
@@ -255,7 +277,8 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
         for (int u = 0; u < SD2_PN; u++) {  // chains of 1 or 2 read positions are the rule: straight-line code with
           const int cu = hv[u] >> 9;        // predicated stores (@P STS; a select of a spare slot cost one more instruction each)
           const uint32_t i0 = hv[u] & 511u;
-          const uint32_t gk = (uint32_t)(g0 + u) << 16;
+          // bit 15: the position was indexed twice (Q1); the read position needs 9 bits
+          const uint32_t gk = ((uint32_t)(g0 + u) << 16) | (((u & 1) ? (pw[u >> 1] >> 16) : pw[u >> 1]) & 0x8000u);
           if (cu) queue[o] = gk | i0;
           uint32_t i = nxt[i0];
           if (cu > 1) queue[o + 1] = gk | i;
@@ -283,15 +306,15 @@ __global__ void __launch_bounds__(1024, 1) seed_gen_kernel(Seed2Args A) {
           const int q = q0 + 32 * u + lane;
           const bool ok = q < nq;
           const uint32_t e = ok ? queue[q] : 0u;
-          const int g = (int)(e >> 16), i = (int)(e & 0xFFFFu);
+          const int g = (int)(e >> 16), i = (int)(e & 0x1FFu);
           gg[u] = g, ii[u] = i;
-          const uint8_t ca = rd[max(i - 1, 0)], cb = ref[max(g - 1, 0)];
-          const bool start = (i == 0) | (g == 0) | (ca != cb);
+          const uint8_t ca = rd[i - 1], cb = ref[max(g - 1, 0)];  // rd[-1] never equals a reference byte
+          const bool start = (g == 0) | (ca != cb);
           const int maxLen = min(L - i - K, G - g - K);
           const uint32_t x0 = sd_load4(rd, i + K) ^ sd_load4(ref, g + K);
           const int len = x0 ? (__ffs(x0) - 1) >> 3 : 4;
           // Q1: a chain passing through a twice-indexed position adds a zero-length hit
-          em[u] = ok & (start | ((poscode[g] & 0x8000u) != 0));
+          em[u] = ok & (start | ((e & 0x8000u) != 0));
           ll[u] = start ? min(len, maxLen) : 0;
           mx[u] = maxLen;
           more[u] = ok & start & (x0 == 0) & (maxLen > 4);

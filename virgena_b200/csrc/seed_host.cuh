@@ -354,7 +354,7 @@ static int seed_launch(vg_ctx* c, bool msa, const uint8_t* d_bases, const int64_
   memset(&A, 0, sizeof A);
   int genWarps = 0, winWarps = 0;
   if (fast) {
-    A.rdBytes = (maxReadLen + 16 + 15) & ~15;
+    A.rdBytes = (maxReadLen + 32 + 15) & ~15;  // 4 bytes in front (sentinel), >= 12 behind the read for the 4-byte compares
     if (!msa) {
       A.emptyId = (1 << (2 * K)) + nExoRef;
       A.tabBytes = ((A.emptyId + 1) * 2 + 15) & ~15;
