@@ -35,6 +35,12 @@
 __device__ __forceinline__ uint8_t sw_s1_byte(const uint8_t* s1, int m, int rc, int idx) {
   return rc ? vg_complement(s1[m - 1 - idx]) : s1[idx];
 }
+// the same with Constants.complement as a 128-byte table in shared memory: one load, no divergence on the base (the traceback
+// fetches a read byte per row of every tile and per walk step, and the lanes of its warps hold different reads)
+__device__ __forceinline__ uint8_t sw_s1_byte_lut(const uint8_t* s1, int m, int rc, int idx, const uint8_t* lut) {
+  const uint8_t b = s1[rc ? m - 1 - idx : idx];
+  return rc ? lut[b & 127] : b;
+}
 
 // Checkpoint layout (written by the fill kernel, read by the traceback kernel), per *pair* p of tasks
 // (2p, 2p+1) whose values sit in the lo / hi s16 lanes:
@@ -104,6 +110,9 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
                                                       int nT, int nTb, SwFillOut* __restrict__ out,
                                                       int* __restrict__ counter, int smemWordsPerWarp) {
   extern __shared__ uint32_t sw_smem[];
+  __shared__ uint8_t compLut[128];  // Constants.complement as a table (sw_s1_byte_lut)
+  if (threadIdx.x < 128) compLut[threadIdx.x] = vg_complement((uint8_t)threadIdx.x);
+  __syncthreads();
   constexpr int NG = 32 / W;  // pairs per warp
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -162,8 +171,8 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
 #pragma unroll
     for (int r = 0; r < R; r++) {
       int idx = gl * R + r;
-      uint32_t ca = (idx < ta.m) ? ((uint32_t)sw_s1_byte(a1, ta.m, ta.rc, idx) << 8) : SW_PAD_S1;
-      uint32_t cb = (idx < tb.m) ? ((uint32_t)sw_s1_byte(b1, tb.m, tb.rc, idx) << 8) : SW_PAD_S1;
+      uint32_t ca = (idx < ta.m) ? ((uint32_t)sw_s1_byte_lut(a1, ta.m, ta.rc, idx, compLut) << 8) : SW_PAD_S1;
+      uint32_t cb = (idx < tb.m) ? ((uint32_t)sw_s1_byte_lut(b1, tb.m, tb.rc, idx, compLut) << 8) : SW_PAD_S1;
       a[r] = ~(ca | (cb << 16));  // complemented: a[r] ^ b is the XNOR of the codes in one LOP3
       V[r] = 0;
       F[r] = NEGp;
@@ -308,7 +317,8 @@ __device__ __forceinline__ void sw_tile_recompute(const SwTask& tk, const uint8_
                                                   const typename SwCk<COMPACT>::T* __restrict__ rowckP,
                                                   const typename SwCk<COMPACT>::T* __restrict__ colckP,
                                                   int nT, int hi, int k, int cl, int jmax, uint32_t* __restrict__ flags,
-                                                  int fstride, int probeS, int probeCol, int& bestI, int& bestJ) {
+                                                  int fstride, int probeS, int probeCol, int& bestI, int& bestJ,
+                                                  const uint8_t* __restrict__ lut) {
   constexpr int WPC = SwTb<R>::WPC;
   const int r0 = k * R;
   int v[R], hs[R];
@@ -322,7 +332,7 @@ __device__ __forceinline__ void sw_tile_recompute(const SwTask& tk, const uint8_
     hs[r] = SW_NEG;
     asym[r] = 0;
     if (i <= tk.m) {
-      asym[r] = sw_s1_byte(s1, tk.m, tk.rc, i - 1);
+      asym[r] = sw_s1_byte_lut(s1, tk.m, tk.rc, i - 1, lut);
       if (cl > 0) {
         SwCk<COMPACT>::get(colckP[(int64_t)tb * (W * R) + (i - 1)], hi, prm.gep, v[r], hs[r]);
       }
@@ -410,7 +420,10 @@ __global__ void __launch_bounds__(128, 7) sw_traceback_kernel(const SwTask* __re
                                                            int64_t revStride) {
   constexpr int WPC = SwTb<R>::WPC;
   __shared__ uint32_t flagS[SW_TC * WPC * 128];
+  __shared__ uint8_t compLut[128];
   const int tid = threadIdx.x;
+  compLut[tid & 127] = vg_complement((uint8_t)(tid & 127));  // blockDim.x == 128
+  __syncthreads();
   const int ti = blockIdx.x * blockDim.x + tid;
   const bool valid = ti < ntasks;
   SwTask tk;
@@ -442,12 +455,12 @@ __global__ void __launch_bounds__(128, 7) sw_traceback_kernel(const SwTask* __re
     if (!fo.tie) {
       const int jEnd = min(fo.col, tk.n);  // fo.col = last column of the group of 4 that reached the maximum
       int cl = sw_tile_left(fo.strip, jEnd);
-      sw_tile_recompute<R, COMPACT, true, W>(tk, s1, s2, prm, rowckP, colckP, nT, hi, fo.strip, cl, jEnd, flags, 128, fo.score, fo.col, bi, bj);
+      sw_tile_recompute<R, COMPACT, true, W>(tk, s1, s2, prm, rowckP, colckP, nT, hi, fo.strip, cl, jEnd, flags, 128, fo.score, fo.col, bi, bj, compLut);
       haveK = fo.strip, haveCl = cl;
     } else {
       for (int jj = tk.n; jj >= 1;) {  // rare: the strip reached S at several columns
         int cl = sw_tile_left(fo.strip, jj);
-        sw_tile_recompute<R, COMPACT, true, W>(tk, s1, s2, prm, rowckP, colckP, nT, hi, fo.strip, cl, jj, flags, 128, fo.score, -1, bi, bj);
+        sw_tile_recompute<R, COMPACT, true, W>(tk, s1, s2, prm, rowckP, colckP, nT, hi, fo.strip, cl, jj, flags, 128, fo.score, -1, bi, bj, compLut);
         jj = cl;
       }
     }
@@ -462,7 +475,7 @@ __global__ void __launch_bounds__(128, 7) sw_traceback_kernel(const SwTask* __re
       k = (i - 1) / R;
       cl = sw_tile_left(k, j);
       if (k != haveK || cl != haveCl)
-        sw_tile_recompute<R, COMPACT, false, W>(tk, s1, s2, prm, rowckP, colckP, nT, hi, k, cl, j, flags, 128, -1, -1, no1, no2);
+        sw_tile_recompute<R, COMPACT, false, W>(tk, s1, s2, prm, rowckP, colckP, nT, hi, k, cl, j, flags, 128, -1, -1, no1, no2, compLut);
       haveK = -1;
     }
     while (!done) {
@@ -480,7 +493,7 @@ __global__ void __launch_bounds__(128, 7) sw_traceback_kernel(const SwTask* __re
           break;
         }
         if (dir == 2u) {  // DIAGONAL
-          uint8_t c1 = sw_s1_byte(s1, tk.m, tk.rc, i - 1), c2 = s2[j - 1];
+          uint8_t c1 = sw_s1_byte_lut(s1, tk.m, tk.rc, i - 1, compLut), c2 = s2[j - 1];
           out[len++] = c1;
           if (c1 == c2) identity++;
           i--, j--;
@@ -489,7 +502,7 @@ __global__ void __launch_bounds__(128, 7) sw_traceback_kernel(const SwTask* __re
         mode = (dir == 3u) ? 1 : 2;
       }
       if (mode == 1) {  // UP: sizesOfVerticalGaps[k+j] lower-case read bases
-        out[len++] = vg_lower(sw_s1_byte(s1, tk.m, tk.rc, i - 1));
+        out[len++] = vg_lower(sw_s1_byte_lut(s1, tk.m, tk.rc, i - 1, compLut));
         const bool ext = ((fw >> (16 + (rr & 7))) & 1u) != 0;
         i--;
         if (!ext) mode = 0;
