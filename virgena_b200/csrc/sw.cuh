@@ -110,9 +110,6 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
                                                       int nT, int nTb, SwFillOut* __restrict__ out,
                                                       int* __restrict__ counter, int smemWordsPerWarp) {
   extern __shared__ uint32_t sw_smem[];
-  __shared__ uint8_t compLut[128];  // Constants.complement as a table (sw_s1_byte_lut)
-  if (threadIdx.x < 128) compLut[threadIdx.x] = vg_complement((uint8_t)threadIdx.x);
-  __syncthreads();
   constexpr int NG = 32 / W;  // pairs per warp
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -171,8 +168,8 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
 #pragma unroll
     for (int r = 0; r < R; r++) {
       int idx = gl * R + r;
-      uint32_t ca = (idx < ta.m) ? ((uint32_t)sw_s1_byte_lut(a1, ta.m, ta.rc, idx, compLut) << 8) : SW_PAD_S1;
-      uint32_t cb = (idx < tb.m) ? ((uint32_t)sw_s1_byte_lut(b1, tb.m, tb.rc, idx, compLut) << 8) : SW_PAD_S1;
+      uint32_t ca = (idx < ta.m) ? ((uint32_t)sw_s1_byte(a1, ta.m, ta.rc, idx) << 8) : SW_PAD_S1;
+      uint32_t cb = (idx < tb.m) ? ((uint32_t)sw_s1_byte(b1, tb.m, tb.rc, idx) << 8) : SW_PAD_S1;
       a[r] = ~(ca | (cb << 16));  // complemented: a[r] ^ b is the XNOR of the codes in one LOP3
       V[r] = 0;
       F[r] = NEGp;
@@ -378,9 +375,10 @@ __device__ __forceinline__ void sw_tile_recompute(const SwTask& tk, const uint8_
       vd = v[r];
       const int m1 = __vibmax_s32(f, es - gop, &fGeE);
       const int m2 = __vibmax_s32(m1, hs[r] - gop, &mGeF);
-      const int V = max(m2, 0);
+      bool nonPos;
+      const int V = __vibmax_s32(0, m2, &nonPos);  // nonPos = (0 >= m2): the maximum and the STOP test in one instruction
       // STOP (V == 0) > DIAGONAL (V == f) > UP (V == E) > LEFT (:135-143)
-      const uint32_t dir = (m2 > 0) ? (mGeF ? (fGeE ? 2u : 3u) : 1u) : 0u;
+      const uint32_t dir = nonPos ? 0u : (mGeF ? (fGeE ? 2u : 3u) : 1u);
       uint32_t wv = word[r >> 3] + (dir << (2 * (r & 7)));
       if (!keepV) wv |= 1u << (16 + (r & 7));
       if (!keepH) wv |= 1u << (24 + (r & 7));
