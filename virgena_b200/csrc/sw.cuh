@@ -69,8 +69,10 @@ struct SwCk<true> {
   using T = uint32_t;
   static __device__ __forceinline__ T make(uint32_t v, uint32_t xs, uint32_t ngepP) {
     // max(Xs - gep, V) - V per lane, 0 .. 15: no half is negative, so the 32-bit subtraction is exact per half (FMA pipe)
-    const uint32_t d = __viaddmax_s16x2(xs, ngepP, v) - v;
-    return d * 4096u + v;  // = v | d << 12 (the fields do not overlap); a multiply-add issues on the FMA pipe
+    // t = max(Xs - gep, V) >= V in both halves, so (t - v) * 4096 + v is exact per half in 32-bit arithmetic; written as
+    // t * 4096 + v * (1 - 4096) it is two multiply-adds on the FMA pipe and nothing on the ALU / DPX pipe that bounds the kernel
+    const uint32_t t = __viaddmax_s16x2(xs, ngepP, v);
+    return t * 4096u + v * 0xFFFFF001u;  // = v | d << 12, d = t - v (the fields do not overlap)
   }
   static __device__ __forceinline__ void get(T w, int hi, int gep, int& v, int& xs) {
     const uint32_t h = hi ? (w >> 16) : (w & 0xFFFFu);
@@ -188,6 +190,7 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
     typename CK::T* rowp = rowck + ((int64_t)pi * W + gl) * nT;
     typename CK::T* colp = colck + ((int64_t)pi * nTb) * (W * R) + gl * R;
     const int tEnd4 = (tEnd + 3) & ~3;  // steps beyond tEnd find every lane inactive
+    const unsigned nAct = gl <= lastLane ? (unsigned)nmax : 0u;  // columns this lane computes
 
 #pragma unroll 1
     for (int tg = 0; tg < tEnd4; tg += 4) {
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(256) sw_fill_kernel(const SwTask* __restrict__
           ein = NEGp;
         }
         const int j = t - gl;
-        const bool active = (j >= 1 && j <= nmax && gl <= lastLane);
+        const bool active = (unsigned)(j - 1) < nAct;  // 1 <= j <= nmax on a lane that holds rows: one unsigned compare
         if (active) {
           const uint32_t b = wsym[j];
           uint32_t vd = vup_prev, vu = vin, e = ein, cm = cm4;  // running maximum of the current group of 4 steps
