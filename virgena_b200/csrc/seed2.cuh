@@ -908,7 +908,15 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
 #pragma unroll 1
       for (int j0 = 0; j0 < nR && !bad; j0 += 32) {
         const int j = j0 + lane;
-        int qg[3], qr[3], ql[3], np2 = 0;
+        SE q0 = 0, q1 = 0, q2 = 0;  // the pieces, packed (three named registers: an indexed array would live in local memory)
+        int np2 = 0;
+        auto put = [&](int g_, int r_, int l_) {
+          const SE e = W::pack(g_, r_, l_);
+          if (np2 == 0) q0 = e;
+          else if (np2 == 1) q1 = e;
+          else if (np2 == 2) q2 = e;
+          np2++;
+        };
         if (j < nR) {
           const SE v = S[j];
           int g = W::g(v), r = W::r(v), len = W::l(v);
@@ -922,10 +930,7 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
             }
             const int contigEnd = cEnds[lo2];
             if (g + K + len > contigEnd) {
-              if (contigEnd - g >= K) {
-                if (np2 < 3) qg[np2] = g, qr[np2] = r, ql[np2] = contigEnd - g - K;
-                np2++;
-              }
+              if (contigEnd - g >= K) put(g, r, contigEnd - g - K);
               if (g + K + len - contigEnd >= K) {
                 r += contigEnd - g;
                 len -= contigEnd - g;
@@ -934,8 +939,7 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
               }
               break;
             }
-            if (np2 < 3) qg[np2] = g, qr[np2] = r, ql[np2] = len;
-            np2++;
+            put(g, r, len);
             break;
           }
           if (np2 > 3) bad = true, np2 = 3;  // a hit across > 2 contig boundaries (contigs shorter than K + 1)
@@ -947,9 +951,9 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
           bad = true;
           break;
         }
-#pragma unroll
-        for (int t = 0; t < 3; t++)
-          if (t < np2) S2[o + t] = W::pack(qg[t], qr[t], ql[t]);
+        if (np2 >= 1) S2[o] = q0;
+        if (np2 >= 2) S2[o + 1] = q1;
+        if (np2 >= 3) S2[o + 2] = q2;
       }
       __syncwarp();
       __threadfence_block();
