@@ -990,6 +990,12 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
       auto phaseEF = [&](auto inShared, uint16_t* hitG, uint16_t* Pp, uint8_t* hitL) {
         (void)inShared;
         if (lane < 8) hitG[nR + lane] = 0xFFFFu;  // sentinels for the branch-free searches of phase F
+        // bucket[b] = first hit index with g >= 32 b: the first hit of every bucket is marked on the way through the loop
+        // below (it has the previous hit's genomePos at hand), the empty buckets are filled from the right afterwards
+        const int nb = A.nBuckets;
+  #pragma unroll 1
+        for (int b = lane; b < nb; b += 32) bucket[b] = (uint16_t)nR;
+        __syncwarp();
         int carry = 0, pgLast = 0, prLast = 0;
         SE vNext = (lane < nR) ? S[lane] : 0;  // the slot is in L2: the next chunk is requested one trip ahead
   #pragma unroll 1
@@ -1010,21 +1016,12 @@ __global__ void __launch_bounds__(1024, 1) seed_win_kernel(Seed2Args A) {
             const float rate = __fdiv_rn((float)(g - pg), (float)(r - pr));
             if (A.lowCoef <= rate && rate <= A.highCoef) val++;
           }
+          if (j < nR && (j == 0 || (pg >> 5) != (g >> 5))) bucket[g >> 5] = (uint16_t)j;
           const int incl = sd_warp_incl_scan(val, lane);
           if (j < nR) Pp[j] = (uint16_t)(carry + incl);
           carry += __shfl_sync(VG_FULL, incl, 31);
           pgLast = __shfl_sync(VG_FULL, g, 31);
           prLast = __shfl_sync(VG_FULL, r, 31);
-        }
-        // bucket[b] = first hit index with g >= 32 b
-        const int nb = A.nBuckets;
-  #pragma unroll 1
-        for (int b = lane; b < nb; b += 32) bucket[b] = (uint16_t)nR;
-        __syncwarp();
-  #pragma unroll 1
-        for (int j = lane; j < nR; j += 32) {
-          const int b = hitG[j] >> 5;
-          if (j == 0 || (hitG[j - 1] >> 5) != b) bucket[b] = (uint16_t)j;
         }
         __syncwarp();
         {  // suffix fill of empty buckets (serial over chunks from the top, parallel inside a chunk)
