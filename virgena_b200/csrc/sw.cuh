@@ -475,6 +475,17 @@ __global__ void __launch_bounds__(128, 7) sw_traceback_kernel(const SwTask* __re
     if (!done) {
       k = (i - 1) / R;
       cl = sw_tile_left(k, j);
+      {  // the path leaves this tile to the left (same strip, previous checkpoint column) or upwards (strip k - 1, this or the
+         // previous checkpoint column): ask for the left boundaries of the three candidates now, they come from HBM
+        const int tbc = (cl + k) / SW_TC;
+        const typename SwCk<COMPACT>::T* cb = colckP + (int64_t)tbc * (W * R) + k * R;
+        if (tbc > 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(cb - (W * R)));
+        if (k > 0) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(cb - R));
+          if (tbc > 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(cb - (W * R) - R));
+          if (k > 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowckP + (int64_t)(k - 2) * nT + (k - 3) + max(cl, 1)));
+        }
+      }
       if (k != haveK || cl != haveCl)
         sw_tile_recompute<R, COMPACT, false, W>(tk, s1, s2, prm, rowckP, colckP, nT, hi, k, cl, j, flags, 128, -1, -1, no1, no2, compLut);
       haveK = -1;
